@@ -1,0 +1,48 @@
+"""Shared helpers for the parity tests (fixture parsing, tolerances)."""
+import os
+import re
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def loss_cases():
+    """-> list of (loss_key, case, dict(scores, labels, loss, grad[, perm]))."""
+    z = load("losses.npz")
+    groups = {}
+    for k in z.files:
+        head, case, field = k.split("__")
+        groups.setdefault((head, case), {})[field] = z[k]
+    return [(h, c, v) for (h, c), v in sorted(groups.items())]
+
+
+def parse_loss_key(head):
+    """'LambdaLoss_NDCG_Loss2++_k5_unsorted' -> (name, params, presort)."""
+    presort = True
+    if head.endswith("_unsorted"):
+        presort, head = False, head[: -len("_unsorted")]
+    if head.endswith("_saturated"):
+        head = head[: -len("_saturated")]
+    name = head.split("_")[0]
+    params = {}
+    m = re.search(r"sigma([0-9.]+)", head)
+    if m:
+        params["sigma"] = float(m.group(1))
+    m = re.search(r"alpha([0-9.]+)", head)
+    if m:
+        params["alpha"] = float(m.group(1))
+    if name == "LambdaLoss":
+        m = re.match(r"LambdaLoss_(NDCG_Loss(?:1|2\+\+|2))_k(\d+)", head)
+        params.update(loss_type=m.group(1), k=int(m.group(2)), sigma=1.0, mu=5.0)
+    return name, params, presort
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    denom = max(np.abs(b).max(), 1e-30)
+    return float(np.abs(a - b).max() / denom)
