@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- queries/sec of one LambdaRank training step (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" = scorer forward + fused LambdaRank loss/gradient + scorer backward + gradient
+all-reduce (N>1) + optimizer step over one batch of B synthetic 256-doc x 136-feature queries
+per GPU (weak scaling).  Prints ONE JSON line on rank 0 (contract in the task statement):
+
+  value      whole-job queries/s, inputs resident in HBM (CUDA events, max over ranks)
+  e2e        same metric through the reference-facing call ranker.train(host batches):
+             pinned-host -> device copy of every batch and a device -> host read of every
+             step's loss inside the timed region
+  roofline   dominant kernel of the step, timed per launch with CUDA events in an
+             instrumented pass of the same steps (ptrb200_timing_*)
+  cpu_baseline  the oracle restatement of the reference's CPU PyTorch path on this box's cores
+--impl reference times that CPU restatement alone (rank 0 only) and prints the same line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+N_DOCS, N_FEAT = 256, 136
+MSLR_P = np.array([1940952, 1225770, 504958, 69010, 30435], dtype=np.float64)
+MSLR_P /= MSLR_P.sum()
+SEED = 137                                   # ptranking/ltr_global.py:5
+
+
+def default_sf(dropout=0.1):
+    """The reference's default pointwise scorer (ptranking/ltr_adhoc/eval/parameter.py:142-146)."""
+    return dict(sf_id="pointsf", opt="Adam", lr=1e-4,
+                pointsf=dict(num_features=N_FEAT, num_layers=5, AF="GE", TL_AF="S", apply_tl_af=True,
+                             BN=True, bn_type="BN", bn_affine=True, dropout=dropout))
+
+
+def synth_batch(rng, B, n=N_DOCS, F=N_FEAT):
+    """MSLR-WEB30K-shaped synthetic batch: N(0,1) features, graded labels with the dataset's
+    marginals, >=1 relevant doc per query, labels presorted descending."""
+    X = rng.standard_normal((B, n, F), dtype=np.float32)
+    y = rng.choice(5, size=(B, n), p=MSLR_P).astype(np.float32)
+    y[:, 0] = np.maximum(y[:, 0], 1.0)
+    y = -np.sort(-y, axis=1)
+    return torch.from_numpy(X), torch.from_numpy(y)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"],
+                    bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+# --------------------------------------------------------------------------- #
+# CPU arm: oracle restatement of the reference's PyTorch path
+# --------------------------------------------------------------------------- #
+def cpu_reference_run(steps, warmup, B_cpu, budget_s=20.0):
+    from oracle import ref_port as rp
+    torch.manual_seed(SEED)
+    rng = np.random.default_rng(SEED)
+    sf = default_sf()
+    net = rp.point_scorer(**sf["pointsf"])
+    net.train()
+    opt, _ = rp.make_optimizer(net.parameters(), sf["opt"], sf["lr"])
+    batches = [synth_batch(rng, B_cpu) for _ in range(2)]
+    for i in range(warmup):
+        rp.train_op(net, opt, "LambdaRank", *batches[i % 2], sigma=1.0)
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(steps):
+        rp.train_op(net, opt, "LambdaRank", *batches[i % 2], sigma=1.0)
+        done += 1
+        if time.perf_counter() - t0 > budget_s and done >= 3:
+            break
+    dt = time.perf_counter() - t0
+    return dict(qps=done * B_cpu / dt, ms_per_step=1e3 * dt / done, steps=done, B=B_cpu,
+                cores=torch.get_num_threads())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B_cpu = args.cpu_batch
+    r = cpu_reference_run(args.steps, args.warmup, B_cpu, budget_s=120.0)
+    sample = f"{r['steps']} steps x {B_cpu} queries x {N_DOCS} docs x {N_FEAT} feat, oracle/ref_port.py train_op"
+    line = {
+        "impl": "reference", "metric": "queries/sec (LambdaRank train step, 256-doc lists)", "value": r["qps"],
+        "unit": "queries/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "LambdaRank + pointwise-MLP (5x100 GELU, BN affine, sigmoid tail), 136 feat x 256 docs",
+                   "queries_per_step": B_cpu, "n_docs": N_DOCS, "n_features": N_FEAT, "device": "cpu"},
+        "cpu_baseline": {"value": r["qps"], "unit": "queries/s", "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["qps"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- #
+# B200 arm
+# --------------------------------------------------------------------------- #
+class HostBatches:
+    """Iterable of (ids, X, y) pinned-host batches -- what ranker.train() consumes (the reference's
+    DataLoader contract: data_utils.py:683-742, uniform n per batch)."""
+
+    def __init__(self, batches, count):
+        self.batches, self.count = batches, count
+
+    def __iter__(self):
+        for i in range(self.count):
+            X, y = self.batches[i % len(self.batches)]
+            yield [str(q) for q in range(X.size(0))], X, y
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    import ptranking_b200
+    from ptranking_b200 import _lib, LABEL_TYPE
+    from ptranking_b200 import dist as b200dist
+
+    rank, local, world = b200dist.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    B = args.batch
+    torch.manual_seed(SEED)
+    rng = np.random.default_rng(SEED + rank)
+    ranker = ptranking_b200.LambdaRank(sf_para_dict=default_sf(), model_para_dict=dict(model_id="LambdaRank", sigma=1.0),
+                                       gpu=True, device=dev)
+    ranker.init()
+    if world > 1:   # identical initial weights on every rank
+        for p in ranker.get_parameters():
+            dist.broadcast(p.data, src=0)
+    ranker.train_mode()
+    host = [tuple(t.pin_memory() for t in synth_batch(rng, B)) for _ in range(2)]
+    devb = [(X.to(dev), y.to(dev)) for X, y in host]
+    kw = dict(presort=True, label_type=LABEL_TYPE.MultiLabel, epoch_k=1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t)
+        return ms
+
+    # ---- value: device-resident inputs -----------------------------------------
+    for i in range(args.warmup):
+        ranker.train_op(*devb[i % 2], **kw)
+    barrier()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            loss, _ = ranker.train_op(*devb[i % 2], **kw)
+        e1.record()
+        barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = _lib.launch_count() - l0
+    value = world * B * args.steps / (ms / 1e3)
+    last_loss = float(loss)
+
+    # ---- e2e: host batches through ranker.train ---------------------------------
+    loader_w = HostBatches(host, args.warmup)
+    ranker.train(loader_w, epoch_k=1, presort=True, label_type=LABEL_TYPE.MultiLabel)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    ep_loss, _ = ranker.train(HostBatches(host, args.steps), epoch_k=1, presort=True, label_type=LABEL_TYPE.MultiLabel)
+    ep_loss_host = float(ep_loss.cpu())
+    t1.record()
+    barrier()
+    ms_e2e = max_over_ranks(t0.elapsed_time(t1))
+    e2e = world * B * args.steps / (ms_e2e / 1e3)
+    h2d = int(host[0][0].numel() * 4 + host[0][1].numel() * 4)
+
+    # ---- roofline pass: per-launch CUDA events around every kernel of the same steps ----
+    roof = None
+    if rank == 0:
+        _lib.kernel_timings(enable=True)
+        for i in range(min(args.steps, 5)):
+            ranker.train_op(*devb[i % 2], **kw)
+        torch.cuda.synchronize()
+        tm = _lib.kernel_timings()
+        _lib.kernel_timings(enable=False)
+        total_ms = sum(v[1] for v in tm.values())
+        name, (cnt, kms) = max(tm.items(), key=lambda kv: kv[1][1])
+        peaks = measured_peaks()
+        rows = B * N_DOCS
+        if name.startswith("gemm"):
+            # fused-step FLOPs the three GEMM families execute per step (107,400 FLOP/doc fwd,
+            # x2 more for dgrad + wgrad); per-family share: fwd = bwd_weight = 107,400, bwd_data = 107,400 - 2*136*100
+            per_doc = {"gemm_simt_fwd": 107400.0, "gemm_simt_bwd_weight": 107400.0,
+                       "gemm_simt_bwd_data": 107400.0 - 2.0 * 136 * 100}.get(name, 107400.0)
+            steps_timed = min(args.steps, 5)
+            flops_per_launch = per_doc * rows * steps_timed / cnt
+            achieved = flops_per_launch / (kms / cnt * 1e-3) / 1e12
+            peak = peaks["bf16_tflops_sustained"]
+            roof = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] + " (sustained bf16 cuBLAS)",
+                    "share_of_step": kms / total_ms,
+                    "note": "fp32 SIMT GEMM (no tensor cores yet); fraction is against the bf16 tensor peak"}
+        else:
+            bytes_per_launch = 12.0 * N_DOCS * B
+            achieved = bytes_per_launch / (kms / cnt * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                    "share_of_step": kms / total_ms}
+        roof["kernels_ms_per_step"] = {k: round(v[1] / min(args.steps, 5), 4) for k, v in sorted(tm.items(), key=lambda kv: -kv[1][1])}
+    barrier()
+
+    # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(steps=40, warmup=2, B_cpu=args.cpu_batch, budget_s=15.0)
+        cpu = {"value": r["qps"], "unit": "queries/s", "cores": r["cores"], "kind": "port",
+               "sample": f"{r['steps']} steps x {r['B']} queries x {N_DOCS} docs (oracle/ref_port.py train_op, fp32 CPU PyTorch ops)"}
+
+    if rank == 0:
+        line = {
+            "metric": "queries/sec (LambdaRank train step, 256-doc lists)", "value": value, "unit": "queries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "LambdaRank + pointwise-MLP (5x100 GELU, BN affine, sigmoid tail, dropout 0.1, Adam), "
+                                   "136 feat x 256 docs (BASELINE.json configs[1])",
+                       "queries_per_gpu_per_step": B, "n_docs": N_DOCS, "n_features": N_FEAT,
+                       "parallelism": f"dp{world}", "l2": "inputs (2 x 143 MB rotating batches) larger than the 126 MB L2",
+                       "normalisation": "BN (reference default, batch statistics per rank)"},
+            "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps, "epoch_loss": ep_loss_host},
+            "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu,
+            "last_loss": last_loss,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="queries per GPU per step")
+    ap.add_argument("--cpu-batch", type=int, default=64, help="queries per step on the CPU arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

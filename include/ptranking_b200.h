@@ -1,0 +1,190 @@
+/* ptranking_b200.h -- C ABI of the B200-native PTRanking hot path (libptranking_b200.so).
+ *
+ * PTRanking has no FFI of its own: its plugin API is a Python class contract
+ * (SURVEY.md 8b).  This header is the boundary a maintainer binds from that
+ * contract (ctypes stub in INTEGRATION.md): every entry point replaces the
+ * PyTorch-eager body of one reference function, cited per declaration
+ * (paths relative to the wildltr/ptranking checkout, commit f1d366c).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     marked "host"; tensors are dense row-major fp32 ([B,n] scores/labels,
+ *     [B,n,F] features), int32 for index data.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - no allocation inside the library: the caller passes every output and
+ *     workspace buffer; ptrb200_*_workspace_bytes() says how much.
+ *   - return 0 on success or a negative PTRB200_ERR_* code; nothing throws
+ *     across the boundary.  ptrb200_last_error() returns a host string
+ *     describing the last failure on the calling thread.
+ *   - every launch is asynchronous on `stream`; results are ordered after it.
+ */
+#ifndef PTRANKING_B200_H
+#define PTRANKING_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* every entry point below is exported with default visibility; the rest of the library is hidden */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define PTRB200_OK               0
+#define PTRB200_ERR_INVALID     -1   /* bad argument (null pointer, non-positive size, unknown enum) */
+#define PTRB200_ERR_UNSUPPORTED -2   /* size outside what the kernels are built for (see limits below) */
+#define PTRB200_ERR_CUDA        -3   /* CUDA runtime / launch failure */
+#define PTRB200_ERR_WORKSPACE   -4   /* workspace too small */
+
+#define PTRB200_MAX_LIST_LEN  4096   /* docs per query handled by the per-list kernels */
+#define PTRB200_MAX_FF_LAYERS   16   /* linear layers in one stacked feed-forward net */
+#define PTRB200_MAX_CUTOFFS     32   /* nDCG cutoffs per call */
+
+typedef void* ptrb200_stream_t;
+
+/* ---- library bookkeeping -------------------------------------------------- */
+int                ptrb200_version(void);
+const char*        ptrb200_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long ptrb200_launch_count(void);
+/* 1 if the current device is compute capability 10.x (the only target built) */
+int                ptrb200_device_ok(void);
+/* Per-launch CUDA-event timing on the launching stream (bench.py's roofline pass; off by default).
+ * ptrb200_timing_report synchronises the recorded events and writes one line per kernel,
+ * "name<TAB>launches<TAB>total_ms", into the host buffer, then clears the record. */
+int                ptrb200_timing_enable(int on);
+int                ptrb200_timing_report(char* buf_host, int buflen);
+
+/* ---- ranking losses: loss value per query + d(sum loss)/d(scores) ---------- */
+/* Each call writes loss_per_query[B] (the reference returns their sum) and
+ * grad[B,n] = d(sum_b loss_b)/d scores -- the tensor autograd would hand back
+ * to the scorer after the reference's `batch_loss.backward()`. */
+
+/* RankNet.custom_loss_function, ptranking/ltr_adhoc/pairwise/ranknet.py:25-36
+ * (+ get_pairwise_comp_probs, ltr_adhoc/util/lambda_utils.py:5-23). */
+int ptrb200_ranknet_fwd_bwd(const float* scores, const float* labels, float* grad, float* loss_per_query,
+                            int B, int n, float sigma, ptrb200_stream_t stream);
+
+/* LambdaRank.custom_loss_function, ptranking/ltr_adhoc/listwise/lambdarank.py:27-56
+ * (+ get_delta_ndcg, metric/metric_utils.py:19-45).  Labels must be presorted
+ * descending (lambdarank.py:36). */
+int ptrb200_lambdarank_fwd_bwd(const float* scores, const float* labels, float* grad, float* loss_per_query,
+                               int B, int n, float sigma, ptrb200_stream_t stream);
+
+#define PTRB200_NDCG_LOSS1    0
+#define PTRB200_NDCG_LOSS2    1
+#define PTRB200_NDCG_LOSS2PP  2
+/* LambdaLoss.custom_loss_function, ptranking/ltr_adhoc/listwise/lambdaloss.py:73-132.
+ * NDCG_Loss1 is evaluated per query (the reference's broadcast only works for B==1). */
+int ptrb200_lambdaloss_fwd_bwd(const float* scores, const float* labels, float* grad, float* loss_per_query,
+                               int B, int n, int k, float sigma, float mu, int loss_type, int presort,
+                               ptrb200_stream_t stream);
+
+/* ListNet.custom_loss_function, ptranking/ltr_adhoc/listwise/listnet.py:39. */
+int ptrb200_listnet_fwd_bwd(const float* scores, const float* labels, float* grad, float* loss_per_query,
+                            int B, int n, ptrb200_stream_t stream);
+
+/* ListMLE.custom_loss_function, ptranking/ltr_adhoc/listwise/listmle.py:83-97, with the
+ * tie-shuffled ordering `perm[B,n]` (int32 doc indices, labels descending) supplied. */
+int ptrb200_listmle_fwd_bwd(const float* scores, const int32_t* perm, float* grad, float* loss_per_query,
+                            int B, int n, ptrb200_stream_t stream);
+
+/* arg_shuffle_ties, ptranking/ltr_adhoc/util/sampling_utils.py:13-28: perm[B,n] orders each
+ * row's labels descending with ties broken uniformly at random (Philox4x32-10 keyed by
+ * (seed, offset, b, doc); not the torch RNG stream). */
+int ptrb200_shuffle_ties_perm(const float* labels, int32_t* perm, int B, int n,
+                              uint64_t seed, uint64_t offset, ptrb200_stream_t stream);
+
+/* ApproxNDCG.custom_loss_function, ptranking/ltr_adhoc/listwise/approxNDCG.py:83-101
+ * (+ get_approx_ranks :19-28, approxNDCG_loss :45-62, Robust_Sigmoid base/utils.py:57-92).
+ * batch_coupled != 0 keeps the reference's [B]/[B,1] broadcast (every query scaled by
+ * sum_a 1/iDCG_a, :58-61).  scratch: B+1 floats. */
+int ptrb200_approxndcg_fwd_bwd(const float* scores, const float* labels, float* grad, float* loss_per_query,
+                               float* scratch, int B, int n, float alpha, int presort, int batch_coupled,
+                               ptrb200_stream_t stream);
+
+/* deterministic (fixed-order) sum of n floats into out[0] -- the `torch.sum` over queries
+ * that ends every reference loss (e.g. lambdarank.py:56). */
+int ptrb200_sum_f32(const float* x, float* out, int n, ptrb200_stream_t stream);
+
+/* ---- evaluation metric ------------------------------------------------------ */
+/* Evaluator.ndcg_at_ks ranking + torch_ndcg_at_ks, ptranking/base/ranker.py:67-95 and
+ * metric/adhoc/adhoc_metric.py:219-260.  out[B,nks]; cutoffs > n yield 0 (the reference's
+ * zero padding).  order[B,n] (optional, may be NULL) receives the doc indices in predicted
+ * rank order (score descending, index ascending among equal scores).  ks: host pointer. */
+int ptrb200_ndcg_at_ks(const float* scores, const float* labels, const int32_t* ks_host, int nks,
+                       float* out, int32_t* order, int B, int n, int presort, ptrb200_stream_t stream);
+
+/* ---- stacked feed-forward scorer (pointwise MLP; also the head/tail nets of listsf) ---- */
+/* get_stacked_FFNet, ptranking/base/utils.py:288-356; PointNeuralRanker.forward,
+ * base/point_ranker.py:45-55; LTRBatchNorm / LTRBatchNorm2, base/utils.py:201-282;
+ * get_AF, base/utils.py:101-143. */
+#define PTRB200_AF_NONE   0
+#define PTRB200_AF_RELU   1   /* 'R'  */
+#define PTRB200_AF_GELU   2   /* 'GE' exact erf */
+#define PTRB200_AF_SIGM   3   /* 'S'  */
+#define PTRB200_AF_TANH   4   /* 'T'  */
+#define PTRB200_AF_CELU   5   /* 'CE' alpha=1 */
+#define PTRB200_AF_ELU    6   /* 'E'  alpha=1 */
+#define PTRB200_AF_LRELU  7   /* 'LR' slope 0.01 */
+#define PTRB200_AF_SELU   8   /* 'SE' */
+
+#define PTRB200_NORM_NONE 0
+#define PTRB200_NORM_BN   1   /* LTRBatchNorm: statistics over all B*n rows, train and eval */
+#define PTRB200_NORM_BN2  2   /* LTRBatchNorm2: statistics per query */
+
+typedef struct ptrb200_ffnet {
+    int num_linear;                        /* linear layers, output layer included            */
+    int dims[PTRB200_MAX_FF_LAYERS + 1];   /* dims[0]=in features ... dims[num_linear]=out    */
+    int act_hidden;                        /* PTRB200_AF_* after every hidden layer           */
+    int act_tail;                          /* PTRB200_AF_* after the last layer, AF_NONE when apply_tl_af is false */
+    int norm;                              /* PTRB200_NORM_* on every layer that has an activation */
+    int norm_affine;                       /* bn_affine                                       */
+    float dropout_p;                       /* Dropout before every hidden Linear; 0 disables  */
+    /* parameters, one pointer per linear layer l = 0..num_linear-1 (nn.Linear layout [out,in]) */
+    const float* weight[PTRB200_MAX_FF_LAYERS];
+    const float* bias[PTRB200_MAX_FF_LAYERS];
+    /* norm parameters per layer (NULL where absent): BN: gamma/beta = bn.weight/bn.bias when affine;
+     * BN2: gamma/beta always, plus aff_w/aff_b when affine */
+    const float* gamma[PTRB200_MAX_FF_LAYERS];
+    const float* beta[PTRB200_MAX_FF_LAYERS];
+    const float* aff_w[PTRB200_MAX_FF_LAYERS];
+    const float* aff_b[PTRB200_MAX_FF_LAYERS];
+} ptrb200_ffnet;
+
+typedef struct ptrb200_ffnet_grads {       /* same layout as the parameter pointers; written (not accumulated) */
+    float* weight[PTRB200_MAX_FF_LAYERS];
+    float* bias[PTRB200_MAX_FF_LAYERS];
+    float* gamma[PTRB200_MAX_FF_LAYERS];
+    float* beta[PTRB200_MAX_FF_LAYERS];
+    float* aff_w[PTRB200_MAX_FF_LAYERS];
+    float* aff_b[PTRB200_MAX_FF_LAYERS];
+} ptrb200_ffnet_grads;
+
+/* bytes of activation workspace the forward pass fills for the backward pass
+ * (rows = B*n documents) */
+int64_t ptrb200_ffnet_workspace_bytes(const ptrb200_ffnet* net, int B, int n);
+
+/* forward: X[B,n,dims[0]] -> out[B,n,dims[last]].  `workspace` keeps pre-activations and
+ * statistics for ptrb200_ffnet_backward.  dropout uses Philox keyed by (seed, offset). */
+int ptrb200_ffnet_forward(const ptrb200_ffnet* net, const float* X, float* out, void* workspace,
+                          int64_t workspace_bytes, int B, int n, int training,
+                          uint64_t seed, uint64_t offset, ptrb200_stream_t stream);
+
+/* backward: dOut[B,n,dims[last]] -> parameter grads (+ dX[B,n,dims[0]] when dX != NULL).
+ * Must follow a forward call with the same net/X/workspace/seed/offset. */
+int ptrb200_ffnet_backward(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grads, const float* X,
+                           const float* dOut, float* dX, void* workspace, int64_t workspace_bytes,
+                           int B, int n, int training, uint64_t seed, uint64_t offset,
+                           ptrb200_stream_t stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTRANKING_B200_H */

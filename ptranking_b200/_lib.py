@@ -1,0 +1,121 @@
+"""ctypes binding of libptranking_b200.so (the C ABI declared in include/ptranking_b200.h).
+
+There is no CPU fallback: if the shared library is missing or the device is not
+sm_100, loading raises -- the product path never routes around the CUDA kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libptranking_b200.so")
+
+MAX_FF_LAYERS = 16
+MAX_CUTOFFS = 32
+MAX_LIST_LEN = 4096
+
+AF_CODES = {None: 0, "R": 1, "GE": 2, "S": 3, "T": 4, "CE": 5, "E": 6, "LR": 7, "SE": 8}
+NORM_CODES = {None: 0, "BN": 1, "BN2": 2}
+LAMBDALOSS_TYPES = {"NDCG_Loss1": 0, "NDCG_Loss2": 1, "NDCG_Loss2++": 2}
+
+_fp = C.c_void_p   # device pointers travel as integers
+
+
+class FFNetDesc(C.Structure):
+    """struct ptrb200_ffnet"""
+    _fields_ = [
+        ("num_linear", C.c_int),
+        ("dims", C.c_int * (MAX_FF_LAYERS + 1)),
+        ("act_hidden", C.c_int),
+        ("act_tail", C.c_int),
+        ("norm", C.c_int),
+        ("norm_affine", C.c_int),
+        ("dropout_p", C.c_float),
+        ("weight", _fp * MAX_FF_LAYERS),
+        ("bias", _fp * MAX_FF_LAYERS),
+        ("gamma", _fp * MAX_FF_LAYERS),
+        ("beta", _fp * MAX_FF_LAYERS),
+        ("aff_w", _fp * MAX_FF_LAYERS),
+        ("aff_b", _fp * MAX_FF_LAYERS),
+    ]
+
+
+class FFNetGrads(C.Structure):
+    """struct ptrb200_ffnet_grads"""
+    _fields_ = [(name, _fp * MAX_FF_LAYERS) for name in ("weight", "bias", "gamma", "beta", "aff_w", "aff_b")]
+
+
+# name -> (restype, argtypes); mirrors include/ptranking_b200.h one to one
+_I, _F, _U64, _I64 = C.c_int, C.c_float, C.c_uint64, C.c_int64
+SIGNATURES = {
+    "ptrb200_version": (_I, []),
+    "ptrb200_last_error": (C.c_char_p, []),
+    "ptrb200_launch_count": (C.c_ulonglong, []),
+    "ptrb200_device_ok": (_I, []),
+    "ptrb200_timing_enable": (_I, [_I]),
+    "ptrb200_timing_report": (_I, [C.c_char_p, _I]),
+    "ptrb200_ranknet_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _I, _I, _F, _fp]),
+    "ptrb200_lambdarank_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _I, _I, _F, _fp]),
+    "ptrb200_lambdaloss_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _I, _I, _I, _F, _F, _I, _I, _fp]),
+    "ptrb200_listnet_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _I, _I, _fp]),
+    "ptrb200_listmle_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _I, _I, _fp]),
+    "ptrb200_shuffle_ties_perm": (_I, [_fp, _fp, _I, _I, _U64, _U64, _fp]),
+    "ptrb200_approxndcg_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _fp, _I, _I, _F, _I, _I, _fp]),
+    "ptrb200_sum_f32": (_I, [_fp, _fp, _I, _fp]),
+    "ptrb200_ndcg_at_ks": (_I, [_fp, _fp, C.POINTER(C.c_int32), _I, _fp, _fp, _I, _I, _I, _fp]),
+    "ptrb200_ffnet_workspace_bytes": (_I64, [C.POINTER(FFNetDesc), _I, _I]),
+    "ptrb200_ffnet_forward": (_I, [C.POINTER(FFNetDesc), _fp, _fp, _fp, _I64, _I, _I, _I, _U64, _U64, _fp]),
+    "ptrb200_ffnet_backward": (_I, [C.POINTER(FFNetDesc), C.POINTER(FFNetGrads), _fp, _fp, _fp, _fp, _I64,
+                                    _I, _I, _I, _U64, _U64, _fp]),
+}
+
+_lib = None
+
+
+class B200LibraryError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the shared library once and attach the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m ptranking_b200.build` "
+            "(nvcc, sm_100a).  ptranking_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().ptrb200_last_error()
+        raise B200LibraryError(f"{what} failed with code {rc}: {msg.decode() if msg else ''}")
+
+
+def launch_count() -> int:
+    return int(load().ptrb200_launch_count())
+
+
+def kernel_timings(enable=None):
+    """enable=True/False switches per-launch event timing; enable=None drains the record ->
+    {kernel name: (launches, total_ms)}."""
+    lib = load()
+    if enable is not None:
+        check(lib.ptrb200_timing_enable(int(bool(enable))), "timing_enable")
+        return None
+    buf = C.create_string_buffer(1 << 16)
+    check(lib.ptrb200_timing_report(buf, len(buf)), "timing_report")
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split("\t")
+        out[name] = (int(cnt), float(ms))
+    return out

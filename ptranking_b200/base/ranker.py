@@ -1,0 +1,194 @@
+"""NeuralRanker / Evaluator with the reference's method set (ptranking/base/ranker.py:28-65,
+:67-95, :189-200, :479-630) driving the B200 kernels.
+
+Differences kept deliberately small and listed in DESIGN.md: tensors live on the CUDA
+device for the whole step; nDCG is computed by the in-CTA sort kernel on the device
+(the reference copies predictions to the host and sorts there, ranker.py:46-50)."""
+from __future__ import annotations
+
+from enum import Enum, auto, unique
+
+import torch
+import torch.optim as optim
+from torch.optim.lr_scheduler import StepLR
+
+from .. import ops
+from .. import dist as b200dist
+
+
+@unique
+class LABEL_TYPE(Enum):
+    """Same members as ptranking.data.data_utils.LABEL_TYPE (data_utils.py:88-91)."""
+    MultiLabel = auto()
+    Permutation = auto()
+
+
+def _is_multilabel(label_type) -> bool:
+    return getattr(label_type, "name", label_type) == "MultiLabel"
+
+
+class Evaluator:
+    """nDCG evaluation API of ptranking.base.ranker.Evaluator."""
+
+    def _scores_and_labels(self, batch_q_doc_vectors, batch_std_labels):
+        dev = self.device
+        preds = self.predict(batch_q_doc_vectors.to(dev, non_blocking=True))
+        return preds.detach(), batch_std_labels.to(dev, non_blocking=True)
+
+    def ndcg_at_k(self, test_data=None, k=10, label_type=LABEL_TYPE.MultiLabel, presort=False, device='cpu'):
+        """ranker.py:31-65: average nDCG@k; batches with fewer than k documents are skipped (:41-42)."""
+        assert _is_multilabel(label_type)
+        self.eval_mode()
+        num_queries = 0
+        total = torch.zeros(1, device=self.device)
+        for batch_ids, X, y in test_data:
+            if y.size(1) < k:
+                continue
+            num_queries += len(batch_ids)
+            preds, labels = self._scores_and_labels(X, y)
+            total += ops.sum_f32(ops.ndcg_at_ks(preds, labels, [k], presort=presort))
+        return (total / num_queries).cpu()
+
+    def ndcg_at_ks(self, test_data=None, ks=[1, 5, 10], label_type=LABEL_TYPE.MultiLabel, presort=False, device='cpu'):
+        """ranker.py:67-95."""
+        assert _is_multilabel(label_type)
+        self.eval_mode()
+        num_queries = 0
+        total = torch.zeros(len(ks), device=self.device)
+        for batch_ids, X, y in test_data:
+            preds, labels = self._scores_and_labels(X, y)
+            total += ops.ndcg_at_ks(preds, labels, ks, presort=presort).sum(dim=0)
+            num_queries += len(batch_ids)
+        return (total / num_queries).cpu()
+
+    def validation(self, vali_data=None, vali_metric=None, k=5, presort=False, max_label=None,
+                   label_type=LABEL_TYPE.MultiLabel, device='cpu'):
+        """ranker.py:189-200 (nDCG branch; nERR/AP/P are SURVEY 8f 'next')."""
+        if 'nDCG' == vali_metric:
+            return self.ndcg_at_k(test_data=vali_data, k=k, label_type=label_type, presort=presort, device=device)
+        raise NotImplementedError(f"validation metric {vali_metric!r}: only nDCG is on the B200 path")
+
+
+class NeuralRanker(Evaluator):
+    """ptranking/base/ranker.py:479-630."""
+
+    def __init__(self, id='AbsRanker', sf_para_dict=None, weight_decay=1e-3, gpu=False, device=None):
+        self.id = id
+        self.gpu, self.device = gpu, device
+        self.sf_para_dict = sf_para_dict
+        self.sf_id = sf_para_dict['sf_id']
+        self.opt, self.lr = sf_para_dict['opt'], sf_para_dict['lr']
+        self.weight_decay = weight_decay
+        self.stop_check_freq = 10
+        self._require_cuda()
+
+    def _require_cuda(self):
+        if not self.gpu or self.device is None or not str(self.device).startswith('cuda'):
+            raise RuntimeError("ptranking_b200 rankers run on a CUDA device only (gpu=True, device='cuda:N'); "
+                               "there is no CPU fallback")
+
+    def init(self):
+        pass
+
+    def get_parameters(self):
+        pass
+
+    def config_optimizer(self):
+        """ranker.py:512-525: Adam | RMS | Adagrad with L2-in-gradient weight decay + StepLR(20, 0.5)."""
+        params = list(self.get_parameters())
+        self.grad_bucket = b200dist.GradBucket(params)     # one flat fp32 gradient buffer (one all-reduce per step)
+        if 'Adam' == self.opt:
+            self.optimizer = optim.Adam(params, lr=self.lr, weight_decay=self.weight_decay)
+        elif 'RMS' == self.opt:
+            self.optimizer = optim.RMSprop(params, lr=self.lr, weight_decay=self.weight_decay)
+        elif 'Adagrad' == self.opt:
+            self.optimizer = optim.Adagrad(params, lr=self.lr, weight_decay=self.weight_decay)
+        else:
+            raise NotImplementedError
+        self.scheduler = StepLR(self.optimizer, step_size=20, gamma=0.5)
+
+    def backward_and_step(self, batch_loss):
+        """The tail every reference loss class ends with (e.g. lambdarank.py:58-60), plus the
+        data-parallel gradient all-reduce (sum: every reference loss is a sum over queries)."""
+        self.grad_bucket.zero()
+        batch_loss.backward()
+        self.grad_bucket.all_reduce()
+        self.optimizer.step()
+
+    def eval_mode(self):
+        pass
+
+    def train_mode(self):
+        pass
+
+    def save(self, dir, name):
+        pass
+
+    def load(self, file_model, **kwargs):
+        pass
+
+    def uniform_eval_setting(self, **kwargs):
+        pass
+
+    def stop_training(self, batch_preds):
+        """ranker.py:547-561."""
+        if torch.nonzero(batch_preds, as_tuple=False).size(0) <= 0:
+            print('All zero error.\n')
+            return True
+        if torch.isnan(batch_preds).any():
+            print('Including NaN error.')
+            return True
+        return False
+
+    def train(self, train_data, epoch_k=None, **kwargs):
+        """ranker.py:565-587.  Host batches are copied with non_blocking=True (pinned sources overlap
+        with the previous step).  The reference's blocking ``batch_loss.item()`` per batch (:584) becomes an
+        asynchronous device->host copy of every step's loss into a pinned buffer, read once at the end,
+        so the loop never stalls the GPU."""
+        self.train_mode()
+        assert 'label_type' in kwargs and 'presort' in kwargs
+        label_type, presort = kwargs['label_type'], kwargs['presort']
+        num_queries = 0
+        stop_training = False
+        ring = self._loss_ring()
+        host_sum, filled = 0.0, 0
+        for batch_ids, X, y in train_data:
+            num_queries += len(batch_ids)
+            X, y = X.to(self.device, non_blocking=True), y.to(self.device, non_blocking=True)
+            batch_loss, stop_training = self.train_op(X, y, batch_ids=batch_ids, epoch_k=epoch_k,
+                                                      presort=presort, label_type=label_type)
+            if stop_training:
+                break
+            ring[filled].copy_(batch_loss.detach(), non_blocking=True)
+            filled += 1
+            if filled == ring.numel():
+                torch.cuda.current_stream().synchronize()
+                host_sum += float(ring.double().sum())
+                filled = 0
+        torch.cuda.current_stream().synchronize()
+        host_sum += float(ring[:filled].double().sum())
+        epoch_loss = torch.tensor([host_sum / max(num_queries, 1)], device=self.device)
+        return epoch_loss, stop_training
+
+    def _loss_ring(self):
+        if getattr(self, '_ring', None) is None:
+            self._ring = torch.zeros(1024, dtype=torch.float32).pin_memory()
+        return self._ring
+
+    def train_op(self, batch_q_doc_vectors, batch_std_labels, **kwargs):
+        """ranker.py:589-603."""
+        stop_training = False
+        batch_preds = self.forward(batch_q_doc_vectors)
+        if 'epoch_k' in kwargs and kwargs['epoch_k'] is not None and kwargs['epoch_k'] % self.stop_check_freq == 0:
+            stop_training = self.stop_training(batch_preds)
+        return self.custom_loss_function(batch_preds, batch_std_labels, **kwargs), stop_training
+
+    def custom_loss_function(self, batch_preds, batch_std_labels, **kwargs):
+        pass
+
+    def forward(self, batch_q_doc_vectors):
+        pass
+
+    def predict(self, batch_q_doc_vectors):
+        """ranker.py:623-630."""
+        return self.forward(batch_q_doc_vectors)

@@ -1,0 +1,272 @@
+"""Torch-side glue over the C ABI: device memory, streams and autograd plumbing only.
+
+Every function takes CUDA fp32 tensors, passes raw device pointers + the current
+CUDA stream to libptranking_b200.so and returns tensors allocated by torch.  No
+arithmetic of the hot path happens in Python/ATen here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.B200LibraryError(f"{name} must be a CUDA tensor: ptranking_b200 has no CPU path")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _check_pair(scores: torch.Tensor, labels: torch.Tensor):
+    if scores.dim() != 2 or scores.shape != labels.shape:
+        raise ValueError(f"expected scores/labels of identical shape [B,n], got {tuple(scores.shape)} / {tuple(labels.shape)}")
+    return scores.shape
+
+
+# --------------------------------------------------------------------------- #
+# ranking losses
+# --------------------------------------------------------------------------- #
+def _loss_call(name: str, scores: torch.Tensor, labels: torch.Tensor, params: dict):
+    """-> (loss_per_query[B], grad[B,n]) from one fused kernel launch."""
+    lib = _lib.load()
+    s = _dev_f32(scores, "scores")
+    B, n = s.shape
+    grad = torch.empty_like(s)
+    loss_q = torch.empty(B, dtype=torch.float32, device=s.device)
+    st = _stream_ptr()
+    if name == "ListMLE":
+        perm = params.get("perm")
+        if perm is None:
+            perm = shuffle_ties_perm(labels)
+        perm = perm.to(device=s.device, dtype=torch.int32).contiguous()
+        rc = lib.ptrb200_listmle_fwd_bwd(s.data_ptr(), perm.data_ptr(), grad.data_ptr(), loss_q.data_ptr(), B, n, st)
+    else:
+        y = _dev_f32(labels, "labels")
+        _check_pair(s, y)
+        if name == "RankNet":
+            rc = lib.ptrb200_ranknet_fwd_bwd(s.data_ptr(), y.data_ptr(), grad.data_ptr(), loss_q.data_ptr(), B, n,
+                                             float(params.get("sigma", 1.0)), st)
+        elif name == "LambdaRank":
+            rc = lib.ptrb200_lambdarank_fwd_bwd(s.data_ptr(), y.data_ptr(), grad.data_ptr(), loss_q.data_ptr(), B, n,
+                                                float(params.get("sigma", 1.0)), st)
+        elif name == "LambdaLoss":
+            lt = _lib.LAMBDALOSS_TYPES[params.get("loss_type", "NDCG_Loss2++")]
+            rc = lib.ptrb200_lambdaloss_fwd_bwd(s.data_ptr(), y.data_ptr(), grad.data_ptr(), loss_q.data_ptr(), B, n,
+                                                int(params.get("k", 5)), float(params.get("sigma", 1.0)),
+                                                float(params.get("mu", 5.0)), lt, int(bool(params.get("presort", True))), st)
+        elif name == "ListNet":
+            rc = lib.ptrb200_listnet_fwd_bwd(s.data_ptr(), y.data_ptr(), grad.data_ptr(), loss_q.data_ptr(), B, n, st)
+        elif name == "ApproxNDCG":
+            scratch = torch.empty(B + 1, dtype=torch.float32, device=s.device)
+            rc = lib.ptrb200_approxndcg_fwd_bwd(s.data_ptr(), y.data_ptr(), grad.data_ptr(), loss_q.data_ptr(),
+                                                scratch.data_ptr(), B, n, float(params.get("alpha", 10.0)),
+                                                int(bool(params.get("presort", True))),
+                                                int(bool(params.get("batch_coupled", True))), st)
+        else:
+            raise NotImplementedError(name)
+    _lib.check(rc, f"{name} loss kernel")
+    return loss_q, grad
+
+
+def sum_f32(x: torch.Tensor) -> torch.Tensor:
+    """Fixed-order device sum -> 0-dim tensor."""
+    lib = _lib.load()
+    x = _dev_f32(x, "x").reshape(-1)
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    _lib.check(lib.ptrb200_sum_f32(x.data_ptr(), out.data_ptr(), x.numel(), _stream_ptr()), "sum_f32")
+    return out.reshape(())
+
+
+class _RankLoss(torch.autograd.Function):
+    """batch loss = sum of per-query losses; backward hands the fused gradient to the scorer."""
+
+    @staticmethod
+    def forward(ctx, scores, labels, name, params):
+        loss_q, grad = _loss_call(name, scores.detach(), labels, params)
+        ctx.save_for_backward(grad)
+        ctx.mark_non_differentiable(loss_q)
+        return sum_f32(loss_q), loss_q
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_lq):
+        (grad,) = ctx.saved_tensors
+        return grad * g_loss, None, None, None
+
+
+def rank_loss(name: str, scores: torch.Tensor, labels: torch.Tensor, **params) -> torch.Tensor:
+    """0-dim batch loss of the named ranking loss, differentiable w.r.t. ``scores``."""
+    loss, _ = _RankLoss.apply(scores, labels, name, params)
+    return loss
+
+
+def rank_loss_and_grad(name: str, scores: torch.Tensor, labels: torch.Tensor, **params):
+    """(batch loss, per-query losses, d loss / d scores) without autograd."""
+    loss_q, grad = _loss_call(name, scores.detach(), labels, params)
+    return sum_f32(loss_q), loss_q, grad
+
+
+_tie_offset = 0
+
+
+def shuffle_ties_perm(labels: torch.Tensor, seed: Optional[int] = None, offset: Optional[int] = None) -> torch.Tensor:
+    """int32 [B,n] ordering of each row's labels, descending, ties in random order."""
+    global _tie_offset
+    lib = _lib.load()
+    y = _dev_f32(labels, "labels")
+    B, n = y.shape
+    perm = torch.empty((B, n), dtype=torch.int32, device=y.device)
+    if seed is None:
+        seed = torch.initial_seed()
+    if offset is None:
+        _tie_offset += 1
+        offset = _tie_offset
+    _lib.check(lib.ptrb200_shuffle_ties_perm(y.data_ptr(), perm.data_ptr(), B, n, seed & (2 ** 64 - 1),
+                                             offset & (2 ** 64 - 1), _stream_ptr()), "shuffle_ties_perm")
+    return perm
+
+
+# --------------------------------------------------------------------------- #
+# metric
+# --------------------------------------------------------------------------- #
+def ndcg_at_ks(scores: torch.Tensor, labels: torch.Tensor, ks: Sequence[int], presort: bool = False,
+               return_order: bool = False):
+    """Per-query nDCG at the cutoffs ``ks`` -> [B, len(ks)] (zero where k > n)."""
+    lib = _lib.load()
+    s, y = _dev_f32(scores, "scores"), _dev_f32(labels, "labels")
+    B, n = _check_pair(s, y)
+    ks = [int(k) for k in ks]
+    order_ix = sorted(range(len(ks)), key=lambda i: ks[i])
+    ks_sorted = [ks[i] for i in order_ix]
+    arr = (C.c_int32 * len(ks))(*ks_sorted)
+    out = torch.empty((B, len(ks)), dtype=torch.float32, device=s.device)
+    order = torch.empty((B, n), dtype=torch.int32, device=s.device) if return_order else None
+    _lib.check(lib.ptrb200_ndcg_at_ks(s.data_ptr(), y.data_ptr(), arr, len(ks), out.data_ptr(),
+                                      order.data_ptr() if return_order else None, B, n, int(bool(presort)),
+                                      _stream_ptr()), "ndcg_at_ks")
+    if order_ix != list(range(len(ks))):
+        inv = torch.empty(len(ks), dtype=torch.long)
+        inv[torch.tensor(order_ix)] = torch.arange(len(ks))
+        out = out[:, inv.to(out.device)]
+    return (out, order) if return_order else out
+
+
+# --------------------------------------------------------------------------- #
+# stacked feed-forward scorer
+# --------------------------------------------------------------------------- #
+_dropout_offset = 0
+
+
+def next_dropout_offset() -> int:
+    global _dropout_offset
+    _dropout_offset += 1
+    return _dropout_offset
+
+
+class FFNetSpec:
+    """Static description of one stacked FF net + the order its parameters are passed in."""
+
+    def __init__(self, dims, act_hidden, act_tail, norm, norm_affine, dropout_p):
+        if len(dims) - 1 > _lib.MAX_FF_LAYERS:
+            raise ValueError("too many layers")
+        self.dims = [int(d) for d in dims]
+        self.act_hidden, self.act_tail = act_hidden, act_tail
+        self.norm, self.norm_affine, self.dropout_p = norm, bool(norm_affine), float(dropout_p)
+        self.L = len(dims) - 1
+        # slots[l] = names of the parameter tensors layer l owns, in flattening order
+        self.slots = []
+        for l in range(self.L):
+            names = ["weight", "bias"]
+            has_act = l < self.L - 1 or act_tail is not None
+            if has_act and norm == "BN" and self.norm_affine:
+                names += ["gamma", "beta"]
+            if has_act and norm == "BN2":
+                names += ["gamma", "beta"] + (["aff_w", "aff_b"] if self.norm_affine else [])
+            self.slots.append(names)
+
+    def describe(self, params: Sequence[torch.Tensor]) -> "_lib.FFNetDesc":
+        d = _lib.FFNetDesc()
+        d.num_linear = self.L
+        for i, v in enumerate(self.dims):
+            d.dims[i] = v
+        d.act_hidden = _lib.AF_CODES[self.act_hidden]
+        d.act_tail = _lib.AF_CODES[self.act_tail]
+        d.norm = _lib.NORM_CODES[self.norm]
+        d.norm_affine = int(self.norm_affine)
+        d.dropout_p = self.dropout_p
+        it = iter(params)
+        for l, names in enumerate(self.slots):
+            for nm in names:
+                getattr(d, nm)[l] = next(it).data_ptr()
+        return d
+
+    def grads(self, params: Sequence[torch.Tensor]):
+        g = _lib.FFNetGrads()
+        outs = []
+        it = iter(params)
+        for l, names in enumerate(self.slots):
+            for nm in names:
+                p = next(it)
+                t = torch.empty_like(p)
+                outs.append(t)
+                getattr(g, nm)[l] = t.data_ptr()
+        return g, outs
+
+
+class _FFNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, spec: FFNetSpec, training: bool, seed: int, offset: int, *params):
+        lib = _lib.load()
+        X = _dev_f32(X, "X")
+        B, n, F = X.shape
+        if F != spec.dims[0]:
+            raise ValueError(f"feature width {F} != net input width {spec.dims[0]}")
+        params = [p.detach().contiguous() for p in params]
+        desc = spec.describe(params)
+        nbytes = lib.ptrb200_ffnet_workspace_bytes(C.byref(desc), B, n)
+        if nbytes < 0:
+            _lib.check(int(nbytes), "ffnet_workspace_bytes")
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=X.device)
+        out = torch.empty((B, n, spec.dims[-1]), dtype=torch.float32, device=X.device)
+        _lib.check(lib.ptrb200_ffnet_forward(C.byref(desc), X.data_ptr(), out.data_ptr(), ws.data_ptr(), int(nbytes),
+                                             B, n, int(training), seed, offset, _stream_ptr()), "ffnet_forward")
+        ctx.spec, ctx.training, ctx.seed, ctx.offset = spec, training, seed, offset
+        ctx.ws, ctx.nbytes = ws, int(nbytes)
+        ctx.need_dx = X.requires_grad
+        ctx.save_for_backward(X, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        X, *params = ctx.saved_tensors
+        spec = ctx.spec
+        B, n, _ = X.shape
+        desc = spec.describe(params)
+        gdesc, gouts = spec.grads(params)
+        d_out = _dev_f32(d_out, "d_out")
+        dX = torch.empty_like(X) if ctx.need_dx else None
+        _lib.check(lib.ptrb200_ffnet_backward(C.byref(desc), C.byref(gdesc), X.data_ptr(), d_out.data_ptr(),
+                                              dX.data_ptr() if dX is not None else None, ctx.ws.data_ptr(), ctx.nbytes,
+                                              B, n, int(ctx.training), ctx.seed, ctx.offset, _stream_ptr()),
+                   "ffnet_backward")
+        ctx.ws = None
+        return (dX, None, None, None, None, *gouts)
+
+
+def ffnet_apply(X: torch.Tensor, spec: FFNetSpec, params: Sequence[torch.Tensor], training: bool,
+                seed: Optional[int] = None, offset: Optional[int] = None) -> torch.Tensor:
+    """[B,n,F] -> [B,n,out] through the fused stacked-FF kernels (differentiable)."""
+    if seed is None:
+        seed = torch.initial_seed() & (2 ** 64 - 1)
+    if offset is None:
+        offset = next_dropout_offset()
+    return _FFNetFn.apply(X, spec, bool(training), int(seed), int(offset), *params)
