@@ -180,6 +180,14 @@ int ptrb200_ffnet_backward(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* 
                            int B, int n, int training, uint64_t seed, uint64_t offset,
                            ptrb200_stream_t stream);
 
+/* ---- tensor-core GEMM building block ---------------------------------------------------- */
+/* C[M,N] = A[M,K] * B[N,K]^T in fp32 through tcgen05.mma kind::tf32 with TMEM accumulation
+ * (the contraction of nn.Linear: torch.nn.functional.linear as called by every ff_* layer of
+ * get_stacked_FFNet, ptranking/base/utils.py:302,320).  passes = 1: plain TF32 operands;
+ * passes = 3: error-compensated 3xTF32 (fp32-equivalent accuracy).  N <= 256. */
+int ptrb200_tc_gemm_nt(const float* A, const float* B, float* C, int M, int N, int K, int passes,
+                       ptrb200_stream_t stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -230,35 +230,54 @@ __global__ void colstat_kernel(const float* __restrict__ Z, const float* __restr
     }
 }
 
-// forward finalize: partials -> mean, rstd (biased variance, eps = 1e-5)
+// forward finalize: partials -> mean, rstd (biased variance, eps = 1e-5).  One warp per (group, channel);
+// lanes stride over the slices, fixed-order butterfly -> deterministic.
+static __device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 __global__ void moments_finalize_kernel(const double* __restrict__ partials, float* __restrict__ mean,
                                         float* __restrict__ rstd, int G, int C, int S, int gr) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= G * C) return;
     const int g = i / C, c = i % C;
     double s1 = 0.0, s2 = 0.0;
-    for (int s = 0; s < S; ++s) { const double* p = partials + (((size_t)g * S + s) * C + c) * 2; s1 += p[0]; s2 += p[1]; }
-    const double m = s1 / gr;
-    double var = s2 / gr - m * m;
-    if (var < 0.0) var = 0.0;
-    mean[i] = (float)m;
-    rstd[i] = (float)(1.0 / sqrt(var + 1e-5));
+    for (int s = lane; s < S; s += 32) { const double* p = partials + (((size_t)g * S + s) * C + c) * 2; s1 += p[0]; s2 += p[1]; }
+    s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
+    if (lane == 0) {
+        const double m = s1 / gr;
+        double var = s2 / gr - m * m;
+        if (var < 0.0) var = 0.0;
+        mean[i] = (float)m;
+        rstd[i] = (float)(1.0 / sqrt(var + 1e-5));
+    }
 }
 
-// backward finalize: per-(group,channel) sums S1,S2 (float) + totals over groups T1,T2 per channel
+// backward finalize: per-(group,channel) sums S1,S2 (float) + totals over groups T1,T2 per channel.
+// One warp per channel; lanes stride over (group, slice) pairs.
 __global__ void dy_finalize_kernel(const double* __restrict__ partials, float* __restrict__ S1, float* __restrict__ S2,
                                    float* __restrict__ T1, float* __restrict__ T2, int G, int C, int S) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
     double t1 = 0.0, t2 = 0.0;
-    for (int g = 0; g < G; ++g) {
-        double s1 = 0.0, s2 = 0.0;
-        for (int s = 0; s < S; ++s) { const double* p = partials + (((size_t)g * S + s) * C + c) * 2; s1 += p[0]; s2 += p[1]; }
-        if (S1) { S1[(size_t)g * C + c] = (float)s1; S2[(size_t)g * C + c] = (float)s2; }
-        t1 += s1; t2 += s2;
+    if (S == 1) {
+        for (int g = lane; g < G; g += 32) {
+            const double* p = partials + ((size_t)g * C + c) * 2;
+            if (S1) { S1[(size_t)g * C + c] = (float)p[0]; S2[(size_t)g * C + c] = (float)p[1]; }
+            t1 += p[0]; t2 += p[1];
+        }
+    } else {
+        for (int g = 0; g < G; ++g) {
+            double s1 = 0.0, s2 = 0.0;
+            for (int s = lane; s < S; s += 32) { const double* p = partials + (((size_t)g * S + s) * C + c) * 2; s1 += p[0]; s2 += p[1]; }
+            s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
+            if (S1 && lane == 0) { S1[(size_t)g * C + c] = (float)s1; S2[(size_t)g * C + c] = (float)s2; }
+            if (lane == 0) { t1 += s1; t2 += s2; }
+        }
     }
-    T1[c] = (float)t1;
-    if (T2) T2[c] = (float)t2;
+    t1 = warp_sum_d(t1); t2 = warp_sum_d(t2);
+    if (lane == 0) { T1[c] = (float)t1; if (T2) T2[c] = (float)t2; }
 }
 
 // ------------------------------------------------------------------ elementwise passes
@@ -444,7 +463,7 @@ int ptrb200_ffnet_forward(const ptrb200_ffnet* net, const float* X, float* out, 
                 PTRB200_LAUNCH(colstat_kernel<STAT_MOMENTS>, grid, dim3(32, 8), 0, st, (const float*)Z, (const float*)nullptr,
                                (float*)nullptr, nr, part, p.gr, lp.d_out, p.S_stat, p.slice_rows);
                 const int cnt = p.G * lp.d_out;
-                PTRB200_LAUNCH(moments_finalize_kernel, (cnt + 255) / 256, 256, 0, st, (const double*)part,
+                PTRB200_LAUNCH(moments_finalize_kernel, (cnt * 32 + 255) / 256, 256, 0, st, (const double*)part,
                                reinterpret_cast<float*>(ws + lp.mean_off), reinterpret_cast<float*>(ws + lp.rstd_off),
                                p.G, lp.d_out, p.S_stat, p.gr);
             }
@@ -489,7 +508,7 @@ int ptrb200_ffnet_backward(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* 
             float* dY = dbuf[flip]; flip ^= 1;
             dim3 grid(p.G, p.S_stat);
             PTRB200_LAUNCH(colstat_kernel<STAT_DY>, grid, dim3(32, 8), 0, st, Z, dA, dY, nr, part, p.gr, lp.d_out, p.S_stat, p.slice_rows);
-            PTRB200_LAUNCH(dy_finalize_kernel, (lp.d_out + 127) / 128, 128, 0, st, (const double*)part,
+            PTRB200_LAUNCH(dy_finalize_kernel, (lp.d_out * 32 + 127) / 128, 128, 0, st, (const double*)part,
                            lp.has_norm ? S1 : (float*)nullptr, lp.has_norm ? S2 : (float*)nullptr, T1, T2, p.G, lp.d_out, p.S_stat);
             if (lp.has_norm) {
                 float *dg = nullptr, *db = nullptr, *dw = nullptr, *dbw = nullptr;
@@ -499,7 +518,7 @@ int ptrb200_ffnet_backward(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* 
                 PTRB200_LAUNCH(norm_bwd_apply_kernel, elementwise_blocks(total), 256, 0, st, Z, dY, nr, (const float*)S1, (const float*)S2, total, lp.d_out, p.gr);
                 // bias gradient = column sums of dZ (zero up to rounding under a norm, as in the reference)
                 PTRB200_LAUNCH(colstat_kernel<STAT_COLSUM>, grid, dim3(32, 8), 0, st, (const float*)dY, (const float*)nullptr, (float*)nullptr, nr, part, p.gr, lp.d_out, p.S_stat, p.slice_rows);
-                PTRB200_LAUNCH(dy_finalize_kernel, (lp.d_out + 127) / 128, 128, 0, st, (const double*)part, (float*)nullptr, (float*)nullptr, grads->bias[l], (float*)nullptr, p.G, lp.d_out, p.S_stat);
+                PTRB200_LAUNCH(dy_finalize_kernel, (lp.d_out * 32 + 127) / 128, 128, 0, st, (const double*)part, (float*)nullptr, (float*)nullptr, grads->bias[l], (float*)nullptr, p.G, lp.d_out, p.S_stat);
             } else {
                 cudaMemcpyAsync(grads->bias[l], T1, (size_t)lp.d_out * 4, cudaMemcpyDeviceToDevice, st);
             }
@@ -507,7 +526,7 @@ int ptrb200_ffnet_backward(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* 
         } else {
             dim3 grid(p.G, p.S_stat);
             PTRB200_LAUNCH(colstat_kernel<STAT_COLSUM>, grid, dim3(32, 8), 0, st, dA, (const float*)nullptr, (float*)nullptr, nr, part, p.gr, lp.d_out, p.S_stat, p.slice_rows);
-            PTRB200_LAUNCH(dy_finalize_kernel, (lp.d_out + 127) / 128, 128, 0, st, (const double*)part, (float*)nullptr, (float*)nullptr, grads->bias[l], (float*)nullptr, p.G, lp.d_out, p.S_stat);
+            PTRB200_LAUNCH(dy_finalize_kernel, (lp.d_out * 32 + 127) / 128, 128, 0, st, (const double*)part, (float*)nullptr, (float*)nullptr, grads->bias[l], (float*)nullptr, p.G, lp.d_out, p.S_stat);
         }
         const bool last = l == p.L - 1;
         const float layer_drop = last ? 0.0f : drop;

@@ -39,10 +39,13 @@ def test_point_scorer_forward_backward(name, shape):
     assert s.shape == (B, n)
     assert rel_err(s.detach().cpu().numpy(), z[key + "__scores"]) <= 1e-5
     (s * torch.from_numpy(z[key + "__dscores"]).to(DEV)).sum().backward()
+    gscale = max(np.abs(z[f"{key}__grad::{k}"]).max() for k, _ in r.point_sf.named_parameters())
     for k, p in r.point_sf.named_parameters():
         ref = z[f"{key}__grad::{k}"]
         err = np.abs(p.grad.cpu().numpy() - ref).max()
-        assert err <= 2e-5 * max(np.abs(ref).max(), 1e-3), (k, err, np.abs(ref).max())
+        # Linear biases feeding a norm have an exactly-zero true gradient: both sides hold pure rounding
+        # noise there, hence the floor relative to the net's gradient scale
+        assert err <= 2e-5 * np.abs(ref).max() + 1e-6 * gscale + 1e-9, (k, err, np.abs(ref).max(), gscale)
 
 
 def test_state_dict_keys_match_reference_checkpoint_format():
