@@ -135,6 +135,10 @@ int ptrb200_ndcg_at_ks(const float* scores, const float* labels, const int32_t* 
 #define PTRB200_NORM_BN   1   /* LTRBatchNorm: statistics over all B*n rows, train and eval */
 #define PTRB200_NORM_BN2  2   /* LTRBatchNorm2: statistics per query */
 
+#define PTRB200_MATH_SIMT   0   /* fp32 FMA on the SIMT pipes (any shape)                              */
+#define PTRB200_MATH_3XTF32 1   /* tcgen05 kind::tf32, error-compensated 3-pass split: fp32-equivalent */
+#define PTRB200_MATH_TF32   2   /* tcgen05 kind::tf32, single pass (10-bit mantissa operands)           */
+
 typedef struct ptrb200_ffnet {
     int num_linear;                        /* linear layers, output layer included            */
     int dims[PTRB200_MAX_FF_LAYERS + 1];   /* dims[0]=in features ... dims[num_linear]=out    */
@@ -143,6 +147,8 @@ typedef struct ptrb200_ffnet {
     int norm;                              /* PTRB200_NORM_* on every layer that has an activation */
     int norm_affine;                       /* bn_affine                                       */
     float dropout_p;                       /* Dropout before every hidden Linear; 0 disables  */
+    int math_mode;                         /* PTRB200_MATH_*: tensor-core modes fall back to SIMT when a width is
+                                              not a multiple of 4 or exceeds 256                              */
     /* parameters, one pointer per linear layer l = 0..num_linear-1 (nn.Linear layout [out,in]) */
     const float* weight[PTRB200_MAX_FF_LAYERS];
     const float* bias[PTRB200_MAX_FF_LAYERS];

@@ -8,6 +8,8 @@ nn.Sequential through ATen.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -42,8 +44,11 @@ class StackedFFNet(nn.Module):
     """Dropout -> Linear -> (BN|BN2) -> AF per hidden layer, Linear [-> norm -> TL_AF] tail."""
 
     def __init__(self, ff_dims, AF=None, TL_AF=None, apply_tl_af=False, dropout=0.1,
-                 BN=True, bn_type=None, bn_affine=False, device=None):
+                 BN=True, bn_type=None, bn_affine=False, device=None, math_mode=None):
         super().__init__()
+        # "3xtf32" (default): tcgen05 tensor cores with the fp32-equivalent 3-pass TF32 split;
+        # "tf32": single pass; "simt": fp32 FMA kernels (also the fallback for widths the MMA tiles reject)
+        math_mode = math_mode or os.environ.get("PTRANKING_B200_MATH", "3xtf32")
         assert ff_dims is not None and len(ff_dims) >= 2
         for code in ([AF] if len(ff_dims) > 2 else []) + ([TL_AF] if apply_tl_af else []):
             if code not in SUPPORTED_AF:
@@ -70,7 +75,7 @@ class StackedFFNet(nn.Module):
                         self._order += [holder.weight, holder.bias]
                 self.add_module(f"bn_{i + 1}", holder)
         self.spec = ops.FFNetSpec(ff_dims, AF if L > 2 else None, TL_AF if apply_tl_af else None,
-                                  bn_type if BN else None, bn_affine, dropout)
+                                  bn_type if BN else None, bn_affine, dropout, math_mode=math_mode)
 
     def ordered_parameters(self):
         return list(self._order)

@@ -13,34 +13,10 @@
 // workspace keeps Z (pre-normalisation Linear output), A (post-activation) and, when a norm
 // is present, mean/rstd per (group, channel); group = whole batch (BN) or one query (BN2).
 #include "common.cuh"
+#include "ffnet_act.cuh"
+#include "ffnet_tc.cuh"
 
 namespace ptrb200 {
-
-// ------------------------------------------------------------------ activations
-struct ActOut { float y, dy; };
-static __device__ __forceinline__ ActOut activate(int af, float x) {
-    ActOut r;
-    switch (af) {
-        case PTRB200_AF_RELU: r.y = fmaxf(x, 0.0f); r.dy = x > 0.0f ? 1.0f : 0.0f; break;
-        case PTRB200_AF_GELU: {
-            const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-            r.y = x * cdf;
-            r.dy = cdf + x * 0.3989422804014327f * expf(-0.5f * x * x);
-        } break;
-        case PTRB200_AF_SIGM: { const float s = __fdividef(1.0f, 1.0f + expf(-x)); r.y = s; r.dy = s * (1.0f - s); } break;
-        case PTRB200_AF_TANH: { const float t = tanhf(x); r.y = t; r.dy = 1.0f - t * t; } break;
-        case PTRB200_AF_CELU:
-        case PTRB200_AF_ELU: { const float e = expf(x); r.y = x > 0.0f ? x : e - 1.0f; r.dy = x > 0.0f ? 1.0f : e; } break;
-        case PTRB200_AF_LRELU: r.y = x > 0.0f ? x : 0.01f * x; r.dy = x > 0.0f ? 1.0f : 0.01f; break;
-        case PTRB200_AF_SELU: {
-            const float sc = 1.0507009873554805f, al = 1.6732632423543772f, e = expf(x);
-            r.y = sc * (x > 0.0f ? x : al * (e - 1.0f));
-            r.dy = sc * (x > 0.0f ? 1.0f : al * e);
-        } break;
-        default: r.y = x; r.dy = 1.0f; break;
-    }
-    return r;
-}
 
 // ------------------------------------------------------------------ SIMT GEMM
 // C[M,N] = Aop[M,K] * Bop[K,N] with operand accessors chosen by MODE.
@@ -238,7 +214,8 @@ static __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 __global__ void moments_finalize_kernel(const double* __restrict__ partials, float* __restrict__ mean,
-                                        float* __restrict__ rstd, int G, int C, int S, int gr) {
+                                        float* __restrict__ rstd, float* __restrict__ scale, float* __restrict__ shift,
+                                        NormRef nr, int G, int C, int S, int gr) {
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= G * C) return;
     const int g = i / C, c = i % C;
@@ -249,8 +226,15 @@ __global__ void moments_finalize_kernel(const double* __restrict__ partials, flo
         const double m = s1 / gr;
         double var = s2 / gr - m * m;
         if (var < 0.0) var = 0.0;
-        mean[i] = (float)m;
-        rstd[i] = (float)(1.0 / sqrt(var + 1e-5));
+        const float mf = (float)m, rf = (float)(1.0 / sqrt(var + 1e-5));
+        mean[i] = mf;
+        rstd[i] = rf;
+        if (scale) {            // y = a*(z-mean)*rstd + c  ==  z*scale + shift
+            float a, cc;
+            norm_coeffs(nr, c, a, cc);
+            scale[i] = a * rf;
+            shift[i] = cc - a * rf * mf;
+        }
     }
 }
 
@@ -331,8 +315,12 @@ struct LayerPlan {
     bool has_act, has_norm;
     int d_in, d_out, act;
     size_t z_off, a_off, mean_off, rstd_off;     // byte offsets into the workspace (a_off unused for the last layer)
+    size_t scale_off, shift_off, wt_off;         // tensor-core mode: fused prologue coefficients [G,d_out], W^T [d_in,d_out]
 };
 struct Plan {
+    bool use_tc;                                 // every layer fits the tcgen05 kernels (else the SIMT path runs)
+    int passes;                                  // 3 = 3xTF32 (fp32-equivalent), 1 = TF32
+    int tile_rows, seg_len, group_rows, tiles_per_group, ntiles, wg_grid, wg_rows;
     int L, G, gr, S_stat, slice_rows, S_w, k_chunk;
     size_t rows;
     LayerPlan layer[PTRB200_MAX_FF_LAYERS];
@@ -348,9 +336,27 @@ static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p) {
     p.rows = (size_t)B * n;
     p.G = net->norm == PTRB200_NORM_BN2 ? B : 1;
     p.gr = net->norm == PTRB200_NORM_BN2 ? n : (int)p.rows;
+    if (net->math_mode < PTRB200_MATH_SIMT || net->math_mode > PTRB200_MATH_TF32) { set_error("ffnet: bad math_mode %d", net->math_mode); return PTRB200_ERR_INVALID; }
+    p.use_tc = net->math_mode != PTRB200_MATH_SIMT;
+    p.passes = net->math_mode == PTRB200_MATH_TF32 ? 1 : 3;
+    for (int l = 0; l < net->num_linear && p.use_tc; ++l) {
+        const int di = net->dims[l], dn = net->dims[l + 1];
+        // float4 row access needs widths % 4; one MMA N-tile holds <= 256 columns
+        if (di % 4 != 0 || di > 256 || dn > 256 || (dn % 4 != 0 && dn > 4)) p.use_tc = false;
+    }
     // statistics slices: one CTA per (group, slice); aim for ~4 CTAs per SM when there is a single group
     if (p.G == 1) { p.slice_rows = 512; p.S_stat = (int)((p.rows + 511) / 512); if (p.S_stat > 1024) { p.S_stat = 1024; p.slice_rows = (int)((p.rows + 1023) / 1024); p.S_stat = (int)((p.rows + p.slice_rows - 1) / p.slice_rows); } }
     else { p.slice_rows = p.gr; p.S_stat = 1; }
+    p.tile_rows = 128; p.seg_len = 128; p.group_rows = 0; p.tiles_per_group = 0;
+    if (p.use_tc) {
+        // row tiles of the tensor-core kernels never straddle a statistics group in a way that splits a segment
+        if (net->norm == PTRB200_NORM_BN2) {
+            if (n <= 128) { p.tile_rows = (128 / n) * n; p.seg_len = n; p.S_stat = 1; p.slice_rows = n; }
+            else { p.group_rows = n; p.tiles_per_group = (n + 127) / 128; p.S_stat = p.tiles_per_group; p.slice_rows = 128; }
+        } else { p.slice_rows = 128; p.S_stat = (int)((p.rows + 127) / 128); }
+        p.ntiles = p.group_rows > 0 ? B * p.tiles_per_group : (int)((p.rows + p.tile_rows - 1) / p.tile_rows);
+        p.wg_rows = 32; p.wg_grid = 296;
+    }
     p.k_chunk = 2048; p.S_w = (int)((p.rows + 2047) / 2048);
     if (p.S_w > 592) { p.S_w = 592; p.k_chunk = (int)((p.rows + 591) / 592); p.S_w = (int)((p.rows + p.k_chunk - 1) / p.k_chunk); }
     size_t off = 0;
@@ -365,9 +371,13 @@ static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p) {
         lp.has_norm = lp.has_act && net->norm != PTRB200_NORM_NONE;
         if (lp.has_norm && net->norm == PTRB200_NORM_BN2 && (!net->gamma[l] || !net->beta[l])) { set_error("ffnet: BN2 layer %d needs gamma/beta", l); return PTRB200_ERR_INVALID; }
         lp.z_off = off; off = align_up(off + p.rows * lp.d_out * 4, 256);
-        lp.a_off = off; if (l < p.L - 1) off = align_up(off + p.rows * lp.d_out * 4, 256);
-        lp.mean_off = off; lp.rstd_off = off;
-        if (lp.has_norm) { lp.mean_off = off; off = align_up(off + (size_t)p.G * lp.d_out * 4, 256); lp.rstd_off = off; off = align_up(off + (size_t)p.G * lp.d_out * 4, 256); }
+        lp.a_off = off; if (l < p.L - 1 && !p.use_tc) off = align_up(off + p.rows * lp.d_out * 4, 256);
+        lp.mean_off = off; lp.rstd_off = off; lp.scale_off = off; lp.shift_off = off; lp.wt_off = off;
+        if (lp.has_norm) {
+            lp.mean_off = off; off = align_up(off + (size_t)p.G * lp.d_out * 4, 256); lp.rstd_off = off; off = align_up(off + (size_t)p.G * lp.d_out * 4, 256);
+            lp.scale_off = off; off = align_up(off + (size_t)p.G * lp.d_out * 4, 256); lp.shift_off = off; off = align_up(off + (size_t)p.G * lp.d_out * 4, 256);
+        }
+        if (p.use_tc) { lp.wt_off = off; off = align_up(off + (size_t)lp.d_in * lp.d_out * 4, 256); }
         maxd = lp.d_in > maxd ? lp.d_in : maxd; maxd = lp.d_out > maxd ? lp.d_out : maxd;
         const size_t w = (size_t)lp.d_in * lp.d_out; maxw = w > maxw ? w : maxw;
     }
@@ -378,7 +388,7 @@ static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p) {
     p.t2_off = off; off = align_up(off + (size_t)maxd * 4, 256);
     p.dbuf0_off = off; off = align_up(off + p.rows * maxd * 4, 256);
     p.dbuf1_off = off; off = align_up(off + p.rows * maxd * 4, 256);
-    p.wpart_off = off; off = align_up(off + (size_t)p.S_w * maxw * 4, 256);
+    p.wpart_off = off; off = align_up(off + (size_t)(p.use_tc ? (p.wg_grid > p.S_w ? p.wg_grid : p.S_w) : p.S_w) * maxw * 4, 256);
     p.total = off;
     return PTRB200_OK;
 }
@@ -418,6 +428,190 @@ static int elementwise_blocks(size_t total) {
     return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
 }
 
+
+// ------------------------------------------------------------------ tensor-core host paths
+__global__ void transpose_kernel(const float* __restrict__ W, float* __restrict__ Wt, int rows, int cols) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;       // Wt[c][r] = W[r][c]
+    if (i >= rows * cols) return;
+    const int c = i / rows, r = i % rows;
+    Wt[i] = W[(size_t)r * cols + c];
+}
+
+template <typename K>
+static int opt_in_smem(K kernel, size_t bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(%zu B): %s", bytes, cudaGetErrorString(e)); return PTRB200_ERR_CUDA; }
+    return PTRB200_OK;
+}
+
+static size_t rows_gemm_smem(int N, int NP) {
+    const size_t operands = 32768 + (size_t)NP * 256, otile = (size_t)128 * N * 4;
+    return 1024 + (operands > otile ? operands : otile) + 64;
+}
+
+static int launch_rows_gemm(int mode, int passes, RowsGemmArgs& g, int ntiles, cudaStream_t st) {
+    g.NP = ((g.N + 15) / 16) * 16;
+    const size_t operands = 32768 + (size_t)g.NP * 256, otile = (size_t)128 * g.N * 4;
+    g.tail_off = (int)(((operands > otile ? operands : otile) + 15) / 16 * 16);
+    const size_t smem = rows_gemm_smem(g.N, g.NP);
+    int rc;
+#define RG_CASE(M, P, TAG)                                                                      \
+    if (mode == M && passes == P) {                                                             \
+        if ((rc = opt_in_smem(rows_gemm_tc_kernel<M, P>, smem))) return rc;                     \
+        PTRB200_LAUNCH_TAG(TAG, (rows_gemm_tc_kernel<M, P>), ntiles, RG_THREADS, smem, st, g);  \
+        return PTRB200_OK;                                                                      \
+    }
+    RG_CASE(RG_FWD, 3, "rows_gemm_tc_fwd")
+    RG_CASE(RG_FWD, 1, "rows_gemm_tc_fwd")
+    RG_CASE(RG_DGRAD, 3, "rows_gemm_tc_dgrad")
+    RG_CASE(RG_DGRAD, 1, "rows_gemm_tc_dgrad")
+#undef RG_CASE
+    return PTRB200_ERR_INVALID;
+}
+
+static void set_tiling(RowsGemmArgs& g, const Plan& p) {
+    g.tile_rows = p.tile_rows; g.seg_len = p.seg_len; g.group_rows = p.group_rows; g.tiles_per_group = p.tiles_per_group;
+}
+
+// prologue that rebuilds the post-activation input of layer l from what layer l-1 stored
+static void set_prologue(const ptrb200_ffnet* net, const Plan& p, int l, char* ws, const float* X,
+                         const float*& P, const float*& scale, const float*& shift, int& act) {
+    if (l == 0) { P = X; scale = shift = nullptr; act = PTRB200_AF_NONE; return; }
+    const LayerPlan& prev = p.layer[l - 1];
+    P = reinterpret_cast<const float*>(ws + prev.z_off);
+    scale = prev.has_norm ? reinterpret_cast<const float*>(ws + prev.scale_off) : nullptr;
+    shift = prev.has_norm ? reinterpret_cast<const float*>(ws + prev.shift_off) : nullptr;
+    act = prev.has_act ? prev.act : PTRB200_AF_NONE;
+}
+
+static int forward_tc(const ptrb200_ffnet* net, const Plan& p, const float* X, float* out, char* ws,
+                      float drop, uint64_t seed, uint64_t offset, cudaStream_t st) {
+    int rc;
+    for (int l = 0; l < p.L; ++l) {
+        const LayerPlan& lp = p.layer[l];
+        const bool last = l == p.L - 1;
+        float* Z = (last && !lp.has_act && !lp.has_norm) ? out : reinterpret_cast<float*>(ws + lp.z_off);
+        RowsGemmArgs g{};
+        set_prologue(net, p, l, ws, X, g.P, g.scale, g.shift, g.act);
+        g.gr_prev = p.gr;
+        g.drop_p = last ? 0.0f : drop; g.drop_scale = 1.0f / (1.0f - g.drop_p);
+        g.seed = seed; g.offset = offset * 64 + (uint64_t)l;
+        g.Bm = net->weight[l]; g.bias = net->bias[l]; g.Out = Z;
+        g.partials = lp.has_norm ? reinterpret_cast<double*>(ws + p.partials_off) : nullptr;
+        g.rows = (int)p.rows; g.K = lp.d_in; g.N = lp.d_out;
+        set_tiling(g, p);
+        if ((rc = launch_rows_gemm(RG_FWD, p.passes, g, p.ntiles, st))) return rc;
+        NormRef nr = norm_ref(net, p, l, ws);
+        if (lp.has_norm) {
+            const int cnt = p.G * lp.d_out;
+            PTRB200_LAUNCH(moments_finalize_kernel, (cnt * 32 + 255) / 256, 256, 0, st, (const double*)g.partials,
+                           reinterpret_cast<float*>(ws + lp.mean_off), reinterpret_cast<float*>(ws + lp.rstd_off),
+                           reinterpret_cast<float*>(ws + lp.scale_off), reinterpret_cast<float*>(ws + lp.shift_off),
+                           nr, p.G, lp.d_out, p.S_stat, p.gr);
+        }
+        if (last && (lp.has_act || lp.has_norm)) {
+            const size_t total = p.rows * lp.d_out;
+            PTRB200_LAUNCH(norm_act_fwd_kernel, elementwise_blocks(total), 256, 0, st, (const float*)Z, out, nr, total, lp.d_out, p.gr);
+        }
+    }
+    return check_launch("ffnet_forward(tc)");
+}
+
+static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grads, const Plan& p, const float* X,
+                       const float* dOut, float* dX, char* ws, float drop, uint64_t seed, uint64_t offset, cudaStream_t st) {
+    int rc;
+    double* part = reinterpret_cast<double*>(ws + p.partials_off);
+    float* S1 = reinterpret_cast<float*>(ws + p.s1_off);
+    float* S2 = reinterpret_cast<float*>(ws + p.s2_off);
+    float* T1 = reinterpret_cast<float*>(ws + p.t1_off);
+    float* T2 = reinterpret_cast<float*>(ws + p.t2_off);
+    float* dbuf[2] = {reinterpret_cast<float*>(ws + p.dbuf0_off), reinterpret_cast<float*>(ws + p.dbuf1_off)};
+    float* wpart = reinterpret_cast<float*>(ws + p.wpart_off);
+    const float* dA = dOut;
+    int flip = 0;
+    for (int l = p.L - 1; l >= 0; --l) {
+        const LayerPlan& lp = p.layer[l];
+        const bool last = l == p.L - 1;
+        if (!grads->weight[l] || !grads->bias[l]) { set_error("ffnet_backward: layer %d grad buffers NULL", l); return PTRB200_ERR_INVALID; }
+        const float* Z = reinterpret_cast<const float*>(ws + lp.z_off);
+        const float* dZ = dA;
+        NormRef nr = norm_ref(net, p, l, ws);
+        const size_t total = p.rows * lp.d_out;
+        dim3 sgrid(p.G, p.S_stat);
+        if (lp.has_act || lp.has_norm) {
+            float* dY = dbuf[flip]; flip ^= 1;
+            PTRB200_LAUNCH(colstat_kernel<STAT_DY>, sgrid, dim3(32, 8), 0, st, Z, dA, dY, nr, part, p.gr, lp.d_out, p.S_stat, p.slice_rows);
+            PTRB200_LAUNCH(dy_finalize_kernel, (lp.d_out * 32 + 127) / 128, 128, 0, st, (const double*)part,
+                           lp.has_norm ? S1 : (float*)nullptr, lp.has_norm ? S2 : (float*)nullptr, T1, T2, p.G, lp.d_out, p.S_stat);
+            if (lp.has_norm) {
+                float *dg = nullptr, *db = nullptr, *dw = nullptr, *dbw = nullptr;
+                if (net->norm == PTRB200_NORM_BN) { if (net->norm_affine) { dg = grads->gamma[l]; db = grads->beta[l]; } }
+                else { dg = grads->gamma[l]; db = grads->beta[l]; if (net->norm_affine) { dw = grads->aff_w[l]; dbw = grads->aff_b[l]; } }
+                PTRB200_LAUNCH(norm_param_grad_kernel, (lp.d_out + 127) / 128, 128, 0, st, nr, (const float*)T1, (const float*)T2, dg, db, dw, dbw, lp.d_out);
+                PTRB200_LAUNCH(norm_bwd_apply_kernel, elementwise_blocks(total), 256, 0, st, Z, dY, nr, (const float*)S1, (const float*)S2, total, lp.d_out, p.gr);
+                PTRB200_LAUNCH(colstat_kernel<STAT_COLSUM>, sgrid, dim3(32, 8), 0, st, (const float*)dY, (const float*)nullptr, (float*)nullptr, nr, part, p.gr, lp.d_out, p.S_stat, p.slice_rows);
+                PTRB200_LAUNCH(dy_finalize_kernel, (lp.d_out * 32 + 127) / 128, 128, 0, st, (const double*)part, (float*)nullptr, (float*)nullptr, grads->bias[l], (float*)nullptr, p.G, lp.d_out, p.S_stat);
+            } else {
+                cudaMemcpyAsync(grads->bias[l], T1, (size_t)lp.d_out * 4, cudaMemcpyDeviceToDevice, st);
+            }
+            dZ = dY;
+        } else {
+            PTRB200_LAUNCH(colstat_kernel<STAT_COLSUM>, sgrid, dim3(32, 8), 0, st, dA, (const float*)nullptr, (float*)nullptr, nr, part, p.gr, lp.d_out, p.S_stat, p.slice_rows);
+            PTRB200_LAUNCH(dy_finalize_kernel, (lp.d_out * 32 + 127) / 128, 128, 0, st, (const double*)part, (float*)nullptr, (float*)nullptr, grads->bias[l], (float*)nullptr, p.G, lp.d_out, p.S_stat);
+        }
+        const float layer_drop = last ? 0.0f : drop;
+        // ---- dW on tensor cores: sum_rows dZ^T (x) rebuilt layer input ----
+        {
+            WgradArgs w{};
+            w.dZ = dZ;
+            set_prologue(net, p, l, ws, X, w.P, w.scale, w.shift, w.act);
+            w.gr_prev = p.gr;
+            w.drop_p = layer_drop; w.drop_scale = 1.0f / (1.0f - layer_drop);
+            w.seed = seed; w.offset = offset * 64 + (uint64_t)l;
+            w.partials = wpart;
+            w.rows = (int)p.rows; w.K = lp.d_in; w.N = lp.d_out;
+            w.KP = ((lp.d_in + 15) / 16) * 16;
+            w.tile_rows = p.wg_rows;
+            const int p_chunks = (w.KP + 31) / 32;
+            size_t smem = 1024 + (size_t)(4 + p_chunks) * 2 * w.tile_rows * 128 + 64;
+            if (w.KP > 128 && smem < 80 * 1024) smem = 80 * 1024;        // 256 TMEM columns per CTA: keep <= 2 CTAs per SM
+            const int grid = p.wg_grid;
+            if (p.passes == 3) { if ((rc = opt_in_smem(wgrad_tc_kernel<3>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<3>, grid, WG_THREADS, smem, st, w); }
+            else { if ((rc = opt_in_smem(wgrad_tc_kernel<1>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<1>, grid, WG_THREADS, smem, st, w); }
+            const int cnt = lp.d_in * lp.d_out;
+            PTRB200_LAUNCH(reduce_splits_kernel, (cnt + 255) / 256, 256, 0, st, (const float*)wpart, grads->weight[l], grid, cnt);
+        }
+        // ---- dIn = dropmask(dZ * W) ----
+        if (l > 0 || dX) {
+            float* dIn = l == 0 ? dX : dbuf[flip];
+            if (l > 0) flip ^= 1;
+            if (lp.d_out % 4 == 0 && lp.d_in <= 256) {
+                float* Wt = reinterpret_cast<float*>(ws + lp.wt_off);
+                const int cnt = lp.d_in * lp.d_out;
+                PTRB200_LAUNCH(transpose_kernel, (cnt + 255) / 256, 256, 0, st, net->weight[l], Wt, lp.d_out, lp.d_in);
+                RowsGemmArgs g{};
+                g.P = dZ; g.scale = g.shift = nullptr; g.act = PTRB200_AF_NONE; g.gr_prev = (int)p.rows;
+                g.drop_p = layer_drop; g.drop_scale = 1.0f / (1.0f - layer_drop);
+                g.seed = seed; g.offset = offset * 64 + (uint64_t)l;
+                g.Bm = Wt; g.bias = nullptr; g.Out = dIn; g.partials = nullptr;
+                g.rows = (int)p.rows; g.K = lp.d_out; g.N = lp.d_in;
+                g.tile_rows = 128; g.seg_len = 128; g.group_rows = 0; g.tiles_per_group = 0;
+                if ((rc = launch_rows_gemm(RG_DGRAD, p.passes, g, (int)((p.rows + 127) / 128), st))) return rc;
+            } else {
+                GemmArgs g{};
+                g.A = dZ; g.Bm = net->weight[l]; g.C = dIn;
+                g.rows = (int)p.rows; g.d_in = lp.d_in; g.d_out = lp.d_out;
+                g.M = (int)p.rows; g.N = lp.d_in; g.K = lp.d_out;
+                g.drop_p = layer_drop; g.drop_scale = 1.0f / (1.0f - layer_drop);
+                g.seed = seed; g.offset = offset * 64 + (uint64_t)l;
+                launch_gemm<GEMM_BWD_DATA>(g, 1, st);
+            }
+            dA = dIn;
+        }
+    }
+    return check_launch("ffnet_backward(tc)");
+}
+
 }  // namespace ptrb200
 
 using namespace ptrb200;
@@ -441,6 +635,7 @@ int ptrb200_ffnet_forward(const ptrb200_ffnet* net, const float* X, float* out, 
     char* ws = static_cast<char*>(workspace);
     cudaStream_t st = (cudaStream_t)stream;
     const float drop = training ? net->dropout_p : 0.0f;
+    if (p.use_tc) return forward_tc(net, p, X, out, ws, drop, seed, offset, st);
     const float* in = X;
     for (int l = 0; l < p.L; ++l) {
         const LayerPlan& lp = p.layer[l];
@@ -465,7 +660,7 @@ int ptrb200_ffnet_forward(const ptrb200_ffnet* net, const float* X, float* out, 
                 const int cnt = p.G * lp.d_out;
                 PTRB200_LAUNCH(moments_finalize_kernel, (cnt * 32 + 255) / 256, 256, 0, st, (const double*)part,
                                reinterpret_cast<float*>(ws + lp.mean_off), reinterpret_cast<float*>(ws + lp.rstd_off),
-                               p.G, lp.d_out, p.S_stat, p.gr);
+                               (float*)nullptr, (float*)nullptr, nr, p.G, lp.d_out, p.S_stat, p.gr);
             }
             const size_t total = p.rows * lp.d_out;
             PTRB200_LAUNCH(norm_act_fwd_kernel, elementwise_blocks(total), 256, 0, st, (const float*)Z, A, nr, total, lp.d_out, p.gr);
@@ -487,6 +682,7 @@ int ptrb200_ffnet_backward(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* 
     char* ws = static_cast<char*>(workspace);
     cudaStream_t st = (cudaStream_t)stream;
     const float drop = training ? net->dropout_p : 0.0f;
+    if (p.use_tc) return backward_tc(net, grads, p, X, dOut, dX, ws, drop, seed, offset, st);
     double* part = reinterpret_cast<double*>(ws + p.partials_off);
     float* S1 = reinterpret_cast<float*>(ws + p.s1_off);
     float* S2 = reinterpret_cast<float*>(ws + p.s2_off);

@@ -1,0 +1,372 @@
+// ffnet_tc.cuh -- tcgen05 layer kernels of the stacked feed-forward scorer.
+//
+// Three kernels cover one Linear layer in both directions; post-activation tensors are never
+// written to HBM -- they are rebuilt from the previous layer's pre-activation Z in the operand
+// staging prologue (one FMA + activation per element, free next to the HBM stream):
+//
+//   rows_gemm<FWD>    Z_l[rows,N]  = drop(act(Z_{l-1}*scale+shift)) * W^T + b     (+ BN partial sums)
+//   rows_gemm<DGRAD>  dA[rows,K]   = dropmask( dZ_l * W )                           (Wt = W^T staged)
+//   wgrad             dW[N,K]      = sum_rows dZ_l[r,:]^T (x) drop(act(Z_{l-1}*scale+shift))[r,:]
+//
+// All contractions run as kind::tf32 tcgen05.mma with fp32 accumulation in TMEM; PASSES = 3 is the
+// error-compensated 3xTF32 split (fp32-equivalent, the default), PASSES = 1 plain TF32.
+#pragma once
+#include "common.cuh"
+#include "tc.cuh"
+#include "ffnet_act.cuh"
+
+namespace ptrb200 {
+
+struct RowsGemmArgs {
+    // A-side source and its prologue
+    const float* P;        // [rows, K]
+    const float* scale;    // [Gp, K] or NULL (identity)
+    const float* shift;    // [Gp, K]
+    int act;               // PTRB200_AF_* applied after scale/shift (AF_NONE = identity)
+    int gr_prev;           // rows per statistics group of P's normalisation
+    float drop_p, drop_scale;
+    uint64_t seed, offset; // dropout stream: FWD masks A elements (row*K+k), DGRAD masks outputs (row*N+n)
+    // B side
+    const float* Bm;       // [N, K] row-major (W for FWD, W^T for DGRAD)
+    const float* bias;     // [N] (FWD) or NULL
+    float* Out;            // [rows, N]
+    double* partials;      // [slots, N, 2] column sum / sum of squares per statistics slot, or NULL
+    int rows, K, N, NP;
+    int tail_off;          // byte offset of the mbarrier / TMEM slot behind max(operand buffers, output tile)
+    // tile -> rows mapping
+    int tile_rows;         // rows advanced per tile (<= 128)
+    int seg_len;           // rows per statistics segment inside a tile
+    int group_rows;        // BN2 with n > 128: rows per group (tiles restart at every group), else 0
+    int tiles_per_group;
+};
+
+enum { RG_FWD = 0, RG_DGRAD = 1 };
+
+// prologue transform of 4 consecutive elements (row r, columns k..k+3) of P
+static __device__ __forceinline__ float4 prologue4(const RowsGemmArgs& g, float4 v, int row, int k, bool with_dropout) {
+    if (g.scale) {
+        const size_t o = (size_t)(row / g.gr_prev) * g.K + k;
+        const float4 sc = *reinterpret_cast<const float4*>(g.scale + o);
+        const float4 sh = *reinterpret_cast<const float4*>(g.shift + o);
+        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+    }
+    if (g.act != PTRB200_AF_NONE) {
+        v.x = activate(g.act, v.x).y; v.y = activate(g.act, v.y).y; v.z = activate(g.act, v.z).y; v.w = activate(g.act, v.w).y;
+    }
+    if (with_dropout && g.drop_p > 0.0f) {
+        const uint64_t e = (uint64_t)row * g.K + k;          // K % 4 == 0: the 4 elements share one Philox block
+        Philox ph(g.seed);
+        const uint4 rb = ph(e >> 2, g.offset);
+        const float inv = 1.0f / 16777216.0f;
+        v.x = ((float)(rb.x >> 8) * inv >= g.drop_p) ? v.x * g.drop_scale : 0.0f;
+        v.y = ((float)(rb.y >> 8) * inv >= g.drop_p) ? v.y * g.drop_scale : 0.0f;
+        v.z = ((float)(rb.z >> 8) * inv >= g.drop_p) ? v.z * g.drop_scale : 0.0f;
+        v.w = ((float)(rb.w >> 8) * inv >= g.drop_p) ? v.w * g.drop_scale : 0.0f;
+    }
+    return v;
+}
+
+static __device__ __forceinline__ void store_split(unsigned char* hi, unsigned char* lo, uint32_t off, float4 v, bool split) {
+    if (split) {
+        float4 h, l;
+        tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y);
+        tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
+        *reinterpret_cast<float4*>(hi + off) = h;
+        *reinterpret_cast<float4*>(lo + off) = l;
+    } else {
+        *reinterpret_cast<float4*>(hi + off) = v;
+    }
+}
+
+static __device__ __forceinline__ float4 ldg4_guard(const float* p, int k, int K) {
+    // K % 4 == 0 and 16-byte aligned rows are guaranteed by the host launcher
+    return (k < K) ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+constexpr int RG_THREADS = 256;
+
+template <int MODE, int PASSES>
+__global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int NP = g.NP;
+    unsigned char* a_hi = base;                       // 128 rows x 128 B
+    unsigned char* a_lo = a_hi + 16384;
+    unsigned char* b_hi = a_lo + 16384;               // NP rows x 128 B
+    unsigned char* b_lo = b_hi + NP * 128;
+    unsigned char* tail = base + g.tail_off;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(tail);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 1);
+    float* otile = reinterpret_cast<float*>(base);    // epilogue staging [128][N], aliases the operand buffers
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // ---- tile -> rows ------------------------------------------------------------
+    int row0, nrows, slot0;
+    {
+        const int t = blockIdx.x;
+        if (g.group_rows > 0) {
+            const int grp = t / g.tiles_per_group, tt = t % g.tiles_per_group;
+            row0 = grp * g.group_rows + tt * 128;
+            nrows = min(128, g.group_rows - tt * 128);
+            slot0 = t;
+        } else {
+            row0 = t * g.tile_rows;
+            nrows = min(g.tile_rows, g.rows - row0);
+            slot0 = (row0 / g.seg_len);
+        }
+    }
+    const uint32_t tmem_cols = NP <= 32 ? 32 : NP <= 64 ? 64 : NP <= 128 ? 128 : 256;
+    if (tid == 0) { tc::mbar_init(mbar, 1); tc::mbar_fence_init(); }
+    if (warp == 0) tc::tmem_alloc(slot, tmem_cols);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *slot;
+    const uint32_t idesc = tc::instr_desc(2, 128, NP);
+    const int K = g.K;
+    const int nchunks = (K + 31) / 32;
+    constexpr int A_UNITS = 128 * 8 / RG_THREADS;      // 4 units of 16 B per thread per chunk
+
+    for (int c = 0; c < nchunks; ++c) {
+        const int k0 = c * 32;
+        // ---- global -> registers (issued before waiting on the previous chunk's MMAs) ----
+        float4 av[A_UNITS];
+#pragma unroll
+        for (int i = 0; i < A_UNITS; ++i) {
+            const int u = tid + i * RG_THREADS, r = u >> 3, j = u & 7, k = k0 + j * 4;
+            av[i] = (r < nrows) ? ldg4_guard(g.P + (size_t)(row0 + r) * K + k, k, K) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (c > 0) tc::mbar_wait(mbar, (c - 1) & 1);
+        // ---- A: prologue + split + swizzled store ----
+#pragma unroll
+        for (int i = 0; i < A_UNITS; ++i) {
+            const int u = tid + i * RG_THREADS, r = u >> 3, j = u & 7, k = k0 + j * 4;
+            float4 v = av[i];
+            if (r < nrows && k < K) v = prologue4(g, v, row0 + r, k, MODE == RG_FWD);
+            else v = make_float4(0.f, 0.f, 0.f, 0.f);
+            store_split(a_hi, a_lo, tc::swz_offset(r, j), v, PASSES == 3);
+        }
+        // ---- B: weights chunk (L2 resident) ----
+        for (int u = tid; u < NP * 8; u += RG_THREADS) {
+            const int r = u >> 3, j = u & 7, k = k0 + j * 4;
+            const float4 v = (r < g.N) ? ldg4_guard(g.Bm + (size_t)r * K + k, k, K) : make_float4(0.f, 0.f, 0.f, 0.f);
+            store_split(b_hi, b_lo, tc::swz_offset(r, j), v, PASSES == 3);
+        }
+        tc::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            const int ksteps = min(4, (K - k0 + 7) / 8);
+            for (int s = 0; s < ksteps; ++s) {
+                const uint64_t ah = tc::smem_desc_sw128(tc::smem_u32(a_hi) + s * 32, 1024);
+                const uint64_t bh = tc::smem_desc_sw128(tc::smem_u32(b_hi) + s * 32, 1024);
+                const uint32_t acc = (c == 0 && s == 0) ? 0u : 1u;
+                if (PASSES == 3) {
+                    const uint64_t al = tc::smem_desc_sw128(tc::smem_u32(a_lo) + s * 32, 1024);
+                    const uint64_t bl = tc::smem_desc_sw128(tc::smem_u32(b_lo) + s * 32, 1024);
+                    tc::mma_tf32(tmem, al, bh, idesc, acc);
+                    tc::mma_tf32(tmem, ah, bl, idesc, 1u);
+                    tc::mma_tf32(tmem, ah, bh, idesc, 1u);
+                } else {
+                    tc::mma_tf32(tmem, ah, bh, idesc, acc);
+                }
+            }
+            tc::mma_commit(mbar);
+        }
+    }
+    tc::mbar_wait(mbar, (nchunks - 1) & 1);
+    tc::fence_after_sync();
+
+    // ---- epilogue: TMEM -> registers -> (+bias | dropout mask) -> smem tile [128][N] ----
+    const int N = g.N;
+    {
+        const int q = warp & 3, half = warp >> 2;                 // lane quarter, column half
+        const int r = q * 32 + lane;
+        const int cols_half = ((NP / 8 + 1) / 2) * 8;             // columns handled by half 0
+        const int c_begin = half == 0 ? 0 : cols_half, c_end = half == 0 ? min(cols_half, NP) : NP;
+        for (int c0 = c_begin; c0 < c_end; c0 += 8) {
+            float v[8];
+            tc::tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (c0 < N) {
+                if (MODE == RG_FWD) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) if (c0 + e < N) v[e] += __ldg(g.bias + c0 + e);
+                } else if (g.drop_p > 0.0f) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (c0 + e < N) v[e] = dropout_keep(g.seed, g.offset, (uint64_t)(row0 + r) * N + c0 + e, g.drop_p) ? v[e] * g.drop_scale : 0.0f;
+                }
+                float* dst = otile + (size_t)r * N + c0;
+                if (c0 + 8 <= N && (N & 3) == 0) {
+                    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) if (c0 + e < N) dst[e] = v[e];
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    // ---- tile -> global: the tile's rows are contiguous in Out ----
+    {
+        const size_t total = (size_t)nrows * N;
+        float* dst = g.Out + (size_t)row0 * N;
+        if ((N & 3) == 0) {
+            const float4* s4 = reinterpret_cast<const float4*>(otile);
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            for (size_t i = tid; i < total / 4; i += RG_THREADS) d4[i] = s4[i];
+        } else {
+            for (size_t i = tid; i < total; i += RG_THREADS) dst[i] = otile[i];
+        }
+    }
+    // ---- per-segment column sums for the layer's normalisation (fixed order: deterministic) ----
+    if (MODE == RG_FWD && g.partials) {
+        for (int cidx = tid; cidx < N; cidx += RG_THREADS) {
+            int seg = 0;
+            for (int rbeg = 0; rbeg < nrows; rbeg += g.seg_len, ++seg) {
+                const int rend = min(nrows, rbeg + g.seg_len);
+                double s1 = 0.0, s2 = 0.0;
+                for (int r = rbeg; r < rend; ++r) {
+                    const float z = otile[(size_t)r * N + cidx];
+                    s1 += (double)z; s2 += (double)z * (double)z;
+                }
+                double* p = g.partials + ((size_t)(slot0 + seg) * N + cidx) * 2;
+                p[0] = s1; p[1] = s2;
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, tmem_cols);
+}
+
+// --------------------------------------------------------------------------------------------
+// weight gradient: dW[N,K] = sum_r dZ[r,n] * Ain[r,k],  Ain = drop(act(P*scale+shift)).
+// Both operands are staged row-major ([r][col], 128-byte column chunks, 8-row swizzle atoms) and
+// consumed as MN-major tcgen05 operands: the contraction runs over rows, 8 rows per MMA.
+// Persistent CTAs accumulate their row tiles in TMEM and write one partial per CTA.
+// --------------------------------------------------------------------------------------------
+struct WgradArgs {
+    const float* dZ;       // [rows, N]
+    const float* P;        // [rows, K]
+    const float* scale;    // [Gp, K] or NULL
+    const float* shift;
+    int act, gr_prev;
+    float drop_p, drop_scale;
+    uint64_t seed, offset;
+    float* partials;       // [gridDim.x, N, K]
+    int rows, K, N;
+    int KP;                // K rounded up to 16 (MMA N extent)
+    int tile_rows;         // R: rows per tile (multiple of 8, <= 64)
+};
+
+constexpr int WG_THREADS = 256;
+
+template <int PASSES>
+__global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int R = g.tile_rows;
+    const int z_chunks = 4;                                  // dZ columns padded to 128 (MMA M = 128)
+    const int p_chunks = (g.KP + 31) / 32;
+    const int chunk_bytes = R * 128;
+    unsigned char* z_hi = base;
+    unsigned char* z_lo = z_hi + z_chunks * chunk_bytes;
+    unsigned char* p_hi = z_lo + z_chunks * chunk_bytes;
+    unsigned char* p_lo = p_hi + p_chunks * chunk_bytes;
+    unsigned char* tail = p_lo + p_chunks * chunk_bytes;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(tail);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tmem_cols = g.KP <= 32 ? 32 : g.KP <= 64 ? 64 : g.KP <= 128 ? 128 : 256;
+    if (tid == 0) { tc::mbar_init(mbar, 1); tc::mbar_fence_init(); }
+    if (warp == 0) tc::tmem_alloc(slot, tmem_cols);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *slot;
+    // A (dZ^T) and B (Ain^T) are MN-major: bits 15 and 16 of the instruction descriptor
+    const uint32_t idesc = tc::instr_desc(2, 128, g.KP) | (1u << 15) | (1u << 16);
+
+    const int ntiles = (g.rows + R - 1) / R;
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int row0 = t * R, nrows = min(R, g.rows - row0);
+        if (it > 0) tc::mbar_wait(mbar, (it - 1) & 1);            // previous tile's MMAs have consumed smem
+        // ---- dZ tile: [R][128 cols] ----
+        for (int u = tid; u < R * z_chunks * 8; u += WG_THREADS) {
+            const int r = u / (z_chunks * 8), cu = u % (z_chunks * 8), ch = cu >> 3, j = cu & 7, n = ch * 32 + j * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nrows && n < g.N) {
+                const float* p = g.dZ + (size_t)(row0 + r) * g.N + n;
+                if (n + 3 < g.N && (g.N & 3) == 0) v = __ldg(reinterpret_cast<const float4*>(p));
+                else { v.x = p[0]; if (n + 1 < g.N) v.y = p[1]; if (n + 2 < g.N) v.z = p[2]; if (n + 3 < g.N) v.w = p[3]; }
+            }
+            store_split(z_hi + ch * chunk_bytes, z_lo + ch * chunk_bytes, tc::swz_offset(r, j), v, PASSES == 3);
+        }
+        // ---- Ain tile: [R][KP cols] rebuilt from P ----
+        RowsGemmArgs pg{};
+        pg.scale = g.scale; pg.shift = g.shift; pg.act = g.act; pg.gr_prev = g.gr_prev; pg.K = g.K;
+        pg.drop_p = g.drop_p; pg.drop_scale = g.drop_scale; pg.seed = g.seed; pg.offset = g.offset;
+        for (int u = tid; u < R * p_chunks * 8; u += WG_THREADS) {
+            const int r = u / (p_chunks * 8), cu = u % (p_chunks * 8), ch = cu >> 3, j = cu & 7, k = ch * 32 + j * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nrows && k < g.K) {
+                v = __ldg(reinterpret_cast<const float4*>(g.P + (size_t)(row0 + r) * g.K + k));
+                v = prologue4(pg, v, row0 + r, k, true);
+            }
+            store_split(p_hi + ch * chunk_bytes, p_lo + ch * chunk_bytes, tc::swz_offset(r, j), v, PASSES == 3);
+        }
+        tc::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            const int ksteps = (nrows + 7) / 8;
+            for (int s = 0; s < ksteps; ++s) {
+                // MN-major: leading byte offset = distance between 128-byte column chunks, stride = 8-row atoms
+                const uint64_t zh = tc::smem_desc_sw128_mn(tc::smem_u32(z_hi) + s * 1024, chunk_bytes, 1024);
+                const uint64_t ph = tc::smem_desc_sw128_mn(tc::smem_u32(p_hi) + s * 1024, chunk_bytes, 1024);
+                const uint32_t acc = (it == 0 && s == 0) ? 0u : 1u;
+                if (PASSES == 3) {
+                    const uint64_t zl = tc::smem_desc_sw128_mn(tc::smem_u32(z_lo) + s * 1024, chunk_bytes, 1024);
+                    const uint64_t pl = tc::smem_desc_sw128_mn(tc::smem_u32(p_lo) + s * 1024, chunk_bytes, 1024);
+                    tc::mma_tf32(tmem, zl, ph, idesc, acc);
+                    tc::mma_tf32(tmem, zh, pl, idesc, 1u);
+                    tc::mma_tf32(tmem, zh, ph, idesc, 1u);
+                } else {
+                    tc::mma_tf32(tmem, zh, ph, idesc, acc);
+                }
+            }
+            tc::mma_commit(mbar);
+        }
+    }
+    // ---- epilogue: this CTA's partial dW[n][k], n = TMEM lane ----
+    if (it > 0) { tc::mbar_wait(mbar, (it - 1) & 1); }
+    tc::fence_after_sync();
+    {
+        const int q = warp & 3, half = warp >> 2;
+        const int n = q * 32 + lane;
+        float* dst = g.partials + (size_t)blockIdx.x * g.N * g.K;
+        const int cols_half = ((g.KP / 8 + 1) / 2) * 8;
+        const int c_begin = half == 0 ? 0 : cols_half, c_end = half == 0 ? min(cols_half, g.KP) : g.KP;
+        for (int c0 = c_begin; c0 < c_end; c0 += 8) {
+            float v[8];
+            if (it > 0) tc::tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = 0.0f;
+            }
+            if (n < g.N) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (c0 + e < g.K) dst[(size_t)n * g.K + c0 + e] = v[e];
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, tmem_cols);
+}
+
+}  // namespace ptrb200

@@ -111,6 +111,17 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr, uint32_t
     d |= (uint64_t)2 << 61;                                     // layout type SWIZZLE_128B [61,64)
     return d;
 }
+// MN-major operand (the contraction index runs over rows of a row-major staged tile): `lbo_bytes` is the
+// distance between consecutive 128-byte blocks along M/N, `sbo_bytes` between consecutive 8-row groups along K
+__device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 // instruction descriptor: D fp32, A/B format (0 f16, 1 bf16, 2 tf32), both K-major, M x N tile
 __host__ __device__ constexpr uint32_t instr_desc(int fmt, int M, int N) {
     return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -137,7 +148,7 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 // split an fp32 value into tf32-representable hi and the fp32 remainder lo (hi + lo == x exactly)
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-    lo = x - hi;
+    lo = (fabsf(x) <= 3.0e38f) ? x - hi : 0.0f;      // inf/nan stay in hi only
 }
 
 }  // namespace tc

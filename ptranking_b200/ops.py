@@ -174,12 +174,15 @@ def next_dropout_offset() -> int:
 class FFNetSpec:
     """Static description of one stacked FF net + the order its parameters are passed in."""
 
-    def __init__(self, dims, act_hidden, act_tail, norm, norm_affine, dropout_p):
+    def __init__(self, dims, act_hidden, act_tail, norm, norm_affine, dropout_p, math_mode="3xtf32"):
         if len(dims) - 1 > _lib.MAX_FF_LAYERS:
             raise ValueError("too many layers")
         self.dims = [int(d) for d in dims]
         self.act_hidden, self.act_tail = act_hidden, act_tail
         self.norm, self.norm_affine, self.dropout_p = norm, bool(norm_affine), float(dropout_p)
+        if math_mode not in _lib.MATH_MODES:
+            raise ValueError(f"math_mode must be one of {sorted(_lib.MATH_MODES)}")
+        self.math_mode = math_mode
         self.L = len(dims) - 1
         # slots[l] = names of the parameter tensors layer l owns, in flattening order
         self.slots = []
@@ -202,6 +205,7 @@ class FFNetSpec:
         d.norm = _lib.NORM_CODES[self.norm]
         d.norm_affine = int(self.norm_affine)
         d.dropout_p = self.dropout_p
+        d.math_mode = _lib.MATH_MODES[self.math_mode]
         it = iter(params)
         for l, names in enumerate(self.slots):
             for nm in names:

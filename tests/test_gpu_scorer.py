@@ -116,3 +116,65 @@ def test_dropout_mask_statistics_and_consistency():
     # a bare Linear equals the torch op (sanity of the tall-skinny GEMM path)
     ref = torch.nn.functional.linear(X.detach(), net.ff_2.weight, net.ff_2.bias)
     assert rel_err(net(X.detach()).detach().cpu().numpy(), ref.detach().cpu().numpy()) <= 1e-5
+
+
+TC_CASES = [
+    # B, n, dims, AF, TL_AF(None = no tail AF), norm, affine, dropout
+    (4, 256, [136, 100, 100, 1], "GE", "S", "BN", True, 0.1),
+    (3, 200, [136, 100, 100, 1], "R", "S", "BN2", False, 0.1),       # n > 128: groups span several row tiles
+    (5, 50, [136, 100, 1], "GE", "S", "BN2", True, 0.0),             # n < 128: several groups per row tile
+    (7, 33, [64, 48, 32, 1], "CE", None, None, False, 0.2),          # no norm, bare last Linear, ragged rows
+    (2, 300, [136, 100, 8], "S", "R", "BN", False, 0.0),             # wider output, rows % 128 != 0
+    (1, 1, [136, 100, 1], "GE", "S", None, False, 0.0),              # a single document
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=[f"tc{i}" for i in range(len(TC_CASES))])
+def test_tensor_core_path_matches_simt_path(case):
+    """The tcgen05 (3xTF32) layer kernels against the fp32 SIMT kernels on identical inputs,
+    dropout streams included: forward scores, parameter gradients and dX."""
+    from ptranking_b200 import ops
+    B, n, dims, AF, TL, norm, affine, p = case
+    torch.manual_seed(B * 100 + n)
+    specs = {m: ops.FFNetSpec(dims, AF if len(dims) > 2 else None, TL, norm, affine, p, math_mode=m) for m in ("simt", "3xtf32")}
+    params = []
+    for names, l in zip(specs["simt"].slots, range(len(dims) - 1)):
+        for nm in names:
+            if nm == "weight":
+                t = torch.randn(dims[l + 1], dims[l], device=DEV) / np.sqrt(dims[l])
+            elif nm in ("gamma", "aff_w"):
+                t = 1.0 + 0.1 * torch.randn(dims[l + 1], device=DEV)
+            else:
+                t = 0.1 * torch.randn(dims[l + 1], device=DEV)
+            params.append(t.requires_grad_(True))
+    X = torch.randn(B, n, dims[0], device=DEV)
+    dO = torch.randn(B, n, dims[-1], device=DEV)
+    res = {}
+    for m, spec in specs.items():
+        Xm = X.clone().requires_grad_(True)
+        pm = [q.detach().clone().requires_grad_(True) for q in params]
+        out = ops.ffnet_apply(Xm, spec, pm, training=True, seed=1234, offset=7)
+        (out * dO).sum().backward()
+        res[m] = (out.detach().cpu().numpy(), [q.grad.cpu().numpy() for q in pm], Xm.grad.cpu().numpy())
+    o_s, g_s, dx_s = res["simt"]
+    o_t, g_t, dx_t = res["3xtf32"]
+    assert rel_err(o_t, o_s) <= 1e-5, rel_err(o_t, o_s)
+    gscale = max(np.abs(g).max() for g in g_s)
+    for i, (a, b) in enumerate(zip(g_t, g_s)):
+        assert np.abs(a - b).max() <= 2e-5 * np.abs(b).max() + 2e-6 * gscale + 1e-9, (i, np.abs(a - b).max(), np.abs(b).max())
+    assert rel_err(dx_t, dx_s) <= 2e-5, rel_err(dx_t, dx_s)
+
+
+def test_tf32_single_pass_is_looser_than_3xtf32():
+    from ptranking_b200 import ops
+    dims = [136, 100, 100, 1]
+    torch.manual_seed(0)
+    X = torch.randn(4, 128, 136, device=DEV)
+    params = []
+    spec0 = ops.FFNetSpec(dims, "GE", "S", None, False, 0.0, math_mode="simt")
+    for names, l in zip(spec0.slots, range(3)):
+        params += [torch.randn(dims[l + 1], dims[l], device=DEV) / np.sqrt(dims[l]), torch.zeros(dims[l + 1], device=DEV)]
+    outs = {m: ops.ffnet_apply(X, ops.FFNetSpec(dims, "GE", "S", None, False, 0.0, math_mode=m), params, training=False).cpu().numpy()
+            for m in ("simt", "3xtf32", "tf32")}
+    e3, e1 = rel_err(outs["3xtf32"], outs["simt"]), rel_err(outs["tf32"], outs["simt"])
+    assert e3 <= 1e-5 and 1e-5 < e1 <= 5e-3, (e3, e1)
