@@ -194,6 +194,11 @@ int ptrb200_ffnet_backward(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* 
 int ptrb200_tc_gemm_nt(const float* A, const float* B, float* C, int M, int N, int K, int passes,
                        ptrb200_stream_t stream);
 
+/* dW[N,K] = dZ[rows,N]^T * P[rows,K] (the weight gradient autograd forms for nn.Linear) with both operands
+ * consumed MN-major by tcgen05.mma; partials: 296*N*K floats of scratch.  N <= 128, K <= 256, K % 4 == 0. */
+int ptrb200_tc_wgrad(const float* dZ, const float* P, float* dW, float* partials, int rows, int N, int K, int passes,
+                     ptrb200_stream_t stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -618,6 +618,25 @@ using namespace ptrb200;
 
 extern "C" {
 
+int ptrb200_tc_wgrad(const float* dZ, const float* P, float* dW, float* partials, int rows, int N, int K, int passes,
+                     ptrb200_stream_t stream) {
+    if (!dZ || !P || !dW || !partials || rows <= 0 || N <= 0 || K <= 0) { set_error("tc_wgrad: bad arguments"); return PTRB200_ERR_INVALID; }
+    if (N > 128 || K > 256 || K % 4 != 0) { set_error("tc_wgrad: needs N <= 128, K <= 256, K %% 4 == 0"); return PTRB200_ERR_UNSUPPORTED; }
+    WgradArgs w{};
+    w.dZ = dZ; w.P = P; w.scale = w.shift = nullptr; w.act = PTRB200_AF_NONE; w.gr_prev = rows;
+    w.drop_p = 0.0f; w.drop_scale = 1.0f; w.partials = partials;
+    w.rows = rows; w.K = K; w.N = N; w.KP = ((K + 15) / 16) * 16; w.tile_rows = 32;
+    const int p_chunks = (w.KP + 31) / 32, grid = 296;
+    size_t smem = 1024 + (size_t)(4 + p_chunks) * 2 * w.tile_rows * 128 + 64;
+    if (w.KP > 128 && smem < 80 * 1024) smem = 80 * 1024;
+    int rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (passes == 3) { if ((rc = opt_in_smem(wgrad_tc_kernel<3>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<3>, grid, WG_THREADS, smem, st, w); }
+    else { if ((rc = opt_in_smem(wgrad_tc_kernel<1>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<1>, grid, WG_THREADS, smem, st, w); }
+    PTRB200_LAUNCH(reduce_splits_kernel, (N * K + 255) / 256, 256, 0, st, (const float*)partials, dW, grid, N * K);
+    return check_launch("tc_wgrad");
+}
+
 int64_t ptrb200_ffnet_workspace_bytes(const ptrb200_ffnet* net, int B, int n) {
     Plan p;
     const int rc = make_plan(net, B, n, p);

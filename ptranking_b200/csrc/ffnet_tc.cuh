@@ -243,8 +243,8 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
 
 // --------------------------------------------------------------------------------------------
 // weight gradient: dW[N,K] = sum_r dZ[r,n] * Ain[r,k],  Ain = drop(act(P*scale+shift)).
-// Both operands are staged row-major ([r][col], 128-byte column chunks, 8-row swizzle atoms) and
-// consumed as MN-major tcgen05 operands: the contraction runs over rows, 8 rows per MMA.
+// Both operands are staged row-major ([r][col], 128-byte column chunks, 4-row SWIZZLE_128B_BASE32B
+// atoms) and consumed as MN-major tcgen05 operands: the contraction runs over rows, 8 rows per MMA.
 // Persistent CTAs accumulate their row tiles in TMEM and write one partial per CTA.
 // --------------------------------------------------------------------------------------------
 struct WgradArgs {
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
                 if (n + 3 < g.N && (g.N & 3) == 0) v = __ldg(reinterpret_cast<const float4*>(p));
                 else { v.x = p[0]; if (n + 1 < g.N) v.y = p[1]; if (n + 2 < g.N) v.z = p[2]; if (n + 3 < g.N) v.w = p[3]; }
             }
-            store_split(z_hi + ch * chunk_bytes, z_lo + ch * chunk_bytes, tc::swz_offset(r, j), v, PASSES == 3);
+            store_split(z_hi + ch * chunk_bytes, z_lo + ch * chunk_bytes, tc::swz32_offset(r, j), v, PASSES == 3);
         }
         // ---- Ain tile: [R][KP cols] rebuilt from P ----
         RowsGemmArgs pg{};
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
                 v = __ldg(reinterpret_cast<const float4*>(g.P + (size_t)(row0 + r) * g.K + k));
                 v = prologue4(pg, v, row0 + r, k, true);
             }
-            store_split(p_hi + ch * chunk_bytes, p_lo + ch * chunk_bytes, tc::swz_offset(r, j), v, PASSES == 3);
+            store_split(p_hi + ch * chunk_bytes, p_lo + ch * chunk_bytes, tc::swz32_offset(r, j), v, PASSES == 3);
         }
         tc::fence_proxy_async();
         __syncthreads();
@@ -325,13 +325,13 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
             tc::fence_after_sync();
             const int ksteps = (nrows + 7) / 8;
             for (int s = 0; s < ksteps; ++s) {
-                // MN-major: leading byte offset = distance between 128-byte column chunks, stride = 8-row atoms
-                const uint64_t zh = tc::smem_desc_sw128_mn(tc::smem_u32(z_hi) + s * 1024, chunk_bytes, 1024);
-                const uint64_t ph = tc::smem_desc_sw128_mn(tc::smem_u32(p_hi) + s * 1024, chunk_bytes, 1024);
+                // MN-major: leading byte offset = distance between 128-byte column chunks, stride = 4-row atoms
+                const uint64_t zh = tc::smem_desc_sw128_mn(tc::smem_u32(z_hi) + s * 1024, chunk_bytes, 512);
+                const uint64_t ph = tc::smem_desc_sw128_mn(tc::smem_u32(p_hi) + s * 1024, chunk_bytes, 512);
                 const uint32_t acc = (it == 0 && s == 0) ? 0u : 1u;
                 if (PASSES == 3) {
-                    const uint64_t zl = tc::smem_desc_sw128_mn(tc::smem_u32(z_lo) + s * 1024, chunk_bytes, 1024);
-                    const uint64_t pl = tc::smem_desc_sw128_mn(tc::smem_u32(p_lo) + s * 1024, chunk_bytes, 1024);
+                    const uint64_t zl = tc::smem_desc_sw128_mn(tc::smem_u32(z_lo) + s * 1024, chunk_bytes, 512);
+                    const uint64_t pl = tc::smem_desc_sw128_mn(tc::smem_u32(p_lo) + s * 1024, chunk_bytes, 512);
                     tc::mma_tf32(tmem, zl, ph, idesc, acc);
                     tc::mma_tf32(tmem, zh, pl, idesc, 1u);
                     tc::mma_tf32(tmem, zh, ph, idesc, 1u);

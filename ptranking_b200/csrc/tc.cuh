@@ -111,15 +111,20 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr, uint32_t
     d |= (uint64_t)2 << 61;                                     // layout type SWIZZLE_128B [61,64)
     return d;
 }
-// MN-major operand (the contraction index runs over rows of a row-major staged tile): `lbo_bytes` is the
-// distance between consecutive 128-byte blocks along M/N, `sbo_bytes` between consecutive 8-row groups along K
+// MN-major tf32 operand (the contraction index runs over the ROWS of a row-major staged tile).
+// The only legal layout for 32-bit MN-major operands is SWIZZLE_128B_BASE32B: atoms of 4 rows x 128 B,
+// the 32-byte unit u of row r stored at unit (u ^ (r & 3)).  `lbo_bytes` = distance between consecutive
+// 128-byte blocks along M/N, `sbo_bytes` = distance between consecutive 4-row groups along K.
+__device__ __forceinline__ uint32_t swz32_offset(int r, int j16) {
+    return (uint32_t)(r * 128 + ((((j16 >> 1) ^ (r & 3)) << 5) | ((j16 & 1) << 4)));
+}
 __device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)1 << 61;                                     // layout type SWIZZLE_128B_BASE32B
     return d;
 }
 // instruction descriptor: D fp32, A/B format (0 f16, 1 bf16, 2 tf32), both K-major, M x N tile
