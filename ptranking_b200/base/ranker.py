@@ -141,10 +141,10 @@ class NeuralRanker(Evaluator):
         return False
 
     def train(self, train_data, epoch_k=None, **kwargs):
-        """ranker.py:565-587.  Host batches are copied with non_blocking=True (pinned sources overlap
-        with the previous step).  The reference's blocking ``batch_loss.item()`` per batch (:584) becomes an
-        asynchronous device->host copy of every step's loss into a pinned buffer, read once at the end,
-        so the loop never stalls the GPU."""
+        """ranker.py:565-587, restructured for the device: the host->device copy of batch i+1 runs on a
+        side stream while batch i trains (the reference copies synchronously from pageable memory, :577),
+        and the blocking ``batch_loss.item()`` per batch (:584) becomes an asynchronous device->host copy
+        of every step's loss into a pinned ring that is read once at the end."""
         self.train_mode()
         assert 'label_type' in kwargs and 'presort' in kwargs
         label_type, presort = kwargs['label_type'], kwargs['presort']
@@ -152,9 +152,27 @@ class NeuralRanker(Evaluator):
         stop_training = False
         ring = self._loss_ring()
         host_sum, filled = 0.0, 0
-        for batch_ids, X, y in train_data:
+        compute = torch.cuda.current_stream()
+        copier = self._copy_stream()
+
+        def upload(batch):
+            ids, X, y = batch
+            with torch.cuda.stream(copier):
+                Xd, yd = X.to(self.device, non_blocking=True), y.to(self.device, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copier)
+            return ids, Xd, yd, ready
+
+        it = iter(train_data)
+        nxt = next(it, None)
+        pending = upload(nxt) if nxt is not None else None
+        while pending is not None:
+            batch_ids, X, y, ready = pending
+            nxt = next(it, None)
+            pending = upload(nxt) if nxt is not None else None       # overlaps with the step below
+            compute.wait_event(ready)
+            X.record_stream(compute); y.record_stream(compute)
             num_queries += len(batch_ids)
-            X, y = X.to(self.device, non_blocking=True), y.to(self.device, non_blocking=True)
             batch_loss, stop_training = self.train_op(X, y, batch_ids=batch_ids, epoch_k=epoch_k,
                                                       presort=presort, label_type=label_type)
             if stop_training:
@@ -162,13 +180,18 @@ class NeuralRanker(Evaluator):
             ring[filled].copy_(batch_loss.detach(), non_blocking=True)
             filled += 1
             if filled == ring.numel():
-                torch.cuda.current_stream().synchronize()
+                compute.synchronize()
                 host_sum += float(ring.double().sum())
                 filled = 0
-        torch.cuda.current_stream().synchronize()
+        compute.synchronize()
         host_sum += float(ring[:filled].double().sum())
         epoch_loss = torch.tensor([host_sum / max(num_queries, 1)], device=self.device)
         return epoch_loss, stop_training
+
+    def _copy_stream(self):
+        if getattr(self, '_copier', None) is None:
+            self._copier = torch.cuda.Stream(device=self.device)
+        return self._copier
 
     def _loss_ring(self):
         if getattr(self, '_ring', None) is None:

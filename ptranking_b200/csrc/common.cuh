@@ -147,9 +147,33 @@ __host__ __device__ __forceinline__ uint32_t dropout_bits(uint64_t seed, uint64_
     const uint32_t lane = (uint32_t)(elem & 3);
     return lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
 }
-__host__ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t offset, uint64_t elem, float p) {
-    // uniform in [0,1) from the top 24 bits; keep when u >= p
-    return (float)(dropout_bits(seed, offset, elem) >> 8) * (1.0f / 16777216.0f) >= p;
+
+// ---- dropout masks: splitmix64 counter stream, 16 random bits per element ---------------------------
+// One 64-bit draw covers 4 consecutive elements (element e uses bits [16*(e&3), 16*(e&3)+16) of draw e>>2);
+// an element is KEPT when its 16-bit value >= thr = round(p * 65536).  The mask of an element depends only
+// on (key, element index), so forward, backward and every kernel variant regenerate identical masks.
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27; x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return x;
+}
+__host__ __device__ __forceinline__ uint64_t dropout_key(uint64_t seed, uint64_t offset) {
+    return mix64(seed + 0x9e3779b97f4a7c15ull * (offset + 1));
+}
+__host__ __device__ __forceinline__ uint64_t dropout_draw4(uint64_t key, uint64_t quad) {
+    return mix64(key + 0x9e3779b97f4a7c15ull * quad);
+}
+__host__ __device__ __forceinline__ bool dropout_keep(uint64_t key, uint64_t elem, uint32_t thr) {
+    return (uint32_t)((dropout_draw4(key, elem >> 2) >> (16 * (elem & 3))) & 0xffffu) >= thr;
+}
+struct DropCfg { uint32_t thr; float scale; uint64_t key; };      // thr == 0: dropout off
+static inline DropCfg make_drop(float p, uint64_t seed, uint64_t offset) {
+    DropCfg d;
+    d.thr = p > 0.0f ? (uint32_t)(p * 65536.0f + 0.5f) : 0u;
+    d.scale = d.thr ? 65536.0f / (float)(65536u - d.thr) : 1.0f;
+    d.key = dropout_key(seed, offset);
+    return d;
 }
 
 }  // namespace ptrb200

@@ -30,16 +30,14 @@ struct GemmArgs {
     int rows, d_in, d_out;
     int M, N, K;         // GEMM extents
     int k_chunk;         // BWD_WEIGHT: rows per split
-    float drop_p;        // dropout on the layer input (0 = none)
-    float drop_scale;    // 1/(1-p)
-    uint64_t seed, offset;
+    DropCfg drop;        // dropout on the layer input (thr == 0: none)
 };
 
 template <int MODE>
 static __device__ __forceinline__ float load_a(const GemmArgs& g, int m, int k) {
     if (MODE == GEMM_FWD) {
         float v = g.A[(size_t)m * g.d_in + k];
-        if (g.drop_p > 0.0f) v = dropout_keep(g.seed, g.offset, (uint64_t)m * g.d_in + k, g.drop_p) ? v * g.drop_scale : 0.0f;
+        if (g.drop.thr) v = dropout_keep(g.drop.key, (uint64_t)m * g.d_in + k, g.drop.thr) ? v * g.drop.scale : 0.0f;
         return v;
     } else if (MODE == GEMM_BWD_DATA) {
         return g.A[(size_t)m * g.d_out + k];                 // dZ[m, k]
@@ -55,7 +53,7 @@ static __device__ __forceinline__ float load_b(const GemmArgs& g, int k, int n) 
         return g.Bm[(size_t)k * g.d_in + n];                 // W[k, n]
     } else {
         float v = g.Bm[(size_t)k * g.d_in + n];              // input[row k, n]
-        if (g.drop_p > 0.0f) v = dropout_keep(g.seed, g.offset, (uint64_t)k * g.d_in + n, g.drop_p) ? v * g.drop_scale : 0.0f;
+        if (g.drop.thr) v = dropout_keep(g.drop.key, (uint64_t)k * g.d_in + n, g.drop.thr) ? v * g.drop.scale : 0.0f;
         return v;
     }
 }
@@ -122,7 +120,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
             if (MODE == GEMM_FWD) {
                 g.C[(size_t)m * g.d_out + n] = v + g.bias[n];
             } else if (MODE == GEMM_BWD_DATA) {
-                if (g.drop_p > 0.0f) v = dropout_keep(g.seed, g.offset, (uint64_t)m * g.d_in + n, g.drop_p) ? v * g.drop_scale : 0.0f;
+                if (g.drop.thr) v = dropout_keep(g.drop.key, (uint64_t)m * g.d_in + n, g.drop.thr) ? v * g.drop.scale : 0.0f;
                 g.C[(size_t)m * g.d_in + n] = v;
             } else {
                 g.C[((size_t)blockIdx.z * g.d_out + m) * g.d_in + n] = v;
@@ -206,30 +204,117 @@ __global__ void colstat_kernel(const float* __restrict__ Z, const float* __restr
     }
 }
 
-// forward finalize: partials -> mean, rstd (biased variance, eps = 1e-5).  One warp per (group, channel);
-// lanes stride over the slices, fixed-order butterfly -> deterministic.
+// Vectorised column statistics for widths that are multiples of 4: thread (q, ry) owns channels 4q..4q+3 and
+// walks rows ry, ry+RY, ... of its slice, so a warp reads 512 contiguous bytes per step.  Same partial layout
+// as colstat_kernel.  blockDim = (Q = C/4, RY); dynamic smem = RY*Q*8 doubles.
+template <int WHAT>
+__global__ void colstat4_kernel(const float* __restrict__ Z, const float* __restrict__ dA, float* __restrict__ dY_out,
+                                NormRef nr, double* __restrict__ partials, int gr, int C, int S, int slice_rows) {
+    extern __shared__ double sh4[];
+    const int Q = blockDim.x, RY = blockDim.y, q = threadIdx.x, ry = threadIdx.y, c = q * 4;
+    const int g = blockIdx.x, sl = blockIdx.y;
+    const int r0 = sl * slice_rows, r1 = min(gr, r0 + slice_rows);
+    float a[4] = {1.f, 1.f, 1.f, 1.f}, cc[4] = {0.f, 0.f, 0.f, 0.f}, mu[4] = {0.f, 0.f, 0.f, 0.f}, rs[4] = {1.f, 1.f, 1.f, 1.f};
+    if (WHAT == STAT_DY) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            norm_coeffs(nr, c + e, a[e], cc[e]);
+            if (nr.mean) { mu[e] = nr.mean[(size_t)g * C + c + e]; rs[e] = nr.rstd[(size_t)g * C + c + e]; }
+        }
+    }
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    for (int r = r0 + ry; r < r1; r += RY) {
+        const size_t off = ((size_t)g * gr + r) * C + c;
+        const float4 z4 = __ldg(reinterpret_cast<const float4*>(Z + off));
+        const float z[4] = {z4.x, z4.y, z4.z, z4.w};
+        if (WHAT == STAT_MOMENTS) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { s1[e] += (double)z[e]; s2[e] += (double)z[e] * (double)z[e]; }
+        } else if (WHAT == STAT_COLSUM) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s1[e] += (double)z[e];
+        } else {
+            const float4 d4 = __ldg(reinterpret_cast<const float4*>(dA + off));
+            const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float xh = nr.mean ? (z[e] - mu[e]) * rs[e] : z[e];
+                const float dy = d[e] * activate(nr.act, a[e] * xh + cc[e]).dy;
+                o[e] = dy;
+                s1[e] += (double)dy; s2[e] += (double)dy * (double)xh;
+            }
+            *reinterpret_cast<float4*>(dY_out + off) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    double* mine = sh4 + ((size_t)ry * Q + q) * 8;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { mine[e] = s1[e]; mine[4 + e] = s2[e]; }
+    __syncthreads();
+    if (ry == 0) {
+        for (int y = 1; y < RY; ++y) {
+            const double* o = sh4 + ((size_t)y * Q + q) * 8;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { s1[e] += o[e]; s2[e] += o[4 + e]; }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            double* p = partials + (((size_t)g * S + sl) * C + c + e) * 2;
+            p[0] = s1[e]; p[1] = s2[e];
+        }
+    }
+}
+
+template <int WHAT>
+static void launch_colstat(cudaStream_t st, const char* tag, const float* Z, const float* dA, float* dY, const NormRef& nr,
+                           double* part, int G, int S, int gr, int C, int slice_rows) {
+    dim3 grid(G, S);
+    if (C % 4 == 0 && C / 4 <= 256) {
+        const int Q = C / 4;
+        int RY = 256 / Q; if (RY < 1) RY = 1; if (RY > 16) RY = 16;
+        PTRB200_LAUNCH_TAG(tag, colstat4_kernel<WHAT>, grid, dim3(Q, RY), (size_t)RY * Q * 8 * sizeof(double), st, Z, dA, dY, nr, part, gr, C, S, slice_rows);
+    } else {
+        PTRB200_LAUNCH_TAG(tag, colstat_kernel<WHAT>, grid, dim3(32, 8), 0, st, Z, dA, dY, nr, part, gr, C, S, slice_rows);
+    }
+}
+
+// Finalize kernels: one CTA of FIN_THREADS per (group, channel) [moments] or per channel [dY sums]; threads
+// stride over the partial slots and a fixed-shape tree combines them (deterministic).
+constexpr int FIN_THREADS = 128;
 static __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__global__ void moments_finalize_kernel(const double* __restrict__ partials, float* __restrict__ mean,
-                                        float* __restrict__ rstd, float* __restrict__ scale, float* __restrict__ shift,
-                                        NormRef nr, int G, int C, int S, int gr) {
-    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (i >= G * C) return;
-    const int g = i / C, c = i % C;
+static __device__ __forceinline__ void block_sum2_d(double& a, double& b) {
+    __shared__ double sh[2][FIN_THREADS / 32];
+    a = warp_sum_d(a); b = warp_sum_d(b);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) { sh[0][warp] = a; sh[1][warp] = b; }
+    __syncthreads();
+    a = 0.0; b = 0.0;
+#pragma unroll
+    for (int w = 0; w < FIN_THREADS / 32; ++w) { a += sh[0][w]; b += sh[1][w]; }
+}
+
+// forward finalize: partials [G,S,C,2] -> mean, rstd (biased variance, eps = 1e-5) and the fused prologue
+// coefficients  y = a*(z-mean)*rstd + c  ==  z*scale + shift.   grid = G*C
+__global__ void __launch_bounds__(FIN_THREADS) moments_finalize_kernel(
+        const double* __restrict__ partials, float* __restrict__ mean, float* __restrict__ rstd,
+        float* __restrict__ scale, float* __restrict__ shift, NormRef nr, int G, int C, int S, int gr) {
+    const int i = blockIdx.x, g = i / C, c = i % C;
     double s1 = 0.0, s2 = 0.0;
-    for (int s = lane; s < S; s += 32) { const double* p = partials + (((size_t)g * S + s) * C + c) * 2; s1 += p[0]; s2 += p[1]; }
-    s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
-    if (lane == 0) {
+    for (int s = threadIdx.x; s < S; s += FIN_THREADS) { const double* p = partials + (((size_t)g * S + s) * C + c) * 2; s1 += p[0]; s2 += p[1]; }
+    block_sum2_d(s1, s2);
+    if (threadIdx.x == 0) {
         const double m = s1 / gr;
         double var = s2 / gr - m * m;
         if (var < 0.0) var = 0.0;
         const float mf = (float)m, rf = (float)(1.0 / sqrt(var + 1e-5));
         mean[i] = mf;
         rstd[i] = rf;
-        if (scale) {            // y = a*(z-mean)*rstd + c  ==  z*scale + shift
+        if (scale) {
             float a, cc;
             norm_coeffs(nr, c, a, cc);
             scale[i] = a * rf;
@@ -238,30 +323,29 @@ __global__ void moments_finalize_kernel(const double* __restrict__ partials, flo
     }
 }
 
-// backward finalize: per-(group,channel) sums S1,S2 (float) + totals over groups T1,T2 per channel.
-// One warp per channel; lanes stride over (group, slice) pairs.
-__global__ void dy_finalize_kernel(const double* __restrict__ partials, float* __restrict__ S1, float* __restrict__ S2,
-                                   float* __restrict__ T1, float* __restrict__ T2, int G, int C, int S) {
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (c >= C) return;
+// backward finalize: per-(group,channel) sums S1,S2 (float, optional) + totals over groups T1,T2 per channel.  grid = C
+__global__ void __launch_bounds__(FIN_THREADS) dy_finalize_kernel(
+        const double* __restrict__ partials, float* __restrict__ S1, float* __restrict__ S2,
+        float* __restrict__ T1, float* __restrict__ T2, int G, int C, int S) {
+    const int c = blockIdx.x;
     double t1 = 0.0, t2 = 0.0;
     if (S == 1) {
-        for (int g = lane; g < G; g += 32) {
+        for (int g = threadIdx.x; g < G; g += FIN_THREADS) {
             const double* p = partials + ((size_t)g * C + c) * 2;
             if (S1) { S1[(size_t)g * C + c] = (float)p[0]; S2[(size_t)g * C + c] = (float)p[1]; }
             t1 += p[0]; t2 += p[1];
         }
+        block_sum2_d(t1, t2);
     } else {
         for (int g = 0; g < G; ++g) {
             double s1 = 0.0, s2 = 0.0;
-            for (int s = lane; s < S; s += 32) { const double* p = partials + (((size_t)g * S + s) * C + c) * 2; s1 += p[0]; s2 += p[1]; }
-            s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
-            if (S1 && lane == 0) { S1[(size_t)g * C + c] = (float)s1; S2[(size_t)g * C + c] = (float)s2; }
-            if (lane == 0) { t1 += s1; t2 += s2; }
+            for (int s = threadIdx.x; s < S; s += FIN_THREADS) { const double* p = partials + (((size_t)g * S + s) * C + c) * 2; s1 += p[0]; s2 += p[1]; }
+            block_sum2_d(s1, s2);
+            if (S1 && threadIdx.x == 0) { S1[(size_t)g * C + c] = (float)s1; S2[(size_t)g * C + c] = (float)s2; }
+            t1 += s1; t2 += s2;
         }
     }
-    t1 = warp_sum_d(t1); t2 = warp_sum_d(t2);
-    if (lane == 0) { T1[c] = (float)t1; if (T2) T2[c] = (float)t2; }
+    if (threadIdx.x == 0) { T1[c] = (float)t1; if (T2) T2[c] = (float)t2; }
 }
 
 // ------------------------------------------------------------------ elementwise passes
@@ -276,6 +360,49 @@ __global__ void norm_act_fwd_kernel(const float* __restrict__ Z, float* __restri
         float xh = Z[i];
         if (nr.mean) { const size_t g = row / gr; xh = (xh - nr.mean[g * C + c]) * nr.rstd[g * C + c]; }
         A[i] = activate(nr.act, a * xh + cc).y;
+    }
+}
+
+// float4 variants of the two elementwise passes (C % 4 == 0)
+__global__ void norm_act_fwd4_kernel(const float* __restrict__ Z, float* __restrict__ A, NormRef nr, size_t units, int C, int gr) {
+    const int Q = C >> 2;
+    for (size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(u % Q) * 4;
+        const size_t row = u / Q, g = row / gr;
+        const float4 z4 = __ldg(reinterpret_cast<const float4*>(Z) + u);
+        const float z[4] = {z4.x, z4.y, z4.z, z4.w};
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float a, cc;
+            norm_coeffs(nr, c + e, a, cc);
+            float xh = z[e];
+            if (nr.mean) xh = (xh - nr.mean[g * C + c + e]) * nr.rstd[g * C + c + e];
+            o[e] = activate(nr.act, a * xh + cc).y;
+        }
+        reinterpret_cast<float4*>(A)[u] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+__global__ void norm_bwd_apply4_kernel(const float* __restrict__ Z, float* __restrict__ dY, NormRef nr,
+                                       const float* __restrict__ S1, const float* __restrict__ S2, size_t units, int C, int gr) {
+    const int Q = C >> 2;
+    const float invN = 1.0f / (float)gr;
+    for (size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(u % Q) * 4;
+        const size_t g = (u / Q) / gr;
+        const float4 z4 = __ldg(reinterpret_cast<const float4*>(Z) + u);
+        const float4 d4 = reinterpret_cast<const float4*>(dY)[u];
+        const float z[4] = {z4.x, z4.y, z4.z, z4.w}, d[4] = {d4.x, d4.y, d4.z, d4.w};
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float a, cc;
+            norm_coeffs(nr, c + e, a, cc);
+            const float mu = nr.mean[g * C + c + e], rs = nr.rstd[g * C + c + e];
+            const float xh = (z[e] - mu) * rs;
+            o[e] = a * rs * (d[e] - S1[g * C + c + e] * invN - xh * (S2[g * C + c + e] * invN));
+        }
+        reinterpret_cast<float4*>(dY)[u] = make_float4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -315,7 +442,8 @@ struct LayerPlan {
     bool has_act, has_norm;
     int d_in, d_out, act;
     size_t z_off, a_off, mean_off, rstd_off;     // byte offsets into the workspace (a_off unused for the last layer)
-    size_t scale_off, shift_off, wt_off;         // tensor-core mode: fused prologue coefficients [G,d_out], W^T [d_in,d_out]
+    size_t scale_off, shift_off;                 // tensor-core mode: fused prologue coefficients [G,d_out]
+    size_t img_f_hi, img_f_lo, img_d_hi, img_d_lo;   // tensor-core mode: pre-swizzled B images of W (fwd) and W^T (dgrad)
 };
 struct Plan {
     bool use_tc;                                 // every layer fits the tcgen05 kernels (else the SIMT path runs)
@@ -355,7 +483,7 @@ static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p) {
             else { p.group_rows = n; p.tiles_per_group = (n + 127) / 128; p.S_stat = p.tiles_per_group; p.slice_rows = 128; }
         } else { p.slice_rows = 128; p.S_stat = (int)((p.rows + 127) / 128); }
         p.ntiles = p.group_rows > 0 ? B * p.tiles_per_group : (int)((p.rows + p.tile_rows - 1) / p.tile_rows);
-        p.wg_rows = 32; p.wg_grid = 296;
+        p.wg_rows = 32; p.wg_grid = 444;
     }
     p.k_chunk = 2048; p.S_w = (int)((p.rows + 2047) / 2048);
     if (p.S_w > 592) { p.S_w = 592; p.k_chunk = (int)((p.rows + 591) / 592); p.S_w = (int)((p.rows + p.k_chunk - 1) / p.k_chunk); }
@@ -372,12 +500,18 @@ static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p) {
         if (lp.has_norm && net->norm == PTRB200_NORM_BN2 && (!net->gamma[l] || !net->beta[l])) { set_error("ffnet: BN2 layer %d needs gamma/beta", l); return PTRB200_ERR_INVALID; }
         lp.z_off = off; off = align_up(off + p.rows * lp.d_out * 4, 256);
         lp.a_off = off; if (l < p.L - 1 && !p.use_tc) off = align_up(off + p.rows * lp.d_out * 4, 256);
-        lp.mean_off = off; lp.rstd_off = off; lp.scale_off = off; lp.shift_off = off; lp.wt_off = off;
+        lp.mean_off = off; lp.rstd_off = off; lp.scale_off = off; lp.shift_off = off;
+        lp.img_f_hi = lp.img_f_lo = lp.img_d_hi = lp.img_d_lo = off;
         if (lp.has_norm) {
             lp.mean_off = off; off = align_up(off + (size_t)p.G * lp.d_out * 4, 256); lp.rstd_off = off; off = align_up(off + (size_t)p.G * lp.d_out * 4, 256);
             lp.scale_off = off; off = align_up(off + (size_t)p.G * lp.d_out * 4, 256); lp.shift_off = off; off = align_up(off + (size_t)p.G * lp.d_out * 4, 256);
         }
-        if (p.use_tc) { lp.wt_off = off; off = align_up(off + (size_t)lp.d_in * lp.d_out * 4, 256); }
+        if (p.use_tc) {
+            const size_t fbytes = (size_t)((lp.d_in + 31) / 32) * (((lp.d_out + 15) / 16) * 16) * 128;
+            const size_t dbytes = (size_t)((lp.d_out + 31) / 32) * (((lp.d_in + 15) / 16) * 16) * 128;
+            lp.img_f_hi = off; off = align_up(off + fbytes, 1024); lp.img_f_lo = off; off = align_up(off + fbytes, 1024);
+            lp.img_d_hi = off; off = align_up(off + dbytes, 1024); lp.img_d_lo = off; off = align_up(off + dbytes, 1024);
+        }
         maxd = lp.d_in > maxd ? lp.d_in : maxd; maxd = lp.d_out > maxd ? lp.d_out : maxd;
         const size_t w = (size_t)lp.d_in * lp.d_out; maxw = w > maxw ? w : maxw;
     }
@@ -494,17 +628,23 @@ static int forward_tc(const ptrb200_ffnet* net, const Plan& p, const float* X, f
         RowsGemmArgs g{};
         set_prologue(net, p, l, ws, X, g.P, g.scale, g.shift, g.act);
         g.gr_prev = p.gr;
-        g.drop_p = last ? 0.0f : drop; g.drop_scale = 1.0f / (1.0f - g.drop_p);
-        g.seed = seed; g.offset = offset * 64 + (uint64_t)l;
-        g.Bm = net->weight[l]; g.bias = net->bias[l]; g.Out = Z;
+        g.drop = make_drop(last ? 0.0f : drop, seed, offset * 64 + (uint64_t)l);
+        g.bias = net->bias[l]; g.Out = Z;
         g.partials = lp.has_norm ? reinterpret_cast<double*>(ws + p.partials_off) : nullptr;
         g.rows = (int)p.rows; g.K = lp.d_in; g.N = lp.d_out;
+        {
+            const int NPl = ((lp.d_out + 15) / 16) * 16, nch = (lp.d_in + 31) / 32;
+            unsigned char* ih = reinterpret_cast<unsigned char*>(ws + lp.img_f_hi);
+            unsigned char* il = p.passes == 3 ? reinterpret_cast<unsigned char*>(ws + lp.img_f_lo) : nullptr;
+            PTRB200_LAUNCH(pack_b_image_kernel<false>, (nch * NPl * 8 + 255) / 256, 256, 0, st, net->weight[l], lp.d_out, lp.d_in, ih, il, lp.d_out, NPl, lp.d_in, nch);
+            g.b_img_hi = ih; g.b_img_lo = il;
+        }
         set_tiling(g, p);
         if ((rc = launch_rows_gemm(RG_FWD, p.passes, g, p.ntiles, st))) return rc;
         NormRef nr = norm_ref(net, p, l, ws);
         if (lp.has_norm) {
             const int cnt = p.G * lp.d_out;
-            PTRB200_LAUNCH(moments_finalize_kernel, (cnt * 32 + 255) / 256, 256, 0, st, (const double*)g.partials,
+            PTRB200_LAUNCH(moments_finalize_kernel, cnt, FIN_THREADS, 0, st, (const double*)g.partials,
                            reinterpret_cast<float*>(ws + lp.mean_off), reinterpret_cast<float*>(ws + lp.rstd_off),
                            reinterpret_cast<float*>(ws + lp.scale_off), reinterpret_cast<float*>(ws + lp.shift_off),
                            nr, p.G, lp.d_out, p.S_stat, p.gr);
@@ -540,24 +680,26 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
         dim3 sgrid(p.G, p.S_stat);
         if (lp.has_act || lp.has_norm) {
             float* dY = dbuf[flip]; flip ^= 1;
-            PTRB200_LAUNCH(colstat_kernel<STAT_DY>, sgrid, dim3(32, 8), 0, st, Z, dA, dY, nr, part, p.gr, lp.d_out, p.S_stat, p.slice_rows);
-            PTRB200_LAUNCH(dy_finalize_kernel, (lp.d_out * 32 + 127) / 128, 128, 0, st, (const double*)part,
+            launch_colstat<STAT_DY>(st, "colstat_dy", Z, dA, dY, nr, part, p.G, p.S_stat, p.gr, lp.d_out, p.slice_rows);
+            PTRB200_LAUNCH(dy_finalize_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)part,
                            lp.has_norm ? S1 : (float*)nullptr, lp.has_norm ? S2 : (float*)nullptr, T1, T2, p.G, lp.d_out, p.S_stat);
             if (lp.has_norm) {
                 float *dg = nullptr, *db = nullptr, *dw = nullptr, *dbw = nullptr;
                 if (net->norm == PTRB200_NORM_BN) { if (net->norm_affine) { dg = grads->gamma[l]; db = grads->beta[l]; } }
                 else { dg = grads->gamma[l]; db = grads->beta[l]; if (net->norm_affine) { dw = grads->aff_w[l]; dbw = grads->aff_b[l]; } }
                 PTRB200_LAUNCH(norm_param_grad_kernel, (lp.d_out + 127) / 128, 128, 0, st, nr, (const float*)T1, (const float*)T2, dg, db, dw, dbw, lp.d_out);
-                PTRB200_LAUNCH(norm_bwd_apply_kernel, elementwise_blocks(total), 256, 0, st, Z, dY, nr, (const float*)S1, (const float*)S2, total, lp.d_out, p.gr);
-                PTRB200_LAUNCH(colstat_kernel<STAT_COLSUM>, sgrid, dim3(32, 8), 0, st, (const float*)dY, (const float*)nullptr, (float*)nullptr, nr, part, p.gr, lp.d_out, p.S_stat, p.slice_rows);
-                PTRB200_LAUNCH(dy_finalize_kernel, (lp.d_out * 32 + 127) / 128, 128, 0, st, (const double*)part, (float*)nullptr, (float*)nullptr, grads->bias[l], (float*)nullptr, p.G, lp.d_out, p.S_stat);
+                if (lp.d_out % 4 == 0) PTRB200_LAUNCH(norm_bwd_apply4_kernel, elementwise_blocks(total / 4), 256, 0, st, Z, dY, nr, (const float*)S1, (const float*)S2, total / 4, lp.d_out, p.gr);
+                else PTRB200_LAUNCH(norm_bwd_apply_kernel, elementwise_blocks(total), 256, 0, st, Z, dY, nr, (const float*)S1, (const float*)S2, total, lp.d_out, p.gr);
+                // A Linear bias feeding a normalisation has an exactly-zero gradient (the norm removes every
+                // per-channel shift); the reference's autograd produces rounding noise there.
+                cudaMemsetAsync(grads->bias[l], 0, (size_t)lp.d_out * 4, st);
             } else {
                 cudaMemcpyAsync(grads->bias[l], T1, (size_t)lp.d_out * 4, cudaMemcpyDeviceToDevice, st);
             }
             dZ = dY;
         } else {
             PTRB200_LAUNCH(colstat_kernel<STAT_COLSUM>, sgrid, dim3(32, 8), 0, st, dA, (const float*)nullptr, (float*)nullptr, nr, part, p.gr, lp.d_out, p.S_stat, p.slice_rows);
-            PTRB200_LAUNCH(dy_finalize_kernel, (lp.d_out * 32 + 127) / 128, 128, 0, st, (const double*)part, (float*)nullptr, (float*)nullptr, grads->bias[l], (float*)nullptr, p.G, lp.d_out, p.S_stat);
+            PTRB200_LAUNCH(dy_finalize_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)part, (float*)nullptr, (float*)nullptr, grads->bias[l], (float*)nullptr, p.G, lp.d_out, p.S_stat);
         }
         const float layer_drop = last ? 0.0f : drop;
         // ---- dW on tensor cores: sum_rows dZ^T (x) rebuilt layer input ----
@@ -566,8 +708,7 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
             w.dZ = dZ;
             set_prologue(net, p, l, ws, X, w.P, w.scale, w.shift, w.act);
             w.gr_prev = p.gr;
-            w.drop_p = layer_drop; w.drop_scale = 1.0f / (1.0f - layer_drop);
-            w.seed = seed; w.offset = offset * 64 + (uint64_t)l;
+            w.drop = make_drop(layer_drop, seed, offset * 64 + (uint64_t)l);
             w.partials = wpart;
             w.rows = (int)p.rows; w.K = lp.d_in; w.N = lp.d_out;
             w.KP = ((lp.d_in + 15) / 16) * 16;
@@ -575,7 +716,7 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
             const int p_chunks = (w.KP + 31) / 32;
             size_t smem = 1024 + (size_t)(4 + p_chunks) * 2 * w.tile_rows * 128 + 64;
             if (w.KP > 128 && smem < 80 * 1024) smem = 80 * 1024;        // 256 TMEM columns per CTA: keep <= 2 CTAs per SM
-            const int grid = p.wg_grid;
+            const int grid = w.KP > 128 ? 296 : 444;     // TMEM columns per CTA (256 / 128) bound the CTAs per SM
             if (p.passes == 3) { if ((rc = opt_in_smem(wgrad_tc_kernel<3>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<3>, grid, WG_THREADS, smem, st, w); }
             else { if ((rc = opt_in_smem(wgrad_tc_kernel<1>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<1>, grid, WG_THREADS, smem, st, w); }
             const int cnt = lp.d_in * lp.d_out;
@@ -586,14 +727,14 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
             float* dIn = l == 0 ? dX : dbuf[flip];
             if (l > 0) flip ^= 1;
             if (lp.d_out % 4 == 0 && lp.d_in <= 256) {
-                float* Wt = reinterpret_cast<float*>(ws + lp.wt_off);
-                const int cnt = lp.d_in * lp.d_out;
-                PTRB200_LAUNCH(transpose_kernel, (cnt + 255) / 256, 256, 0, st, net->weight[l], Wt, lp.d_out, lp.d_in);
+                const int NPl = ((lp.d_in + 15) / 16) * 16, nch = (lp.d_out + 31) / 32;
+                unsigned char* ih = reinterpret_cast<unsigned char*>(ws + lp.img_d_hi);
+                unsigned char* il = p.passes == 3 ? reinterpret_cast<unsigned char*>(ws + lp.img_d_lo) : nullptr;
+                PTRB200_LAUNCH(pack_b_image_kernel<true>, (nch * NPl * 8 + 255) / 256, 256, 0, st, net->weight[l], lp.d_out, lp.d_in, ih, il, lp.d_in, NPl, lp.d_out, nch);
                 RowsGemmArgs g{};
                 g.P = dZ; g.scale = g.shift = nullptr; g.act = PTRB200_AF_NONE; g.gr_prev = (int)p.rows;
-                g.drop_p = layer_drop; g.drop_scale = 1.0f / (1.0f - layer_drop);
-                g.seed = seed; g.offset = offset * 64 + (uint64_t)l;
-                g.Bm = Wt; g.bias = nullptr; g.Out = dIn; g.partials = nullptr;
+                g.drop = make_drop(layer_drop, seed, offset * 64 + (uint64_t)l);
+                g.b_img_hi = ih; g.b_img_lo = il; g.bias = nullptr; g.Out = dIn; g.partials = nullptr;
                 g.rows = (int)p.rows; g.K = lp.d_out; g.N = lp.d_in;
                 g.tile_rows = 128; g.seg_len = 128; g.group_rows = 0; g.tiles_per_group = 0;
                 if ((rc = launch_rows_gemm(RG_DGRAD, p.passes, g, (int)((p.rows + 127) / 128), st))) return rc;
@@ -602,8 +743,7 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
                 g.A = dZ; g.Bm = net->weight[l]; g.C = dIn;
                 g.rows = (int)p.rows; g.d_in = lp.d_in; g.d_out = lp.d_out;
                 g.M = (int)p.rows; g.N = lp.d_in; g.K = lp.d_out;
-                g.drop_p = layer_drop; g.drop_scale = 1.0f / (1.0f - layer_drop);
-                g.seed = seed; g.offset = offset * 64 + (uint64_t)l;
+                g.drop = make_drop(layer_drop, seed, offset * 64 + (uint64_t)l);
                 launch_gemm<GEMM_BWD_DATA>(g, 1, st);
             }
             dA = dIn;
@@ -624,7 +764,7 @@ int ptrb200_tc_wgrad(const float* dZ, const float* P, float* dW, float* partials
     if (N > 128 || K > 256 || K % 4 != 0) { set_error("tc_wgrad: needs N <= 128, K <= 256, K %% 4 == 0"); return PTRB200_ERR_UNSUPPORTED; }
     WgradArgs w{};
     w.dZ = dZ; w.P = P; w.scale = w.shift = nullptr; w.act = PTRB200_AF_NONE; w.gr_prev = rows;
-    w.drop_p = 0.0f; w.drop_scale = 1.0f; w.partials = partials;
+    w.drop = make_drop(0.0f, 0, 0); w.partials = partials;
     w.rows = rows; w.K = K; w.N = N; w.KP = ((K + 15) / 16) * 16; w.tile_rows = 32;
     const int p_chunks = (w.KP + 31) / 32, grid = 296;
     size_t smem = 1024 + (size_t)(4 + p_chunks) * 2 * w.tile_rows * 128 + 64;
@@ -666,8 +806,7 @@ int ptrb200_ffnet_forward(const ptrb200_ffnet* net, const float* X, float* out, 
         g.A = in; g.Bm = net->weight[l]; g.bias = net->bias[l]; g.C = lin_out;
         g.rows = (int)p.rows; g.d_in = lp.d_in; g.d_out = lp.d_out;
         g.M = (int)p.rows; g.N = lp.d_out; g.K = lp.d_in;
-        g.drop_p = last ? 0.0f : drop; g.drop_scale = 1.0f / (1.0f - g.drop_p);
-        g.seed = seed; g.offset = offset * 64 + (uint64_t)l;
+        g.drop = make_drop(last ? 0.0f : drop, seed, offset * 64 + (uint64_t)l);
         launch_gemm<GEMM_FWD>(g, 1, st);
         if (lp.has_act || lp.has_norm) {
             NormRef nr = norm_ref(net, p, l, ws);
@@ -677,7 +816,7 @@ int ptrb200_ffnet_forward(const ptrb200_ffnet* net, const float* X, float* out, 
                 PTRB200_LAUNCH(colstat_kernel<STAT_MOMENTS>, grid, dim3(32, 8), 0, st, (const float*)Z, (const float*)nullptr,
                                (float*)nullptr, nr, part, p.gr, lp.d_out, p.S_stat, p.slice_rows);
                 const int cnt = p.G * lp.d_out;
-                PTRB200_LAUNCH(moments_finalize_kernel, (cnt * 32 + 255) / 256, 256, 0, st, (const double*)part,
+                PTRB200_LAUNCH(moments_finalize_kernel, cnt, FIN_THREADS, 0, st, (const double*)part,
                                reinterpret_cast<float*>(ws + lp.mean_off), reinterpret_cast<float*>(ws + lp.rstd_off),
                                (float*)nullptr, (float*)nullptr, nr, p.G, lp.d_out, p.S_stat, p.gr);
             }
@@ -723,7 +862,7 @@ int ptrb200_ffnet_backward(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* 
             float* dY = dbuf[flip]; flip ^= 1;
             dim3 grid(p.G, p.S_stat);
             PTRB200_LAUNCH(colstat_kernel<STAT_DY>, grid, dim3(32, 8), 0, st, Z, dA, dY, nr, part, p.gr, lp.d_out, p.S_stat, p.slice_rows);
-            PTRB200_LAUNCH(dy_finalize_kernel, (lp.d_out * 32 + 127) / 128, 128, 0, st, (const double*)part,
+            PTRB200_LAUNCH(dy_finalize_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)part,
                            lp.has_norm ? S1 : (float*)nullptr, lp.has_norm ? S2 : (float*)nullptr, T1, T2, p.G, lp.d_out, p.S_stat);
             if (lp.has_norm) {
                 float *dg = nullptr, *db = nullptr, *dw = nullptr, *dbw = nullptr;
@@ -733,7 +872,7 @@ int ptrb200_ffnet_backward(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* 
                 PTRB200_LAUNCH(norm_bwd_apply_kernel, elementwise_blocks(total), 256, 0, st, Z, dY, nr, (const float*)S1, (const float*)S2, total, lp.d_out, p.gr);
                 // bias gradient = column sums of dZ (zero up to rounding under a norm, as in the reference)
                 PTRB200_LAUNCH(colstat_kernel<STAT_COLSUM>, grid, dim3(32, 8), 0, st, (const float*)dY, (const float*)nullptr, (float*)nullptr, nr, part, p.gr, lp.d_out, p.S_stat, p.slice_rows);
-                PTRB200_LAUNCH(dy_finalize_kernel, (lp.d_out * 32 + 127) / 128, 128, 0, st, (const double*)part, (float*)nullptr, (float*)nullptr, grads->bias[l], (float*)nullptr, p.G, lp.d_out, p.S_stat);
+                PTRB200_LAUNCH(dy_finalize_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)part, (float*)nullptr, (float*)nullptr, grads->bias[l], (float*)nullptr, p.G, lp.d_out, p.S_stat);
             } else {
                 cudaMemcpyAsync(grads->bias[l], T1, (size_t)lp.d_out * 4, cudaMemcpyDeviceToDevice, st);
             }
@@ -741,7 +880,7 @@ int ptrb200_ffnet_backward(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* 
         } else {
             dim3 grid(p.G, p.S_stat);
             PTRB200_LAUNCH(colstat_kernel<STAT_COLSUM>, grid, dim3(32, 8), 0, st, dA, (const float*)nullptr, (float*)nullptr, nr, part, p.gr, lp.d_out, p.S_stat, p.slice_rows);
-            PTRB200_LAUNCH(dy_finalize_kernel, (lp.d_out * 32 + 127) / 128, 128, 0, st, (const double*)part, (float*)nullptr, (float*)nullptr, grads->bias[l], (float*)nullptr, p.G, lp.d_out, p.S_stat);
+            PTRB200_LAUNCH(dy_finalize_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)part, (float*)nullptr, (float*)nullptr, grads->bias[l], (float*)nullptr, p.G, lp.d_out, p.S_stat);
         }
         const bool last = l == p.L - 1;
         const float layer_drop = last ? 0.0f : drop;
@@ -751,8 +890,7 @@ int ptrb200_ffnet_backward(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* 
             g.A = dZ; g.Bm = layer_in; g.C = wpart;
             g.rows = (int)p.rows; g.d_in = lp.d_in; g.d_out = lp.d_out;
             g.M = lp.d_out; g.N = lp.d_in; g.K = (int)p.rows; g.k_chunk = p.k_chunk;
-            g.drop_p = layer_drop; g.drop_scale = 1.0f / (1.0f - layer_drop);
-            g.seed = seed; g.offset = offset * 64 + (uint64_t)l;
+            g.drop = make_drop(layer_drop, seed, offset * 64 + (uint64_t)l);
             launch_gemm<GEMM_BWD_WEIGHT>(g, p.S_w, st);
             const int cnt = lp.d_in * lp.d_out;
             PTRB200_LAUNCH(reduce_splits_kernel, (cnt + 255) / 256, 256, 0, st, (const float*)wpart, grads->weight[l], p.S_w, cnt);
@@ -765,8 +903,7 @@ int ptrb200_ffnet_backward(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* 
             g.A = dZ; g.Bm = net->weight[l]; g.C = dIn;
             g.rows = (int)p.rows; g.d_in = lp.d_in; g.d_out = lp.d_out;
             g.M = (int)p.rows; g.N = lp.d_in; g.K = lp.d_out;
-            g.drop_p = layer_drop; g.drop_scale = 1.0f / (1.0f - layer_drop);
-            g.seed = seed; g.offset = offset * 64 + (uint64_t)l;
+            g.drop = make_drop(layer_drop, seed, offset * 64 + (uint64_t)l);
             launch_gemm<GEMM_BWD_DATA>(g, 1, st);
             dA = dIn;
         }

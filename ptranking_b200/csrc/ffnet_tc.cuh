@@ -24,10 +24,11 @@ struct RowsGemmArgs {
     const float* shift;    // [Gp, K]
     int act;               // PTRB200_AF_* applied after scale/shift (AF_NONE = identity)
     int gr_prev;           // rows per statistics group of P's normalisation
-    float drop_p, drop_scale;
-    uint64_t seed, offset; // dropout stream: FWD masks A elements (row*K+k), DGRAD masks outputs (row*N+n)
-    // B side
-    const float* Bm;       // [N, K] row-major (W for FWD, W^T for DGRAD)
+    DropCfg drop;          // dropout stream: FWD masks A elements (row*K+k), DGRAD masks outputs (row*N+n)
+    // B side: pre-split, pre-swizzled operand images written by pack_b_image_kernel:
+    // chunk c of the image = [NP rows x 128 B] in the exact shared-memory layout (one bulk copy each)
+    const unsigned char* b_img_hi;
+    const unsigned char* b_img_lo;
     const float* bias;     // [N] (FWD) or NULL
     float* Out;            // [rows, N]
     double* partials;      // [slots, N, 2] column sum / sum of squares per statistics slot, or NULL
@@ -53,15 +54,13 @@ static __device__ __forceinline__ float4 prologue4(const RowsGemmArgs& g, float4
     if (g.act != PTRB200_AF_NONE) {
         v.x = activate(g.act, v.x).y; v.y = activate(g.act, v.y).y; v.z = activate(g.act, v.z).y; v.w = activate(g.act, v.w).y;
     }
-    if (with_dropout && g.drop_p > 0.0f) {
-        const uint64_t e = (uint64_t)row * g.K + k;          // K % 4 == 0: the 4 elements share one Philox block
-        Philox ph(g.seed);
-        const uint4 rb = ph(e >> 2, g.offset);
-        const float inv = 1.0f / 16777216.0f;
-        v.x = ((float)(rb.x >> 8) * inv >= g.drop_p) ? v.x * g.drop_scale : 0.0f;
-        v.y = ((float)(rb.y >> 8) * inv >= g.drop_p) ? v.y * g.drop_scale : 0.0f;
-        v.z = ((float)(rb.z >> 8) * inv >= g.drop_p) ? v.z * g.drop_scale : 0.0f;
-        v.w = ((float)(rb.w >> 8) * inv >= g.drop_p) ? v.w * g.drop_scale : 0.0f;
+    if (with_dropout && g.drop.thr) {
+        const uint64_t e = (uint64_t)row * g.K + k;          // K % 4 == 0: the 4 elements share one draw
+        const uint64_t d = dropout_draw4(g.drop.key, e >> 2);
+        v.x = ((uint32_t)(d) & 0xffffu) >= g.drop.thr ? v.x * g.drop.scale : 0.0f;
+        v.y = ((uint32_t)(d >> 16) & 0xffffu) >= g.drop.thr ? v.y * g.drop.scale : 0.0f;
+        v.z = ((uint32_t)(d >> 32) & 0xffffu) >= g.drop.thr ? v.z * g.drop.scale : 0.0f;
+        v.w = ((uint32_t)(d >> 48)) >= g.drop.thr ? v.w * g.drop.scale : 0.0f;
     }
     return v;
 }
@@ -83,6 +82,34 @@ static __device__ __forceinline__ float4 ldg4_guard(const float* p, int k, int K
     return (k < K) ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// Builds the B-operand image of a [N,K] row-major matrix (TRANSPOSE=false) or of its transpose
+// (TRANSPOSE=true: image rows = columns of the source, used for dgrad's W^T): hi/lo tf32 split,
+// rows padded to NP, K cut into 128-byte chunks, each chunk [NP][128 B] in SWIZZLE_128B order.
+template <bool TRANSPOSE>
+__global__ void pack_b_image_kernel(const float* __restrict__ src, int src_rows, int src_cols,
+                                    unsigned char* __restrict__ img_hi, unsigned char* __restrict__ img_lo,
+                                    int N, int NP, int K, int nchunks) {
+    const int total = nchunks * NP * 8;                        // 16-byte units
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < total; u += gridDim.x * blockDim.x) {
+        const int c = u / (NP * 8), rem = u % (NP * 8), r = rem >> 3, j = rem & 7, k = c * 32 + j * 4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (r < N) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (k + e < K) v[e] = TRANSPOSE ? src[(size_t)(k + e) * src_cols + r] : src[(size_t)r * src_cols + k + e];
+        }
+        const size_t off = (size_t)c * NP * 128 + tc::swz_offset(r, j);
+        float4 h, l;
+        tc::split_tf32(v[0], h.x, l.x); tc::split_tf32(v[1], h.y, l.y); tc::split_tf32(v[2], h.z, l.z); tc::split_tf32(v[3], h.w, l.w);
+        if (img_lo) {
+            *reinterpret_cast<float4*>(img_hi + off) = h;
+            *reinterpret_cast<float4*>(img_lo + off) = l;
+        } else {
+            *reinterpret_cast<float4*>(img_hi + off) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
 constexpr int RG_THREADS = 256;
 
 template <int MODE, int PASSES>
@@ -96,7 +123,8 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
     unsigned char* b_lo = b_hi + NP * 128;
     unsigned char* tail = base + g.tail_off;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(tail);
-    uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 1);
+    uint64_t* bbar = mbar + 1;
+    uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 2);
     float* otile = reinterpret_cast<float*>(base);    // epilogue staging [128][N], aliases the operand buffers
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -116,7 +144,7 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
         }
     }
     const uint32_t tmem_cols = NP <= 32 ? 32 : NP <= 64 ? 64 : NP <= 128 ? 128 : 256;
-    if (tid == 0) { tc::mbar_init(mbar, 1); tc::mbar_fence_init(); }
+    if (tid == 0) { tc::mbar_init(mbar, 1); tc::mbar_init(bbar, 1); tc::mbar_fence_init(); }
     if (warp == 0) tc::tmem_alloc(slot, tmem_cols);
     tc::fence_before_sync();
     __syncthreads();
@@ -137,6 +165,13 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
             av[i] = (r < nrows) ? ldg4_guard(g.P + (size_t)(row0 + r) * K + k, k, K) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (c > 0) tc::mbar_wait(mbar, (c - 1) & 1);
+        // ---- B: one TMA bulk copy per operand image chunk (no SM instructions beyond the issue) ----
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)NP * 128u;
+            tc::mbar_expect_tx(bbar, PASSES == 3 ? 2 * bytes : bytes);
+            tc::bulk_g2s(b_hi, g.b_img_hi + (size_t)c * bytes, bytes, bbar);
+            if (PASSES == 3) tc::bulk_g2s(b_lo, g.b_img_lo + (size_t)c * bytes, bytes, bbar);
+        }
         // ---- A: prologue + split + swizzled store ----
 #pragma unroll
         for (int i = 0; i < A_UNITS; ++i) {
@@ -146,15 +181,10 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
             else v = make_float4(0.f, 0.f, 0.f, 0.f);
             store_split(a_hi, a_lo, tc::swz_offset(r, j), v, PASSES == 3);
         }
-        // ---- B: weights chunk (L2 resident) ----
-        for (int u = tid; u < NP * 8; u += RG_THREADS) {
-            const int r = u >> 3, j = u & 7, k = k0 + j * 4;
-            const float4 v = (r < g.N) ? ldg4_guard(g.Bm + (size_t)r * K + k, k, K) : make_float4(0.f, 0.f, 0.f, 0.f);
-            store_split(b_hi, b_lo, tc::swz_offset(r, j), v, PASSES == 3);
-        }
         tc::fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
+            tc::mbar_wait(bbar, c & 1);                       // weights chunk has landed
             tc::fence_after_sync();
             const int ksteps = min(4, (K - k0 + 7) / 8);
             for (int s = 0; s < ksteps; ++s) {
@@ -191,10 +221,20 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
                 if (MODE == RG_FWD) {
 #pragma unroll
                     for (int e = 0; e < 8; ++e) if (c0 + e < N) v[e] += __ldg(g.bias + c0 + e);
-                } else if (g.drop_p > 0.0f) {
+                } else if (g.drop.thr) {
+                    if ((N & 3) == 0) {                   // rows start on a draw boundary: 2 draws cover the 8 columns
+                        const uint64_t q = ((uint64_t)(row0 + r) * N + c0) >> 2;
+                        const uint64_t d0 = dropout_draw4(g.drop.key, q), d1 = dropout_draw4(g.drop.key, q + 1);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        if (c0 + e < N) v[e] = dropout_keep(g.seed, g.offset, (uint64_t)(row0 + r) * N + c0 + e, g.drop_p) ? v[e] * g.drop_scale : 0.0f;
+                        for (int e = 0; e < 4; ++e) {
+                            v[e] = ((uint32_t)(d0 >> (16 * e)) & 0xffffu) >= g.drop.thr ? v[e] * g.drop.scale : 0.0f;
+                            v[4 + e] = ((uint32_t)(d1 >> (16 * e)) & 0xffffu) >= g.drop.thr ? v[4 + e] * g.drop.scale : 0.0f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            if (c0 + e < N) v[e] = dropout_keep(g.drop.key, (uint64_t)(row0 + r) * N + c0 + e, g.drop.thr) ? v[e] * g.drop.scale : 0.0f;
+                    }
                 }
                 float* dst = otile + (size_t)r * N + c0;
                 if (c0 + 8 <= N && (N & 3) == 0) {
@@ -253,8 +293,7 @@ struct WgradArgs {
     const float* scale;    // [Gp, K] or NULL
     const float* shift;
     int act, gr_prev;
-    float drop_p, drop_scale;
-    uint64_t seed, offset;
+    DropCfg drop;
     float* partials;       // [gridDim.x, N, K]
     int rows, K, N;
     int KP;                // K rounded up to 16 (MMA N extent)
@@ -295,29 +334,32 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
         const int row0 = t * R, nrows = min(R, g.rows - row0);
         if (it > 0) tc::mbar_wait(mbar, (it - 1) & 1);            // previous tile's MMAs have consumed smem
-        // ---- dZ tile: [R][128 cols] ----
-        for (int u = tid; u < R * z_chunks * 8; u += WG_THREADS) {
-            const int r = u / (z_chunks * 8), cu = u % (z_chunks * 8), ch = cu >> 3, j = cu & 7, n = ch * 32 + j * 4;
+        // ---- dZ tile: [R][128 cols]; one 16-byte unit per thread per 32-column chunk (R*8 <= WG_THREADS) ----
+        const int r = tid >> 3, j = tid & 7;
+        const bool row_ok = tid < R * 8 && r < nrows;
+#pragma unroll
+        for (int ch = 0; ch < z_chunks; ++ch) {
+            const int n = ch * 32 + j * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < nrows && n < g.N) {
+            if (row_ok && n < g.N) {
                 const float* p = g.dZ + (size_t)(row0 + r) * g.N + n;
                 if (n + 3 < g.N && (g.N & 3) == 0) v = __ldg(reinterpret_cast<const float4*>(p));
                 else { v.x = p[0]; if (n + 1 < g.N) v.y = p[1]; if (n + 2 < g.N) v.z = p[2]; if (n + 3 < g.N) v.w = p[3]; }
             }
-            store_split(z_hi + ch * chunk_bytes, z_lo + ch * chunk_bytes, tc::swz32_offset(r, j), v, PASSES == 3);
+            if (tid < R * 8) store_split(z_hi + ch * chunk_bytes, z_lo + ch * chunk_bytes, tc::swz32_offset(r, j), v, PASSES == 3);
         }
         // ---- Ain tile: [R][KP cols] rebuilt from P ----
         RowsGemmArgs pg{};
         pg.scale = g.scale; pg.shift = g.shift; pg.act = g.act; pg.gr_prev = g.gr_prev; pg.K = g.K;
-        pg.drop_p = g.drop_p; pg.drop_scale = g.drop_scale; pg.seed = g.seed; pg.offset = g.offset;
-        for (int u = tid; u < R * p_chunks * 8; u += WG_THREADS) {
-            const int r = u / (p_chunks * 8), cu = u % (p_chunks * 8), ch = cu >> 3, j = cu & 7, k = ch * 32 + j * 4;
+        pg.drop = g.drop;
+        for (int ch = 0; ch < p_chunks; ++ch) {
+            const int k = ch * 32 + j * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < nrows && k < g.K) {
+            if (row_ok && k < g.K) {
                 v = __ldg(reinterpret_cast<const float4*>(g.P + (size_t)(row0 + r) * g.K + k));
                 v = prologue4(pg, v, row0 + r, k, true);
             }
-            store_split(p_hi + ch * chunk_bytes, p_lo + ch * chunk_bytes, tc::swz32_offset(r, j), v, PASSES == 3);
+            if (tid < R * 8) store_split(p_hi + ch * chunk_bytes, p_lo + ch * chunk_bytes, tc::swz32_offset(r, j), v, PASSES == 3);
         }
         tc::fence_proxy_async();
         __syncthreads();
