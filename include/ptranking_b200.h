@@ -186,6 +186,38 @@ int ptrb200_ffnet_backward(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* 
                            int B, int n, int training, uint64_t seed, uint64_t offset,
                            ptrb200_stream_t stream);
 
+/* ---- multi-head self-attention list scorer ------------------------------------------------ */
+/* MultiheadAttention.forward, ptranking/base/list_ranker.py:226-248: for every (query b, head h)
+ * O = dropout(softmax(Q K^T / sqrt(D))) V, flash-style (no [n,n] tensor in HBM).  Q,K,V,O: [B,n,H*D] with head h
+ * in columns [h*D,(h+1)*D) (the reference's view/permute, :222-224, :251).  LSE[B,H,n] is kept for backward. */
+int ptrb200_attention_fwd(const float* Q, const float* K, const float* V, float* O, float* LSE,
+                          int B, int n, int H, int D, float dropout_p, uint64_t seed, uint64_t offset,
+                          ptrb200_stream_t stream);
+/* autograd of the above; scratch: B*H*n floats. */
+int ptrb200_attention_bwd(const float* Q, const float* K, const float* V, const float* O, const float* dO, const float* LSE,
+                          float* dQ, float* dK, float* dV, float* scratch,
+                          int B, int n, int H, int D, float dropout_p, uint64_t seed, uint64_t offset,
+                          ptrb200_stream_t stream);
+/* LayerNorm.forward, ptranking/base/list_ranker.py:165-174: y = a_2 (x - mean) / (std_unbiased + eps) + b_2 per row;
+ * mean/std[rows] are kept for backward. */
+int ptrb200_layernorm_fwd(const float* x, const float* a2, const float* b2, float* y, float* mean, float* stdv,
+                          int rows, int F, float eps, ptrb200_stream_t stream);
+/* scratch: 297*2*F floats. */
+int ptrb200_layernorm_bwd(const float* x, const float* a2, const float* dy, const float* mean, const float* stdv,
+                          float* dx, float* da2, float* db2, float* scratch,
+                          int rows, int F, float eps, ptrb200_stream_t stream);
+/* elementwise glue of the encoder variants (list_ranker.py:138-149, 357-373) and of PositionwiseFeedForward (:269-277):
+ * op 0: a+b   1: (a+1)*b (DASALC latent cross)   2: a*b   3: relu(a)   4: b>0 ? a : 0   5: dropout(a)   6: a*(b+1) */
+#define PTRB200_EW_ADD 0
+#define PTRB200_EW_LATENT_CROSS 1
+#define PTRB200_EW_MUL 2
+#define PTRB200_EW_RELU 3
+#define PTRB200_EW_RELU_BWD 4
+#define PTRB200_EW_DROPOUT 5
+#define PTRB200_EW_SCALE_ADD1 6
+int ptrb200_elementwise(int op, const float* a, const float* b, float* out, int64_t count,
+                        float dropout_p, uint64_t seed, uint64_t offset, ptrb200_stream_t stream);
+
 /* ---- tensor-core GEMM building block ---------------------------------------------------- */
 /* C[M,N] = A[M,K] * B[N,K]^T in fp32 through tcgen05.mma kind::tf32 with TMEM accumulation
  * (the contraction of nn.Linear: torch.nn.functional.linear as called by every ff_* layer of

@@ -274,3 +274,173 @@ def ffnet_apply(X: torch.Tensor, spec: FFNetSpec, params: Sequence[torch.Tensor]
     if offset is None:
         offset = next_dropout_offset()
     return _FFNetFn.apply(X, spec, bool(training), int(seed), int(offset), *params)
+
+
+# --------------------------------------------------------------------------- #
+# list scorer pieces: linear, attention core, reference LayerNorm, elementwise glue
+# --------------------------------------------------------------------------- #
+_linear_specs = {}
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, math_mode: str = "3xtf32") -> torch.Tensor:
+    """nn.Linear over [B,n,in] through the stacked-FF kernels (a one-layer net without activation)."""
+    key = (weight.shape[1], weight.shape[0], math_mode)
+    if key not in _linear_specs:
+        _linear_specs[key] = FFNetSpec([key[0], key[1]], None, None, None, False, 0.0, math_mode=math_mode)
+    return ffnet_apply(x, _linear_specs[key], [weight, bias], training=False, seed=0, offset=0)
+
+
+class _Attention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Q, K, V, n_heads, dropout_p, seed, offset):
+        lib = _lib.load()
+        Q, K, V = _dev_f32(Q, "Q"), _dev_f32(K, "K"), _dev_f32(V, "V")
+        B, n, F = Q.shape
+        D = F // n_heads
+        O = torch.empty_like(Q)
+        lse = torch.empty((B, n_heads, n), dtype=torch.float32, device=Q.device)
+        _lib.check(lib.ptrb200_attention_fwd(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), lse.data_ptr(),
+                                             B, n, n_heads, D, float(dropout_p), seed, offset, _stream_ptr()), "attention_fwd")
+        ctx.save_for_backward(Q, K, V, O, lse)
+        ctx.cfg = (n_heads, float(dropout_p), seed, offset)
+        return O
+
+    @staticmethod
+    def backward(ctx, dO):
+        lib = _lib.load()
+        Q, K, V, O, lse = ctx.saved_tensors
+        H, p, seed, offset = ctx.cfg
+        B, n, F = Q.shape
+        dO = _dev_f32(dO, "dO")
+        dQ, dK, dV = torch.empty_like(Q), torch.empty_like(K), torch.empty_like(V)
+        scratch = torch.empty(B * H * n, dtype=torch.float32, device=Q.device)
+        _lib.check(lib.ptrb200_attention_bwd(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), dO.data_ptr(),
+                                             lse.data_ptr(), dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(), scratch.data_ptr(),
+                                             B, n, H, F // H, p, seed, offset, _stream_ptr()), "attention_bwd")
+        return dQ, dK, dV, None, None, None, None
+
+
+def attention(Q, K, V, n_heads: int, dropout_p: float = 0.0, seed: Optional[int] = None, offset: Optional[int] = None):
+    """softmax(Q K^T / sqrt(d)) [dropout] V per head; Q,K,V: [B,n,H*d]."""
+    if seed is None:
+        seed = torch.initial_seed() & (2 ** 64 - 1)
+    if offset is None:
+        offset = next_dropout_offset()
+    return _Attention.apply(Q, K, V, int(n_heads), float(dropout_p), int(seed), int(offset))
+
+
+class _LayerNormRef(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, a2, b2, eps):
+        lib = _lib.load()
+        x = _dev_f32(x, "x")
+        F = x.shape[-1]
+        rows = x.numel() // F
+        y = torch.empty_like(x)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        std = torch.empty(rows, dtype=torch.float32, device=x.device)
+        a2c, b2c = a2.detach().contiguous(), b2.detach().contiguous()
+        _lib.check(lib.ptrb200_layernorm_fwd(x.data_ptr(), a2c.data_ptr(), b2c.data_ptr(), y.data_ptr(), mean.data_ptr(),
+                                             std.data_ptr(), rows, F, float(eps), _stream_ptr()), "layernorm_fwd")
+        ctx.save_for_backward(x, a2c, mean, std)
+        ctx.eps = float(eps)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, a2, mean, std = ctx.saved_tensors
+        F = x.shape[-1]
+        rows = x.numel() // F
+        dy = _dev_f32(dy, "dy")
+        dx = torch.empty_like(x)
+        da2, db2 = torch.empty_like(a2), torch.empty_like(a2)
+        scratch = torch.empty(297 * 2 * F, dtype=torch.float32, device=x.device)
+        _lib.check(lib.ptrb200_layernorm_bwd(x.data_ptr(), a2.data_ptr(), dy.data_ptr(), mean.data_ptr(), std.data_ptr(),
+                                             dx.data_ptr(), da2.data_ptr(), db2.data_ptr(), scratch.data_ptr(), rows, F,
+                                             ctx.eps, _stream_ptr()), "layernorm_bwd")
+        return dx, da2, db2, None
+
+
+def layernorm_ref(x, a2, b2, eps: float = 1e-6):
+    """The reference's hand-written LayerNorm (unbiased std, eps added to the std)."""
+    return _LayerNormRef.apply(x, a2, b2, eps)
+
+
+EW_ADD, EW_LATENT_CROSS, EW_MUL, EW_RELU, EW_RELU_BWD, EW_DROPOUT, EW_SCALE_ADD1 = range(7)
+
+
+def _ew(op, a, b=None, p=0.0, seed=0, offset=0):
+    lib = _lib.load()
+    a = _dev_f32(a, "a")
+    bb = _dev_f32(b, "b") if b is not None else None
+    out = torch.empty_like(a)
+    _lib.check(lib.ptrb200_elementwise(op, a.data_ptr(), bb.data_ptr() if bb is not None else None, out.data_ptr(),
+                                       a.numel(), float(p), seed, offset, _stream_ptr()), "elementwise")
+    return out
+
+
+class _Add(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return _ew(EW_ADD, a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+class _LatentCross(torch.autograd.Function):
+    """(enc + 1) * head -- DASALC's latent cross (list_ranker.py:366)."""
+
+    @staticmethod
+    def forward(ctx, enc, head):
+        ctx.save_for_backward(enc, head)
+        return _ew(EW_LATENT_CROSS, enc, head)
+
+    @staticmethod
+    def backward(ctx, g):
+        enc, head = ctx.saved_tensors
+        return _ew(EW_MUL, g, head), _ew(EW_SCALE_ADD1, g, enc)
+
+
+class _Relu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return _ew(EW_RELU, x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return _ew(EW_RELU_BWD, g, x)
+
+
+class _Dropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, seed, offset):
+        ctx.cfg = (p, seed, offset)
+        return _ew(EW_DROPOUT, x, None, p, seed, offset)
+
+    @staticmethod
+    def backward(ctx, g):
+        p, seed, offset = ctx.cfg
+        return _ew(EW_DROPOUT, g, None, p, seed, offset), None, None, None
+
+
+def add(a, b):
+    return _Add.apply(a, b)
+
+
+def latent_cross(enc, head):
+    return _LatentCross.apply(enc, head)
+
+
+def relu(x):
+    return _Relu.apply(x)
+
+
+def dropout(x, p: float, training: bool):
+    if not training or p <= 0.0:
+        return x
+    return _Dropout.apply(x, float(p), torch.initial_seed() & (2 ** 64 - 1), next_dropout_offset())
