@@ -444,6 +444,7 @@ struct LayerPlan {
     size_t z_off, a_off, mean_off, rstd_off;     // byte offsets into the workspace (a_off unused for the last layer)
     size_t scale_off, shift_off;                 // tensor-core mode: fused prologue coefficients [G,d_out]
     size_t img_f_hi, img_f_lo, img_d_hi, img_d_lo;   // tensor-core mode: pre-swizzled B images of W (fwd) and W^T (dgrad)
+    size_t ain_off;                              // tensor-core mode, l >= 1: the layer's rebuilt input dropout(act(norm(Z_{l-1}))) [rows,d_in]
 };
 struct Plan {
     bool use_tc;                                 // every layer fits the tcgen05 kernels (else the SIMT path runs)
@@ -501,7 +502,7 @@ static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p) {
         lp.z_off = off; off = align_up(off + p.rows * lp.d_out * 4, 256);
         lp.a_off = off; if (l < p.L - 1 && !p.use_tc) off = align_up(off + p.rows * lp.d_out * 4, 256);
         lp.mean_off = off; lp.rstd_off = off; lp.scale_off = off; lp.shift_off = off;
-        lp.img_f_hi = lp.img_f_lo = lp.img_d_hi = lp.img_d_lo = off;
+        lp.img_f_hi = lp.img_f_lo = lp.img_d_hi = lp.img_d_lo = lp.ain_off = off;
         if (lp.has_norm) {
             lp.mean_off = off; off = align_up(off + (size_t)p.G * lp.d_out * 4, 256); lp.rstd_off = off; off = align_up(off + (size_t)p.G * lp.d_out * 4, 256);
             lp.scale_off = off; off = align_up(off + (size_t)p.G * lp.d_out * 4, 256); lp.shift_off = off; off = align_up(off + (size_t)p.G * lp.d_out * 4, 256);
@@ -511,6 +512,7 @@ static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p) {
             const size_t dbytes = (size_t)((lp.d_out + 31) / 32) * (((lp.d_in + 15) / 16) * 16) * 128;
             lp.img_f_hi = off; off = align_up(off + fbytes, 1024); lp.img_f_lo = off; off = align_up(off + fbytes, 1024);
             lp.img_d_hi = off; off = align_up(off + dbytes, 1024); lp.img_d_lo = off; off = align_up(off + dbytes, 1024);
+            if (l > 0) { lp.ain_off = off; off = align_up(off + p.rows * lp.d_in * 4, 256); }
         }
         maxd = lp.d_in > maxd ? lp.d_in : maxd; maxd = lp.d_out > maxd ? lp.d_out : maxd;
         const size_t w = (size_t)lp.d_in * lp.d_out; maxw = w > maxw ? w : maxw;
@@ -578,6 +580,22 @@ static int opt_in_smem(K kernel, size_t bytes) {
     return PTRB200_OK;
 }
 
+
+// picks the row-tile height R (32/16/8) and ring depth so the kernel's buffers fit the 227 KB of one SM
+static size_t wgrad_smem(int N, int K, int KP, int& R, int passes, int& stages) {
+    const int p_chunks = (KP + 31) / 32;
+    const size_t limit = 227 * 1024;
+    for (R = 32; R >= 8; R >>= 1) {
+        const size_t op = (size_t)(4 + p_chunks) * R * 128 * (passes == 3 ? 2 : 1);
+        const size_t rawz = ((size_t)R * N * 4 + 127) / 128 * 128, rawp = ((size_t)R * K * 4 + 127) / 128 * 128;
+        const size_t fixed = 1024 + 2 * op + 128;
+        for (stages = WG_MAX_STAGES; stages >= 2; --stages)
+            if (fixed + stages * (rawz + rawp) <= limit) return fixed + stages * (rawz + rawp);
+    }
+    R = 8; stages = 2;
+    return limit;
+}
+
 static size_t rows_gemm_smem(int N, int NP) {
     const size_t operands = 32768 + (size_t)NP * 256, otile = (size_t)128 * N * 4;
     return 1024 + (operands > otile ? operands : otile) + 64;
@@ -630,6 +648,7 @@ static int forward_tc(const ptrb200_ffnet* net, const Plan& p, const float* X, f
         g.gr_prev = p.gr;
         g.drop = make_drop(last ? 0.0f : drop, seed, offset * 64 + (uint64_t)l);
         g.bias = net->bias[l]; g.Out = Z;
+        g.a_out = l > 0 ? reinterpret_cast<float*>(ws + lp.ain_off) : nullptr;
         g.partials = lp.has_norm ? reinterpret_cast<double*>(ws + p.partials_off) : nullptr;
         g.rows = (int)p.rows; g.K = lp.d_in; g.N = lp.d_out;
         {
@@ -706,17 +725,20 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
         {
             WgradArgs w{};
             w.dZ = dZ;
-            set_prologue(net, p, l, ws, X, w.P, w.scale, w.shift, w.act);
+            if (l == 0) {          // layer 0 input = dropout(X): rebuilt on the fly
+                w.P = X; w.scale = w.shift = nullptr; w.act = PTRB200_AF_NONE;
+                w.drop = make_drop(layer_drop, seed, offset * 64 + (uint64_t)l);
+            } else {               // deeper layers read the operand the forward kernel already built
+                w.P = reinterpret_cast<const float*>(ws + lp.ain_off); w.scale = w.shift = nullptr; w.act = PTRB200_AF_NONE;
+                w.drop = make_drop(0.0f, 0, 0);
+            }
             w.gr_prev = p.gr;
-            w.drop = make_drop(layer_drop, seed, offset * 64 + (uint64_t)l);
             w.partials = wpart;
             w.rows = (int)p.rows; w.K = lp.d_in; w.N = lp.d_out;
             w.KP = ((lp.d_in + 15) / 16) * 16;
             w.tile_rows = p.wg_rows;
-            const int p_chunks = (w.KP + 31) / 32;
-            size_t smem = 1024 + (size_t)(4 + p_chunks) * 2 * w.tile_rows * 128 + 64;
-            if (w.KP > 128 && smem < 80 * 1024) smem = 80 * 1024;        // 256 TMEM columns per CTA: keep <= 2 CTAs per SM
-            const int grid = w.KP > 128 ? 296 : 444;     // TMEM columns per CTA (256 / 128) bound the CTAs per SM
+            const size_t smem = wgrad_smem(w.N, w.K, w.KP, w.tile_rows, p.passes, w.stages);
+            const int grid = 148;                        // persistent: one CTA per SM, fed by the TMA ring
             if (p.passes == 3) { if ((rc = opt_in_smem(wgrad_tc_kernel<3>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<3>, grid, WG_THREADS, smem, st, w); }
             else { if ((rc = opt_in_smem(wgrad_tc_kernel<1>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<1>, grid, WG_THREADS, smem, st, w); }
             const int cnt = lp.d_in * lp.d_out;
@@ -766,9 +788,8 @@ int ptrb200_tc_wgrad(const float* dZ, const float* P, float* dW, float* partials
     w.dZ = dZ; w.P = P; w.scale = w.shift = nullptr; w.act = PTRB200_AF_NONE; w.gr_prev = rows;
     w.drop = make_drop(0.0f, 0, 0); w.partials = partials;
     w.rows = rows; w.K = K; w.N = N; w.KP = ((K + 15) / 16) * 16; w.tile_rows = 32;
-    const int p_chunks = (w.KP + 31) / 32, grid = 296;
-    size_t smem = 1024 + (size_t)(4 + p_chunks) * 2 * w.tile_rows * 128 + 64;
-    if (w.KP > 128 && smem < 80 * 1024) smem = 80 * 1024;
+    const int grid = 296;
+    const size_t smem = wgrad_smem(N, K, w.KP, w.tile_rows, passes, w.stages);
     int rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (passes == 3) { if ((rc = opt_in_smem(wgrad_tc_kernel<3>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<3>, grid, WG_THREADS, smem, st, w); }

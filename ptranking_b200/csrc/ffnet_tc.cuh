@@ -30,6 +30,8 @@ struct RowsGemmArgs {
     const unsigned char* b_img_hi;
     const unsigned char* b_img_lo;
     const float* bias;     // [N] (FWD) or NULL
+    float* a_out;          // FWD: when non-NULL the rebuilt (post-activation, post-dropout) A operand is also written
+                           // here [rows, K] so the weight-gradient kernel can read it back instead of recomputing it
     float* Out;            // [rows, N]
     double* partials;      // [slots, N, 2] column sum / sum of squares per statistics slot, or NULL
     int rows, K, N, NP;
@@ -44,9 +46,9 @@ struct RowsGemmArgs {
 enum { RG_FWD = 0, RG_DGRAD = 1 };
 
 // prologue transform of 4 consecutive elements (row r, columns k..k+3) of P
-static __device__ __forceinline__ float4 prologue4(const RowsGemmArgs& g, float4 v, int row, int k, bool with_dropout) {
+static __device__ __forceinline__ float4 prologue4(const RowsGemmArgs& g, float4 v, int row, int k, bool with_dropout, size_t coef_row_off) {
     if (g.scale) {
-        const size_t o = (size_t)(row / g.gr_prev) * g.K + k;
+        const size_t o = coef_row_off + k;
         const float4 sc = *reinterpret_cast<const float4*>(g.scale + o);
         const float4 sh = *reinterpret_cast<const float4*>(g.shift + o);
         v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
@@ -154,6 +156,12 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
     const int K = g.K;
     const int nchunks = (K + 31) / 32;
     constexpr int A_UNITS = 128 * 8 / RG_THREADS;      // 4 units of 16 B per thread per chunk
+    size_t coef_off[A_UNITS];                           // (statistics group of the thread's rows) * K
+#pragma unroll
+    for (int i = 0; i < A_UNITS; ++i) {
+        const int r = (tid + i * RG_THREADS) >> 3;
+        coef_off[i] = (g.scale && g.gr_prev < g.rows) ? (size_t)((row0 + min(r, nrows - 1)) / g.gr_prev) * K : 0;
+    }
 
     for (int c = 0; c < nchunks; ++c) {
         const int k0 = c * 32;
@@ -177,8 +185,10 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
         for (int i = 0; i < A_UNITS; ++i) {
             const int u = tid + i * RG_THREADS, r = u >> 3, j = u & 7, k = k0 + j * 4;
             float4 v = av[i];
-            if (r < nrows && k < K) v = prologue4(g, v, row0 + r, k, MODE == RG_FWD);
-            else v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nrows && k < K) {
+                v = prologue4(g, v, row0 + r, k, MODE == RG_FWD, coef_off[i]);
+                if (MODE == RG_FWD && g.a_out) *reinterpret_cast<float4*>(g.a_out + (size_t)(row0 + r) * K + k) = v;
+            } else v = make_float4(0.f, 0.f, 0.f, 0.f);
             store_split(a_hi, a_lo, tc::swz_offset(r, j), v, PASSES == 3);
         }
         tc::fence_proxy_async();
@@ -297,11 +307,19 @@ struct WgradArgs {
     float* partials;       // [gridDim.x, N, K]
     int rows, K, N;
     int KP;                // K rounded up to 16 (MMA N extent)
-    int tile_rows;         // R: rows per tile (multiple of 8, <= 64)
+    int tile_rows;         // R: rows per tile (multiple of 8, <= 32)
+    int stages;            // raw-tile ring depth (2..WG_MAX_STAGES), chosen by the host to fit shared memory
 };
 
-constexpr int WG_THREADS = 256;
+constexpr int WG_PRODUCERS = 256;      // 8 warps split raw fp32 tiles into hi/lo TF32 operand buffers
+constexpr int WG_THREADS = WG_PRODUCERS + 32;   // + 1 control warp: TMA bulk loads and tcgen05.mma issue
+constexpr int WG_MAX_STAGES = 4;      // raw-tile ring depth bound (TMA bulk copies in flight)
 
+// Persistent, warp-specialised, TMA-fed.  Row tiles of dZ and of the layer input are contiguous in HBM, so
+// the control warp streams them into a raw shared-memory ring with 1-D bulk copies (cp.async.bulk + mbarrier
+// complete_tx) `stages` tiles ahead.  The 8 producer warps turn a raw tile into hi/lo TF32 operand buffers
+// (double buffered) and signal `opready`; the control warp issues the MMAs of that tile (they accumulate in TMEM
+// across all tiles of the CTA), commits to `opfree`, and refills the raw slot.  No CTA-wide barrier in the loop.
 template <int PASSES>
 __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -310,84 +328,146 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
     const int z_chunks = 4;                                  // dZ columns padded to 128 (MMA M = 128)
     const int p_chunks = (g.KP + 31) / 32;
     const int chunk_bytes = R * 128;
-    unsigned char* z_hi = base;
-    unsigned char* z_lo = z_hi + z_chunks * chunk_bytes;
-    unsigned char* p_hi = z_lo + z_chunks * chunk_bytes;
-    unsigned char* p_lo = p_hi + p_chunks * chunk_bytes;
-    unsigned char* tail = p_lo + p_chunks * chunk_bytes;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(tail);
-    uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 1);
+    const int op_bytes = (z_chunks + p_chunks) * chunk_bytes * (PASSES == 3 ? 2 : 1);
+    const int rawz_bytes = ((R * g.N * 4 + 127) / 128) * 128, rawp_bytes = ((R * g.K * 4 + 127) / 128) * 128;
+    const int stages = g.stages;
+    unsigned char* opbuf = base;                             // [2][op_bytes]
+    unsigned char* rawbuf = opbuf + 2 * op_bytes;            // [stages][rawz + rawp]
+    unsigned char* tail = rawbuf + stages * (rawz_bytes + rawp_bytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(tail);      // [stages] raw tile landed (TMA complete_tx)
+    uint64_t* opready = full + WG_MAX_STAGES;                // [2] operand buffer staged (one arrive per producer warp)
+    uint64_t* opfree = opready + 2;                          // [2] MMAs reading the operand buffer have completed
+    uint32_t* slot = reinterpret_cast<uint32_t*>(opfree + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t tmem_cols = g.KP <= 32 ? 32 : g.KP <= 64 ? 64 : g.KP <= 128 ? 128 : 256;
-    if (tid == 0) { tc::mbar_init(mbar, 1); tc::mbar_fence_init(); }
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) tc::mbar_init(full + s, 1);
+        for (int o = 0; o < 2; ++o) { tc::mbar_init(opready + o, WG_PRODUCERS / 32); tc::mbar_init(opfree + o, 1); }
+        tc::mbar_fence_init();
+    }
     if (warp == 0) tc::tmem_alloc(slot, tmem_cols);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = *slot;
-    // A (dZ^T) and B (Ain^T) are MN-major: bits 15 and 16 of the instruction descriptor
-    const uint32_t idesc = tc::instr_desc(2, 128, g.KP) | (1u << 15) | (1u << 16);
-
     const int ntiles = (g.rows + R - 1) / R;
-    int it = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-        const int row0 = t * R, nrows = min(R, g.rows - row0);
-        if (it > 0) tc::mbar_wait(mbar, (it - 1) & 1);            // previous tile's MMAs have consumed smem
-        // ---- dZ tile: [R][128 cols]; one 16-byte unit per thread per 32-column chunk (R*8 <= WG_THREADS) ----
-        const int r = tid >> 3, j = tid & 7;
-        const bool row_ok = tid < R * 8 && r < nrows;
-#pragma unroll
-        for (int ch = 0; ch < z_chunks; ++ch) {
-            const int n = ch * 32 + j * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row_ok && n < g.N) {
-                const float* p = g.dZ + (size_t)(row0 + r) * g.N + n;
-                if (n + 3 < g.N && (g.N & 3) == 0) v = __ldg(reinterpret_cast<const float4*>(p));
-                else { v.x = p[0]; if (n + 1 < g.N) v.y = p[1]; if (n + 2 < g.N) v.z = p[2]; if (n + 3 < g.N) v.w = p[3]; }
-            }
-            if (tid < R * 8) store_split(z_hi + ch * chunk_bytes, z_lo + ch * chunk_bytes, tc::swz32_offset(r, j), v, PASSES == 3);
-        }
-        // ---- Ain tile: [R][KP cols] rebuilt from P ----
-        RowsGemmArgs pg{};
-        pg.scale = g.scale; pg.shift = g.shift; pg.act = g.act; pg.gr_prev = g.gr_prev; pg.K = g.K;
-        pg.drop = g.drop;
-        for (int ch = 0; ch < p_chunks; ++ch) {
-            const int k = ch * 32 + j * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row_ok && k < g.K) {
-                v = __ldg(reinterpret_cast<const float4*>(g.P + (size_t)(row0 + r) * g.K + k));
-                v = prologue4(pg, v, row0 + r, k, true);
-            }
-            if (tid < R * 8) store_split(p_hi + ch * chunk_bytes, p_lo + ch * chunk_bytes, tc::swz32_offset(r, j), v, PASSES == 3);
-        }
-        tc::fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-            tc::fence_after_sync();
-            const int ksteps = (nrows + 7) / 8;
-            for (int s = 0; s < ksteps; ++s) {
-                // MN-major: leading byte offset = distance between 128-byte column chunks, stride = 4-row atoms
-                const uint64_t zh = tc::smem_desc_sw128_mn(tc::smem_u32(z_hi) + s * 1024, chunk_bytes, 512);
-                const uint64_t ph = tc::smem_desc_sw128_mn(tc::smem_u32(p_hi) + s * 1024, chunk_bytes, 512);
-                const uint32_t acc = (it == 0 && s == 0) ? 0u : 1u;
-                if (PASSES == 3) {
-                    const uint64_t zl = tc::smem_desc_sw128_mn(tc::smem_u32(z_lo) + s * 1024, chunk_bytes, 512);
-                    const uint64_t pl = tc::smem_desc_sw128_mn(tc::smem_u32(p_lo) + s * 1024, chunk_bytes, 512);
-                    tc::mma_tf32(tmem, zl, ph, idesc, acc);
-                    tc::mma_tf32(tmem, zh, pl, idesc, 1u);
-                    tc::mma_tf32(tmem, zh, ph, idesc, 1u);
+    const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const bool z_aligned = ((R * g.N * 4) & 15) == 0;       // every full dZ tile is a whole number of 16-byte units
+
+    if (warp == WG_PRODUCERS / 32) {
+        // ======================= control warp (one lane active) =======================
+        if (lane == 0) {
+            const uint32_t idesc = tc::instr_desc(2, 128, g.KP) | (1u << 15) | (1u << 16);   // A and B MN-major
+            auto issue_load = [&](int it, int s) {
+                const int t = blockIdx.x + it * gridDim.x;
+                const int row0 = t * R, nrows = min(R, g.rows - row0);
+                const uint32_t zb = (uint32_t)nrows * g.N * 4, pb = (uint32_t)nrows * g.K * 4;
+                unsigned char* rz = rawbuf + s * (rawz_bytes + rawp_bytes);
+                if ((zb & 15) == 0) {
+                    tc::mbar_expect_tx(full + s, zb + pb);
+                    tc::bulk_g2s(rz, g.dZ + (size_t)row0 * g.N, zb, full + s);
                 } else {
-                    tc::mma_tf32(tmem, zh, ph, idesc, acc);
+                    tc::mbar_expect_tx(full + s, pb);             // odd-sized dZ tail tile: producers copy it by hand
+                }
+                tc::bulk_g2s(rz + rawz_bytes, g.P + (size_t)row0 * g.K, pb, full + s);
+            };
+            int s_load = 0;
+            for (int it = 0; it < min(stages, my_tiles); ++it) { issue_load(it, s_load); s_load = s_load + 1 == stages ? 0 : s_load + 1; }
+            int s_cons = 0, next_load = min(stages, my_tiles);
+            for (int it = 0; it < my_tiles; ++it) {
+                const int o = it & 1;
+                const int t = blockIdx.x + it * gridDim.x, nrows = min(R, g.rows - t * R);
+                tc::mbar_wait(opready + o, (it >> 1) & 1);          // operands staged => raw slot s_cons drained too
+                if (next_load < my_tiles) { issue_load(next_load, s_cons); ++next_load; }
+                s_cons = s_cons + 1 == stages ? 0 : s_cons + 1;
+                tc::fence_after_sync();
+                const uint32_t zb_hi = tc::smem_u32(opbuf + o * op_bytes);
+                const uint32_t zb_lo = zb_hi + z_chunks * chunk_bytes;
+                const uint32_t pb_hi = zb_hi + (PASSES == 3 ? 2 : 1) * z_chunks * chunk_bytes;
+                const uint32_t pb_lo = pb_hi + p_chunks * chunk_bytes;
+                // MN-major descriptors: leading offset = distance between 128-byte column chunks, stride = 4-row atoms;
+                // a K-step of 8 rows advances the start address by 1024 B (64 in descriptor units)
+                uint64_t zh = tc::smem_desc_sw128_mn(zb_hi, chunk_bytes, 512), ph = tc::smem_desc_sw128_mn(pb_hi, chunk_bytes, 512);
+                uint64_t zl = tc::smem_desc_sw128_mn(zb_lo, chunk_bytes, 512), pl = tc::smem_desc_sw128_mn(pb_lo, chunk_bytes, 512);
+                const int ksteps = (nrows + 7) / 8;
+                for (int st = 0; st < ksteps; ++st) {
+                    const uint32_t acc = (it == 0 && st == 0) ? 0u : 1u;
+                    if (PASSES == 3) {
+                        tc::mma_tf32(tmem, zl, ph, idesc, acc);
+                        tc::mma_tf32(tmem, zh, pl, idesc, 1u);
+                        tc::mma_tf32(tmem, zh, ph, idesc, 1u);
+                    } else {
+                        tc::mma_tf32(tmem, zh, ph, idesc, acc);
+                    }
+                    zh += 64; ph += 64; zl += 64; pl += 64;
+                }
+                tc::mma_commit(opfree + o);
+            }
+        }
+    } else {
+        // ======================= producer warps =======================
+        RowsGemmArgs pg{};
+        pg.scale = g.scale; pg.shift = g.shift; pg.act = g.act; pg.gr_prev = g.gr_prev; pg.K = g.K; pg.drop = g.drop;
+        const bool plain_p = !g.scale && g.act == PTRB200_AF_NONE && !g.drop.thr;   // layer input already materialised
+        const int r = tid >> 3, j = tid & 7;              // one 16-byte unit per thread per 32-column chunk (R*8 <= 256)
+        const bool vec_z = (g.N & 3) == 0;
+        const bool active = tid < R * 8;
+        const uint32_t sw = tc::swz32_offset(r, j);       // this thread's slot inside every operand chunk
+        const int zoff = r * g.N + j * 4, poff = r * g.K + j * 4;
+        int s = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int t = blockIdx.x + it * gridDim.x, o = it & 1;
+            const int row0 = t * R, nrows = min(R, g.rows - row0);
+            unsigned char* z_hi = opbuf + o * op_bytes + sw;
+            unsigned char* z_lo = z_hi + z_chunks * chunk_bytes;
+            unsigned char* p_hi = z_hi + (PASSES == 3 ? 2 : 1) * z_chunks * chunk_bytes;
+            unsigned char* p_lo = p_hi + p_chunks * chunk_bytes;
+            float* rz = reinterpret_cast<float*>(rawbuf + s * (rawz_bytes + rawp_bytes));
+            const float* rp = reinterpret_cast<const float*>(rawbuf + s * (rawz_bytes + rawp_bytes) + rawz_bytes);
+            uint64_t* fbar = full + s;
+            const int fpar = (it / stages) & 1;
+            s = s + 1 == stages ? 0 : s + 1;
+            if (it >= 2) tc::mbar_wait(opfree + o, ((it - 2) >> 1) & 1);    // MMAs of tile it-2 are done with this buffer
+            if ((((uint32_t)nrows * g.N * 4) & 15) != 0) {                   // odd-sized dZ tail: copy by hand, producers only
+                for (int e = tid; e < nrows * g.N; e += WG_PRODUCERS) rz[e] = g.dZ[(size_t)row0 * g.N + e];
+                asm volatile("bar.sync 1, %0;" ::"n"(WG_PRODUCERS) : "memory");
+            }
+            tc::mbar_wait(fbar, fpar);
+            if (active) {
+                const bool row_ok = r < nrows;
+                const float* zsrc = rz + zoff;
+#pragma unroll
+                for (int ch = 0; ch < z_chunks; ++ch) {
+                    const int n = ch * 32 + j * 4;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row_ok && n < g.N) {
+                        if (vec_z) v = *reinterpret_cast<const float4*>(zsrc + ch * 32);
+                        else { const float* p = zsrc + ch * 32; v.x = p[0]; if (n + 1 < g.N) v.y = p[1]; if (n + 2 < g.N) v.z = p[2]; if (n + 3 < g.N) v.w = p[3]; }
+                    }
+                    store_split(z_hi + ch * chunk_bytes, z_lo + ch * chunk_bytes, 0, v, PASSES == 3);
+                }
+                const float* psrc = rp + poff;
+                for (int ch = 0; ch < p_chunks; ++ch) {
+                    const int k = ch * 32 + j * 4;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row_ok && k < g.K) {
+                        v = *reinterpret_cast<const float4*>(psrc + ch * 32);
+                        if (!plain_p) v = prologue4(pg, v, row0 + r, k, true, (g.scale && g.gr_prev < g.rows) ? (size_t)((row0 + r) / g.gr_prev) * g.K : 0);
+                    }
+                    store_split(p_hi + ch * chunk_bytes, p_lo + ch * chunk_bytes, 0, v, PASSES == 3);
                 }
             }
-            tc::mma_commit(mbar);
+            tc::fence_proxy_async();                       // this thread's operand stores -> visible to the MMA (async proxy)
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(opready + o);
         }
+        (void)z_aligned;
     }
-    // ---- epilogue: this CTA's partial dW[n][k], n = TMEM lane ----
-    if (it > 0) { tc::mbar_wait(mbar, (it - 1) & 1); }
-    tc::fence_after_sync();
-    {
+    // ---- epilogue (producer warps 0..7): this CTA's partial dW[n][k], n = TMEM lane ----
+    if (warp < WG_PRODUCERS / 32) {
+        if (my_tiles >= 1) { const int it = my_tiles - 1; tc::mbar_wait(opfree + (it & 1), (it >> 1) & 1); }
+        tc::fence_after_sync();
         const int q = warp & 3, half = warp >> 2;
         const int n = q * 32 + lane;
         float* dst = g.partials + (size_t)blockIdx.x * g.N * g.K;
@@ -395,7 +475,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
         const int c_begin = half == 0 ? 0 : cols_half, c_end = half == 0 ? min(cols_half, g.KP) : g.KP;
         for (int c0 = c_begin; c0 < c_end; c0 += 8) {
             float v[8];
-            if (it > 0) tc::tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (my_tiles > 0) tc::tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             else {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = 0.0f;

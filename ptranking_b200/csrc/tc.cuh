@@ -153,7 +153,7 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 // split an fp32 value into tf32-representable hi and the fp32 remainder lo (hi + lo == x exactly)
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-    lo = (fabsf(x) <= 3.0e38f) ? x - hi : 0.0f;      // inf/nan stay in hi only
+    lo = x - hi;                                       // (an infinite x yields lo = NaN, i.e. NaN instead of inf downstream)
 }
 
 }  // namespace tc
