@@ -601,12 +601,45 @@ static size_t rows_gemm_smem(int N, int NP) {
     return 1024 + (operands > otile ? operands : otile) + 64;
 }
 
-static int launch_rows_gemm(int mode, int passes, RowsGemmArgs& g, int ntiles, cudaStream_t st) {
+// stats_kind: 0 none, 1 one statistics group over the whole batch (BN), 2 per-query groups (BN2).
+// *S_out receives the number of partial slots per group the kernel wrote.
+static int launch_rows_gemm(int mode, int passes, RowsGemmArgs& g, int ntiles, cudaStream_t st,
+                            int stats_kind = 0, int* S_out = nullptr, int S_default = 1) {
     g.NP = ((g.N + 15) / 16) * 16;
+    int rc;
+    const int nchunks = (g.K + 31) / 32;
+    // ---- persistent warp-specialised kernel when the whole weight image fits beside the A ring ----
+    const size_t ws_smem = 1024 + (size_t)nchunks * g.NP * 128 * (passes == 3 ? 2 : 1) + 65536 + (size_t)RW_EPI_WARPS * g.NP * 8 + 128;
+    const bool seg_ok = !g.partials || g.seg_len == g.tile_rows || g.group_rows > 0;     // no sub-tile statistics segments
+    if (ws_smem <= 227 * 1024 && seg_ok && g.N <= 256) {
+        RowsWsExtra x{};
+        x.ntiles = ntiles; x.nchunks = nchunks;
+        x.stats_mode = (!g.partials || stats_kind == 0) ? 0 : (stats_kind == 1 ? 1 : 2);
+        const int grid = ntiles < 148 ? ntiles : 148;
+        if (S_out) *S_out = x.stats_mode == 1 ? grid : S_default;
+#define RW_CASE(M, P, A, TAG)                                                                       \
+        if (mode == M && passes == P && act_t == A) {                                               \
+            if ((rc = opt_in_smem(rows_gemm_ws_kernel<M, P, A>, ws_smem))) return rc;               \
+            PTRB200_LAUNCH_TAG(TAG, (rows_gemm_ws_kernel<M, P, A>), grid, RW_THREADS, ws_smem, st, g, x); \
+            return PTRB200_OK;                                                                      \
+        }
+        // the prologue activation is a template parameter for the common codes, -1 = generic run-time switch
+        const int act_t = (g.act == PTRB200_AF_NONE || g.act == PTRB200_AF_RELU || g.act == PTRB200_AF_GELU || g.act == PTRB200_AF_SIGM) ? g.act : -1;
+        RW_CASE(RG_FWD, 3, PTRB200_AF_NONE, "rows_gemm_ws_fwd") RW_CASE(RG_FWD, 3, PTRB200_AF_RELU, "rows_gemm_ws_fwd")
+        RW_CASE(RG_FWD, 3, PTRB200_AF_GELU, "rows_gemm_ws_fwd") RW_CASE(RG_FWD, 3, PTRB200_AF_SIGM, "rows_gemm_ws_fwd")
+        RW_CASE(RG_FWD, 3, -1, "rows_gemm_ws_fwd")
+        RW_CASE(RG_FWD, 1, PTRB200_AF_NONE, "rows_gemm_ws_fwd") RW_CASE(RG_FWD, 1, PTRB200_AF_RELU, "rows_gemm_ws_fwd")
+        RW_CASE(RG_FWD, 1, PTRB200_AF_GELU, "rows_gemm_ws_fwd") RW_CASE(RG_FWD, 1, PTRB200_AF_SIGM, "rows_gemm_ws_fwd")
+        RW_CASE(RG_FWD, 1, -1, "rows_gemm_ws_fwd")
+        RW_CASE(RG_DGRAD, 3, PTRB200_AF_NONE, "rows_gemm_ws_dgrad")
+        RW_CASE(RG_DGRAD, 1, PTRB200_AF_NONE, "rows_gemm_ws_dgrad")
+#undef RW_CASE
+        return PTRB200_ERR_INVALID;
+    }
+    if (S_out) *S_out = S_default;
     const size_t operands = 32768 + (size_t)g.NP * 256, otile = (size_t)128 * g.N * 4;
     g.tail_off = (int)(((operands > otile ? operands : otile) + 15) / 16 * 16);
     const size_t smem = rows_gemm_smem(g.N, g.NP);
-    int rc;
 #define RG_CASE(M, P, TAG)                                                                      \
     if (mode == M && passes == P) {                                                             \
         if ((rc = opt_in_smem(rows_gemm_tc_kernel<M, P>, smem))) return rc;                     \
@@ -659,14 +692,16 @@ static int forward_tc(const ptrb200_ffnet* net, const Plan& p, const float* X, f
             g.b_img_hi = ih; g.b_img_lo = il;
         }
         set_tiling(g, p);
-        if ((rc = launch_rows_gemm(RG_FWD, p.passes, g, p.ntiles, st))) return rc;
+        int S_fwd = p.S_stat;
+        const int stats_kind = !lp.has_norm ? 0 : (net->norm == PTRB200_NORM_BN ? 1 : 2);
+        if ((rc = launch_rows_gemm(RG_FWD, p.passes, g, p.ntiles, st, stats_kind, &S_fwd, p.S_stat))) return rc;
         NormRef nr = norm_ref(net, p, l, ws);
         if (lp.has_norm) {
             const int cnt = p.G * lp.d_out;
             PTRB200_LAUNCH(moments_finalize_kernel, cnt, FIN_THREADS, 0, st, (const double*)g.partials,
                            reinterpret_cast<float*>(ws + lp.mean_off), reinterpret_cast<float*>(ws + lp.rstd_off),
                            reinterpret_cast<float*>(ws + lp.scale_off), reinterpret_cast<float*>(ws + lp.shift_off),
-                           nr, p.G, lp.d_out, p.S_stat, p.gr);
+                           nr, p.G, lp.d_out, S_fwd, p.gr);
         }
         if (last && (lp.has_act || lp.has_norm)) {
             const size_t total = p.rows * lp.d_out;

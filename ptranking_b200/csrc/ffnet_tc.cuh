@@ -292,6 +292,320 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
 }
 
 // --------------------------------------------------------------------------------------------
+// rows_gemm, persistent warp-specialised variant (used whenever the whole weight image fits next to the
+// A ring in shared memory, i.e. for every layer of the pointwise scorer).
+//
+//   warps 0-3   epilogue : TMEM -> registers -> (+bias | dropout mask) -> global rows, BN column sums
+//   warp  4     control  : one-time TMA bulk load of the resident W image; per K-chunk tcgen05.mma issue
+//   warps 5-20  producers: global -> registers (prefetched one chunk ahead) -> prologue -> hi/lo split ->
+//                          swizzled A stage (ring of 2)
+// TMEM holds two accumulators so the epilogue of tile t overlaps the MMAs of tile t+1; producers, control
+// and epilogue only meet through mbarriers (aready/afree per A stage, accfull/accfree per accumulator).
+// --------------------------------------------------------------------------------------------
+constexpr int RW_EPI_WARPS = 4, RW_PROD_WARPS = 16;
+constexpr int RW_THREADS = (RW_EPI_WARPS + 1 + RW_PROD_WARPS) * 32;
+constexpr int RW_PRODUCERS = RW_PROD_WARPS * 32;
+
+struct RowsWsExtra {
+    int ntiles;
+    int stats_mode;        // 0 none, 1 one partial per CTA (BN over the whole batch), 2 one partial per tile (BN2)
+    int nchunks;
+};
+
+static __device__ __forceinline__ void rw_tile(const RowsGemmArgs& g, int t, int& row0, int& nrows) {
+    if (g.group_rows > 0) {
+        const int grp = t / g.tiles_per_group, tt = t - grp * g.tiles_per_group;
+        row0 = grp * g.group_rows + tt * 128;
+        nrows = min(128, g.group_rows - tt * 128);
+    } else {
+        row0 = t * g.tile_rows;
+        nrows = min(g.tile_rows, g.rows - row0);
+    }
+}
+
+// sum of v[i] over the 32 lanes for 8 values per lane: 9 shuffles; every lane returns the total of column
+// ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1)
+static __device__ __forceinline__ float warp_colsum8(const float (&v)[8], int lane) {
+    float a[4], b[2];
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float mine = h16 ? v[4 + i] : v[i], other = h16 ? v[i] : v[4 + i];
+        a[i] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float mine = h8 ? a[2 + i] : a[i], other = h8 ? a[i] : a[2 + i];
+        b[i] = mine + __shfl_xor_sync(0xffffffffu, other, 8);
+    }
+    const float mine = h4 ? b[1] : b[0], other = h4 ? b[0] : b[1];
+    float c = mine + __shfl_xor_sync(0xffffffffu, other, 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    return c;
+}
+
+// ACT: the prologue activation as a compile-time constant (PTRB200_AF_*), or -1 to read g.act at run time
+template <int MODE, int PASSES, int ACT>
+__global__ void __launch_bounds__(RW_THREADS, 1) rows_gemm_ws_kernel(RowsGemmArgs g, RowsWsExtra x) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int NP = g.NP, K = g.K, N = g.N, nchunks = x.nchunks;
+    const int wchunk = NP * 128;
+    unsigned char* w_hi = base;                                   // [nchunks][NP][128 B]
+    unsigned char* w_lo = w_hi + (size_t)nchunks * wchunk;
+    unsigned char* a_ring = w_lo + (PASSES == 3 ? (size_t)nchunks * wchunk : 0);   // [2][hi 16 KB | lo 16 KB]
+    float* stat_sm = reinterpret_cast<float*>(a_ring + 2 * 32768);                 // [4 warps][NP][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stat_sm + RW_EPI_WARPS * NP * 2);
+    uint64_t* wfull = bars;            // W image landed
+    uint64_t* aready = bars + 1;       // [2] A stage staged            (one arrive per producer warp)
+    uint64_t* afree = bars + 3;        // [2] MMAs done with the stage  (tcgen05.commit)
+    uint64_t* accfull = bars + 5;      // [2] accumulator complete      (tcgen05.commit)
+    uint64_t* accfree = bars + 7;      // [2] accumulator drained       (one arrive per epilogue warp)
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t acc_cols = NP <= 32 ? 32 : NP <= 64 ? 64 : NP <= 128 ? 128 : 256;   // one accumulator
+    const uint32_t tmem_cols = acc_cols * 2;
+    if (tid == 0) {
+        tc::mbar_init(wfull, 1);
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(aready + i, RW_PROD_WARPS); tc::mbar_init(afree + i, 1); tc::mbar_init(accfull + i, 1); tc::mbar_init(accfree + i, RW_EPI_WARPS); }
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) tc::tmem_alloc(slot, tmem_cols);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *slot;
+    const int my_tiles = blockIdx.x < x.ntiles ? (x.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp == RW_EPI_WARPS) {
+        // ================================ control warp ================================
+        // the whole warp runs the loop (warp-uniform descriptors); one elected lane issues TMA / MMA / commit
+        if (my_tiles > 0) {
+            const uint32_t idesc = tc::instr_desc(2, 128, NP);
+            const bool leader = tc::elect_one();
+            if (leader) {
+                tc::mbar_expect_tx(wfull, (uint32_t)(nchunks * wchunk * (PASSES == 3 ? 2 : 1)));
+                for (int c = 0; c < nchunks; ++c) {
+                    tc::bulk_g2s(w_hi + (size_t)c * wchunk, g.b_img_hi + (size_t)c * wchunk, wchunk, wfull);
+                    if (PASSES == 3) tc::bulk_g2s(w_lo + (size_t)c * wchunk, g.b_img_lo + (size_t)c * wchunk, wchunk, wfull);
+                }
+            }
+            tc::mbar_wait(wfull, 0);
+            const uint32_t a_base = tc::smem_u32(a_ring), wh_base = tc::smem_u32(w_hi), wl_base = tc::smem_u32(w_lo);
+            int q = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int b = it & 1;
+                if (it >= 2) tc::mbar_wait(accfree + b, ((it - 2) >> 1) & 1);
+                tc::fence_after_sync();
+                const uint32_t dacc = tmem + (uint32_t)b * acc_cols;
+                for (int c = 0; c < nchunks; ++c, ++q) {
+                    const int s = q & 1;
+                    tc::mbar_wait(aready + s, (q >> 1) & 1);
+                    tc::fence_after_sync();
+                    const uint32_t a_addr = a_base + s * 32768;
+                    uint64_t ah = tc::smem_desc_sw128(a_addr, 1024), al = tc::smem_desc_sw128(a_addr + 16384, 1024);
+                    uint64_t bh = tc::smem_desc_sw128(wh_base + c * wchunk, 1024), bl = tc::smem_desc_sw128(wl_base + c * wchunk, 1024);
+                    const int ksteps = min(4, (K - c * 32 + 7) / 8);
+                    if (leader) {
+                        for (int st = 0; st < ksteps; ++st) {
+                            const uint32_t acc = (c == 0 && st == 0) ? 0u : 1u;
+                            if (PASSES == 3) {
+                                tc::mma_tf32(dacc, al, bh, idesc, acc);
+                                tc::mma_tf32(dacc, ah, bl, idesc, 1u);
+                                tc::mma_tf32(dacc, ah, bh, idesc, 1u);
+                            } else {
+                                tc::mma_tf32(dacc, ah, bh, idesc, acc);
+                            }
+                            ah += 2; al += 2; bh += 2; bl += 2;          // +32 B along K inside the swizzle atom
+                        }
+                        tc::mma_commit(afree + s);
+                        if (c == nchunks - 1) tc::mma_commit(accfull + b);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp > RW_EPI_WARPS) {
+        // ================================ producer warps ================================
+        const int ptid = tid - (RW_EPI_WARPS + 1) * 32;
+        const int j4 = (ptid & 7) * 4;                              // first column of this thread's 16-byte unit inside a chunk
+        const int r_[2] = {ptid >> 3, (ptid >> 3) + 64};
+        const uint32_t sw_[2] = {tc::swz_offset(r_[0], ptid & 7), tc::swz_offset(r_[1], ptid & 7)};
+        const int total_q = my_tiles * nchunks;
+        const bool has_coef = g.scale != nullptr;
+        const bool per_group = has_coef && g.gr_prev < g.rows;
+        float4 pre[2];
+        const float* src[2];                                        // P + row * K + j4 for the tile being fetched
+        bool ok[2];
+        auto point = [&](int it) {                                  // set src/ok for tile `it`
+            int r0, nr;
+            rw_tile(g, blockIdx.x + it * gridDim.x, r0, nr);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { ok[i] = r_[i] < nr; src[i] = g.P + (size_t)(r0 + min(r_[i], nr - 1)) * K + j4; }
+        };
+        auto fetch = [&](int c) {
+            const bool kv = c * 32 + j4 < K;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                pre[i] = (ok[i] && kv) ? __ldg(reinterpret_cast<const float4*>(src[i] + c * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        if (total_q > 0) { point(0); fetch(0); }
+        int q = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            int row0, nrows;
+            rw_tile(g, blockIdx.x + it * gridDim.x, row0, nrows);
+            // per-tile invariants of this thread's two rows
+            bool live[2];
+            float* aout[2];
+            const float* sc[2];
+            const float* sh[2];
+            uint64_t dq[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                live[i] = r_[i] < nrows;
+                const size_t e0 = (size_t)(row0 + min(r_[i], nrows - 1)) * K + j4;
+                aout[i] = (MODE == RG_FWD && g.a_out) ? g.a_out + e0 : nullptr;
+                const size_t co = per_group ? (size_t)((row0 + min(r_[i], nrows - 1)) / g.gr_prev) * K + j4 : (size_t)j4;
+                sc[i] = has_coef ? g.scale + co : nullptr;
+                sh[i] = has_coef ? g.shift + co : nullptr;
+                dq[i] = (uint64_t)e0 >> 2;
+            }
+            for (int c = 0; c < nchunks; ++c, ++q) {
+                const int s = q & 1;
+                const float4 cur[2] = {pre[0], pre[1]};
+                if (q + 1 < total_q) {                              // prefetch the next chunk (possibly of the next tile)
+                    if (c + 1 < nchunks) fetch(c + 1); else { point(it + 1); fetch(0); }
+                }
+                if (q >= 2) tc::mbar_wait(afree + s, ((q - 2) >> 1) & 1);
+                unsigned char* a_hi = a_ring + s * 32768;
+                const bool kv = c * 32 + j4 < K;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    float4 v = cur[i];
+                    if (live[i] && kv) {
+                        if (has_coef) {
+                            const float4 a = __ldg(reinterpret_cast<const float4*>(sc[i] + c * 32));
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(sh[i] + c * 32));
+                            v.x = fmaf(v.x, a.x, b.x); v.y = fmaf(v.y, a.y, b.y); v.z = fmaf(v.z, a.z, b.z); v.w = fmaf(v.w, a.w, b.w);
+                        }
+                        if (ACT != PTRB200_AF_NONE) {
+                            const int af = ACT < 0 ? g.act : ACT;
+                            v.x = activate(af, v.x).y; v.y = activate(af, v.y).y; v.z = activate(af, v.z).y; v.w = activate(af, v.w).y;
+                        }
+                        if (MODE == RG_FWD && g.drop.thr) {
+                            const uint64_t d = dropout_draw4(g.drop.key, dq[i] + c * 8);
+                            v.x = ((uint32_t)(d) & 0xffffu) >= g.drop.thr ? v.x * g.drop.scale : 0.0f;
+                            v.y = ((uint32_t)(d >> 16) & 0xffffu) >= g.drop.thr ? v.y * g.drop.scale : 0.0f;
+                            v.z = ((uint32_t)(d >> 32) & 0xffffu) >= g.drop.thr ? v.z * g.drop.scale : 0.0f;
+                            v.w = ((uint32_t)(d >> 48)) >= g.drop.thr ? v.w * g.drop.scale : 0.0f;
+                        }
+                        if (MODE == RG_FWD && aout[i]) *reinterpret_cast<float4*>(aout[i] + c * 32) = v;
+                    } else v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    store_split(a_hi, a_hi + 16384, sw_[i], v, PASSES == 3);
+                }
+                tc::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(aready + s);
+            }
+        }
+    } else {
+        // ================================ epilogue warps (0..3) ================================
+        const int r = warp * 32 + lane;                       // TMEM lane = row inside the tile
+        double acc1[2] = {0.0, 0.0}, acc2[2] = {0.0, 0.0};    // per-CTA column sums for columns tid and tid+128
+        for (int it = 0; it < my_tiles; ++it) {
+            const int b = it & 1, t = blockIdx.x + it * gridDim.x;
+            int row0, nrows;
+            rw_tile(g, t, row0, nrows);
+            const bool live = r < nrows;
+            tc::mbar_wait_relaxed(accfull + b, (it >> 1) & 1);
+            tc::fence_after_sync();
+            const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)b * acc_cols;
+            float* orow = g.Out + (size_t)(row0 + r) * N;
+            for (int c0 = 0; c0 < NP; c0 += 8) {
+                float v[8];
+                tc::tmem_ld8(tbase + (uint32_t)c0, v);
+                if (c0 >= N) continue;
+                if (MODE == RG_FWD) {
+                    if (c0 + 8 <= N && (N & 3) == 0) {
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + c0)), b1 = __ldg(reinterpret_cast<const float4*>(g.bias + c0 + 4));
+                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = (c0 + e < N) ? v[e] + __ldg(g.bias + c0 + e) : 0.0f;
+                    }
+                } else if (g.drop.thr) {
+                    if ((N & 3) == 0) {
+                        const uint64_t qd = ((uint64_t)(row0 + r) * N + c0) >> 2;
+                        const uint64_t d0 = dropout_draw4(g.drop.key, qd), d1 = dropout_draw4(g.drop.key, qd + 1);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            v[e] = ((uint32_t)(d0 >> (16 * e)) & 0xffffu) >= g.drop.thr ? v[e] * g.drop.scale : 0.0f;
+                            v[4 + e] = ((uint32_t)(d1 >> (16 * e)) & 0xffffu) >= g.drop.thr ? v[4 + e] * g.drop.scale : 0.0f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            if (c0 + e < N) v[e] = dropout_keep(g.drop.key, (uint64_t)(row0 + r) * N + c0 + e, g.drop.thr) ? v[e] * g.drop.scale : 0.0f;
+                    }
+                }
+                if (live) {
+                    if (c0 + 8 <= N && (N & 3) == 0) {
+                        *reinterpret_cast<float4*>(orow + c0) = make_float4(v[0], v[1], v[2], v[3]);
+                        *reinterpret_cast<float4*>(orow + c0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) if (c0 + e < N) orow[c0 + e] = v[e];
+                    }
+                }
+                if (MODE == RG_FWD && x.stats_mode) {
+                    float w1[8], w2[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { w1[e] = live ? v[e] : 0.0f; w2[e] = w1[e] * w1[e]; }
+                    const float s1 = warp_colsum8(w1, lane), s2 = warp_colsum8(w2, lane);
+                    if ((lane & 3) == 0) {
+                        const int col = c0 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                        stat_sm[(warp * NP + col) * 2] = s1;
+                        stat_sm[(warp * NP + col) * 2 + 1] = s2;
+                    }
+                }
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(accfree + b);
+            if (MODE == RG_FWD && x.stats_mode) {
+                asm volatile("bar.sync 2, 128;" ::: "memory");               // the 4 warps' column sums are in smem
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int col = tid + h * 128;
+                    if (col < N) {
+                        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                        for (int w = 0; w < RW_EPI_WARPS; ++w) { s1 += (double)stat_sm[(w * NP + col) * 2]; s2 += (double)stat_sm[(w * NP + col) * 2 + 1]; }
+                        if (x.stats_mode == 2) {
+                            double* p = g.partials + ((size_t)t * N + col) * 2;
+                            p[0] = s1; p[1] = s2;
+                        } else { acc1[h] += s1; acc2[h] += s2; }
+                    }
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");               // smem free for the next tile
+            }
+        }
+        if (MODE == RG_FWD && x.stats_mode == 1) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int col = tid + h * 128;
+                if (col < N) { double* p = g.partials + ((size_t)blockIdx.x * N + col) * 2; p[0] = acc1[h]; p[1] = acc2[h]; }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, tmem_cols);
+}
+
+// --------------------------------------------------------------------------------------------
 // weight gradient: dW[N,K] = sum_r dZ[r,n] * Ain[r,k],  Ain = drop(act(P*scale+shift)).
 // Both operands are staged row-major ([r][col], 128-byte column chunks, 4-row SWIZZLE_128B_BASE32B
 // atoms) and consumed as MN-major tcgen05 operands: the contraction runs over rows, 8 rows per MMA.
@@ -356,9 +670,11 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
     const bool z_aligned = ((R * g.N * 4) & 15) == 0;       // every full dZ tile is a whole number of 16-byte units
 
     if (warp == WG_PRODUCERS / 32) {
-        // ======================= control warp (one lane active) =======================
-        if (lane == 0) {
+        // ======================= control warp =======================
+        // warp-uniform loop (descriptors in uniform registers); one elected lane issues TMA / MMA / commit
+        {
             const uint32_t idesc = tc::instr_desc(2, 128, g.KP) | (1u << 15) | (1u << 16);   // A and B MN-major
+            const bool leader = tc::elect_one();
             auto issue_load = [&](int it, int s) {
                 const int t = blockIdx.x + it * gridDim.x;
                 const int row0 = t * R, nrows = min(R, g.rows - row0);
@@ -373,16 +689,17 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
                 tc::bulk_g2s(rz + rawz_bytes, g.P + (size_t)row0 * g.K, pb, full + s);
             };
             int s_load = 0;
-            for (int it = 0; it < min(stages, my_tiles); ++it) { issue_load(it, s_load); s_load = s_load + 1 == stages ? 0 : s_load + 1; }
+            for (int it = 0; it < min(stages, my_tiles); ++it) { if (leader) issue_load(it, s_load); s_load = s_load + 1 == stages ? 0 : s_load + 1; }
             int s_cons = 0, next_load = min(stages, my_tiles);
+            const uint32_t op_base = tc::smem_u32(opbuf);
             for (int it = 0; it < my_tiles; ++it) {
                 const int o = it & 1;
                 const int t = blockIdx.x + it * gridDim.x, nrows = min(R, g.rows - t * R);
                 tc::mbar_wait(opready + o, (it >> 1) & 1);          // operands staged => raw slot s_cons drained too
-                if (next_load < my_tiles) { issue_load(next_load, s_cons); ++next_load; }
+                if (next_load < my_tiles) { if (leader) issue_load(next_load, s_cons); ++next_load; }
                 s_cons = s_cons + 1 == stages ? 0 : s_cons + 1;
                 tc::fence_after_sync();
-                const uint32_t zb_hi = tc::smem_u32(opbuf + o * op_bytes);
+                const uint32_t zb_hi = op_base + o * op_bytes;
                 const uint32_t zb_lo = zb_hi + z_chunks * chunk_bytes;
                 const uint32_t pb_hi = zb_hi + (PASSES == 3 ? 2 : 1) * z_chunks * chunk_bytes;
                 const uint32_t pb_lo = pb_hi + p_chunks * chunk_bytes;
@@ -391,18 +708,21 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
                 uint64_t zh = tc::smem_desc_sw128_mn(zb_hi, chunk_bytes, 512), ph = tc::smem_desc_sw128_mn(pb_hi, chunk_bytes, 512);
                 uint64_t zl = tc::smem_desc_sw128_mn(zb_lo, chunk_bytes, 512), pl = tc::smem_desc_sw128_mn(pb_lo, chunk_bytes, 512);
                 const int ksteps = (nrows + 7) / 8;
-                for (int st = 0; st < ksteps; ++st) {
-                    const uint32_t acc = (it == 0 && st == 0) ? 0u : 1u;
-                    if (PASSES == 3) {
-                        tc::mma_tf32(tmem, zl, ph, idesc, acc);
-                        tc::mma_tf32(tmem, zh, pl, idesc, 1u);
-                        tc::mma_tf32(tmem, zh, ph, idesc, 1u);
-                    } else {
-                        tc::mma_tf32(tmem, zh, ph, idesc, acc);
+                if (leader) {
+                    for (int st = 0; st < ksteps; ++st) {
+                        const uint32_t acc = (it == 0 && st == 0) ? 0u : 1u;
+                        if (PASSES == 3) {
+                            tc::mma_tf32(tmem, zl, ph, idesc, acc);
+                            tc::mma_tf32(tmem, zh, pl, idesc, 1u);
+                            tc::mma_tf32(tmem, zh, ph, idesc, 1u);
+                        } else {
+                            tc::mma_tf32(tmem, zh, ph, idesc, acc);
+                        }
+                        zh += 64; ph += 64; zl += 64; pl += 64;
                     }
-                    zh += 64; ph += 64; zl += 64; pl += 64;
+                    tc::mma_commit(opfree + o);
                 }
-                tc::mma_commit(opfree + o);
+                __syncwarp();
             }
         }
     } else {
