@@ -609,7 +609,7 @@ static int launch_rows_gemm(int mode, int passes, RowsGemmArgs& g, int ntiles, c
     int rc;
     const int nchunks = (g.K + 31) / 32;
     // ---- persistent warp-specialised kernel when the whole weight image fits beside the A ring ----
-    const size_t ws_smem = 1024 + (size_t)nchunks * g.NP * 128 * (passes == 3 ? 2 : 1) + 65536 + (size_t)RW_EPI_WARPS * g.NP * 8 + 128;
+    const size_t ws_smem = 1024 + (size_t)nchunks * g.NP * 128 * (passes == 3 ? 2 : 1) + 65536 + (size_t)4 * g.NP * 8 + 128;
     const bool seg_ok = !g.partials || g.seg_len == g.tile_rows || g.group_rows > 0;     // no sub-tile statistics segments
     if (ws_smem <= 227 * 1024 && seg_ok && g.N <= 256) {
         RowsWsExtra x{};

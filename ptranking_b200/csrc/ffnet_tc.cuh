@@ -295,14 +295,14 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
 // rows_gemm, persistent warp-specialised variant (used whenever the whole weight image fits next to the
 // A ring in shared memory, i.e. for every layer of the pointwise scorer).
 //
-//   warps 0-3   epilogue : TMEM -> registers -> (+bias | dropout mask) -> global rows, BN column sums
-//   warp  4     control  : one-time TMA bulk load of the resident W image; per K-chunk tcgen05.mma issue
-//   warps 5-20  producers: global -> registers (prefetched one chunk ahead) -> prologue -> hi/lo split ->
+//   warps 0-7   epilogue : TMEM -> registers -> (+bias | dropout mask) -> global rows, BN column sums
+//   warp  8     control  : one-time TMA bulk load of the resident W image; per K-chunk tcgen05.mma issue
+//   warps 9-24  producers: global -> registers (prefetched one chunk ahead) -> prologue -> hi/lo split ->
 //                          swizzled A stage (ring of 2)
 // TMEM holds two accumulators so the epilogue of tile t overlaps the MMAs of tile t+1; producers, control
 // and epilogue only meet through mbarriers (aready/afree per A stage, accfull/accfree per accumulator).
 // --------------------------------------------------------------------------------------------
-constexpr int RW_EPI_WARPS = 4, RW_PROD_WARPS = 16;
+constexpr int RW_EPI_WARPS = 8, RW_PROD_WARPS = 16;      // epilogue: 2 warps per TMEM lane quarter (column halves)
 constexpr int RW_THREADS = (RW_EPI_WARPS + 1 + RW_PROD_WARPS) * 32;
 constexpr int RW_PRODUCERS = RW_PROD_WARPS * 32;
 
@@ -355,8 +355,8 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rows_gemm_ws_kernel(RowsGemmArg
     unsigned char* w_hi = base;                                   // [nchunks][NP][128 B]
     unsigned char* w_lo = w_hi + (size_t)nchunks * wchunk;
     unsigned char* a_ring = w_lo + (PASSES == 3 ? (size_t)nchunks * wchunk : 0);   // [2][hi 16 KB | lo 16 KB]
-    float* stat_sm = reinterpret_cast<float*>(a_ring + 2 * 32768);                 // [4 warps][NP][2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stat_sm + RW_EPI_WARPS * NP * 2);
+    float* stat_sm = reinterpret_cast<float*>(a_ring + 2 * 32768);                 // [4 lane quarters][NP][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stat_sm + 4 * NP * 2);
     uint64_t* wfull = bars;            // W image landed
     uint64_t* aready = bars + 1;       // [2] A stage staged            (one arrive per producer warp)
     uint64_t* afree = bars + 3;        // [2] MMAs done with the stage  (tcgen05.commit)
@@ -511,9 +511,14 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rows_gemm_ws_kernel(RowsGemmArg
             }
         }
     } else {
-        // ================================ epilogue warps (0..3) ================================
-        const int r = warp * 32 + lane;                       // TMEM lane = row inside the tile
-        double acc1[2] = {0.0, 0.0}, acc2[2] = {0.0, 0.0};    // per-CTA column sums for columns tid and tid+128
+        // ================================ epilogue warps (0..7) ================================
+        // warp w reads TMEM lanes [32*(w&3), +32) (hardware restriction: lane quarter = warp id mod 4) and the
+        // column half (w>>2) of the accumulator, 16 columns per tcgen05.ld.
+        const int quarter = warp & 3, half = warp >> 2;
+        const int r = quarter * 32 + lane;                    // TMEM lane = row inside the tile
+        const int ch_cols = ((NP / 16 + 1) / 2) * 16;         // columns of half 0 (multiple of 16)
+        const int c_begin = half == 0 ? 0 : ch_cols, c_end = half == 0 ? min(ch_cols, NP) : NP;
+        double acc1 = 0.0, acc2 = 0.0;                        // per-CTA column sums for column `tid` (tid < 256)
         for (int it = 0; it < my_tiles; ++it) {
             const int b = it & 1, t = blockIdx.x + it * gridDim.x;
             int row0, nrows;
@@ -521,53 +526,59 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rows_gemm_ws_kernel(RowsGemmArg
             const bool live = r < nrows;
             tc::mbar_wait_relaxed(accfull + b, (it >> 1) & 1);
             tc::fence_after_sync();
-            const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)b * acc_cols;
-            float* orow = g.Out + (size_t)(row0 + r) * N;
-            for (int c0 = 0; c0 < NP; c0 += 8) {
-                float v[8];
-                tc::tmem_ld8(tbase + (uint32_t)c0, v);
+            const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)b * acc_cols;
+            float* orow = g.Out + (size_t)(row0 + min(r, nrows - 1)) * N;
+            for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+                float v[16];
+                tc::tmem_ld16(tbase + (uint32_t)c0, v);
                 if (c0 >= N) continue;
-                if (MODE == RG_FWD) {
-                    if (c0 + 8 <= N && (N & 3) == 0) {
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + c0)), b1 = __ldg(reinterpret_cast<const float4*>(g.bias + c0 + 4));
-                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                    } else {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = (c0 + e < N) ? v[e] + __ldg(g.bias + c0 + e) : 0.0f;
-                    }
-                } else if (g.drop.thr) {
-                    if ((N & 3) == 0) {
-                        const uint64_t qd = ((uint64_t)(row0 + r) * N + c0) >> 2;
-                        const uint64_t d0 = dropout_draw4(g.drop.key, qd), d1 = dropout_draw4(g.drop.key, qd + 1);
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int cc = c0 + hh * 8;
+                    float* w = v + hh * 8;
+                    if (cc >= N) break;
+                    if (MODE == RG_FWD) {
+                        if (cc + 8 <= N && (N & 3) == 0) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + cc)), b1 = __ldg(reinterpret_cast<const float4*>(g.bias + cc + 4));
+                            w[0] += b0.x; w[1] += b0.y; w[2] += b0.z; w[3] += b0.w; w[4] += b1.x; w[5] += b1.y; w[6] += b1.z; w[7] += b1.w;
+                        } else {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            v[e] = ((uint32_t)(d0 >> (16 * e)) & 0xffffu) >= g.drop.thr ? v[e] * g.drop.scale : 0.0f;
-                            v[4 + e] = ((uint32_t)(d1 >> (16 * e)) & 0xffffu) >= g.drop.thr ? v[4 + e] * g.drop.scale : 0.0f;
+                            for (int e = 0; e < 8; ++e) w[e] = (cc + e < N) ? w[e] + __ldg(g.bias + cc + e) : 0.0f;
                         }
-                    } else {
+                    } else if (g.drop.thr) {
+                        if ((N & 3) == 0) {
+                            const uint64_t qd = ((uint64_t)(row0 + r) * N + cc) >> 2;
+                            const uint64_t d0 = dropout_draw4(g.drop.key, qd), d1 = dropout_draw4(g.drop.key, qd + 1);
 #pragma unroll
-                        for (int e = 0; e < 8; ++e)
-                            if (c0 + e < N) v[e] = dropout_keep(g.drop.key, (uint64_t)(row0 + r) * N + c0 + e, g.drop.thr) ? v[e] * g.drop.scale : 0.0f;
+                            for (int e = 0; e < 4; ++e) {
+                                w[e] = ((uint32_t)(d0 >> (16 * e)) & 0xffffu) >= g.drop.thr ? w[e] * g.drop.scale : 0.0f;
+                                w[4 + e] = ((uint32_t)(d1 >> (16 * e)) & 0xffffu) >= g.drop.thr ? w[4 + e] * g.drop.scale : 0.0f;
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (cc + e < N) w[e] = dropout_keep(g.drop.key, (uint64_t)(row0 + r) * N + cc + e, g.drop.thr) ? w[e] * g.drop.scale : 0.0f;
+                        }
                     }
-                }
-                if (live) {
-                    if (c0 + 8 <= N && (N & 3) == 0) {
-                        *reinterpret_cast<float4*>(orow + c0) = make_float4(v[0], v[1], v[2], v[3]);
-                        *reinterpret_cast<float4*>(orow + c0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                    } else {
+                    if (live) {
+                        if (cc + 8 <= N && (N & 3) == 0) {
+                            *reinterpret_cast<float4*>(orow + cc) = make_float4(w[0], w[1], w[2], w[3]);
+                            *reinterpret_cast<float4*>(orow + cc + 4) = make_float4(w[4], w[5], w[6], w[7]);
+                        } else {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) if (c0 + e < N) orow[c0 + e] = v[e];
+                            for (int e = 0; e < 8; ++e) if (cc + e < N) orow[cc + e] = w[e];
+                        }
                     }
-                }
-                if (MODE == RG_FWD && x.stats_mode) {
-                    float w1[8], w2[8];
+                    if (MODE == RG_FWD && x.stats_mode) {
+                        float w1[8], w2[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) { w1[e] = live ? v[e] : 0.0f; w2[e] = w1[e] * w1[e]; }
-                    const float s1 = warp_colsum8(w1, lane), s2 = warp_colsum8(w2, lane);
-                    if ((lane & 3) == 0) {
-                        const int col = c0 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                        stat_sm[(warp * NP + col) * 2] = s1;
-                        stat_sm[(warp * NP + col) * 2 + 1] = s2;
+                        for (int e = 0; e < 8; ++e) { w1[e] = live ? w[e] : 0.0f; w2[e] = w1[e] * w1[e]; }
+                        const float s1 = warp_colsum8(w1, lane), s2 = warp_colsum8(w2, lane);
+                        if ((lane & 3) == 0) {
+                            const int col = cc + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                            stat_sm[(quarter * NP + col) * 2] = s1;
+                            stat_sm[(quarter * NP + col) * 2 + 1] = s2;
+                        }
                     }
                 }
             }
@@ -575,29 +586,22 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rows_gemm_ws_kernel(RowsGemmArg
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(accfree + b);
             if (MODE == RG_FWD && x.stats_mode) {
-                asm volatile("bar.sync 2, 128;" ::: "memory");               // the 4 warps' column sums are in smem
+                asm volatile("bar.sync 2, 256;" ::: "memory");               // the 8 warps' column sums are in smem
+                if (tid < N) {
+                    double s1 = 0.0, s2 = 0.0;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int col = tid + h * 128;
-                    if (col < N) {
-                        double s1 = 0.0, s2 = 0.0;
-#pragma unroll
-                        for (int w = 0; w < RW_EPI_WARPS; ++w) { s1 += (double)stat_sm[(w * NP + col) * 2]; s2 += (double)stat_sm[(w * NP + col) * 2 + 1]; }
-                        if (x.stats_mode == 2) {
-                            double* p = g.partials + ((size_t)t * N + col) * 2;
-                            p[0] = s1; p[1] = s2;
-                        } else { acc1[h] += s1; acc2[h] += s2; }
-                    }
+                    for (int w = 0; w < 4; ++w) { s1 += (double)stat_sm[(w * NP + tid) * 2]; s2 += (double)stat_sm[(w * NP + tid) * 2 + 1]; }
+                    if (x.stats_mode == 2) {
+                        double* p = g.partials + ((size_t)t * N + tid) * 2;
+                        p[0] = s1; p[1] = s2;
+                    } else { acc1 += s1; acc2 += s2; }
                 }
-                asm volatile("bar.sync 2, 128;" ::: "memory");               // smem free for the next tile
+                asm volatile("bar.sync 2, 256;" ::: "memory");               // smem free for the next tile
             }
         }
-        if (MODE == RG_FWD && x.stats_mode == 1) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int col = tid + h * 128;
-                if (col < N) { double* p = g.partials + ((size_t)blockIdx.x * N + col) * 2; p[0] = acc1[h]; p[1] = acc2[h]; }
-            }
+        if (MODE == RG_FWD && x.stats_mode == 1 && tid < N) {
+            double* p = g.partials + ((size_t)blockIdx.x * N + tid) * 2;
+            p[0] = acc1; p[1] = acc2;
         }
     }
     tc::fence_before_sync();
