@@ -246,11 +246,13 @@ def run_b200(args):
 
     # ---- roofline pass: per-launch CUDA events around every kernel of the same steps ----
     roof = None
+    # every rank runs the same steps (they contain the gradient all-reduce); only rank 0 records events
     if rank == 0:
         _lib.kernel_timings(enable=True)
-        for i in range(min(args.steps, 5)):
-            ranker.train_op(*devb[i % 2], **kw)
-        torch.cuda.synchronize()
+    for i in range(min(args.steps, 5)):
+        ranker.train_op(*devb[i % 2], **kw)
+    torch.cuda.synchronize()
+    if rank == 0:
         tm = _lib.kernel_timings()
         _lib.kernel_timings(enable=False)
         total_ms = sum(v[1] for v in tm.values())
