@@ -117,6 +117,12 @@ int ptrb200_sum_f32(const float* x, float* out, int n, ptrb200_stream_t stream);
 int ptrb200_ndcg_at_ks(const float* scores, const float* labels, const int32_t* ks_host, int nks,
                        float* out, int32_t* order, int B, int n, int presort, ptrb200_stream_t stream);
 
+/* adhoc_performance_at_ks, ptranking/base/ranker.py:202-263 with torch_ndcg_at_ks / torch_nerr_at_ks / torch_ap_at_ks /
+ * torch_precision_at_ks (metric/adhoc/adhoc_metric.py:36-64, 95-128, 132-193, 243-260): out[B][4][nks] in the order
+ * nDCG, nERR, AP, P from one in-CTA sort per query; cutoffs > n yield 0; max_label as the evaluator passes it. */
+int ptrb200_adhoc_metrics_at_ks(const float* scores, const float* labels, const int32_t* ks_host, int nks,
+                                float* out, int B, int n, int presort, float max_label, ptrb200_stream_t stream);
+
 /* ---- stacked feed-forward scorer (pointwise MLP; also the head/tail nets of listsf) ---- */
 /* get_stacked_FFNet, ptranking/base/utils.py:288-356; PointNeuralRanker.forward,
  * base/point_ranker.py:45-55; LTRBatchNorm / LTRBatchNorm2, base/utils.py:201-282;

@@ -477,3 +477,70 @@ def train_op(net, optimizer, loss_name, X, labels, point=True, **loss_params):
     loss.backward()
     optimizer.step()
     return loss.detach()
+
+
+# --------------------------------------------------------------------------- #
+# P / AP / nERR (ptranking/metric/adhoc/adhoc_metric.py:18-193) -- SURVEY 8f "next" row 1
+# --------------------------------------------------------------------------- #
+def _used_ks(ks, n):
+    return ([k for k in ks if k <= n], True) if n < max(ks) else (list(ks), False)
+
+
+def _pad(vals, B, ks, used, padded):
+    if not padded:
+        return vals
+    out = torch.zeros(B, len(ks))
+    out[:, : len(used)] = vals
+    return out
+
+
+def precision_at_ks(sys_rankings, ks):
+    """adhoc_metric.py:36-64."""
+    used, padded = _used_ks(ks, sys_rankings.size(1))
+    m = max(used)
+    idx = torch.tensor(used, dtype=torch.long) - 1
+    bi = torch.clamp(sys_rankings[:, :m], min=0, max=1)
+    prec = torch.cumsum(bi, dim=1) / (torch.arange(m, dtype=torch.float) + 1.0)
+    return _pad(prec[:, idx], sys_rankings.size(0), ks, used, padded)
+
+
+def ap_at_ks(sys_rankings, ideal_rankings, ks):
+    """adhoc_metric.py:95-128 -- the denominator sums the NON-binarised ideal labels."""
+    used, padded = _used_ks(ks, sys_rankings.size(1))
+    m = max(used)
+    idx = torch.tensor(used, dtype=torch.long) - 1
+    bi = torch.clamp(sys_rankings[:, :m], min=0, max=1)
+    prec = torch.cumsum(bi, dim=1) / (torch.arange(m, dtype=torch.float) + 1.0)
+    cum_prec = torch.cumsum(prec * bi, dim=1)
+    ap = cum_prec / torch.cumsum(ideal_rankings, dim=1)[:, :m]
+    return _pad(ap[:, idx], sys_rankings.size(0), ks, used, padded)
+
+
+def _rankwise_err(rankings, max_label, k):
+    """adhoc_metric.py:132-156 (point=False)."""
+    labels = rankings[:, :k]
+    satis = (torch.pow(torch.tensor([2.0]), labels) - 1.0) / torch.pow(torch.tensor([2.0]), max_label)
+    cum_unsatis = torch.cumprod(1.0 - satis, dim=1)
+    cascade = torch.ones_like(satis)
+    cascade[:, 1:k] = cum_unsatis[:, : k - 1]
+    expt_ranks = 1.0 / (torch.arange(k, dtype=torch.float) + 1.0)
+    return torch.cumsum(expt_ranks * satis * cascade, dim=1)
+
+
+def nerr_at_ks(sys_rankings, ideal_rankings, ks, max_label=None):
+    """adhoc_metric.py:171-193; max_label defaults to the maximum over the whole batch."""
+    used, padded = _used_ks(ks, sys_rankings.size(1))
+    if max_label is None:
+        max_label = torch.max(ideal_rankings)
+    m = max(used)
+    idx = torch.tensor(used, dtype=torch.long) - 1
+    out = (_rankwise_err(sys_rankings, max_label, m) / _rankwise_err(ideal_rankings, max_label, m))[:, idx]
+    return _pad(out, sys_rankings.size(0), ks, used, padded)
+
+
+def evaluator_metrics_at_ks(scores, labels, ks, presort, max_label=None):
+    """(nDCG, nERR, AP, P) per query as adhoc_performance_at_ks builds them (base/ranker.py:202-263)."""
+    sys_r, _ = rank_labels_by_scores(scores, labels)
+    ideal = labels if presort else torch.sort(labels, dim=1, descending=True)[0]
+    return (ndcg_at_ks(sys_r, ideal, ks), nerr_at_ks(sys_r, ideal, ks, max_label), ap_at_ks(sys_r, ideal, ks),
+            precision_at_ks(sys_r, ks))

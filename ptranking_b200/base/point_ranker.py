@@ -18,6 +18,10 @@ class PointNeuralRanker(NeuralRanker):
     def init(self):
         self.point_sf = self.config_point_neural_scoring_function()
         self.config_optimizer()
+        # the scorer is a single fused op whose backward overwrites every parameter gradient: let it write
+        # straight into the flat gradient bucket (no per-tensor accumulate kernels, no zero fill)
+        self.point_sf.write_through_grads = True
+        self.grad_bucket_overwritten = True
 
     def config_point_neural_scoring_function(self):
         point_sf = self.ini_pointsf(**self.sf_para_dict[self.sf_para_dict['sf_id']])

@@ -61,12 +61,65 @@ class Evaluator:
             num_queries += len(batch_ids)
         return (total / num_queries).cpu()
 
+    def _metric_at_k(self, which, test_data, k, presort, max_label=None, skip_short=True):
+        """shared body of nerr_at_k / ap_at_k / p_at_k (ranker.py:97-187): batches with fewer than k documents
+        are skipped, the average runs over the remaining queries."""
+        self.eval_mode()
+        num_queries = 0
+        total = torch.zeros(1, device=self.device)
+        for batch_ids, X, y in test_data:
+            if skip_short and y.size(1) < k:
+                continue
+            num_queries += len(batch_ids)
+            preds, labels = self._scores_and_labels(X, y)
+            vals = ops.adhoc_metrics_at_ks(preds, labels, [k], presort=presort, max_label=max_label)[which]
+            total += ops.sum_f32(vals)
+        return (total / num_queries).cpu()
+
+    def nerr_at_k(self, test_data=None, k=10, label_type=LABEL_TYPE.MultiLabel, max_label=None, presort=False, device='cpu'):
+        assert _is_multilabel(label_type)
+        return self._metric_at_k(1, test_data, k, presort, max_label=max_label)
+
+    def ap_at_k(self, test_data=None, k=10, presort=False, device='cpu'):
+        return self._metric_at_k(2, test_data, k, presort)
+
+    def p_at_k(self, test_data=None, k=10, device='cpu'):
+        return self._metric_at_k(3, test_data, k, presort=False)
+
     def validation(self, vali_data=None, vali_metric=None, k=5, presort=False, max_label=None,
                    label_type=LABEL_TYPE.MultiLabel, device='cpu'):
-        """ranker.py:189-200 (nDCG branch; nERR/AP/P are SURVEY 8f 'next')."""
+        """ranker.py:189-200."""
         if 'nDCG' == vali_metric:
             return self.ndcg_at_k(test_data=vali_data, k=k, label_type=label_type, presort=presort, device=device)
-        raise NotImplementedError(f"validation metric {vali_metric!r}: only nDCG is on the B200 path")
+        elif 'nERR' == vali_metric:
+            return self.nerr_at_k(test_data=vali_data, k=k, label_type=label_type, max_label=max_label, presort=presort, device=device)
+        elif 'AP' == vali_metric:
+            return self.ap_at_k(test_data=vali_data, k=k, presort=presort, device=device)
+        elif 'P' == vali_metric:
+            return self.p_at_k(test_data=vali_data, k=k, device=device)
+        else:
+            raise NotImplementedError
+
+    def adhoc_performance_at_ks(self, test_data=None, ks=[1, 5, 10], label_type=LABEL_TYPE.MultiLabel, max_label=None,
+                                presort=False, device='cpu', need_per_q=False):
+        """ranker.py:202-263: average nDCG / nERR / AP / P at every cutoff (one fused kernel per batch)."""
+        assert _is_multilabel(label_type)
+        self.eval_mode()
+        num_queries = 0
+        sums = [torch.zeros(len(ks), device=self.device) for _ in range(4)]
+        per_q = [[] for _ in range(4)]
+        for batch_ids, X, y in test_data:
+            preds, labels = self._scores_and_labels(X, y)
+            vals = ops.adhoc_metrics_at_ks(preds, labels, ks, presort=presort, max_label=max_label)
+            for m in range(4):
+                sums[m] += vals[m].sum(dim=0)
+                if need_per_q:
+                    per_q[m].append(vals[m].cpu())
+            num_queries += len(batch_ids)
+        avgs = [(s_ / num_queries).cpu() for s_ in sums]
+        if need_per_q:
+            return (*avgs, *per_q)
+        return tuple(avgs)
 
 
 class NeuralRanker(Evaluator):
@@ -110,7 +163,7 @@ class NeuralRanker(Evaluator):
     def backward_and_step(self, batch_loss):
         """The tail every reference loss class ends with (e.g. lambdarank.py:58-60), plus the
         data-parallel gradient all-reduce (sum: every reference loss is a sum over queries)."""
-        self.grad_bucket.zero()
+        self.grad_bucket.zero(skip_memset=getattr(self, 'grad_bucket_overwritten', False))
         batch_loss.backward()
         self.grad_bucket.all_reduce()
         self.optimizer.step()

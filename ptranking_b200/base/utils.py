@@ -85,7 +85,13 @@ class StackedFFNet(nn.Module):
         squeeze = X.dim() == 2
         if squeeze:
             X = X.unsqueeze(0)
-        out = ops.ffnet_apply(X, self.spec, self._order, training=self.training)
+        # when every parameter already owns gradient storage (the ranker's flat bucket), the backward kernels write
+        # into it directly instead of handing autograd 2 tensors per layer to accumulate
+        targets = None
+        if torch.is_grad_enabled() and all(p.grad is not None and p.grad.is_contiguous() for p in self._order) \
+                and getattr(self, "write_through_grads", False):
+            targets = [p.grad for p in self._order]
+        out = ops.ffnet_apply(X, self.spec, self._order, training=self.training, grad_targets=targets)
         return out.squeeze(0) if squeeze else out
 
 

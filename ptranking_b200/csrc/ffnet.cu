@@ -732,11 +732,14 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
         NormRef nr = norm_ref(net, p, l, ws);
         const size_t total = p.rows * lp.d_out;
         dim3 sgrid(p.G, p.S_stat);
+        // the backward statistics pass picks its own slicing: long slices amortise the per-CTA reduction
+        int bS = p.S_stat, bslice = p.slice_rows;
+        // (measured: 128-row slices = 2048 CTAs beat longer slices; kept equal to the forward tiling)
         if (lp.has_act || lp.has_norm) {
             float* dY = dbuf[flip]; flip ^= 1;
-            launch_colstat<STAT_DY>(st, "colstat_dy", Z, dA, dY, nr, part, p.G, p.S_stat, p.gr, lp.d_out, p.slice_rows);
+            launch_colstat<STAT_DY>(st, "colstat_dy", Z, dA, dY, nr, part, p.G, bS, p.gr, lp.d_out, bslice);
             PTRB200_LAUNCH(dy_finalize_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)part,
-                           lp.has_norm ? S1 : (float*)nullptr, lp.has_norm ? S2 : (float*)nullptr, T1, T2, p.G, lp.d_out, p.S_stat);
+                           lp.has_norm ? S1 : (float*)nullptr, lp.has_norm ? S2 : (float*)nullptr, T1, T2, p.G, lp.d_out, bS);
             if (lp.has_norm) {
                 float *dg = nullptr, *db = nullptr, *dw = nullptr, *dbw = nullptr;
                 if (net->norm == PTRB200_NORM_BN) { if (net->norm_affine) { dg = grads->gamma[l]; db = grads->beta[l]; } }

@@ -448,6 +448,81 @@ __global__ void ndcg_at_ks_kernel(const float* __restrict__ scores, const float*
     }
 }
 
+
+// nDCG, nERR, AP and P at every cutoff from ONE sort per query (adhoc_performance_at_ks,
+// base/ranker.py:202-263 + metric/adhoc/adhoc_metric.py:18-260).  out[B][4][nks], metric order nDCG,nERR,AP,P.
+__global__ void adhoc_metrics_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
+                                     Cutoffs ks, float* __restrict__ out, int n, int npow2, int presort, float max_label) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64* keys = reinterpret_cast<u64*>(smem_raw);
+    float* ysys = reinterpret_cast<float*>(keys + npow2);   // labels in predicted order
+    float* yide = ysys + n;                                 // labels in ideal order
+    const int b = blockIdx.x;
+    const float* s = scores + (size_t)b * n;
+    const float* y = labels + (size_t)b * n;
+    if (presort) {
+        for (int r = threadIdx.x; r < n; r += blockDim.x) yide[r] = y[r];
+    } else {
+        for (int i = threadIdx.x; i < npow2; i += blockDim.x) keys[i] = i < n ? desc_key(y[i], i) : 0ull;
+        block_sort_desc(keys, npow2);
+        for (int r = threadIdx.x; r < n; r += blockDim.x) yide[r] = y[key_index(keys[r])];
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < npow2; i += blockDim.x) keys[i] = i < n ? desc_key(s[i], i) : 0ull;
+    block_sort_desc(keys, npow2);
+    for (int r = threadIdx.x; r < n; r += blockDim.x) ysys[r] = y[key_index(keys[r])];
+    __syncthreads();
+    // four independent sequential scans (the order torch.cumsum / cumprod use), one warp each
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane != 0 || warp >= 4) return;
+    float* o = out + ((size_t)b * 4 + warp) * ks.n;
+    int c = 0, r = 0;
+    if (warp == 0) {                    // nDCG
+        float cs = 0.0f, ci = 0.0f;
+        for (; c < ks.n; ++c) {
+            const int k = ks.k[c];
+            if (k > n) { o[c] = 0.0f; continue; }
+            for (; r < k; ++r) { const float d = log2_rank(r); cs += gain_of(ysys[r]) / d; ci += gain_of(yide[r]) / d; }
+            o[c] = cs / ci;
+        }
+    } else if (warp == 1) {             // nERR: sum_r (1/rank * satis_r) * prod_{q<r}(1 - satis_q)
+        const float denom = exp2f(max_label);
+        float es = 0.0f, ei = 0.0f, us = 1.0f, ui = 1.0f;
+        for (; c < ks.n; ++c) {
+            const int k = ks.k[c];
+            if (k > n) { o[c] = 0.0f; continue; }
+            for (; r < k; ++r) {
+                const float inv = 1.0f / ((float)r + 1.0f);
+                const float ps = gain_of(ysys[r]) / denom, pi = gain_of(yide[r]) / denom;
+                es += (inv * ps) * us; ei += (inv * pi) * ui;
+                us *= (1.0f - ps); ui *= (1.0f - pi);
+            }
+            o[c] = es / ei;
+        }
+    } else if (warp == 2) {             // AP (ideal labels are NOT binarised in the denominator, as in the reference)
+        float cum_rel = 0.0f, cum_prec = 0.0f, cum_ideal = 0.0f;
+        for (; c < ks.n; ++c) {
+            const int k = ks.k[c];
+            if (k > n) { o[c] = 0.0f; continue; }
+            for (; r < k; ++r) {
+                const float bi = fminf(fmaxf(ysys[r], 0.0f), 1.0f);
+                cum_rel += bi;
+                cum_prec += (cum_rel / ((float)r + 1.0f)) * bi;
+                cum_ideal += yide[r];
+            }
+            o[c] = cum_prec / cum_ideal;
+        }
+    } else {                            // P
+        float cum_rel = 0.0f;
+        for (; c < ks.n; ++c) {
+            const int k = ks.k[c];
+            if (k > n) { o[c] = 0.0f; continue; }
+            for (; r < k; ++r) cum_rel += fminf(fmaxf(ysys[r], 0.0f), 1.0f);
+            o[c] = cum_rel / (float)k;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------
@@ -580,6 +655,25 @@ int ptrb200_ndcg_at_ks(const float* scores, const float* labels, const int32_t* 
     if ((rc = allow_smem(ndcg_at_ks_kernel, smem))) return rc;
     PTRB200_LAUNCH(ndcg_at_ks_kernel, B, block_threads(n), smem, stream, scores, labels, ks, out, order, n, npow2, presort);
     return check_launch("ndcg_at_ks");
+}
+
+int ptrb200_adhoc_metrics_at_ks(const float* scores, const float* labels, const int32_t* ks_host, int nks,
+                                float* out, int B, int n, int presort, float max_label, ptrb200_stream_t stream) {
+    int rc = check_list_args(scores, labels, out, ks_host, B, n);
+    if (rc) return rc;
+    if (nks <= 0 || nks > PTRB200_MAX_CUTOFFS) { set_error("adhoc_metrics: nks=%d outside 1..%d", nks, PTRB200_MAX_CUTOFFS); return PTRB200_ERR_INVALID; }
+    Cutoffs ks;
+    ks.n = nks;
+    for (int c = 0; c < nks; ++c) {
+        ks.k[c] = ks_host[c];
+        if (ks.k[c] <= 0 || (c > 0 && ks.k[c] < ks.k[c - 1])) { set_error("adhoc_metrics: cutoffs must be positive and non-decreasing"); return PTRB200_ERR_INVALID; }
+    }
+    const int npow2 = next_pow2(n);
+    const size_t smem = (size_t)npow2 * 8 + (size_t)n * 4 * 2;
+    if ((rc = allow_smem(adhoc_metrics_kernel, smem))) return rc;
+    int threads = block_threads(n); if (threads < 128) threads = 128;
+    PTRB200_LAUNCH(adhoc_metrics_kernel, B, threads, smem, stream, scores, labels, ks, out, n, npow2, presort, max_label);
+    return check_launch("adhoc_metrics_at_ks");
 }
 
 }  // extern "C"

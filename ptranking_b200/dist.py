@@ -60,9 +60,11 @@ class GradBucket:
             p.grad = self.flat[off: off + p.numel()].view_as(p)
             off += p.numel()
 
-    def zero(self) -> None:
-        """optimizer.zero_grad() that keeps the views alive."""
-        self.flat.zero_()
+    def zero(self, skip_memset: bool = False) -> None:
+        """optimizer.zero_grad() that keeps the views alive.  ``skip_memset``: every gradient is overwritten
+        (not accumulated) by the backward kernels this step, so clearing the buffer is unnecessary."""
+        if not skip_memset:
+            self.flat.zero_()
         for p, v in zip(self.params, self._views()):
             if p.grad is None or p.grad.data_ptr() != v.data_ptr():
                 p.grad = v

@@ -159,6 +159,27 @@ def ndcg_at_ks(scores: torch.Tensor, labels: torch.Tensor, ks: Sequence[int], pr
     return (out, order) if return_order else out
 
 
+def adhoc_metrics_at_ks(scores: torch.Tensor, labels: torch.Tensor, ks: Sequence[int], presort: bool = False,
+                        max_label: Optional[float] = None):
+    """(nDCG, nERR, AP, P) per query at the cutoffs ``ks`` -> four [B, len(ks)] tensors from one kernel."""
+    lib = _lib.load()
+    s, y = _dev_f32(scores, "scores"), _dev_f32(labels, "labels")
+    B, n = _check_pair(s, y)
+    ks = [int(k) for k in ks]
+    order_ix = sorted(range(len(ks)), key=lambda i: ks[i])
+    arr = (C.c_int32 * len(ks))(*[ks[i] for i in order_ix])
+    if max_label is None:                       # the reference falls back to the maximum over the batch
+        max_label = float(y.max())
+    out = torch.empty((B, 4, len(ks)), dtype=torch.float32, device=s.device)
+    _lib.check(lib.ptrb200_adhoc_metrics_at_ks(s.data_ptr(), y.data_ptr(), arr, len(ks), out.data_ptr(), B, n,
+                                               int(bool(presort)), float(max_label), _stream_ptr()), "adhoc_metrics_at_ks")
+    if order_ix != list(range(len(ks))):
+        inv = torch.empty(len(ks), dtype=torch.long)
+        inv[torch.tensor(order_ix)] = torch.arange(len(ks))
+        out = out[:, :, inv.to(out.device)]
+    return out[:, 0], out[:, 1], out[:, 2], out[:, 3]
+
+
 # --------------------------------------------------------------------------- #
 # stacked feed-forward scorer
 # --------------------------------------------------------------------------- #
@@ -212,14 +233,18 @@ class FFNetSpec:
                 getattr(d, nm)[l] = next(it).data_ptr()
         return d
 
-    def grads(self, params: Sequence[torch.Tensor]):
+    def grads(self, params: Sequence[torch.Tensor], targets=None):
+        """Gradient descriptor.  ``targets`` (optional, one tensor per parameter) are written in place --
+        the flat data-parallel gradient bucket -- instead of fresh tensors autograd would have to add."""
         g = _lib.FFNetGrads()
         outs = []
         it = iter(params)
+        i = 0
         for l, names in enumerate(self.slots):
             for nm in names:
                 p = next(it)
-                t = torch.empty_like(p)
+                t = targets[i] if targets is not None else torch.empty_like(p)
+                i += 1
                 outs.append(t)
                 getattr(g, nm)[l] = t.data_ptr()
         return g, outs
@@ -227,7 +252,7 @@ class FFNetSpec:
 
 class _FFNetFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, X, spec: FFNetSpec, training: bool, seed: int, offset: int, *params):
+    def forward(ctx, X, spec: FFNetSpec, training: bool, seed: int, offset: int, grad_targets, *params):
         lib = _lib.load()
         X = _dev_f32(X, "X")
         B, n, F = X.shape
@@ -243,6 +268,7 @@ class _FFNetFn(torch.autograd.Function):
         _lib.check(lib.ptrb200_ffnet_forward(C.byref(desc), X.data_ptr(), out.data_ptr(), ws.data_ptr(), int(nbytes),
                                              B, n, int(training), seed, offset, _stream_ptr()), "ffnet_forward")
         ctx.spec, ctx.training, ctx.seed, ctx.offset = spec, training, seed, offset
+        ctx.grad_targets = grad_targets
         ctx.ws, ctx.nbytes = ws, int(nbytes)
         ctx.need_dx = X.requires_grad
         ctx.save_for_backward(X, *params)
@@ -255,7 +281,7 @@ class _FFNetFn(torch.autograd.Function):
         spec = ctx.spec
         B, n, _ = X.shape
         desc = spec.describe(params)
-        gdesc, gouts = spec.grads(params)
+        gdesc, gouts = spec.grads(params, ctx.grad_targets)
         d_out = _dev_f32(d_out, "d_out")
         dX = torch.empty_like(X) if ctx.need_dx else None
         _lib.check(lib.ptrb200_ffnet_backward(C.byref(desc), C.byref(gdesc), X.data_ptr(), d_out.data_ptr(),
@@ -263,17 +289,20 @@ class _FFNetFn(torch.autograd.Function):
                                               B, n, int(ctx.training), ctx.seed, ctx.offset, _stream_ptr()),
                    "ffnet_backward")
         ctx.ws = None
-        return (dX, None, None, None, None, *gouts)
+        if ctx.grad_targets is not None:            # written straight into the parameters' .grad storage
+            return (dX, None, None, None, None, None, *([None] * len(gouts)))
+        return (dX, None, None, None, None, None, *gouts)
 
 
 def ffnet_apply(X: torch.Tensor, spec: FFNetSpec, params: Sequence[torch.Tensor], training: bool,
-                seed: Optional[int] = None, offset: Optional[int] = None) -> torch.Tensor:
-    """[B,n,F] -> [B,n,out] through the fused stacked-FF kernels (differentiable)."""
+                seed: Optional[int] = None, offset: Optional[int] = None, grad_targets=None) -> torch.Tensor:
+    """[B,n,F] -> [B,n,out] through the fused stacked-FF kernels (differentiable).  ``grad_targets``: tensors the
+    parameter gradients are written into directly (each parameter must be used by exactly one call per step)."""
     if seed is None:
         seed = torch.initial_seed() & (2 ** 64 - 1)
     if offset is None:
         offset = next_dropout_offset()
-    return _FFNetFn.apply(X, spec, bool(training), int(seed), int(offset), *params)
+    return _FFNetFn.apply(X, spec, bool(training), int(seed), int(offset), grad_targets, *params)
 
 
 # --------------------------------------------------------------------------- #

@@ -140,3 +140,23 @@ def test_list_scorer_port(enc, bn):
     net.eval()
     s = net(torch.from_numpy(z[key + "__X"]))
     assert rel_err(s.detach().numpy(), z[key + "__scores"]) <= 5e-6
+
+
+def test_p_ap_nerr_known_answers_and_fixtures():
+    """P / AP / nERR restatements against the reference's own known answers (testing_metric.py:20-60)
+    and against reference outputs on seeded rankings."""
+    z = load("metrics2.npz")
+    for name in ("ap1", "ap2", "ap3"):
+        got = rp.ap_at_ks(torch.from_numpy(z[name + "__sys"]), torch.from_numpy(z[name + "__std"]), list(z[name + "__ks"]))
+        assert np.array_equal(got.numpy(), z[name + "__ap"])
+        assert np.allclose(got.numpy()[0], z[name + "__expect4dp"], atol=5e-5)
+    got = rp.nerr_at_ks(torch.from_numpy(z["nerr__sys"]), torch.from_numpy(z["nerr__std"]), [1, 2, 3])
+    assert np.array_equal(got.numpy(), z["nerr__val"]) and np.allclose(got.numpy()[0], z["nerr__expect4dp"], atol=5e-5)
+    for key in ("B5_n50", "B3_n256", "B2_n7", "B2_n1024"):
+        s, y = torch.from_numpy(z[key + "__scores"]), torch.from_numpy(z[key + "__labels"])
+        ks = [int(k) for k in z[key + "__ks"]]
+        nd, ne, ap, p = rp.evaluator_metrics_at_ks(s, y, ks, presort=True, max_label=4.0)
+        assert np.array_equal(nd.numpy(), z[key + "__ndcg"]) and np.array_equal(ne.numpy(), z[key + "__nerr4"])
+        assert np.array_equal(ap.numpy(), z[key + "__ap"]) and np.array_equal(p.numpy(), z[key + "__p"])
+        ne2 = rp.evaluator_metrics_at_ks(s, y, ks, presort=True, max_label=None)[1]
+        assert np.array_equal(ne2.numpy(), z[key + "__nerrNone"])
