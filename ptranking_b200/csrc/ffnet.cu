@@ -348,6 +348,22 @@ __global__ void __launch_bounds__(FIN_THREADS) dy_finalize_kernel(
     if (threadIdx.x == 0) { T1[c] = (float)t1; if (T2) T2[c] = (float)t2; }
 }
 
+// coefficients of the folded normalisation backward: dZ = k1*dY + k3*z + k0 with
+//   k1 = a*rstd,  k3 = -a*rstd^2*S2/N,  k0 = -a*rstd*S1/N + a*rstd^2*S2/N*mean      (a = gamma*aff_w)
+__global__ void dz_coeff_kernel(NormRef nr, const float* __restrict__ S1, const float* __restrict__ S2,
+                                float* __restrict__ k1, float* __restrict__ k3, float* __restrict__ k0, int G, int C, int gr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G * C) return;
+    const int c = i % C;
+    float a, cc;
+    norm_coeffs(nr, c, a, cc);
+    const float rs = nr.rstd[i], mu = nr.mean[i], invN = 1.0f / (float)gr;
+    const float ar = a * rs, t = ar * rs * (S2[i] * invN);
+    k1[i] = ar;
+    k3[i] = -t;
+    k0[i] = t * mu - ar * (S1[i] * invN);
+}
+
 // ------------------------------------------------------------------ elementwise passes
 // A = act(a * (z - mean) * rstd + c)
 __global__ void norm_act_fwd_kernel(const float* __restrict__ Z, float* __restrict__ A, NormRef nr,
@@ -453,7 +469,7 @@ struct Plan {
     int L, G, gr, S_stat, slice_rows, S_w, k_chunk;
     size_t rows;
     LayerPlan layer[PTRB200_MAX_FF_LAYERS];
-    size_t partials_off, s1_off, s2_off, t1_off, t2_off, dbuf0_off, dbuf1_off, wpart_off, total;
+    size_t partials_off, s1_off, s2_off, t1_off, t2_off, dbuf0_off, dbuf1_off, wpart_off, k1_off, k3_off, k0_off, total;
 };
 
 static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p) {
@@ -522,6 +538,9 @@ static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p) {
     p.s2_off = off; off = align_up(off + (size_t)p.G * maxd * 4, 256);
     p.t1_off = off; off = align_up(off + (size_t)maxd * 4, 256);
     p.t2_off = off; off = align_up(off + (size_t)maxd * 4, 256);
+    p.k1_off = off; off = align_up(off + (size_t)p.G * maxd * 4, 256);
+    p.k3_off = off; off = align_up(off + (size_t)p.G * maxd * 4, 256);
+    p.k0_off = off; off = align_up(off + (size_t)p.G * maxd * 4, 256);
     p.dbuf0_off = off; off = align_up(off + p.rows * maxd * 4, 256);
     p.dbuf1_off = off; off = align_up(off + p.rows * maxd * 4, 256);
     p.wpart_off = off; off = align_up(off + (size_t)(p.use_tc ? (p.wg_grid > p.S_w ? p.wg_grid : p.S_w) : p.S_w) * maxw * 4, 256);
@@ -582,23 +601,29 @@ static int opt_in_smem(K kernel, size_t bytes) {
 
 
 // picks the row-tile height R (32/16/8) and ring depth so the kernel's buffers fit the 227 KB of one SM
-static size_t wgrad_smem(int N, int K, int KP, int& R, int passes, int& stages) {
+static size_t wgrad_smem(int N, int K, int KP, int& R, int passes, int& stages, bool fused_dz = false, int min_R = 8) {
     const int p_chunks = (KP + 31) / 32;
     const size_t limit = 227 * 1024;
-    for (R = 32; R >= 8; R >>= 1) {
+    for (R = 32; R >= min_R; R >>= 1) {
         const size_t op = (size_t)(4 + p_chunks) * R * 128 * (passes == 3 ? 2 : 1);
-        const size_t rawz = ((size_t)R * N * 4 + 127) / 128 * 128, rawp = ((size_t)R * K * 4 + 127) / 128 * 128;
+        const size_t rawz = (((size_t)R * N * 4 + 127) / 128 * 128) * (fused_dz ? 2 : 1), rawp = ((size_t)R * K * 4 + 127) / 128 * 128;
         const size_t fixed = 1024 + 2 * op + 128;
         for (stages = WG_MAX_STAGES; stages >= 2; --stages)
             if (fixed + stages * (rawz + rawp) <= limit) return fixed + stages * (rawz + rawp);
     }
     R = 8; stages = 2;
-    return limit;
+    return limit + 1;        // does not fit
 }
 
 static size_t rows_gemm_smem(int N, int NP) {
     const size_t operands = 32768 + (size_t)NP * 256, otile = (size_t)128 * N * 4;
     return 1024 + (operands > otile ? operands : otile) + 64;
+}
+
+static bool rows_ws_fits(int K, int N, int passes) {
+    const int NP = ((N + 15) / 16) * 16, nchunks = (K + 31) / 32;
+    const size_t ws_smem = 1024 + (size_t)nchunks * NP * 128 * (passes == 3 ? 2 : 1) + 65536 + (size_t)4 * NP * 8 + 128;
+    return ws_smem <= 227 * 1024 && N <= 256;
 }
 
 // stats_kind: 0 none, 1 one statistics group over the whole batch (BN), 2 per-query groups (BN2).
@@ -729,6 +754,7 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
         if (!grads->weight[l] || !grads->bias[l]) { set_error("ffnet_backward: layer %d grad buffers NULL", l); return PTRB200_ERR_INVALID; }
         const float* Z = reinterpret_cast<const float*>(ws + lp.z_off);
         const float* dZ = dA;
+        bool fuse_dz = false;
         NormRef nr = norm_ref(net, p, l, ws);
         const size_t total = p.rows * lp.d_out;
         dim3 sgrid(p.G, p.S_stat);
@@ -745,7 +771,20 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
                 if (net->norm == PTRB200_NORM_BN) { if (net->norm_affine) { dg = grads->gamma[l]; db = grads->beta[l]; } }
                 else { dg = grads->gamma[l]; db = grads->beta[l]; if (net->norm_affine) { dw = grads->aff_w[l]; dbw = grads->aff_b[l]; } }
                 PTRB200_LAUNCH(norm_param_grad_kernel, (lp.d_out + 127) / 128, 128, 0, st, nr, (const float*)T1, (const float*)T2, dg, db, dw, dbw, lp.d_out);
-                if (lp.d_out % 4 == 0) PTRB200_LAUNCH(norm_bwd_apply4_kernel, elementwise_blocks(total / 4), 256, 0, st, Z, dY, nr, (const float*)S1, (const float*)S2, total / 4, lp.d_out, p.gr);
+                // fold dZ = a*rstd*(dY - S1/N - xhat*S2/N) into the operand staging of dgrad and wgrad when both can take it
+                // (saves one 12-bytes-per-element pass); otherwise materialise dZ in place
+                {
+                    int Rf = 32, stf = 0;
+                    const int KPl = ((lp.d_in + 15) / 16) * 16;
+                    fuse_dz = lp.d_out % 4 == 0 && lp.d_out <= 128 && (l == 0 || rows_ws_fits(lp.d_out, lp.d_in, p.passes)) &&
+                              wgrad_smem(lp.d_out, lp.d_in, KPl, Rf, p.passes, stf, true, 32) <= (size_t)227 * 1024;
+                }
+                if (fuse_dz) {
+                    const int cnt = p.G * lp.d_out;
+                    PTRB200_LAUNCH(dz_coeff_kernel, (cnt + 255) / 256, 256, 0, st, nr, (const float*)S1, (const float*)S2,
+                                   reinterpret_cast<float*>(ws + p.k1_off), reinterpret_cast<float*>(ws + p.k3_off), reinterpret_cast<float*>(ws + p.k0_off),
+                                   p.G, lp.d_out, p.gr);
+                } else if (lp.d_out % 4 == 0) PTRB200_LAUNCH(norm_bwd_apply4_kernel, elementwise_blocks(total / 4), 256, 0, st, Z, dY, nr, (const float*)S1, (const float*)S2, total / 4, lp.d_out, p.gr);
                 else PTRB200_LAUNCH(norm_bwd_apply_kernel, elementwise_blocks(total), 256, 0, st, Z, dY, nr, (const float*)S1, (const float*)S2, total, lp.d_out, p.gr);
                 // A Linear bias feeding a normalisation has an exactly-zero gradient (the norm removes every
                 // per-channel shift); the reference's autograd produces rounding noise there.
@@ -775,7 +814,11 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
             w.rows = (int)p.rows; w.K = lp.d_in; w.N = lp.d_out;
             w.KP = ((lp.d_in + 15) / 16) * 16;
             w.tile_rows = p.wg_rows;
-            const size_t smem = wgrad_smem(w.N, w.K, w.KP, w.tile_rows, p.passes, w.stages);
+            if (fuse_dz) {
+                w.Z2 = Z; w.gr_cur = p.gr;
+                w.kc1 = reinterpret_cast<const float*>(ws + p.k1_off); w.kc3 = reinterpret_cast<const float*>(ws + p.k3_off); w.kc0 = reinterpret_cast<const float*>(ws + p.k0_off);
+            }
+            const size_t smem = wgrad_smem(w.N, w.K, w.KP, w.tile_rows, p.passes, w.stages, fuse_dz, fuse_dz ? 32 : 8);
             const int grid = 148;                        // persistent: one CTA per SM, fed by the TMA ring
             if (p.passes == 3) { if ((rc = opt_in_smem(wgrad_tc_kernel<3>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<3>, grid, WG_THREADS, smem, st, w); }
             else { if ((rc = opt_in_smem(wgrad_tc_kernel<1>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<1>, grid, WG_THREADS, smem, st, w); }
@@ -793,6 +836,10 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
                 PTRB200_LAUNCH(pack_b_image_kernel<true>, (nch * NPl * 8 + 255) / 256, 256, 0, st, net->weight[l], lp.d_out, lp.d_in, ih, il, lp.d_in, NPl, lp.d_out, nch);
                 RowsGemmArgs g{};
                 g.P = dZ; g.scale = g.shift = nullptr; g.act = PTRB200_AF_NONE; g.gr_prev = (int)p.rows;
+                if (fuse_dz) {
+                    g.P2 = Z; g.gr_cur = p.gr;
+                    g.kc1 = reinterpret_cast<const float*>(ws + p.k1_off); g.kc3 = reinterpret_cast<const float*>(ws + p.k3_off); g.kc0 = reinterpret_cast<const float*>(ws + p.k0_off);
+                }
                 g.drop = make_drop(layer_drop, seed, offset * 64 + (uint64_t)l);
                 g.b_img_hi = ih; g.b_img_lo = il; g.bias = nullptr; g.Out = dIn; g.partials = nullptr;
                 g.rows = (int)p.rows; g.K = lp.d_out; g.N = lp.d_in;

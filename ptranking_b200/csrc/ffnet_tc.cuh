@@ -25,6 +25,11 @@ struct RowsGemmArgs {
     int act;               // PTRB200_AF_* applied after scale/shift (AF_NONE = identity)
     int gr_prev;           // rows per statistics group of P's normalisation
     DropCfg drop;          // dropout stream: FWD masks A elements (row*K+k), DGRAD masks outputs (row*N+n)
+    // DGRAD with the normalisation backward folded in: A = k1*P + k3*P2 + k0 (P = dY, P2 = Z of this layer,
+    // coefficients per (statistics group, column) from dz_coeff_kernel).  P2 == NULL: A = P.
+    const float* P2;
+    const float *kc1, *kc3, *kc0;
+    int gr_cur;            // rows per statistics group of kc*
     // B side: pre-split, pre-swizzled operand images written by pack_b_image_kernel:
     // chunk c of the image = [NP rows x 128 B] in the exact shared-memory layout (one bulk copy each)
     const unsigned char* b_img_hi;
@@ -436,20 +441,23 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rows_gemm_ws_kernel(RowsGemmArg
         const int total_q = my_tiles * nchunks;
         const bool has_coef = g.scale != nullptr;
         const bool per_group = has_coef && g.gr_prev < g.rows;
-        float4 pre[2];
-        const float* src[2];                                        // P + row * K + j4 for the tile being fetched
+        const bool fused_dz = MODE == RG_DGRAD && g.P2 != nullptr;
+        float4 pre[2], pre2[2];
+        size_t soff[2];                                             // row * K + j4 for the tile being fetched
         bool ok[2];
-        auto point = [&](int it) {                                  // set src/ok for tile `it`
+        auto point = [&](int it) {                                  // set soff/ok for tile `it`
             int r0, nr;
             rw_tile(g, blockIdx.x + it * gridDim.x, r0, nr);
 #pragma unroll
-            for (int i = 0; i < 2; ++i) { ok[i] = r_[i] < nr; src[i] = g.P + (size_t)(r0 + min(r_[i], nr - 1)) * K + j4; }
+            for (int i = 0; i < 2; ++i) { ok[i] = r_[i] < nr; soff[i] = (size_t)(r0 + min(r_[i], nr - 1)) * K + j4; }
         };
         auto fetch = [&](int c) {
             const bool kv = c * 32 + j4 < K;
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
-                pre[i] = (ok[i] && kv) ? __ldg(reinterpret_cast<const float4*>(src[i] + c * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < 2; ++i) {
+                pre[i] = (ok[i] && kv) ? __ldg(reinterpret_cast<const float4*>(g.P + soff[i] + c * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (MODE == RG_DGRAD) pre2[i] = (fused_dz && ok[i] && kv) ? __ldg(reinterpret_cast<const float4*>(g.P2 + soff[i] + c * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         };
         if (total_q > 0) { point(0); fetch(0); }
         int q = 0;
@@ -461,6 +469,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rows_gemm_ws_kernel(RowsGemmArg
             float* aout[2];
             const float* sc[2];
             const float* sh[2];
+            size_t kco[2];
             uint64_t dq[2];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
@@ -470,11 +479,13 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rows_gemm_ws_kernel(RowsGemmArg
                 const size_t co = per_group ? (size_t)((row0 + min(r_[i], nrows - 1)) / g.gr_prev) * K + j4 : (size_t)j4;
                 sc[i] = has_coef ? g.scale + co : nullptr;
                 sh[i] = has_coef ? g.shift + co : nullptr;
+                kco[i] = (fused_dz && g.gr_cur < g.rows) ? (size_t)((row0 + min(r_[i], nrows - 1)) / g.gr_cur) * K + j4 : (size_t)j4;
                 dq[i] = (uint64_t)e0 >> 2;
             }
             for (int c = 0; c < nchunks; ++c, ++q) {
                 const int s = q & 1;
                 const float4 cur[2] = {pre[0], pre[1]};
+                const float4 cur2[2] = {pre2[0], pre2[1]};
                 if (q + 1 < total_q) {                              // prefetch the next chunk (possibly of the next tile)
                     if (c + 1 < nchunks) fetch(c + 1); else { point(it + 1); fetch(0); }
                 }
@@ -485,6 +496,14 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rows_gemm_ws_kernel(RowsGemmArg
                 for (int i = 0; i < 2; ++i) {
                     float4 v = cur[i];
                     if (live[i] && kv) {
+                        if (MODE == RG_DGRAD && fused_dz) {           // dZ = k1*dY + k3*Z + k0
+                            const float4 a1 = __ldg(reinterpret_cast<const float4*>(g.kc1 + kco[i] + c * 32));
+                            const float4 a3 = __ldg(reinterpret_cast<const float4*>(g.kc3 + kco[i] + c * 32));
+                            const float4 a0 = __ldg(reinterpret_cast<const float4*>(g.kc0 + kco[i] + c * 32));
+                            const float4 z = cur2[i];
+                            v.x = fmaf(a1.x, v.x, fmaf(a3.x, z.x, a0.x)); v.y = fmaf(a1.y, v.y, fmaf(a3.y, z.y, a0.y));
+                            v.z = fmaf(a1.z, v.z, fmaf(a3.z, z.z, a0.z)); v.w = fmaf(a1.w, v.w, fmaf(a3.w, z.w, a0.w));
+                        }
                         if (has_coef) {
                             const float4 a = __ldg(reinterpret_cast<const float4*>(sc[i] + c * 32));
                             const float4 b = __ldg(reinterpret_cast<const float4*>(sh[i] + c * 32));
@@ -616,6 +635,10 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rows_gemm_ws_kernel(RowsGemmArg
 // Persistent CTAs accumulate their row tiles in TMEM and write one partial per CTA.
 // --------------------------------------------------------------------------------------------
 struct WgradArgs {
+    // normalisation backward folded in (Z2 != NULL): dZ = k1*dZ_in + k3*Z2 + k0 per (group, column); dZ_in then holds dY
+    const float* Z2;       // [rows, N] pre-activation of this layer, or NULL
+    const float *kc1, *kc3, *kc0;
+    int gr_cur;
     const float* dZ;       // [rows, N]
     const float* P;        // [rows, K]
     const float* scale;    // [Gp, K] or NULL
@@ -647,7 +670,9 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
     const int p_chunks = (g.KP + 31) / 32;
     const int chunk_bytes = R * 128;
     const int op_bytes = (z_chunks + p_chunks) * chunk_bytes * (PASSES == 3 ? 2 : 1);
-    const int rawz_bytes = ((R * g.N * 4 + 127) / 128) * 128, rawp_bytes = ((R * g.K * 4 + 127) / 128) * 128;
+    const bool fused_dz = g.Z2 != nullptr;
+    const int rawz1 = ((R * g.N * 4 + 127) / 128) * 128;
+    const int rawz_bytes = rawz1 * (fused_dz ? 2 : 1), rawp_bytes = ((R * g.K * 4 + 127) / 128) * 128;   // [dY | Z2] then the layer input
     const int stages = g.stages;
     unsigned char* opbuf = base;                             // [2][op_bytes]
     unsigned char* rawbuf = opbuf + 2 * op_bytes;            // [stages][rawz + rawp]
@@ -685,8 +710,9 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
                 const uint32_t zb = (uint32_t)nrows * g.N * 4, pb = (uint32_t)nrows * g.K * 4;
                 unsigned char* rz = rawbuf + s * (rawz_bytes + rawp_bytes);
                 if ((zb & 15) == 0) {
-                    tc::mbar_expect_tx(full + s, zb + pb);
+                    tc::mbar_expect_tx(full + s, (fused_dz ? 2 * zb : zb) + pb);
                     tc::bulk_g2s(rz, g.dZ + (size_t)row0 * g.N, zb, full + s);
+                    if (fused_dz) tc::bulk_g2s(rz + rawz1, g.Z2 + (size_t)row0 * g.N, zb, full + s);
                 } else {
                     tc::mbar_expect_tx(full + s, pb);             // odd-sized dZ tail tile: producers copy it by hand
                 }
@@ -768,6 +794,15 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
                     if (row_ok && n < g.N) {
                         if (vec_z) v = *reinterpret_cast<const float4*>(zsrc + ch * 32);
                         else { const float* p = zsrc + ch * 32; v.x = p[0]; if (n + 1 < g.N) v.y = p[1]; if (n + 2 < g.N) v.z = p[2]; if (n + 3 < g.N) v.w = p[3]; }
+                        if (fused_dz) {                            // host guarantees N % 4 == 0 here
+                            const float4 z = *reinterpret_cast<const float4*>(zsrc + rawz1 / 4 + ch * 32);
+                            const size_t co = (g.gr_cur < g.rows ? (size_t)((row0 + r) / g.gr_cur) * g.N : 0) + n;
+                            const float4 a1 = __ldg(reinterpret_cast<const float4*>(g.kc1 + co));
+                            const float4 a3 = __ldg(reinterpret_cast<const float4*>(g.kc3 + co));
+                            const float4 a0 = __ldg(reinterpret_cast<const float4*>(g.kc0 + co));
+                            v.x = fmaf(a1.x, v.x, fmaf(a3.x, z.x, a0.x)); v.y = fmaf(a1.y, v.y, fmaf(a3.y, z.y, a0.y));
+                            v.z = fmaf(a1.z, v.z, fmaf(a3.z, z.z, a0.z)); v.w = fmaf(a1.w, v.w, fmaf(a3.w, z.w, a0.w));
+                        }
                     }
                     store_split(z_hi + ch * chunk_bytes, z_lo + ch * chunk_bytes, 0, v, PASSES == 3);
                 }

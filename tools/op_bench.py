@@ -1,0 +1,101 @@
+"""Per-op timings at BASELINE.json's config sizes (CUDA events, warm, 20 iterations) -> profiles/<tag>_op_table.md.
+Not the headline bench: explains it (loss-only throughput, scorer forward/backward, metric kernel)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import bench
+import ptranking_b200
+from ptranking_b200 import ops, LABEL_TYPE
+
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+dev = "cuda:0"
+rng = np.random.default_rng(137)
+rows = []
+
+
+def timeit(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def labels(B, n):
+    y = rng.choice(5, size=(B, n), p=bench.MSLR_P).astype(np.float32)
+    y[:, 0] = np.maximum(y[:, 0], 1)
+    return torch.from_numpy(-np.sort(-y, axis=1)).to(dev)
+
+
+HBM = bench.measured_peaks()["hbm_gbs"]
+for name, params, shapes in [
+    ("LambdaRank", dict(sigma=1.0), [(1024, 256), (256, 1024), (4096, 32)]),
+    ("RankNet", dict(sigma=1.0), [(1024, 256)]),
+    ("LambdaLoss", dict(k=5, sigma=1.0, mu=5.0, loss_type="NDCG_Loss2++"), [(1024, 256), (256, 1024)]),
+    ("LambdaLoss", dict(k=1024, sigma=1.0, mu=5.0, loss_type="NDCG_Loss2++"), [(256, 1024)]),
+    ("ListNet", {}, [(1024, 256), (256, 1024)]),
+    ("ListMLE", {}, [(4096, 32), (1024, 256), (256, 1024)]),
+    ("ApproxNDCG", dict(alpha=10.0), [(1024, 256), (512, 512)]),
+]:
+    for (B, n) in shapes:
+        s = torch.sigmoid(torch.randn(B, n, device=dev))
+        y = labels(B, n)
+        kw = dict(params)
+        if name == "ListMLE":
+            kw["perm"] = ops.shuffle_ties_perm(y, seed=1, offset=1)
+        ms = timeit(lambda: ops.rank_loss_and_grad(name, s, y, **kw))
+        algo = (16 if name == "ListMLE" else 12) * n * B
+        rows.append((f"{name} {params.get('loss_type', '')} {('k=%d' % params['k']) if 'k' in params else ''}".strip(), f"B={B} n={n}",
+                     ms, B / ms * 1e3, algo / ms / 1e6, algo / ms / 1e6 / HBM))
+# ndcg / all metrics
+for (B, n) in [(1024, 256), (256, 1024)]:
+    s = torch.randn(B, n, device=dev); y = labels(B, n)
+    ms = timeit(lambda: ops.adhoc_metrics_at_ks(s, y, [1, 3, 5, 10, 20, 50], presort=True, max_label=4.0))
+    rows.append(("nDCG+nERR+AP+P @6 cutoffs", f"B={B} n={n}", ms, B / ms * 1e3, 8 * n * B / ms / 1e6, 8 * n * B / ms / 1e6 / HBM))
+
+# scorer forward / forward+backward (default pointsf) and full step
+sf = bench.default_sf()
+r = ptranking_b200.LambdaRank(sf_para_dict=sf, model_para_dict=dict(model_id="LambdaRank", sigma=1.0), gpu=True, device=dev)
+r.init(); r.train_mode()
+for (B, n) in [(1024, 256), (256, 1024), (4096, 32)]:
+    X, y = bench.synth_batch(rng, B, n)
+    X, y = X.to(dev), y.to(dev)
+    with torch.no_grad():
+        ms_f = timeit(lambda: r.forward(X))
+    ms_s = timeit(lambda: r.train_op(X, y, presort=True, label_type=LABEL_TYPE.MultiLabel, epoch_k=1))
+    algo = n * B * (136 * 4 + 8)
+    rows.append(("pointsf forward (5x100 GELU BN)", f"B={B} n={n}", ms_f, B / ms_f * 1e3, algo / ms_f / 1e6, algo / ms_f / 1e6 / HBM))
+    rows.append(("LambdaRank train step (fwd+loss+bwd+Adam)", f"B={B} n={n}", ms_s, B / ms_s * 1e3, algo / ms_s / 1e6, algo / ms_s / 1e6 / HBM))
+
+# list scorer (DASALC, 2 heads) forward + step, config (c) shape
+for L in (3, 6):
+    sfl = dict(sf_id="listsf", opt="Adagrad", lr=1e-3,
+               listsf=dict(num_features=136, ff_dims=[128, 256, 512], AF="R", TL_AF="GE", apply_tl_af=False, BN=False, bn_type="BN2",
+                           bn_affine=False, n_heads=2, encoder_layers=L, encoder_type="DASALC"))
+    rl = ptranking_b200.ApproxNDCG(sf_para_dict=sfl, model_para_dict=dict(model_id="ApproxNDCG", alpha=10.0), gpu=True, device=dev)
+    rl.init(); rl.train_mode()
+    B, n = 64, 512
+    X, y = bench.synth_batch(rng, B, n)
+    X, y = X.to(dev), y.to(dev)
+    ms_s = timeit(lambda: rl.train_op(X, y, presort=True, label_type=LABEL_TYPE.MultiLabel, epoch_k=1), iters=5, warm=2)
+    flops = 3 * n * (865280 + L * (147968 + 4 * n * 136)) * B
+    rows.append((f"ApproxNDCG + listsf DASALC L={L} train step", f"B={B} n={n}", ms_s, B / ms_s * 1e3, flops / ms_s / 1e9, float('nan')))
+
+os.makedirs("profiles", exist_ok=True)
+with open(f"profiles/{tag}_op_table.md", "w") as f:
+    f.write(f"# {tag}: per-op timings on one B200 (CUDA events, 20 warm iterations; `tools/op_bench.py`)\n\n")
+    f.write("GB/s = ALGORITHMIC bytes (12n per query for a loss, n(4F+8) for the scorer) / time; frac = of the measured copy bandwidth "
+            f"({HBM:.0f} GB/s).  For the list scorer the last-but-one column is GFLOP/s (algorithmic fwd+bwd FLOPs).\n\n")
+    f.write("| op | shape | ms | queries/s | GB/s (GFLOP/s) | frac of HBM |\n|---|---|---|---|---|---|\n")
+    for name, shape, ms, qps, gbs, frac in rows:
+        f.write(f"| {name} | {shape} | {ms:.4f} | {qps:,.0f} | {gbs:,.1f} | {frac:.4f} |\n")
+print(open(f"profiles/{tag}_op_table.md").read())
