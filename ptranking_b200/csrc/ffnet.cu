@@ -222,7 +222,11 @@ __global__ void colstat4_kernel(const float* __restrict__ Z, const float* __rest
             if (nr.mean) { mu[e] = nr.mean[(size_t)g * C + c + e]; rs[e] = nr.rstd[(size_t)g * C + c + e]; }
         }
     }
+    // per-thread partial sums run in fp32 over <= 32 rows at a time and are flushed into float64 accumulators,
+    // which keeps FP64 work and register pressure out of the streaming loop at no loss of accuracy that matters
     double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    float f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4] = {0.f, 0.f, 0.f, 0.f};
+    int since_flush = 0;
     for (int r = r0 + ry; r < r1; r += RY) {
         const size_t off = ((size_t)g * gr + r) * C + c;
         const float4 z4 = __ldg(reinterpret_cast<const float4*>(Z + off));
@@ -232,7 +236,7 @@ __global__ void colstat4_kernel(const float* __restrict__ Z, const float* __rest
             for (int e = 0; e < 4; ++e) { s1[e] += (double)z[e]; s2[e] += (double)z[e] * (double)z[e]; }
         } else if (WHAT == STAT_COLSUM) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) s1[e] += (double)z[e];
+            for (int e = 0; e < 4; ++e) f1[e] += z[e];
         } else {
             const float4 d4 = __ldg(reinterpret_cast<const float4*>(dA + off));
             const float d[4] = {d4.x, d4.y, d4.z, d4.w};
@@ -242,10 +246,19 @@ __global__ void colstat4_kernel(const float* __restrict__ Z, const float* __rest
                 const float xh = nr.mean ? (z[e] - mu[e]) * rs[e] : z[e];
                 const float dy = d[e] * activate(nr.act, a[e] * xh + cc[e]).dy;
                 o[e] = dy;
-                s1[e] += (double)dy; s2[e] += (double)dy * (double)xh;
+                f1[e] += dy; f2[e] = fmaf(dy, xh, f2[e]);
             }
             *reinterpret_cast<float4*>(dY_out + off) = make_float4(o[0], o[1], o[2], o[3]);
         }
+        if (WHAT != STAT_MOMENTS && ++since_flush == 32) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { s1[e] += (double)f1[e]; s2[e] += (double)f2[e]; f1[e] = 0.f; f2[e] = 0.f; }
+            since_flush = 0;
+        }
+    }
+    if (WHAT != STAT_MOMENTS) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { s1[e] += (double)f1[e]; s2[e] += (double)f2[e]; }
     }
     double* mine = sh4 + ((size_t)ry * Q + q) * 8;
 #pragma unroll
@@ -584,6 +597,27 @@ static int elementwise_blocks(size_t total) {
 }
 
 
+// data gradient of a Linear with a single output: dIn[r,k] = dropmask(dz[r] * W[0,k])  (the scorer's last layer)
+__global__ void dgrad_rank1_kernel(const float* __restrict__ dz, const float* __restrict__ W, float* __restrict__ dIn,
+                                   size_t units, int K, DropCfg drop) {
+    const int Q = K >> 2;
+    for (size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (size_t)gridDim.x * blockDim.x) {
+        const size_t row = u / Q;
+        const int k = (int)(u % Q) * 4;
+        const float d = __ldg(dz + row);
+        const float4 w = __ldg(reinterpret_cast<const float4*>(W + k));
+        float4 v = make_float4(d * w.x, d * w.y, d * w.z, d * w.w);
+        if (drop.thr) {
+            const uint64_t dd = dropout_draw4(drop.key, (row * K + k) >> 2);
+            v.x = ((uint32_t)(dd) & 0xffffu) >= drop.thr ? v.x * drop.scale : 0.0f;
+            v.y = ((uint32_t)(dd >> 16) & 0xffffu) >= drop.thr ? v.y * drop.scale : 0.0f;
+            v.z = ((uint32_t)(dd >> 32) & 0xffffu) >= drop.thr ? v.z * drop.scale : 0.0f;
+            v.w = ((uint32_t)(dd >> 48)) >= drop.thr ? v.w * drop.scale : 0.0f;
+        }
+        reinterpret_cast<float4*>(dIn)[u] = v;
+    }
+}
+
 // ------------------------------------------------------------------ tensor-core host paths
 __global__ void transpose_kernel(const float* __restrict__ W, float* __restrict__ Wt, int rows, int cols) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;       // Wt[c][r] = W[r][c]
@@ -845,6 +879,10 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
                 g.rows = (int)p.rows; g.K = lp.d_out; g.N = lp.d_in;
                 g.tile_rows = 128; g.seg_len = 128; g.group_rows = 0; g.tiles_per_group = 0;
                 if ((rc = launch_rows_gemm(RG_DGRAD, p.passes, g, (int)((p.rows + 127) / 128), st))) return rc;
+            } else if (lp.d_out == 1 && lp.d_in % 4 == 0) {
+                const size_t units = p.rows * (lp.d_in / 4);
+                PTRB200_LAUNCH(dgrad_rank1_kernel, elementwise_blocks(units), 256, 0, st, dZ, net->weight[l], dIn, units, lp.d_in,
+                               make_drop(layer_drop, seed, offset * 64 + (uint64_t)l));
             } else {
                 GemmArgs g{};
                 g.A = dZ; g.Bm = net->weight[l]; g.C = dIn;
