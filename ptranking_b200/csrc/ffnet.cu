@@ -485,6 +485,18 @@ struct Plan {
     size_t partials_off, s1_off, s2_off, t1_off, t2_off, dbuf0_off, dbuf1_off, wpart_off, k1_off, k3_off, k0_off, total;
 };
 
+// column blocking of the weight gradient: dZ columns in blocks of 128 (MMA M), input columns in blocks of <= 256 (MMA N)
+struct WgBlocks { int mblocks, kb, kblocks, gx; };
+static WgBlocks wgrad_blocks(int N, int K) {
+    WgBlocks b;
+    b.mblocks = (N + 127) / 128;
+    b.kb = K <= 256 ? K : 256;
+    b.kblocks = (K + b.kb - 1) / b.kb;
+    const int pairs = b.mblocks * b.kblocks;
+    b.gx = pairs == 1 ? 148 : (148 / pairs < 8 ? 8 : 148 / pairs);
+    return b;
+}
+
 static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p) {
     if (!net || B <= 0 || n <= 0) { set_error("ffnet: null net or non-positive B/n"); return PTRB200_ERR_INVALID; }
     if (net->num_linear < 1 || net->num_linear > PTRB200_MAX_FF_LAYERS) { set_error("ffnet: num_linear=%d outside 1..%d", net->num_linear, PTRB200_MAX_FF_LAYERS); return PTRB200_ERR_INVALID; }
@@ -499,8 +511,8 @@ static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p) {
     p.passes = net->math_mode == PTRB200_MATH_TF32 ? 1 : 3;
     for (int l = 0; l < net->num_linear && p.use_tc; ++l) {
         const int di = net->dims[l], dn = net->dims[l + 1];
-        // float4 row access needs widths % 4; one MMA N-tile holds <= 256 columns
-        if (di % 4 != 0 || di > 256 || dn > 256 || (dn % 4 != 0 && dn > 4)) p.use_tc = false;
+        // float4 row access needs widths % 4; wider layers are tiled over output columns / weight-gradient blocks
+        if (di % 4 != 0 || di > 1024 || dn > 1024 || (dn % 4 != 0 && dn > 4)) p.use_tc = false;
     }
     // statistics slices: one CTA per (group, slice); aim for ~4 CTAs per SM when there is a single group
     if (p.G == 1) { p.slice_rows = 512; p.S_stat = (int)((p.rows + 511) / 512); if (p.S_stat > 1024) { p.S_stat = 1024; p.slice_rows = (int)((p.rows + 1023) / 1024); p.S_stat = (int)((p.rows + p.slice_rows - 1) / p.slice_rows); } }
@@ -556,7 +568,15 @@ static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p) {
     p.k0_off = off; off = align_up(off + (size_t)p.G * maxd * 4, 256);
     p.dbuf0_off = off; off = align_up(off + p.rows * maxd * 4, 256);
     p.dbuf1_off = off; off = align_up(off + p.rows * maxd * 4, 256);
-    p.wpart_off = off; off = align_up(off + (size_t)(p.use_tc ? (p.wg_grid > p.S_w ? p.wg_grid : p.S_w) : p.S_w) * maxw * 4, 256);
+    {
+        size_t wbytes = (size_t)p.S_w * maxw * 4;
+        if (p.use_tc) for (int l = 0; l < p.L; ++l) {
+            const WgBlocks wb = wgrad_blocks(p.layer[l].d_out, p.layer[l].d_in);
+            const size_t need = (size_t)wb.gx * p.layer[l].d_in * p.layer[l].d_out * 4;
+            wbytes = need > wbytes ? need : wbytes;
+        }
+        p.wpart_off = off; off = align_up(off + wbytes, 256);
+    }
     p.total = off;
     return PTRB200_OK;
 }
@@ -696,13 +716,18 @@ static int launch_rows_gemm(int mode, int passes, RowsGemmArgs& g, int ntiles, c
         return PTRB200_ERR_INVALID;
     }
     if (S_out) *S_out = S_default;
-    const size_t operands = 32768 + (size_t)g.NP * 256, otile = (size_t)128 * g.N * 4;
+    // one-tile-per-CTA kernel; output columns are tiled (144 per CTA) when the layer is wider than one MMA tile likes
+    g.n_tile = g.N <= 144 ? g.N : 144;
+    const int n_tiles = (g.N + g.n_tile - 1) / g.n_tile;
+    const int NPt = ((g.n_tile + 15) / 16) * 16;
+    const size_t operands = 32768 + (size_t)NPt * 256, otile = (size_t)128 * g.n_tile * 4;
     g.tail_off = (int)(((operands > otile ? operands : otile) + 15) / 16 * 16);
-    const size_t smem = rows_gemm_smem(g.N, g.NP);
+    const size_t smem = 1024 + (size_t)g.tail_off + 64;
+    const dim3 rg_grid(ntiles, n_tiles);
 #define RG_CASE(M, P, TAG)                                                                      \
     if (mode == M && passes == P) {                                                             \
         if ((rc = opt_in_smem(rows_gemm_tc_kernel<M, P>, smem))) return rc;                     \
-        PTRB200_LAUNCH_TAG(TAG, (rows_gemm_tc_kernel<M, P>), ntiles, RG_THREADS, smem, st, g);  \
+        PTRB200_LAUNCH_TAG(TAG, (rows_gemm_tc_kernel<M, P>), rg_grid, RG_THREADS, smem, st, g); \
         return PTRB200_OK;                                                                      \
     }
     RG_CASE(RG_FWD, 3, "rows_gemm_tc_fwd")
@@ -810,7 +835,7 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
                 {
                     int Rf = 32, stf = 0;
                     const int KPl = ((lp.d_in + 15) / 16) * 16;
-                    fuse_dz = lp.d_out % 4 == 0 && lp.d_out <= 128 && (l == 0 || rows_ws_fits(lp.d_out, lp.d_in, p.passes)) &&
+                    fuse_dz = lp.d_out % 4 == 0 && lp.d_out <= 128 && lp.d_in <= 256 && (l == 0 || rows_ws_fits(lp.d_out, lp.d_in, p.passes)) &&
                               wgrad_smem(lp.d_out, lp.d_in, KPl, Rf, p.passes, stf, true, 32) <= (size_t)227 * 1024;
                 }
                 if (fuse_dz) {
@@ -845,25 +870,27 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
             }
             w.gr_prev = p.gr;
             w.partials = wpart;
-            w.rows = (int)p.rows; w.K = lp.d_in; w.N = lp.d_out;
-            w.KP = ((lp.d_in + 15) / 16) * 16;
+            const WgBlocks wb = wgrad_blocks(lp.d_out, lp.d_in);
+            w.rows = (int)p.rows; w.N_full = lp.d_out; w.K_full = lp.d_in; w.kb = wb.kb;
+            w.N = lp.d_out < 128 ? lp.d_out : 128; w.K = wb.kb;       // block maxima (buffer geometry)
+            w.KP = ((w.K + 15) / 16) * 16;
             w.tile_rows = p.wg_rows;
             if (fuse_dz) {
                 w.Z2 = Z; w.gr_cur = p.gr;
                 w.kc1 = reinterpret_cast<const float*>(ws + p.k1_off); w.kc3 = reinterpret_cast<const float*>(ws + p.k3_off); w.kc0 = reinterpret_cast<const float*>(ws + p.k0_off);
             }
             const size_t smem = wgrad_smem(w.N, w.K, w.KP, w.tile_rows, p.passes, w.stages, fuse_dz, fuse_dz ? 32 : 8);
-            const int grid = 148;                        // persistent: one CTA per SM, fed by the TMA ring
+            const dim3 grid(wb.gx, wb.mblocks, wb.kblocks);   // persistent CTAs per (dZ block, input block), fed by the TMA ring
             if (p.passes == 3) { if ((rc = opt_in_smem(wgrad_tc_kernel<3>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<3>, grid, WG_THREADS, smem, st, w); }
             else { if ((rc = opt_in_smem(wgrad_tc_kernel<1>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<1>, grid, WG_THREADS, smem, st, w); }
             const int cnt = lp.d_in * lp.d_out;
-            PTRB200_LAUNCH(reduce_splits_kernel, (cnt + 255) / 256, 256, 0, st, (const float*)wpart, grads->weight[l], grid, cnt);
+            PTRB200_LAUNCH(reduce_splits_kernel, (cnt + 255) / 256, 256, 0, st, (const float*)wpart, grads->weight[l], wb.gx, cnt);
         }
         // ---- dIn = dropmask(dZ * W) ----
         if (l > 0 || dX) {
             float* dIn = l == 0 ? dX : dbuf[flip];
             if (l > 0) flip ^= 1;
-            if (lp.d_out % 4 == 0 && lp.d_in <= 256) {
+            if (lp.d_out % 4 == 0) {
                 const int NPl = ((lp.d_in + 15) / 16) * 16, nch = (lp.d_out + 31) / 32;
                 unsigned char* ih = reinterpret_cast<unsigned char*>(ws + lp.img_d_hi);
                 unsigned char* il = p.passes == 3 ? reinterpret_cast<unsigned char*>(ws + lp.img_d_lo) : nullptr;
@@ -911,6 +938,7 @@ int ptrb200_tc_wgrad(const float* dZ, const float* P, float* dW, float* partials
     w.dZ = dZ; w.P = P; w.scale = w.shift = nullptr; w.act = PTRB200_AF_NONE; w.gr_prev = rows;
     w.drop = make_drop(0.0f, 0, 0); w.partials = partials;
     w.rows = rows; w.K = K; w.N = N; w.KP = ((K + 15) / 16) * 16; w.tile_rows = 32;
+    w.N_full = N; w.K_full = K; w.kb = K;
     const int grid = 296;
     const size_t smem = wgrad_smem(N, K, w.KP, w.tile_rows, passes, w.stages);
     int rc;

@@ -40,6 +40,7 @@ struct RowsGemmArgs {
     float* Out;            // [rows, N]
     double* partials;      // [slots, N, 2] column sum / sum of squares per statistics slot, or NULL
     int rows, K, N, NP;
+    int n_tile;            // one-tile-per-CTA kernel: output columns per CTA (gridDim.y tiles), multiple of 16; N when untiled
     int tail_off;          // byte offset of the mbarrier / TMEM slot behind max(operand buffers, output tile)
     // tile -> rows mapping
     int tile_rows;         // rows advanced per tile (<= 128)
@@ -123,7 +124,11 @@ template <int MODE, int PASSES>
 __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int NP = g.NP;
+    // output-column tile of this CTA (gridDim.y tiles of n_tile columns; the weight image is [NP_full rows] per chunk)
+    const int N_full = g.N, NP_full = g.NP;
+    const int n0 = blockIdx.y * g.n_tile;
+    const int N = min(g.n_tile, N_full - n0);
+    const int NP = ((N + 15) / 16) * 16;
     unsigned char* a_hi = base;                       // 128 rows x 128 B
     unsigned char* a_lo = a_hi + 16384;
     unsigned char* b_hi = a_lo + 16384;               // NP rows x 128 B
@@ -181,9 +186,10 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
         // ---- B: one TMA bulk copy per operand image chunk (no SM instructions beyond the issue) ----
         if (tid == 0) {
             const uint32_t bytes = (uint32_t)NP * 128u;
+            const size_t src = ((size_t)c * NP_full + n0) * 128u;       // rows [n0, n0+NP) of chunk c
             tc::mbar_expect_tx(bbar, PASSES == 3 ? 2 * bytes : bytes);
-            tc::bulk_g2s(b_hi, g.b_img_hi + (size_t)c * bytes, bytes, bbar);
-            if (PASSES == 3) tc::bulk_g2s(b_lo, g.b_img_lo + (size_t)c * bytes, bytes, bbar);
+            tc::bulk_g2s(b_hi, g.b_img_hi + src, bytes, bbar);
+            if (PASSES == 3) tc::bulk_g2s(b_lo, g.b_img_lo + src, bytes, bbar);
         }
         // ---- A: prologue + split + swizzled store ----
 #pragma unroll
@@ -192,7 +198,7 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
             float4 v = av[i];
             if (r < nrows && k < K) {
                 v = prologue4(g, v, row0 + r, k, MODE == RG_FWD, coef_off[i]);
-                if (MODE == RG_FWD && g.a_out) *reinterpret_cast<float4*>(g.a_out + (size_t)(row0 + r) * K + k) = v;
+                if (MODE == RG_FWD && g.a_out && blockIdx.y == 0) *reinterpret_cast<float4*>(g.a_out + (size_t)(row0 + r) * K + k) = v;
             } else v = make_float4(0.f, 0.f, 0.f, 0.f);
             store_split(a_hi, a_lo, tc::swz_offset(r, j), v, PASSES == 3);
         }
@@ -223,7 +229,6 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
     tc::fence_after_sync();
 
     // ---- epilogue: TMEM -> registers -> (+bias | dropout mask) -> smem tile [128][N] ----
-    const int N = g.N;
     {
         const int q = warp & 3, half = warp >> 2;                 // lane quarter, column half
         const int r = q * 32 + lane;
@@ -235,10 +240,10 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
             if (c0 < N) {
                 if (MODE == RG_FWD) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) if (c0 + e < N) v[e] += __ldg(g.bias + c0 + e);
+                    for (int e = 0; e < 8; ++e) if (c0 + e < N) v[e] += __ldg(g.bias + n0 + c0 + e);
                 } else if (g.drop.thr) {
-                    if ((N & 3) == 0) {                   // rows start on a draw boundary: 2 draws cover the 8 columns
-                        const uint64_t q = ((uint64_t)(row0 + r) * N + c0) >> 2;
+                    if ((N_full & 3) == 0) {              // rows start on a draw boundary: 2 draws cover the 8 columns
+                        const uint64_t q = ((uint64_t)(row0 + r) * N_full + n0 + c0) >> 2;
                         const uint64_t d0 = dropout_draw4(g.drop.key, q), d1 = dropout_draw4(g.drop.key, q + 1);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -248,7 +253,7 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
                     } else {
 #pragma unroll
                         for (int e = 0; e < 8; ++e)
-                            if (c0 + e < N) v[e] = dropout_keep(g.drop.key, (uint64_t)(row0 + r) * N + c0 + e, g.drop.thr) ? v[e] * g.drop.scale : 0.0f;
+                            if (c0 + e < N) v[e] = dropout_keep(g.drop.key, (uint64_t)(row0 + r) * N_full + n0 + c0 + e, g.drop.thr) ? v[e] * g.drop.scale : 0.0f;
                     }
                 }
                 float* dst = otile + (size_t)r * N + c0;
@@ -264,8 +269,8 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
     }
     tc::fence_before_sync();
     __syncthreads();
-    // ---- tile -> global: the tile's rows are contiguous in Out ----
-    {
+    // ---- tile -> global: contiguous when untiled, row segments of pitch N_full otherwise ----
+    if (N == N_full) {
         const size_t total = (size_t)nrows * N;
         float* dst = g.Out + (size_t)row0 * N;
         if ((N & 3) == 0) {
@@ -274,6 +279,12 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
             for (size_t i = tid; i < total / 4; i += RG_THREADS) d4[i] = s4[i];
         } else {
             for (size_t i = tid; i < total; i += RG_THREADS) dst[i] = otile[i];
+        }
+    } else {                                           // n0, N and N_full are multiples of 4 here (host guarantees)
+        const int q4 = N >> 2;
+        for (int i = tid; i < nrows * q4; i += RG_THREADS) {
+            const int r = i / q4, qq = i - r * q4;
+            *reinterpret_cast<float4*>(g.Out + (size_t)(row0 + r) * N_full + n0 + qq * 4) = *reinterpret_cast<const float4*>(otile + (size_t)r * N + qq * 4);
         }
     }
     // ---- per-segment column sums for the layer's normalisation (fixed order: deterministic) ----
@@ -287,7 +298,7 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
                     const float z = otile[(size_t)r * N + cidx];
                     s1 += (double)z; s2 += (double)z * (double)z;
                 }
-                double* p = g.partials + ((size_t)(slot0 + seg) * N + cidx) * 2;
+                double* p = g.partials + ((size_t)(slot0 + seg) * N_full + n0 + cidx) * 2;
                 p[0] = s1; p[1] = s2;
             }
         }
@@ -648,6 +659,8 @@ struct WgradArgs {
     float* partials;       // [gridDim.x, N, K]
     int rows, K, N;
     int KP;                // K rounded up to 16 (MMA N extent)
+    int N_full, K_full;    // full widths of dZ and of the layer input; N / K / KP above describe ONE block:
+    int kb;                // CTA (x, y, z) owns dZ columns [128*y, +N) and input columns [kb*z, +K)
     int tile_rows;         // R: rows per tile (multiple of 8, <= 32)
     int stages;            // raw-tile ring depth (2..WG_MAX_STAGES), chosen by the host to fit shared memory
 };
@@ -666,13 +679,18 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int R = g.tile_rows;
+    // column block of this CTA: dZ columns [m0, m0+N), layer-input columns [kk0, kk0+K)
+    const int m0 = blockIdx.y * 128, kk0 = blockIdx.z * g.kb;
+    const int N = min(128, g.N_full - m0), K = min(g.kb, g.K_full - kk0), KP = ((K + 15) / 16) * 16;
+    const int Nmax = min(128, g.N_full), Kmax = min(g.kb, g.K_full);       // buffer geometry is the same in every CTA
+    const bool blocked = gridDim.y > 1 || gridDim.z > 1;
     const int z_chunks = 4;                                  // dZ columns padded to 128 (MMA M = 128)
-    const int p_chunks = (g.KP + 31) / 32;
+    const int p_chunks = (((Kmax + 15) / 16) * 16 + 31) / 32;
     const int chunk_bytes = R * 128;
     const int op_bytes = (z_chunks + p_chunks) * chunk_bytes * (PASSES == 3 ? 2 : 1);
     const bool fused_dz = g.Z2 != nullptr;
-    const int rawz1 = ((R * g.N * 4 + 127) / 128) * 128;
-    const int rawz_bytes = rawz1 * (fused_dz ? 2 : 1), rawp_bytes = ((R * g.K * 4 + 127) / 128) * 128;   // [dY | Z2] then the layer input
+    const int rawz1 = ((R * Nmax * 4 + 127) / 128) * 128;
+    const int rawz_bytes = rawz1 * (fused_dz ? 2 : 1), rawp_bytes = ((R * Kmax * 4 + 127) / 128) * 128;   // [dY | Z2] then the layer input
     const int stages = g.stages;
     unsigned char* opbuf = base;                             // [2][op_bytes]
     unsigned char* rawbuf = opbuf + 2 * op_bytes;            // [stages][rawz + rawp]
@@ -683,7 +701,8 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
     uint32_t* slot = reinterpret_cast<uint32_t*>(opfree + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t tmem_cols = g.KP <= 32 ? 32 : g.KP <= 64 ? 64 : g.KP <= 128 ? 128 : 256;
+    const int KPmax = ((Kmax + 15) / 16) * 16;
+    const uint32_t tmem_cols = KPmax <= 32 ? 32 : KPmax <= 64 ? 64 : KPmax <= 128 ? 128 : 256;
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) tc::mbar_init(full + s, 1);
         for (int o = 0; o < 2; ++o) { tc::mbar_init(opready + o, WG_PRODUCERS / 32); tc::mbar_init(opfree + o, 1); }
@@ -696,37 +715,52 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
     const uint32_t tmem = *slot;
     const int ntiles = (g.rows + R - 1) / R;
     const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const bool z_aligned = ((R * g.N * 4) & 15) == 0;       // every full dZ tile is a whole number of 16-byte units
+    const bool z_aligned = ((R * N * 4) & 15) == 0;
 
     if (warp == WG_PRODUCERS / 32) {
         // ======================= control warp =======================
         // warp-uniform loop (descriptors in uniform registers); one elected lane issues TMA / MMA / commit
         {
-            const uint32_t idesc = tc::instr_desc(2, 128, g.KP) | (1u << 15) | (1u << 16);   // A and B MN-major
+            const uint32_t idesc = tc::instr_desc(2, 128, KP) | (1u << 15) | (1u << 16);   // A and B MN-major
             const bool leader = tc::elect_one();
+            // whole-warp call: un-blocked tiles are contiguous in HBM (one copy per operand, issued by the leader);
+            // column blocks are row segments, one pair of copies per row, issued by lane = row
             auto issue_load = [&](int it, int s) {
                 const int t = blockIdx.x + it * gridDim.x;
                 const int row0 = t * R, nrows = min(R, g.rows - row0);
-                const uint32_t zb = (uint32_t)nrows * g.N * 4, pb = (uint32_t)nrows * g.K * 4;
+                const uint32_t zb = (uint32_t)nrows * N * 4, pb = (uint32_t)nrows * K * 4;
                 unsigned char* rz = rawbuf + s * (rawz_bytes + rawp_bytes);
-                if ((zb & 15) == 0) {
-                    tc::mbar_expect_tx(full + s, (fused_dz ? 2 * zb : zb) + pb);
-                    tc::bulk_g2s(rz, g.dZ + (size_t)row0 * g.N, zb, full + s);
-                    if (fused_dz) tc::bulk_g2s(rz + rawz1, g.Z2 + (size_t)row0 * g.N, zb, full + s);
+                if (!blocked) {
+                    if (leader) {
+                        if ((zb & 15) == 0) {
+                            tc::mbar_expect_tx(full + s, (fused_dz ? 2 * zb : zb) + pb);
+                            tc::bulk_g2s(rz, g.dZ + (size_t)row0 * N, zb, full + s);
+                            if (fused_dz) tc::bulk_g2s(rz + rawz1, g.Z2 + (size_t)row0 * N, zb, full + s);
+                        } else {
+                            tc::mbar_expect_tx(full + s, pb);     // odd-sized dZ tail tile: producers copy it by hand
+                        }
+                        tc::bulk_g2s(rz + rawz_bytes, g.P + (size_t)row0 * K, pb, full + s);
+                    }
                 } else {
-                    tc::mbar_expect_tx(full + s, pb);             // odd-sized dZ tail tile: producers copy it by hand
+                    const bool z_bulk = (N & 3) == 0;            // a dZ row segment must be a multiple of 16 bytes for TMA
+                    if (leader) tc::mbar_expect_tx(full + s, (z_bulk ? zb : 0u) + pb);
+                    __syncwarp();
+                    if (lane < nrows) {
+                        if (z_bulk) tc::bulk_g2s(rz + (size_t)lane * N * 4, g.dZ + (size_t)(row0 + lane) * g.N_full + m0, (uint32_t)N * 4, full + s);
+                        tc::bulk_g2s(rz + rawz_bytes + (size_t)lane * K * 4, g.P + (size_t)(row0 + lane) * g.K_full + kk0, (uint32_t)K * 4, full + s);
+                    }
+                    __syncwarp();
                 }
-                tc::bulk_g2s(rz + rawz_bytes, g.P + (size_t)row0 * g.K, pb, full + s);
             };
             int s_load = 0;
-            for (int it = 0; it < min(stages, my_tiles); ++it) { if (leader) issue_load(it, s_load); s_load = s_load + 1 == stages ? 0 : s_load + 1; }
+            for (int it = 0; it < min(stages, my_tiles); ++it) { issue_load(it, s_load); s_load = s_load + 1 == stages ? 0 : s_load + 1; }
             int s_cons = 0, next_load = min(stages, my_tiles);
             const uint32_t op_base = tc::smem_u32(opbuf);
             for (int it = 0; it < my_tiles; ++it) {
                 const int o = it & 1;
                 const int t = blockIdx.x + it * gridDim.x, nrows = min(R, g.rows - t * R);
                 tc::mbar_wait(opready + o, (it >> 1) & 1);          // operands staged => raw slot s_cons drained too
-                if (next_load < my_tiles) { if (leader) issue_load(next_load, s_cons); ++next_load; }
+                if (next_load < my_tiles) { issue_load(next_load, s_cons); ++next_load; }
                 s_cons = s_cons + 1 == stages ? 0 : s_cons + 1;
                 tc::fence_after_sync();
                 const uint32_t zb_hi = op_base + o * op_bytes;
@@ -758,13 +792,13 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
     } else {
         // ======================= producer warps =======================
         RowsGemmArgs pg{};
-        pg.scale = g.scale; pg.shift = g.shift; pg.act = g.act; pg.gr_prev = g.gr_prev; pg.K = g.K; pg.drop = g.drop;
+        pg.scale = g.scale; pg.shift = g.shift; pg.act = g.act; pg.gr_prev = g.gr_prev; pg.K = g.K_full; pg.drop = g.drop;
         const bool plain_p = !g.scale && g.act == PTRB200_AF_NONE && !g.drop.thr;   // layer input already materialised
         const int r = tid >> 3, j = tid & 7;              // one 16-byte unit per thread per 32-column chunk (R*8 <= 256)
-        const bool vec_z = (g.N & 3) == 0;
+        const bool vec_z = (N & 3) == 0;
         const bool active = tid < R * 8;
         const uint32_t sw = tc::swz32_offset(r, j);       // this thread's slot inside every operand chunk
-        const int zoff = r * g.N + j * 4, poff = r * g.K + j * 4;
+        const int zoff = r * N + j * 4, poff = r * K + j * 4;
         int s = 0;
         for (int it = 0; it < my_tiles; ++it) {
             const int t = blockIdx.x + it * gridDim.x, o = it & 1;
@@ -779,8 +813,8 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
             const int fpar = (it / stages) & 1;
             s = s + 1 == stages ? 0 : s + 1;
             if (it >= 2) tc::mbar_wait(opfree + o, ((it - 2) >> 1) & 1);    // MMAs of tile it-2 are done with this buffer
-            if ((((uint32_t)nrows * g.N * 4) & 15) != 0) {                   // odd-sized dZ tail: copy by hand, producers only
-                for (int e = tid; e < nrows * g.N; e += WG_PRODUCERS) rz[e] = g.dZ[(size_t)row0 * g.N + e];
+            if (blocked ? (N & 3) != 0 : (((uint32_t)nrows * N * 4) & 15) != 0) {   // dZ not TMA-sized: copy by hand, producers only
+                for (int e = tid; e < nrows * N; e += WG_PRODUCERS) rz[e] = g.dZ[(size_t)(row0 + e / N) * g.N_full + m0 + e % N];
                 asm volatile("bar.sync 1, %0;" ::"n"(WG_PRODUCERS) : "memory");
             }
             tc::mbar_wait(fbar, fpar);
@@ -791,12 +825,12 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
                 for (int ch = 0; ch < z_chunks; ++ch) {
                     const int n = ch * 32 + j * 4;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (row_ok && n < g.N) {
+                    if (row_ok && n < N) {
                         if (vec_z) v = *reinterpret_cast<const float4*>(zsrc + ch * 32);
-                        else { const float* p = zsrc + ch * 32; v.x = p[0]; if (n + 1 < g.N) v.y = p[1]; if (n + 2 < g.N) v.z = p[2]; if (n + 3 < g.N) v.w = p[3]; }
+                        else { const float* p = zsrc + ch * 32; v.x = p[0]; if (n + 1 < N) v.y = p[1]; if (n + 2 < N) v.z = p[2]; if (n + 3 < N) v.w = p[3]; }
                         if (fused_dz) {                            // host guarantees N % 4 == 0 here
                             const float4 z = *reinterpret_cast<const float4*>(zsrc + rawz1 / 4 + ch * 32);
-                            const size_t co = (g.gr_cur < g.rows ? (size_t)((row0 + r) / g.gr_cur) * g.N : 0) + n;
+                            const size_t co = (g.gr_cur < g.rows ? (size_t)((row0 + r) / g.gr_cur) * N : 0) + n;
                             const float4 a1 = __ldg(reinterpret_cast<const float4*>(g.kc1 + co));
                             const float4 a3 = __ldg(reinterpret_cast<const float4*>(g.kc3 + co));
                             const float4 a0 = __ldg(reinterpret_cast<const float4*>(g.kc0 + co));
@@ -810,9 +844,9 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
                 for (int ch = 0; ch < p_chunks; ++ch) {
                     const int k = ch * 32 + j * 4;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (row_ok && k < g.K) {
+                    if (row_ok && k < K) {
                         v = *reinterpret_cast<const float4*>(psrc + ch * 32);
-                        if (!plain_p) v = prologue4(pg, v, row0 + r, k, true, (g.scale && g.gr_prev < g.rows) ? (size_t)((row0 + r) / g.gr_prev) * g.K : 0);
+                        if (!plain_p) v = prologue4(pg, v, row0 + r, kk0 + k, true, (g.scale && g.gr_prev < g.rows) ? (size_t)((row0 + r) / g.gr_prev) * g.K_full : 0);
                     }
                     store_split(p_hi + ch * chunk_bytes, p_lo + ch * chunk_bytes, 0, v, PASSES == 3);
                 }
@@ -829,9 +863,9 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
         tc::fence_after_sync();
         const int q = warp & 3, half = warp >> 2;
         const int n = q * 32 + lane;
-        float* dst = g.partials + (size_t)blockIdx.x * g.N * g.K;
-        const int cols_half = ((g.KP / 8 + 1) / 2) * 8;
-        const int c_begin = half == 0 ? 0 : cols_half, c_end = half == 0 ? min(cols_half, g.KP) : g.KP;
+        float* dst = g.partials + (size_t)blockIdx.x * g.N_full * g.K_full + (size_t)m0 * g.K_full + kk0;
+        const int cols_half = ((KP / 8 + 1) / 2) * 8;
+        const int c_begin = half == 0 ? 0 : cols_half, c_end = half == 0 ? min(cols_half, KP) : KP;
         for (int c0 = c_begin; c0 < c_end; c0 += 8) {
             float v[8];
             if (my_tiles > 0) tc::tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
@@ -839,9 +873,9 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = 0.0f;
             }
-            if (n < g.N) {
+            if (n < N) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) if (c0 + e < g.K) dst[(size_t)n * g.K + c0 + e] = v[e];
+                for (int e = 0; e < 8; ++e) if (c0 + e < K) dst[(size_t)n * g.K_full + c0 + e] = v[e];
             }
         }
     }

@@ -178,3 +178,17 @@ def test_tf32_single_pass_is_looser_than_3xtf32():
             for m in ("simt", "3xtf32", "tf32")}
     e3, e1 = rel_err(outs["3xtf32"], outs["simt"]), rel_err(outs["tf32"], outs["simt"])
     assert e3 <= 1e-5 and 1e-5 < e1 <= 5e-3, (e3, e1)
+
+
+WIDE_CASES = [
+    # the list scorer's head / tail nets (list_ranker.py:309-341): widths beyond one MMA tile
+    (2, 96, [136, 128, 256, 512, 136], "R", "R", None, False, 0.1),
+    (2, 64, [136, 128, 256, 512, 1], "R", None, "BN2", False, 0.0),
+    (3, 40, [64, 320, 8], "GE", "S", "BN", True, 0.0),
+]
+
+
+@pytest.mark.parametrize("case", WIDE_CASES, ids=[f"wide{i}" for i in range(len(WIDE_CASES))])
+def test_wide_layers_on_tensor_cores_match_simt(case):
+    """Column-tiled rows_gemm and column-blocked wgrad (layers wider than 256 / 128) vs the fp32 SIMT kernels."""
+    test_tensor_core_path_matches_simt_path(case)
