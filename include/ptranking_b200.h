@@ -204,6 +204,18 @@ int ptrb200_attention_bwd(const float* Q, const float* K, const float* V, const 
                           float* dQ, float* dK, float* dV, float* scratch,
                           int B, int n, int H, int D, float dropout_p, uint64_t seed, uint64_t offset,
                           ptrb200_stream_t stream);
+/* Tensor-core variant of the two calls above (same maths, same dropout stream): every contraction is a batched
+ * tcgen05 kind::tf32 GEMM (passes = 3: 3xTF32 split, fp32-grade; 1: plain TF32); the attention matrix
+ * P[B*H,n,n] is materialised in HBM and kept for the backward pass.
+ * scratch: ptrb200_attention_tc_workspace_floats(B,n,H,D,backward) floats. */
+int64_t ptrb200_attention_tc_workspace_floats(int B, int n, int H, int D, int backward);
+int ptrb200_attention_tc_fwd(const float* Q, const float* K, const float* V, float* O, float* P_out, float* scratch,
+                             int B, int n, int H, int D, float dropout_p, uint64_t seed, uint64_t offset, int passes,
+                             ptrb200_stream_t stream);
+int ptrb200_attention_tc_bwd(const float* Q, const float* K, const float* V, const float* P, const float* dO,
+                             float* dQ, float* dK, float* dV, float* scratch,
+                             int B, int n, int H, int D, float dropout_p, uint64_t seed, uint64_t offset, int passes,
+                             ptrb200_stream_t stream);
 /* LayerNorm.forward, ptranking/base/list_ranker.py:165-174: y = a_2 (x - mean) / (std_unbiased + eps) + b_2 per row;
  * mean/std[rows] are kept for backward. */
 int ptrb200_layernorm_fwd(const float* x, const float* a2, const float* b2, float* y, float* mean, float* stdv,

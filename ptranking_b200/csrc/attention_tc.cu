@@ -1,0 +1,329 @@
+// attention_tc.cu -- multi-head self-attention with every contraction on tcgen05 tensor cores.
+//
+// MultiheadAttention.forward, ptranking/base/list_ranker.py:226-248:
+//     S = Q K^T / sqrt(d)   ->   A = softmax(S)   ->   A_d = dropout(A)   ->   O = A_d V
+// and its autograd.  Round-1 design ("materialised S"): the five contractions of forward + backward
+//     S = Q K^T,   O = A_d V,   dA_d = dO V^T,   dQ = dS K,   dK = dS^T Q,   dV = A_d^T dO
+// all run through ONE batched, strided  C[z] = alpha * op(A[z]) * B[z]^T  kernel (kind::tf32, 3xTF32 split, fp32
+// accumulation in TMEM); row softmax / softmax-backward are streaming SIMT kernels over the [n,n] score tensor, and
+// operands that are needed transposed are transposed explicitly.  The [n,n] tensors live in HBM (n <= 1024 per
+// list: 134 MB per layer at B=64, n=512, 2 heads) -- the fully fused flash variant is the follow-up.
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace ptrb200 {
+
+struct BGemmArgs {
+    const float *A, *B;
+    float* C;
+    int M, N, K;                 // C[M,N] = alpha * A[M,K] * B[N,K]^T
+    int lda, ldb, ldc;           // row pitches (floats)
+    long long sAb, sAh, sBb, sBh, sCb, sCh;   // batch strides (floats) for z = b*H + h
+    int H;
+    float alpha;
+    // optional dropout on A's elements: mode 1: element id = (z*M + row)*K + col ; mode 2 (A is a transposed view of
+    // the attention matrix): id = (z*K + col)*M + row
+    int drop_mode;
+    DropCfg drop;
+};
+
+constexpr int BG_THREADS = 256, BG_NT = 128;
+
+template <int PASSES>
+__global__ void __launch_bounds__(BG_THREADS) bgemm_nt_tc_kernel(BGemmArgs g) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* a_hi = base;
+    unsigned char* a_lo = a_hi + 16384;
+    unsigned char* b_hi = a_lo + 16384;
+    unsigned char* b_lo = b_hi + 16384;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(b_lo + 16384);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int z = blockIdx.z, zb = z / g.H, zh = z % g.H;
+    const float* A = g.A + zb * g.sAb + zh * g.sAh;
+    const float* B = g.B + zb * g.sBb + zh * g.sBh;
+    float* C = g.C + zb * g.sCb + zh * g.sCh;
+    const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BG_NT;
+    const int N = min(BG_NT, g.N - n0), NP = ((N + 15) / 16) * 16;
+    const int K = g.K;
+    const int nchunks = (K + 31) / 32;
+    // The tensor core accumulates with truncation, a bias that grows linearly with the number of accumulation steps.
+    // Long contractions therefore alternate between two main accumulators, and the small a_lo*b_hi + a_hi*b_lo correction
+    // terms get an accumulator of their own; the epilogue adds them up in round-to-nearest fp32.
+    const int nmain = (nchunks > 4 && 3 * NP <= 256) ? 2 : 1;
+    const int nacc = nmain + (PASSES == 3 ? 1 : 0);
+    const uint32_t need = (uint32_t)(nacc * NP);
+    const uint32_t tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : 256;
+    if (tid == 0) { tc::mbar_init(mbar, 1); tc::mbar_fence_init(); }
+    if (warp == 0) tc::tmem_alloc(slot, tmem_cols);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *slot;
+    const uint32_t idesc = tc::instr_desc(2, 128, NP);
+    const bool vecA = (g.lda & 3) == 0 && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    const bool vecB = (g.ldb & 3) == 0 && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+
+    auto load4 = [&](const float* p, int k, bool vec) -> float4 {      // guarded 4-wide load at column k of a row
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k + 3 < K && vec) return __ldg(reinterpret_cast<const float4*>(p + k));
+        if (k < K) v.x = p[k];
+        if (k + 1 < K) v.y = p[k + 1];
+        if (k + 2 < K) v.z = p[k + 2];
+        if (k + 3 < K) v.w = p[k + 3];
+        return v;
+    };
+    for (int c = 0; c < nchunks; ++c) {
+        const int k0 = c * 32;
+        float4 av[4], bv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int u = tid + i * BG_THREADS, r = u >> 3, j = u & 7, k = k0 + j * 4;
+            av[i] = (m0 + r < g.M) ? load4(A + (size_t)(m0 + r) * g.lda, k, vecA) : make_float4(0.f, 0.f, 0.f, 0.f);
+            bv[i] = (r < N) ? load4(B + (size_t)(n0 + r) * g.ldb, k, vecB) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (c > 0) tc::mbar_wait(mbar, (c - 1) & 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int u = tid + i * BG_THREADS, r = u >> 3, j = u & 7, k = k0 + j * 4;
+            float4 v = av[i];
+            if (g.drop_mode && g.drop.thr && m0 + r < g.M) {
+                float* e = &v.x;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const uint64_t id = g.drop_mode == 1 ? ((uint64_t)z * g.M + (m0 + r)) * K + (k + t)
+                                                         : ((uint64_t)z * K + (k + t)) * g.M + (m0 + r);
+                    e[t] = (k + t < K && dropout_keep(g.drop.key, id, g.drop.thr)) ? e[t] * g.drop.scale : 0.0f;
+                }
+            }
+            float4 h, l;
+            tc::split_tf32_rn(v.x, h.x, l.x); tc::split_tf32_rn(v.y, h.y, l.y); tc::split_tf32_rn(v.z, h.z, l.z); tc::split_tf32_rn(v.w, h.w, l.w);
+            const uint32_t off = tc::swz_offset(r, j);
+            *reinterpret_cast<float4*>(a_hi + off) = PASSES == 3 ? h : v;
+            if (PASSES == 3) *reinterpret_cast<float4*>(a_lo + off) = l;
+            const float4 w = bv[i];
+            tc::split_tf32_rn(w.x, h.x, l.x); tc::split_tf32_rn(w.y, h.y, l.y); tc::split_tf32_rn(w.z, h.z, l.z); tc::split_tf32_rn(w.w, h.w, l.w);
+            *reinterpret_cast<float4*>(b_hi + off) = PASSES == 3 ? h : w;
+            if (PASSES == 3) *reinterpret_cast<float4*>(b_lo + off) = l;
+        }
+        tc::fence_proxy_async();
+        __syncthreads();
+        if (warp == 0) {
+            tc::fence_after_sync();
+            const int ksteps = min(4, (K - k0 + 7) / 8);
+            uint64_t ah = tc::smem_desc_sw128(tc::smem_u32(a_hi), 1024), al = tc::smem_desc_sw128(tc::smem_u32(a_lo), 1024);
+            uint64_t bh = tc::smem_desc_sw128(tc::smem_u32(b_hi), 1024), bl = tc::smem_desc_sw128(tc::smem_u32(b_lo), 1024);
+            if (tc::elect_one()) {
+                const uint32_t t_main = tmem + (uint32_t)((c % nmain) * NP), t_corr = tmem + (uint32_t)(nmain * NP);
+                for (int s = 0; s < ksteps; ++s) {
+                    const uint32_t acc_m = (c < nmain && s == 0) ? 0u : 1u;
+                    if (PASSES == 3) {
+                        tc::mma_tf32(t_corr, al, bh, idesc, (c == 0 && s == 0) ? 0u : 1u);
+                        tc::mma_tf32(t_corr, ah, bl, idesc, 1u);
+                    }
+                    tc::mma_tf32(t_main, ah, bh, idesc, acc_m);
+                    ah += 2; al += 2; bh += 2; bl += 2;
+                }
+                tc::mma_commit(mbar);
+            }
+            __syncwarp();
+        }
+    }
+    tc::mbar_wait(mbar, (nchunks - 1) & 1);
+    tc::fence_after_sync();
+    {   // epilogue: TMEM lane = row; warps (q, half) split the columns
+        const int q = warp & 3, half = warp >> 2;
+        const int row = m0 + q * 32 + lane;
+        const int cols_half = ((NP / 8 + 1) / 2) * 8;
+        const int c_begin = half == 0 ? 0 : cols_half, c_end = half == 0 ? min(cols_half, NP) : NP;
+        float* crow = C + (size_t)min(row, g.M - 1) * g.ldc + n0;
+        const bool vecC = (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(C + n0) & 15) == 0);
+        for (int c0 = c_begin; c0 < c_end; c0 += 8) {
+            float v[8];
+            tc::tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            for (int a = 1; a < nacc; ++a) {
+                float w[8];
+                tc::tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * NP + c0), w);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] += w[e];
+            }
+            if (row < g.M && c0 < N) {
+                if (c0 + 8 <= N && vecC) {
+                    *reinterpret_cast<float4*>(crow + c0) = make_float4(v[0] * g.alpha, v[1] * g.alpha, v[2] * g.alpha, v[3] * g.alpha);
+                    *reinterpret_cast<float4*>(crow + c0 + 4) = make_float4(v[4] * g.alpha, v[5] * g.alpha, v[6] * g.alpha, v[7] * g.alpha);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) if (c0 + e < N) crow[c0 + e] = v[e] * g.alpha;
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, tmem_cols);
+}
+
+// in-place row softmax over S[z][i][:] (one warp per row); also emits the per-row log-sum-exp
+__global__ void softmax_rows_kernel(float* __restrict__ S, float* __restrict__ lse, size_t rows, int n) {
+    const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float* s = S + row * n;
+    float m = -INFINITY;
+    for (int j = lane; j < n; j += 32) m = fmaxf(m, s[j]);
+    m = warp_max(m);
+    float l = 0.0f;
+    for (int j = lane; j < n; j += 32) { const float e = expf(s[j] - m); s[j] = e; l += e; }
+    l = warp_sum(l);
+    const float inv = 1.0f / l;
+    for (int j = lane; j < n; j += 32) s[j] *= inv;
+    if (lane == 0 && lse) lse[row] = m + logf(l);
+}
+
+// dS = A * (dA - sum_j A dA) * inv_scale in place over dAd, where dA = dropmask(dAd)  (one warp per row)
+__global__ void softmax_bwd_rows_kernel(const float* __restrict__ P, float* __restrict__ dP, size_t rows, int n,
+                                        float inv_scale, DropCfg drop) {
+    const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* p = P + row * n;
+    float* d = dP + row * n;
+    float acc = 0.0f;
+    for (int j = lane; j < n; j += 32) {
+        float da = d[j];
+        if (drop.thr) da = dropout_keep(drop.key, row * (uint64_t)n + j, drop.thr) ? da * drop.scale : 0.0f;
+        d[j] = da;
+        acc = fmaf(p[j], da, acc);
+    }
+    acc = warp_sum(acc);
+    for (int j = lane; j < n; j += 32) d[j] = p[j] * (d[j] - acc) * inv_scale;
+}
+
+// out[z][c][r] = in[z][r][c] for in with row pitch ld_in and a column window of `cols` columns (32x32 tiles)
+__global__ void btranspose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols, int ld_in,
+                                  long long s_in_b, long long s_in_h, int H, long long s_out) {
+    __shared__ float tile[32][33];
+    const int z = blockIdx.z;
+    const float* src = in + (z / H) * s_in_b + (z % H) * s_in_h;
+    float* dst = out + (size_t)z * s_out;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < rows && c < cols) ? src[(size_t)r * ld_in + c] : 0.0f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (c < cols && r < rows) dst[(size_t)c * rows + r] = tile[threadIdx.x][i];
+    }
+}
+
+static int launch_bgemm(BGemmArgs& g, int Z, int passes, cudaStream_t st, const char* tag) {
+    const size_t smem = 1024 + 4 * 16384 + 64;
+    dim3 grid((g.M + 127) / 128, (g.N + BG_NT - 1) / BG_NT, Z);
+    cudaError_t e;
+    if (passes == 3) {
+        e = cudaFuncSetAttribute(bgemm_nt_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("bgemm smem attr: %s", cudaGetErrorString(e)); return PTRB200_ERR_CUDA; }
+        PTRB200_LAUNCH_TAG(tag, bgemm_nt_tc_kernel<3>, grid, BG_THREADS, smem, st, g);
+    } else {
+        e = cudaFuncSetAttribute(bgemm_nt_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("bgemm smem attr: %s", cudaGetErrorString(e)); return PTRB200_ERR_CUDA; }
+        PTRB200_LAUNCH_TAG(tag, bgemm_nt_tc_kernel<1>, grid, BG_THREADS, smem, st, g);
+    }
+    return PTRB200_OK;
+}
+
+static void launch_transpose(const float* in, float* out, int rows, int cols, int ld_in, long long sb, long long sh, int H, int Z, cudaStream_t st) {
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, Z);
+    PTRB200_LAUNCH(btranspose_kernel, grid, dim3(32, 8), 0, st, in, out, rows, cols, ld_in, sb, sh, H, (long long)rows * cols);
+}
+
+}  // namespace ptrb200
+
+using namespace ptrb200;
+
+extern "C" {
+
+// workspace (floats): forward keeps P[Z,n,n]; scratch Vt[Z,D,n]
+int64_t ptrb200_attention_tc_workspace_floats(int B, int n, int H, int D, int backward) {
+    const int64_t Z = (int64_t)B * H, nn = (int64_t)n * n, dn = (int64_t)D * n;
+    return backward ? Z * (2 * nn + 2 * dn) : Z * dn;
+}
+
+// P_out[B*H, n, n] receives the (un-dropped) attention probabilities and must be kept for the backward pass.
+int ptrb200_attention_tc_fwd(const float* Q, const float* K, const float* V, float* O, float* P_out, float* scratch,
+                             int B, int n, int H, int D, float dropout_p, uint64_t seed, uint64_t offset, int passes,
+                             ptrb200_stream_t stream) {
+    if (!Q || !K || !V || !O || !P_out || !scratch || B <= 0 || n <= 0 || H <= 0 || D <= 0) { set_error("attention_tc_fwd: bad arguments"); return PTRB200_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Z = B * H, HD = H * D;
+    const long long sb = (long long)n * HD, sh = D, nn = (long long)n * n;
+    int rc;
+    BGemmArgs g{};
+    // S = Q K^T / sqrt(D)
+    g.A = Q; g.B = K; g.C = P_out; g.M = n; g.N = n; g.K = D; g.lda = HD; g.ldb = HD; g.ldc = n;
+    g.sAb = sb; g.sAh = sh; g.sBb = sb; g.sBh = sh; g.sCb = nn * H; g.sCh = nn; g.H = H; g.alpha = 1.0f / sqrtf((float)D);
+    if ((rc = launch_bgemm(g, Z, passes, st, "attn_tc_qk"))) return rc;
+    const size_t rows = (size_t)Z * n;
+    PTRB200_LAUNCH(softmax_rows_kernel, (unsigned)((rows + 7) / 8), 256, 0, st, P_out, (float*)nullptr, rows, n);
+    // O = dropout(P) V  ==  dropout(P) (V^T)^T
+    float* Vt = scratch;
+    launch_transpose(V, Vt, n, D, HD, sb, sh, H, Z, st);
+    BGemmArgs o{};
+    o.A = P_out; o.B = Vt; o.C = O; o.M = n; o.N = D; o.K = n; o.lda = n; o.ldb = n; o.ldc = HD;
+    o.sAb = nn * H; o.sAh = nn; o.sBb = (long long)D * n * H; o.sBh = (long long)D * n; o.sCb = sb; o.sCh = sh; o.H = H; o.alpha = 1.0f;
+    o.drop_mode = 1; o.drop = make_drop(dropout_p, seed, offset);
+    if ((rc = launch_bgemm(o, Z, passes, st, "attn_tc_pv"))) return rc;
+    return check_launch("attention_tc_fwd");
+}
+
+int ptrb200_attention_tc_bwd(const float* Q, const float* K, const float* V, const float* P, const float* dO,
+                             float* dQ, float* dK, float* dV, float* scratch,
+                             int B, int n, int H, int D, float dropout_p, uint64_t seed, uint64_t offset, int passes,
+                             ptrb200_stream_t stream) {
+    if (!Q || !K || !V || !P || !dO || !dQ || !dK || !dV || !scratch || B <= 0 || n <= 0 || H <= 0 || D <= 0) { set_error("attention_tc_bwd: bad arguments"); return PTRB200_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Z = B * H, HD = H * D;
+    const long long sb = (long long)n * HD, sh = D, nn = (long long)n * n, dn = (long long)D * n;
+    float* dS = scratch;                    // [Z,n,n]
+    float* T = dS + (size_t)Z * nn;         // [Z,n,n] transposed views (dS^T, then P^T)
+    float* t1 = T + (size_t)Z * nn;         // [Z,D,n]
+    float* t2 = t1 + (size_t)Z * dn;        // [Z,D,n]
+    const DropCfg drop = make_drop(dropout_p, seed, offset);
+    const float inv_scale = 1.0f / sqrtf((float)D);
+    int rc;
+    // dA_d = dO V^T
+    BGemmArgs a{};
+    a.A = dO; a.B = V; a.C = dS; a.M = n; a.N = n; a.K = D; a.lda = HD; a.ldb = HD; a.ldc = n;
+    a.sAb = sb; a.sAh = sh; a.sBb = sb; a.sBh = sh; a.sCb = nn * H; a.sCh = nn; a.H = H; a.alpha = 1.0f;
+    if ((rc = launch_bgemm(a, Z, passes, st, "attn_tc_dp"))) return rc;
+    const size_t rows = (size_t)Z * n;
+    PTRB200_LAUNCH(softmax_bwd_rows_kernel, (unsigned)((rows + 7) / 8), 256, 0, st, P, dS, rows, n, inv_scale, drop);
+    // dQ = dS K = dS (K^T)^T
+    launch_transpose(K, t1, n, D, HD, sb, sh, H, Z, st);
+    BGemmArgs q{};
+    q.A = dS; q.B = t1; q.C = dQ; q.M = n; q.N = D; q.K = n; q.lda = n; q.ldb = n; q.ldc = HD;
+    q.sAb = nn * H; q.sAh = nn; q.sBb = dn * H; q.sBh = dn; q.sCb = sb; q.sCh = sh; q.H = H; q.alpha = 1.0f;
+    if ((rc = launch_bgemm(q, Z, passes, st, "attn_tc_dq"))) return rc;
+    // dK = dS^T Q = dS^T (Q^T)^T
+    launch_transpose(dS, T, n, n, n, nn * H, nn, H, Z, st);
+    launch_transpose(Q, t2, n, D, HD, sb, sh, H, Z, st);
+    BGemmArgs k{};
+    k.A = T; k.B = t2; k.C = dK; k.M = n; k.N = D; k.K = n; k.lda = n; k.ldb = n; k.ldc = HD;
+    k.sAb = nn * H; k.sAh = nn; k.sBb = dn * H; k.sBh = dn; k.sCb = sb; k.sCh = sh; k.H = H; k.alpha = 1.0f;
+    if ((rc = launch_bgemm(k, Z, passes, st, "attn_tc_dk"))) return rc;
+    // dV = dropout(P)^T dO : A = P^T with the dropout mask indexed through the transpose
+    launch_transpose(P, T, n, n, n, nn * H, nn, H, Z, st);
+    launch_transpose(dO, t1, n, D, HD, sb, sh, H, Z, st);
+    BGemmArgs v{};
+    v.A = T; v.B = t1; v.C = dV; v.M = n; v.N = D; v.K = n; v.lda = n; v.ldb = n; v.ldc = HD;
+    v.sAb = nn * H; v.sAh = nn; v.sBb = dn * H; v.sBh = dn; v.sCb = sb; v.sCh = sh; v.H = H; v.alpha = 1.0f;
+    v.drop_mode = 2; v.drop = drop;
+    if ((rc = launch_bgemm(v, Z, passes, st, "attn_tc_dv"))) return rc;
+    return check_launch("attention_tc_bwd");
+}
+
+}  // extern "C"

@@ -167,5 +167,13 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     lo = x - hi;                                       // (an infinite x yields lo = NaN, i.e. NaN instead of inf downstream)
 }
 
+// round-to-nearest variant: hi is x rounded to tf32 (|lo| <= 2^-12 |x|) and lo is itself rounded to tf32, so the hardware's
+// truncation of the low 13 mantissa bits never bites: per-product error 2^-22 instead of 2^-20 for 3 more integer/FP ops.
+__device__ __forceinline__ void split_tf32_rn(float x, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+    const float r = x - hi;
+    lo = __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xffffe000u);
+}
+
 }  // namespace tc
 }  // namespace ptrb200

@@ -9,6 +9,7 @@ from __future__ import annotations
 import ctypes as C
 from typing import Optional, Sequence
 
+import os
 import torch
 
 from . import _lib
@@ -349,13 +350,57 @@ class _Attention(torch.autograd.Function):
         return dQ, dK, dV, None, None, None, None
 
 
-def attention(Q, K, V, n_heads: int, dropout_p: float = 0.0, seed: Optional[int] = None, offset: Optional[int] = None):
-    """softmax(Q K^T / sqrt(d)) [dropout] V per head; Q,K,V: [B,n,H*d]."""
+class _AttentionTC(torch.autograd.Function):
+    """Tensor-core attention: batched tcgen05 GEMMs around a materialised [B*H,n,n] probability tensor."""
+
+    @staticmethod
+    def forward(ctx, Q, K, V, n_heads, dropout_p, seed, offset, passes):
+        lib = _lib.load()
+        Q, K, V = _dev_f32(Q, "Q"), _dev_f32(K, "K"), _dev_f32(V, "V")
+        B, n, F = Q.shape
+        D = F // n_heads
+        O = torch.empty_like(Q)
+        P = torch.empty((B * n_heads, n, n), dtype=torch.float32, device=Q.device)
+        scratch = torch.empty(lib.ptrb200_attention_tc_workspace_floats(B, n, n_heads, D, 0), dtype=torch.float32, device=Q.device)
+        _lib.check(lib.ptrb200_attention_tc_fwd(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), P.data_ptr(),
+                                                scratch.data_ptr(), B, n, n_heads, D, float(dropout_p), seed, offset, passes,
+                                                _stream_ptr()), "attention_tc_fwd")
+        ctx.save_for_backward(Q, K, V, P)
+        ctx.cfg = (n_heads, float(dropout_p), seed, offset, passes)
+        return O
+
+    @staticmethod
+    def backward(ctx, dO):
+        lib = _lib.load()
+        Q, K, V, P = ctx.saved_tensors
+        H, p, seed, offset, passes = ctx.cfg
+        B, n, F = Q.shape
+        dO = _dev_f32(dO, "dO")
+        dQ, dK, dV = torch.empty_like(Q), torch.empty_like(K), torch.empty_like(V)
+        scratch = torch.empty(lib.ptrb200_attention_tc_workspace_floats(B, n, H, F // H, 1), dtype=torch.float32, device=Q.device)
+        _lib.check(lib.ptrb200_attention_tc_bwd(Q.data_ptr(), K.data_ptr(), V.data_ptr(), P.data_ptr(), dO.data_ptr(),
+                                                dQ.data_ptr(), dK.data_ptr(), dV.data_ptr(), scratch.data_ptr(),
+                                                B, n, H, F // H, p, seed, offset, passes, _stream_ptr()), "attention_tc_bwd")
+        return dQ, dK, dV, None, None, None, None, None
+
+
+def attention(Q, K, V, n_heads: int, dropout_p: float = 0.0, seed: Optional[int] = None, offset: Optional[int] = None,
+              impl: Optional[str] = None):
+    """softmax(Q K^T / sqrt(d)) [dropout] V per head; Q,K,V: [B,n,H*d].
+
+    impl: "tc" (tcgen05 3xTF32 GEMMs, default), "tc_tf32" (single-pass TF32), "simt" (flash-style fp32 FMA kernels);
+    None reads PTRANKING_B200_ATTN.  All three draw the same dropout stream."""
     if seed is None:
         seed = torch.initial_seed() & (2 ** 64 - 1)
     if offset is None:
         offset = next_dropout_offset()
-    return _Attention.apply(Q, K, V, int(n_heads), float(dropout_p), int(seed), int(offset))
+    if impl is None:
+        impl = os.environ.get("PTRANKING_B200_ATTN", "tc")
+    if impl == "simt":
+        return _Attention.apply(Q, K, V, int(n_heads), float(dropout_p), int(seed), int(offset))
+    if impl not in ("tc", "tc_tf32"):
+        raise ValueError(f"unknown attention impl {impl!r}")
+    return _AttentionTC.apply(Q, K, V, int(n_heads), float(dropout_p), int(seed), int(offset), 3 if impl == "tc" else 1)
 
 
 class _LayerNormRef(torch.autograd.Function):
