@@ -179,6 +179,10 @@ typedef struct ptrb200_ffnet_grads {       /* same layout as the parameter point
  * (rows = B*n documents) */
 int64_t ptrb200_ffnet_workspace_bytes(const ptrb200_ffnet* net, int B, int n);
 
+/* `training` argument of the two calls below: bit 0 = training mode (dropout active); bit 1 (forward only) tells
+ * ptrb200_ffnet_forward that no backward call will follow, so the by-products the backward pass reads are not written. */
+#define PTRB200_FFNET_TRAINING 1
+#define PTRB200_FFNET_FORWARD_ONLY 2
 /* forward: X[B,n,dims[0]] -> out[B,n,dims[last]].  `workspace` keeps pre-activations and
  * statistics for ptrb200_ffnet_backward.  dropout uses Philox keyed by (seed, offset). */
 int ptrb200_ffnet_forward(const ptrb200_ffnet* net, const float* X, float* out, void* workspace,
@@ -191,6 +195,14 @@ int ptrb200_ffnet_backward(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* 
                            const float* dOut, float* dX, void* workspace, int64_t workspace_bytes,
                            int B, int n, int training, uint64_t seed, uint64_t offset,
                            ptrb200_stream_t stream);
+
+/* ---- optimizer step ---------------------------------------------------------------------- */
+/* torch.optim.Adam.step() (ranker.py:512-525 -> config_optimizer; defaults betas=(0.9,0.999), eps=1e-8) over flat fp32
+ * buffers of `count` elements with identical layouts: parameters, gradients, first and second moments.  `step` is the
+ * 1-based step count (bias correction).  weight_decay is added to the gradient (torch's L2 form).  16-byte aligned. */
+int ptrb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count,
+                      double lr, double beta1, double beta2, double eps, double weight_decay, int step,
+                      ptrb200_stream_t stream);
 
 /* ---- multi-head self-attention list scorer ------------------------------------------------ */
 /* MultiheadAttention.forward, ptranking/base/list_ranker.py:226-248: for every (query b, head h)

@@ -16,6 +16,28 @@ from .. import ops
 from .. import dist as b200dist
 
 
+class FlatAdam(optim.Optimizer):
+    """torch.optim.Adam as the reference configures it (ranker.py:512-525: lr, weight_decay, PyTorch defaults otherwise) run
+    as ONE kernel over the flat parameter / gradient buffers of a :class:`dist.GradBucket` (ops.adam_step).  It is a
+    torch Optimizer, so StepLR (ranker.py:525) drives ``param_groups[0]['lr']`` as usual."""
+
+    def __init__(self, params, bucket, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.bucket = bucket
+        self.exp_avg = torch.zeros_like(bucket.flat_param)
+        self.exp_avg_sq = torch.zeros_like(bucket.flat_param)
+        self.num_steps = 0
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if not self.bucket.params_are_flat():
+            raise RuntimeError("FlatAdam: a parameter was re-allocated outside the flat buffer (use copy_ / load_state_dict)")
+        g = self.param_groups[0]
+        self.num_steps += 1
+        ops.adam_step(self.bucket.flat_param, self.bucket.flat, self.exp_avg, self.exp_avg_sq, self.num_steps,
+                      lr=g['lr'], betas=g['betas'], eps=g['eps'], weight_decay=g['weight_decay'])
+
+
 @unique
 class LABEL_TYPE(Enum):
     """Same members as ptranking.data.data_utils.LABEL_TYPE (data_utils.py:88-91)."""
@@ -149,9 +171,10 @@ class NeuralRanker(Evaluator):
     def config_optimizer(self):
         """ranker.py:512-525: Adam | RMS | Adagrad with L2-in-gradient weight decay + StepLR(20, 0.5)."""
         params = list(self.get_parameters())
-        self.grad_bucket = b200dist.GradBucket(params)     # one flat fp32 gradient buffer (one all-reduce per step)
-        if 'Adam' == self.opt:
-            self.optimizer = optim.Adam(params, lr=self.lr, weight_decay=self.weight_decay)
+        self.grad_bucket = b200dist.GradBucket(params, align=4)     # one flat fp32 gradient buffer (one all-reduce per step)
+        if 'Adam' == self.opt:      # the reference default: one fused kernel over the flat buffers
+            self.grad_bucket.flatten_params()
+            self.optimizer = FlatAdam(params, self.grad_bucket, lr=self.lr, weight_decay=self.weight_decay)
         elif 'RMS' == self.opt:
             self.optimizer = optim.RMSprop(params, lr=self.lr, weight_decay=self.weight_decay)
         elif 'Adagrad' == self.opt:

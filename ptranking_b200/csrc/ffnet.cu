@@ -207,9 +207,13 @@ __global__ void colstat_kernel(const float* __restrict__ Z, const float* __restr
 // Vectorised column statistics for widths that are multiples of 4: thread (q, ry) owns channels 4q..4q+3 and
 // walks rows ry, ry+RY, ... of its slice, so a warp reads 512 contiguous bytes per step.  Same partial layout
 // as colstat_kernel.  blockDim = (Q = C/4, RY); dynamic smem = RY*Q*8 doubles.
+// STAT_DY can take dA in factored form: the scorer's last Linear has one output, so its data gradient is the outer
+// product dA[r,c] = dropmask(dz[r] * w[c]) -- built on the fly here instead of being written and re-read.
+struct Rank1Src { const float* w; DropCfg drop; };     // w == NULL: dA is a dense [rows, C] tensor
+
 template <int WHAT>
 __global__ void colstat4_kernel(const float* __restrict__ Z, const float* __restrict__ dA, float* __restrict__ dY_out,
-                                NormRef nr, double* __restrict__ partials, int gr, int C, int S, int slice_rows) {
+                                NormRef nr, double* __restrict__ partials, int gr, int C, int S, int slice_rows, Rank1Src rk) {
     extern __shared__ double sh4[];
     const int Q = blockDim.x, RY = blockDim.y, q = threadIdx.x, ry = threadIdx.y, c = q * 4;
     const int g = blockIdx.x, sl = blockIdx.y;
@@ -238,7 +242,19 @@ __global__ void colstat4_kernel(const float* __restrict__ Z, const float* __rest
 #pragma unroll
             for (int e = 0; e < 4; ++e) f1[e] += z[e];
         } else {
-            const float4 d4 = __ldg(reinterpret_cast<const float4*>(dA + off));
+            float4 d4;
+            if (rk.w) {
+                const float dz = __ldg(dA + (size_t)g * gr + r);
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(rk.w + c));
+                d4 = make_float4(dz * w4.x, dz * w4.y, dz * w4.z, dz * w4.w);
+                if (rk.drop.thr) {
+                    const uint64_t dd = dropout_draw4(rk.drop.key, off >> 2);
+                    d4.x = ((uint32_t)(dd) & 0xffffu) >= rk.drop.thr ? d4.x * rk.drop.scale : 0.0f;
+                    d4.y = ((uint32_t)(dd >> 16) & 0xffffu) >= rk.drop.thr ? d4.y * rk.drop.scale : 0.0f;
+                    d4.z = ((uint32_t)(dd >> 32) & 0xffffu) >= rk.drop.thr ? d4.z * rk.drop.scale : 0.0f;
+                    d4.w = ((uint32_t)(dd >> 48)) >= rk.drop.thr ? d4.w * rk.drop.scale : 0.0f;
+                }
+            } else d4 = __ldg(reinterpret_cast<const float4*>(dA + off));
             const float d[4] = {d4.x, d4.y, d4.z, d4.w};
             float o[4];
 #pragma unroll
@@ -278,14 +294,15 @@ __global__ void colstat4_kernel(const float* __restrict__ Z, const float* __rest
     }
 }
 
+static bool colstat_vectorised(int C) { return C % 4 == 0 && C / 4 <= 256; }
 template <int WHAT>
 static void launch_colstat(cudaStream_t st, const char* tag, const float* Z, const float* dA, float* dY, const NormRef& nr,
-                           double* part, int G, int S, int gr, int C, int slice_rows) {
+                           double* part, int G, int S, int gr, int C, int slice_rows, Rank1Src r1 = Rank1Src{nullptr, DropCfg{0, 1.0f, 0}}) {
     dim3 grid(G, S);
-    if (C % 4 == 0 && C / 4 <= 256) {
+    if (colstat_vectorised(C)) {
         const int Q = C / 4;
         int RY = 256 / Q; if (RY < 1) RY = 1; if (RY > 16) RY = 16;
-        PTRB200_LAUNCH_TAG(tag, colstat4_kernel<WHAT>, grid, dim3(Q, RY), (size_t)RY * Q * 8 * sizeof(double), st, Z, dA, dY, nr, part, gr, C, S, slice_rows);
+        PTRB200_LAUNCH_TAG(tag, colstat4_kernel<WHAT>, grid, dim3(Q, RY), (size_t)RY * Q * 8 * sizeof(double), st, Z, dA, dY, nr, part, gr, C, S, slice_rows, r1);
     } else {
         PTRB200_LAUNCH_TAG(tag, colstat_kernel<WHAT>, grid, dim3(32, 8), 0, st, Z, dA, dY, nr, part, gr, C, S, slice_rows);
     }
@@ -754,8 +771,27 @@ static void set_prologue(const ptrb200_ffnet* net, const Plan& p, int l, char* w
 }
 
 static int forward_tc(const ptrb200_ffnet* net, const Plan& p, const float* X, float* out, char* ws,
-                      float drop, uint64_t seed, uint64_t offset, cudaStream_t st) {
+                      float drop, uint64_t seed, uint64_t offset, cudaStream_t st, bool fwd_only) {
     int rc;
+    {   // operand images of every weight matrix (and, for the backward pass, of its transpose) in one launch
+        PackJobs jobs{};
+        int nj = 0, max_units = 0;
+        for (int l = 0; l < p.L; ++l) {
+            const LayerPlan& lp = p.layer[l];
+            for (int tr = 0; tr < (fwd_only ? 1 : 2); ++tr) {
+                if (tr == 1 && (l == 0 || lp.d_out % 4 != 0)) continue;     // dgrad images: only where backward_tc runs the tensor-core dgrad
+                PackJob& j = jobs.job[nj++];
+                j.src = net->weight[l]; j.src_cols = lp.d_in; j.transpose = tr;
+                j.N = tr ? lp.d_in : lp.d_out; j.K = tr ? lp.d_out : lp.d_in;
+                j.NP = ((j.N + 15) / 16) * 16; j.nchunks = (j.K + 31) / 32;
+                j.img_hi = reinterpret_cast<unsigned char*>(ws + (tr ? lp.img_d_hi : lp.img_f_hi));
+                j.img_lo = p.passes == 3 ? reinterpret_cast<unsigned char*>(ws + (tr ? lp.img_d_lo : lp.img_f_lo)) : nullptr;
+                const int units = j.nchunks * j.NP * 8;
+                max_units = units > max_units ? units : max_units;
+            }
+        }
+        PTRB200_LAUNCH(pack_b_images_kernel, dim3((max_units + 255) / 256, nj), 256, 0, st, jobs);
+    }
     for (int l = 0; l < p.L; ++l) {
         const LayerPlan& lp = p.layer[l];
         const bool last = l == p.L - 1;
@@ -765,16 +801,11 @@ static int forward_tc(const ptrb200_ffnet* net, const Plan& p, const float* X, f
         g.gr_prev = p.gr;
         g.drop = make_drop(last ? 0.0f : drop, seed, offset * 64 + (uint64_t)l);
         g.bias = net->bias[l]; g.Out = Z;
-        g.a_out = l > 0 ? reinterpret_cast<float*>(ws + lp.ain_off) : nullptr;
+        g.a_out = (l > 0 && !fwd_only) ? reinterpret_cast<float*>(ws + lp.ain_off) : nullptr;     // a by-product for the backward pass
         g.partials = lp.has_norm ? reinterpret_cast<double*>(ws + p.partials_off) : nullptr;
         g.rows = (int)p.rows; g.K = lp.d_in; g.N = lp.d_out;
-        {
-            const int NPl = ((lp.d_out + 15) / 16) * 16, nch = (lp.d_in + 31) / 32;
-            unsigned char* ih = reinterpret_cast<unsigned char*>(ws + lp.img_f_hi);
-            unsigned char* il = p.passes == 3 ? reinterpret_cast<unsigned char*>(ws + lp.img_f_lo) : nullptr;
-            PTRB200_LAUNCH(pack_b_image_kernel<false>, (nch * NPl * 8 + 255) / 256, 256, 0, st, net->weight[l], lp.d_out, lp.d_in, ih, il, lp.d_out, NPl, lp.d_in, nch);
-            g.b_img_hi = ih; g.b_img_lo = il;
-        }
+        g.b_img_hi = reinterpret_cast<unsigned char*>(ws + lp.img_f_hi);
+        g.b_img_lo = p.passes == 3 ? reinterpret_cast<unsigned char*>(ws + lp.img_f_lo) : nullptr;
         set_tiling(g, p);
         int S_fwd = p.S_stat;
         const int stats_kind = !lp.has_norm ? 0 : (net->norm == PTRB200_NORM_BN ? 1 : 2);
@@ -807,6 +838,7 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
     float* wpart = reinterpret_cast<float*>(ws + p.wpart_off);
     const float* dA = dOut;
     int flip = 0;
+    Rank1Src r1{nullptr, DropCfg{0, 1.0f, 0}};   // pending outer-product data gradient of the single-output last layer
     for (int l = p.L - 1; l >= 0; --l) {
         const LayerPlan& lp = p.layer[l];
         const bool last = l == p.L - 1;
@@ -822,7 +854,8 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
         // (measured: 128-row slices = 2048 CTAs beat longer slices; kept equal to the forward tiling)
         if (lp.has_act || lp.has_norm) {
             float* dY = dbuf[flip]; flip ^= 1;
-            launch_colstat<STAT_DY>(st, "colstat_dy", Z, dA, dY, nr, part, p.G, bS, p.gr, lp.d_out, bslice);
+            launch_colstat<STAT_DY>(st, "colstat_dy", Z, dA, dY, nr, part, p.G, bS, p.gr, lp.d_out, bslice, r1);
+            r1.w = nullptr;
             PTRB200_LAUNCH(dy_finalize_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)part,
                            lp.has_norm ? S1 : (float*)nullptr, lp.has_norm ? S2 : (float*)nullptr, T1, T2, p.G, lp.d_out, bS);
             if (lp.has_norm) {
@@ -894,7 +927,8 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
                 const int NPl = ((lp.d_in + 15) / 16) * 16, nch = (lp.d_out + 31) / 32;
                 unsigned char* ih = reinterpret_cast<unsigned char*>(ws + lp.img_d_hi);
                 unsigned char* il = p.passes == 3 ? reinterpret_cast<unsigned char*>(ws + lp.img_d_lo) : nullptr;
-                PTRB200_LAUNCH(pack_b_image_kernel<true>, (nch * NPl * 8 + 255) / 256, 256, 0, st, net->weight[l], lp.d_out, lp.d_in, ih, il, lp.d_in, NPl, lp.d_out, nch);
+                if (l == 0)     // (layer 0's transpose image is only needed when dX is requested; deeper layers were packed by the forward call)
+                    PTRB200_LAUNCH(pack_b_image_kernel<true>, (nch * NPl * 8 + 255) / 256, 256, 0, st, net->weight[l], lp.d_out, lp.d_in, ih, il, lp.d_in, NPl, lp.d_out, nch);
                 RowsGemmArgs g{};
                 g.P = dZ; g.scale = g.shift = nullptr; g.act = PTRB200_AF_NONE; g.gr_prev = (int)p.rows;
                 if (fuse_dz) {
@@ -906,6 +940,13 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
                 g.rows = (int)p.rows; g.K = lp.d_out; g.N = lp.d_in;
                 g.tile_rows = 128; g.seg_len = 128; g.group_rows = 0; g.tiles_per_group = 0;
                 if ((rc = launch_rows_gemm(RG_DGRAD, p.passes, g, (int)((p.rows + 127) / 128), st))) return rc;
+            } else if (lp.d_out == 1 && l > 0 && colstat_vectorised(lp.d_in) && (p.layer[l - 1].has_act || p.layer[l - 1].has_norm)) {
+                // the next iteration's statistics pass rebuilds dIn = dropmask(dz (x) w) on the fly
+                r1.w = net->weight[l];
+                r1.drop = make_drop(layer_drop, seed, offset * 64 + (uint64_t)l);
+                flip ^= 1;                         // dIn's buffer stays unused; dZ (in the other one) must survive the next pass
+                dA = dZ;
+                continue;
             } else if (lp.d_out == 1 && lp.d_in % 4 == 0) {
                 const size_t units = p.rows * (lp.d_in / 4);
                 PTRB200_LAUNCH(dgrad_rank1_kernel, elementwise_blocks(units), 256, 0, st, dZ, net->weight[l], dIn, units, lp.d_in,
@@ -965,8 +1006,8 @@ int ptrb200_ffnet_forward(const ptrb200_ffnet* net, const float* X, float* out, 
     if ((size_t)workspace_bytes < p.total) { set_error("ffnet_forward: workspace %lld < %zu bytes", (long long)workspace_bytes, p.total); return PTRB200_ERR_WORKSPACE; }
     char* ws = static_cast<char*>(workspace);
     cudaStream_t st = (cudaStream_t)stream;
-    const float drop = training ? net->dropout_p : 0.0f;
-    if (p.use_tc) return forward_tc(net, p, X, out, ws, drop, seed, offset, st);
+    const float drop = (training & 1) ? net->dropout_p : 0.0f;
+    if (p.use_tc) return forward_tc(net, p, X, out, ws, drop, seed, offset, st, (training & PTRB200_FFNET_FORWARD_ONLY) != 0);
     const float* in = X;
     for (int l = 0; l < p.L; ++l) {
         const LayerPlan& lp = p.layer[l];
@@ -1011,7 +1052,7 @@ int ptrb200_ffnet_backward(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* 
     if ((size_t)workspace_bytes < p.total) { set_error("ffnet_backward: workspace %lld < %zu bytes", (long long)workspace_bytes, p.total); return PTRB200_ERR_WORKSPACE; }
     char* ws = static_cast<char*>(workspace);
     cudaStream_t st = (cudaStream_t)stream;
-    const float drop = training ? net->dropout_p : 0.0f;
+    const float drop = (training & 1) ? net->dropout_p : 0.0f;
     if (p.use_tc) return backward_tc(net, grads, p, X, dOut, dX, ws, drop, seed, offset, st);
     double* part = reinterpret_cast<double*>(ws + p.partials_off);
     float* S1 = reinterpret_cast<float*>(ws + p.s1_off);

@@ -93,6 +93,43 @@ static __device__ __forceinline__ float4 ldg4_guard(const float* p, int k, int K
 // Builds the B-operand image of a [N,K] row-major matrix (TRANSPOSE=false) or of its transpose
 // (TRANSPOSE=true: image rows = columns of the source, used for dgrad's W^T): hi/lo tf32 split,
 // rows padded to NP, K cut into 128-byte chunks, each chunk [NP][128 B] in SWIZZLE_128B order.
+// One launch packs every image of a net: blockIdx.y picks the job (layer x {forward W, dgrad W^T}).
+struct PackJob {
+    const float* src;
+    unsigned char *img_hi, *img_lo;
+    int src_cols, N, NP, K, nchunks, transpose;
+};
+constexpr int PACK_MAX_JOBS = 2 * PTRB200_MAX_FF_LAYERS;
+struct PackJobs { PackJob job[PACK_MAX_JOBS]; };
+
+__global__ void pack_b_images_kernel(const __grid_constant__ PackJobs jobs) {
+    const PackJob& jb = jobs.job[blockIdx.y];
+    const float* __restrict__ src = jb.src;
+    unsigned char* __restrict__ img_hi = jb.img_hi;
+    unsigned char* __restrict__ img_lo = jb.img_lo;
+    const int src_cols = jb.src_cols, N = jb.N, NP = jb.NP, K = jb.K, nchunks = jb.nchunks;
+    const bool TRANSPOSE = jb.transpose != 0;
+    const int total = nchunks * NP * 8;                        // 16-byte units
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < total; u += gridDim.x * blockDim.x) {
+        const int c = u / (NP * 8), rem = u % (NP * 8), r = rem >> 3, j = rem & 7, k = c * 32 + j * 4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (r < N) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (k + e < K) v[e] = TRANSPOSE ? src[(size_t)(k + e) * src_cols + r] : src[(size_t)r * src_cols + k + e];
+        }
+        const size_t off = (size_t)c * NP * 128 + tc::swz_offset(r, j);
+        float4 h, l;
+        tc::split_tf32(v[0], h.x, l.x); tc::split_tf32(v[1], h.y, l.y); tc::split_tf32(v[2], h.z, l.z); tc::split_tf32(v[3], h.w, l.w);
+        if (img_lo) {
+            *reinterpret_cast<float4*>(img_hi + off) = h;
+            *reinterpret_cast<float4*>(img_lo + off) = l;
+        } else {
+            *reinterpret_cast<float4*>(img_hi + off) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
 template <bool TRANSPOSE>
 __global__ void pack_b_image_kernel(const float* __restrict__ src, int src_rows, int src_cols,
                                     unsigned char* __restrict__ img_hi, unsigned char* __restrict__ img_lo,

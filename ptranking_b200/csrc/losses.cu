@@ -112,6 +112,116 @@ __global__ void pairwise_bce_kernel(const float* __restrict__ scores, const floa
     if (threadIdx.x == 0) loss_q[b] = loss;
 }
 
+// Same loss, every unordered pair {a<b} evaluated ONCE (lists of up to 1024 documents, one thread per position).
+// In step k thread i takes the pair (i, (i+k) mod n), k = 1..floor((n-1)/2) [+ the n/2 diameter for even n]: a circulant
+// schedule that touches each pair exactly once and keeps all lanes busy.  The pair's gradient goes to the thread's own
+// accumulator and, negated, to its partner through a double-buffered shared-memory mailbox (one writer per slot per
+// step, so no atomics and a fixed summation order); KB steps share one barrier.
+constexpr int PAIR_KB = 4;
+
+template <bool LAMBDA>
+static __device__ __forceinline__ float pair_term(float sa, float sb, float ya, float yb, float ga, float gb, float da, float db,
+                                                  float sigma, float& loss) {
+    const float x = sigma * (sa - sb);
+    const float S = fminf(fmaxf(ya - yb, -1.0f), 1.0f);
+    const float w = LAMBDA ? fabsf(ga - gb) * fabsf(da - db) : 1.0f;
+    const float p = sigmoid_aten(x);
+    const float q = 1.0f - p;
+    const float pq = p * q;
+    const float pbar = 0.5f * (1.0f + S);
+    // BCE backward (p-pbar)/max(pq,1e-12), sigmoid backward *pq, then *sigma (the quotient to 2 ulp: a reciprocal and a multiply)
+    const float g = sigma * (w * __fdividef(p - pbar, fmaxf(pq, 1e-12f))) * pq;
+    // A log whose coefficient is zero contributes exactly +-0 (the -100 clamp keeps it finite), so for pbar in {0, 1}
+    // -- always the case when w != 0 under integer relevance grades -- ONE logarithm is evaluated.
+    float acc;
+    if (pbar == 1.0f || pbar == 0.0f) acc = fmaxf(logf(pbar == 1.0f ? p : q), -100.0f);
+    else acc = pbar * fmaxf(logf(p), -100.0f) + (1.0f - pbar) * fmaxf(logf(q), -100.0f);
+    loss -= w * acc;
+    return g;
+}
+
+template <bool LAMBDA>
+__global__ void pairwise_bce_circ_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
+                                         float* __restrict__ grad, float* __restrict__ loss_q,
+                                         int n, int npow2, float sigma) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64* keys = reinterpret_cast<u64*>(smem_raw);
+    float* ss = reinterpret_cast<float*>(keys + (LAMBDA ? npow2 : 0));
+    float* ys = ss + n;
+    float* ng = ys + n;
+    float* dinv = ng + n;
+    float* gout = dinv + n;
+    int* idx = reinterpret_cast<int*>(gout + n);
+    float* red = reinterpret_cast<float*>(idx + n);
+    float* xch = red + 33;                              // [2][PAIR_KB][n] partner mailbox
+
+    const int b = blockIdx.x, i = threadIdx.x;
+    const float* s = scores + (size_t)b * n;
+    const float* y = labels + (size_t)b * n;
+    if (LAMBDA) {
+        const float idcg = block_idcg(y, n, npow2, /*presort=*/true, keys, red);
+        for (int t = threadIdx.x; t < npow2; t += blockDim.x) keys[t] = t < n ? desc_key(s[t], t) : 0ull;
+        block_sort_desc(keys, npow2);
+        for (int r = threadIdx.x; r < n; r += blockDim.x) {
+            const int id = key_index(keys[r]);
+            idx[r] = id;
+            ss[r] = s[id];
+            const float yr = y[id];
+            ys[r] = yr;
+            ng[r] = gain_of(yr) / idcg;
+            dinv[r] = 1.0f / log2_rank(r);
+        }
+    } else {
+        for (int r = threadIdx.x; r < n; r += blockDim.x) { ss[r] = s[r]; ys[r] = y[r]; idx[r] = r; }
+    }
+    __syncthreads();
+
+    const bool mine = i < n;
+    const float si = mine ? ss[i] : 0.0f, yi = mine ? ys[i] : 0.0f;
+    const float gi = (LAMBDA && mine) ? ng[i] : 0.0f, di = (LAMBDA && mine) ? dinv[i] : 0.0f;
+    float own = 0.0f, loss = 0.0f;
+    auto visit = [&](int j, float* slot) {              // pair {i, j}: ordered as (min, max) like the reference's triu
+        const float sj = ss[j], yj = ys[j];
+        const float gj = LAMBDA ? ng[j] : 0.0f, dj = LAMBDA ? dinv[j] : 0.0f;
+        const bool first = i < j;
+        // (operand selects, then ONE evaluation: a conditional between two calls compiles to both)
+        const float g = pair_term<LAMBDA>(first ? si : sj, first ? sj : si, first ? yi : yj, first ? yj : yi,
+                                          first ? gi : gj, first ? gj : gi, first ? di : dj, first ? dj : di, sigma, loss);
+        own += first ? g : -g;
+        slot[j] = first ? -g : g;
+    };
+    const int half = (n - 1) / 2;
+    int buf = 0;
+    for (int k0 = 1; k0 <= half; k0 += PAIR_KB) {
+        float* xb = xch + (size_t)buf * PAIR_KB * n;
+#pragma unroll
+        for (int kk = 0; kk < PAIR_KB; ++kk) {
+            const int k = k0 + kk;
+            if (mine && k <= half) {
+                int j = i + k;
+                if (j >= n) j -= n;
+                visit(j, xb + kk * n);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < PAIR_KB; ++kk)
+            if (mine && k0 + kk <= half) own += xb[kk * n + i];
+        buf ^= 1;
+    }
+    if ((n & 1) == 0 && n >= 2) {                       // the diameter pairs (i, i + n/2)
+        float* xb = xch + (size_t)buf * PAIR_KB * n;
+        if (i < n / 2) visit(i + n / 2, xb);
+        __syncthreads();
+        if (mine && i >= n / 2) own += xb[i];
+    }
+    if (mine) gout[idx[i]] = own;
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) grad[(size_t)b * n + t] = gout[t];
+    loss = block_sum(loss, red);
+    if (threadIdx.x == 0) loss_q[b] = loss;
+}
+
 // ---------------------------------------------------------------------------
 // LambdaLoss (NDCG_Loss1 / NDCG_Loss2 / NDCG_Loss2++), truncated at the top-k
 // predicted positions.
@@ -551,6 +661,13 @@ static int launch_pairwise(const float* scores, const float* labels, float* grad
     if (rc) return rc;
     const int npow2 = next_pow2(n);
     const size_t smem = (LAMBDA ? (size_t)npow2 * 8 : 0) + (size_t)n * 4 * 6 + 33 * 4;
+    if (n <= 1024) {        // one thread per position: each unordered pair once
+        const size_t smem_c = smem + (size_t)2 * PAIR_KB * n * 4;
+        if ((rc = allow_smem(pairwise_bce_circ_kernel<LAMBDA>, smem_c))) return rc;
+        PTRB200_LAUNCH_TAG(LAMBDA ? "pairwise_bce_kernel<LAMBDA>" : "pairwise_bce_kernel<RANKNET>", pairwise_bce_circ_kernel<LAMBDA>, B, block_threads(n), smem_c, stream,
+                           scores, labels, grad, loss_q, n, npow2, sigma);
+        return check_launch(LAMBDA ? "lambdarank" : "ranknet");
+    }
     if ((rc = allow_smem(pairwise_bce_kernel<LAMBDA>, smem))) return rc;
     PTRB200_LAUNCH(pairwise_bce_kernel<LAMBDA>, B, block_threads(n), smem, stream, scores, labels, grad, loss_q, n, npow2, sigma);
     return check_launch(LAMBDA ? "lambdarank" : "ranknet");

@@ -50,15 +50,35 @@ class GradBucket:
     """Flat fp32 gradient buffer: every parameter's ``.grad`` is a view into it, so a step needs
     one ``all_reduce(SUM)`` (220.8 KB for the default pointwise scorer) instead of one per tensor."""
 
-    def __init__(self, params: Sequence[torch.nn.Parameter]):
+    def __init__(self, params: Sequence[torch.nn.Parameter], align: int = 1):
+        """``align``: every tensor starts at a multiple of ``align`` elements (4 keeps float4 access legal when the
+        parameters themselves are re-homed into a buffer of the same layout, see :meth:`flatten_params`)."""
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
-        total = sum(p.numel() for p in self.params)
-        dev = self.params[0].device if self.params else torch.device("cpu")
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.offsets: List[int] = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off: off + p.numel()].view_as(p)
-            off += p.numel()
+            self.offsets.append(off)
+            off += -(-p.numel() // align) * align
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat_param = None
+        for p, v in zip(self.params, self._views()):
+            p.grad = v
+
+    def flatten_params(self) -> torch.Tensor:
+        """Re-home every parameter into one flat buffer laid out exactly like the gradient buffer (values kept), so
+        an optimizer can update all of them in a single elementwise pass.  Modules keep their Parameter objects."""
+        if self.flat_param is None:
+            self.flat_param = torch.zeros_like(self.flat)
+            for p, o in zip(self.params, self.offsets):
+                view = self.flat_param[o: o + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+        return self.flat_param
+
+    def params_are_flat(self) -> bool:
+        return self.flat_param is not None and all(
+            p.data.data_ptr() == self.flat_param.data_ptr() + 4 * o for p, o in zip(self.params, self.offsets))
 
     def zero(self, skip_memset: bool = False) -> None:
         """optimizer.zero_grad() that keeps the views alive.  ``skip_memset``: every gradient is overwritten
@@ -70,10 +90,8 @@ class GradBucket:
                 p.grad = v
 
     def _views(self):
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, self.offsets):
             yield self.flat[off: off + p.numel()].view_as(p)
-            off += p.numel()
 
     def all_reduce(self) -> None:
         if is_distributed():

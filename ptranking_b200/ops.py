@@ -87,6 +87,18 @@ def sum_f32(x: torch.Tensor) -> torch.Tensor:
     return out.reshape(())
 
 
+def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
+              lr: float, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0) -> None:
+    """In-place torch.optim.Adam update of flat fp32 device buffers with identical layouts (one kernel)."""
+    lib = _lib.load()
+    for name, t in (("param", param), ("grad", grad), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == param.numel()):
+            raise ValueError(f"adam_step: {name} must be a contiguous fp32 CUDA tensor of {param.numel()} elements")
+    _lib.check(lib.ptrb200_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
+                                     float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
+                                     _stream_ptr()), "adam_step")
+
+
 class _RankLoss(torch.autograd.Function):
     """batch loss = sum of per-query losses; backward hands the fused gradient to the scorer."""
 
@@ -266,8 +278,10 @@ class _FFNetFn(torch.autograd.Function):
             _lib.check(int(nbytes), "ffnet_workspace_bytes")
         ws = torch.empty(int(nbytes), dtype=torch.uint8, device=X.device)
         out = torch.empty((B, n, spec.dims[-1]), dtype=torch.float32, device=X.device)
+        # bit 1 = forward only (PTRB200_FFNET_FORWARD_ONLY): nothing requires grad, skip the backward by-products
+        flags = int(training) | (0 if any(ctx.needs_input_grad) else 2)
         _lib.check(lib.ptrb200_ffnet_forward(C.byref(desc), X.data_ptr(), out.data_ptr(), ws.data_ptr(), int(nbytes),
-                                             B, n, int(training), seed, offset, _stream_ptr()), "ffnet_forward")
+                                             B, n, flags, seed, offset, _stream_ptr()), "ffnet_forward")
         ctx.spec, ctx.training, ctx.seed, ctx.offset = spec, training, seed, offset
         ctx.grad_targets = grad_targets
         ctx.ws, ctx.nbytes = ws, int(nbytes)

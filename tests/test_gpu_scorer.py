@@ -192,3 +192,49 @@ WIDE_CASES = [
 def test_wide_layers_on_tensor_cores_match_simt(case):
     """Column-tiled rows_gemm and column-blocked wgrad (layers wider than 256 / 128) vs the fp32 SIMT kernels."""
     test_tensor_core_path_matches_simt_path(case)
+
+
+FULL_CASES = [
+    # BASELINE.json configs[1]: 1024 queries x 256 documents x 136 features through the default 5x100 GELU+BN scorer
+    (1024, 256, [136, 100, 100, 100, 100, 100, 1], "GE", "S", "BN", True, 0.1),
+    (256, 1024, [136, 100, 100, 100, 100, 100, 1], "GE", "S", "BN2", False, 0.1),
+]
+
+
+@pytest.mark.parametrize("case", FULL_CASES, ids=[f"full{i}" for i in range(len(FULL_CASES))])
+def test_full_size_tensor_core_path_matches_simt(case):
+    """Same comparison at the benchmark's full size: the weight-gradient contraction runs over 262144 rows."""
+    test_tensor_core_path_matches_simt_path(case)
+
+
+@pytest.mark.parametrize("wd", [0.0, 1e-3])
+def test_flat_adam_matches_torch_adam(wd):
+    """ops.adam_step (one kernel over flat buffers) against torch.optim.Adam over several steps, lr schedule included."""
+    from ptranking_b200 import ops
+    torch.manual_seed(5)
+    n = 55204
+    p0 = torch.randn(n, device=DEV)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-2, weight_decay=wd)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=3, gamma=0.5)
+    p, m, v = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    for step in range(1, 8):
+        g = torch.randn(n, device=DEV) * (10.0 ** float(torch.randint(-3, 2, (1,))))
+        ref.grad = g.clone()
+        opt.step()
+        ops.adam_step(p, g, m, v, step, lr=opt.param_groups[0]["lr"], weight_decay=wd)
+        sched.step()
+        assert rel_err(p.cpu().numpy(), ref.detach().cpu().numpy()) <= 1e-6, step
+    st = opt.state[ref]
+    assert rel_err(m.cpu().numpy(), st["exp_avg"].cpu().numpy()) <= 1e-6
+    assert rel_err(v.cpu().numpy(), st["exp_avg_sq"].cpu().numpy()) <= 1e-6
+
+
+def test_ranker_parameters_live_in_one_flat_buffer():
+    r = _point_ranker("ListNet", 136)
+    b = r.grad_bucket
+    assert b.params_are_flat() and b.flat_param.numel() == b.flat.numel() and b.flat.numel() % 4 == 0
+    assert all(p.data_ptr() % 16 == 0 and p.grad.data_ptr() % 16 == 0 for p in b.params)
+    sd = {k: v.clone() for k, v in r.point_sf.state_dict().items()}
+    r.point_sf.load_state_dict(sd)                      # in-place copies keep the parameters inside the flat buffer
+    assert b.params_are_flat()

@@ -44,7 +44,7 @@ WANT = [("gpu__time_duration.sum", "duration us"), ("dram__bytes_read.sum", "dra
         ("launch__shared_mem_per_block_dynamic", "dyn smem KB")]
 traffic = {}
 NAME_MAP = {"rows_gemm_ws_kernel<0,": "rows_gemm_ws_fwd", "rows_gemm_ws_kernel<1,": "rows_gemm_ws_dgrad", "wgrad_tc_kernel": "wgrad_tc",
-            "colstat4_kernel<1>": "colstat_dy", "norm_bwd_apply4_kernel": "norm_bwd_apply4_kernel", "pairwise_bce_kernel": "pairwise_bce_kernel<LAMBDA>"}
+            "colstat4_kernel<1>": "colstat_dy", "norm_bwd_apply4_kernel": "norm_bwd_apply4_kernel", "pairwise_bce_": "pairwise_bce_kernel<LAMBDA>"}
 with open(os.path.join(P, f"{tag}_kernels_full.md"), "w") as f:
     f.write(f"# {tag}: `ncu --set full --clock-control none --import-source on` of the heavy kernels\n\n")
     f.write("One launch each from the second training step (B=1024 x 256 x 136).  dram bytes are per launch.\n\n")
