@@ -12,6 +12,7 @@
 // Layout in HBM: activations are dense row-major [rows = B*n, width] fp32.  Per layer the
 // workspace keeps Z (pre-normalisation Linear output), A (post-activation) and, when a norm
 // is present, mean/rstd per (group, channel); group = whole batch (BN) or one query (BN2).
+#include <stdlib.h>
 #include "common.cuh"
 #include "ffnet_act.cuh"
 #include "ffnet_tc.cuh"
@@ -130,12 +131,21 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
 }
 
 // sum partials[splits, count] over splits in fixed order -> out[count]
-__global__ void reduce_splits_kernel(const float* __restrict__ partials, float* __restrict__ out, int splits, int count) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
+// out[i] = sum_p partials[p][i].  Block = 64 outputs x 4 split groups: group q adds splits q, q+4, ... (independent
+// loads, unrolled), then the four group sums are combined in a fixed order -- deterministic, and 4x the loads in flight
+// of a one-thread-per-output loop over ~148 splits.
+__global__ void __launch_bounds__(256) reduce_splits_kernel(const float* __restrict__ partials, float* __restrict__ out, int splits, int count) {
+    __shared__ float sh[4][64];
+    const int e = threadIdx.x & 63, q = threadIdx.x >> 6;
+    const int i = blockIdx.x * 64 + e;
     float s = 0.0f;
-    for (int p = 0; p < splits; ++p) s += partials[(size_t)p * count + i];
-    out[i] = s;
+    if (i < count) {
+#pragma unroll 8
+        for (int p = q; p < splits; p += 4) s += __ldg(partials + (size_t)p * count + i);
+    }
+    sh[q][e] = s;
+    __syncthreads();
+    if (q == 0 && i < count) out[i] = (sh[0][e] + sh[1][e]) + (sh[2][e] + sh[3][e]);
 }
 
 // ------------------------------------------------------------------ column statistics
@@ -211,8 +221,10 @@ __global__ void colstat_kernel(const float* __restrict__ Z, const float* __restr
 // product dA[r,c] = dropmask(dz[r] * w[c]) -- built on the fly here instead of being written and re-read.
 struct Rank1Src { const float* w; DropCfg drop; };     // w == NULL: dA is a dense [rows, C] tensor
 
+// (4 resident CTAs per SM = 64 registers: measured best for this latency-bound sweep -- 0.51 ms per step against 0.58 at
+// 3 CTAs/72 registers and 0.62 at 5-6 CTAs with their spills)
 template <int WHAT>
-__global__ void colstat4_kernel(const float* __restrict__ Z, const float* __restrict__ dA, float* __restrict__ dY_out,
+__global__ void __launch_bounds__(256, 4) colstat4_kernel(const float* __restrict__ Z, const float* __restrict__ dA, float* __restrict__ dY_out,
                                 NormRef nr, double* __restrict__ partials, int gr, int C, int S, int slice_rows, Rank1Src rk) {
     extern __shared__ double sh4[];
     const int Q = blockDim.x, RY = blockDim.y, q = threadIdx.x, ry = threadIdx.y, c = q * 4;
@@ -354,15 +366,37 @@ __global__ void __launch_bounds__(FIN_THREADS) moments_finalize_kernel(
 }
 
 // backward finalize: per-(group,channel) sums S1,S2 (float, optional) + totals over groups T1,T2 per channel.  grid = C
+// Everything that depends only on those sums rides along (DyTail): the norm-parameter gradients, the Linear bias gradient
+// and the coefficients of the folded normalisation backward  dZ = k1*dY + k3*z + k0  with
+//   k1 = a*rstd,  k3 = -a*rstd^2*S2/N,  k0 = -a*rstd*S1/N + a*rstd^2*S2/N*mean      (a = gamma*aff_w)
+struct DyTail {
+    NormRef nr;
+    float *dgamma, *dbeta, *daff_w, *daff_b;    // norm parameter gradients from T1 = sum dY, T2 = sum dY*xhat (NULL: skip)
+    float *k1, *k3, *k0;                        // [G,C] or NULL
+    int gr;
+    float* bias_grad;                           // [C] or NULL
+    int bias_mode;                              // 1: exact zero (the bias feeds a normalisation), 2: T1
+};
+static __device__ __forceinline__ void dz_coeff_one(const DyTail& t, size_t i, int c, float s1, float s2) {
+    float a, cc;
+    norm_coeffs(t.nr, c, a, cc);
+    const float rs = t.nr.rstd[i], mu = t.nr.mean[i], invN = 1.0f / (float)t.gr;
+    const float ar = a * rs, q = ar * rs * (s2 * invN);
+    t.k1[i] = ar;
+    t.k3[i] = -q;
+    t.k0[i] = q * mu - ar * (s1 * invN);
+}
+
 __global__ void __launch_bounds__(FIN_THREADS) dy_finalize_kernel(
         const double* __restrict__ partials, float* __restrict__ S1, float* __restrict__ S2,
-        float* __restrict__ T1, float* __restrict__ T2, int G, int C, int S) {
+        float* __restrict__ T1, float* __restrict__ T2, int G, int C, int S, DyTail tail) {
     const int c = blockIdx.x;
     double t1 = 0.0, t2 = 0.0;
     if (S == 1) {
         for (int g = threadIdx.x; g < G; g += FIN_THREADS) {
             const double* p = partials + ((size_t)g * C + c) * 2;
             if (S1) { S1[(size_t)g * C + c] = (float)p[0]; S2[(size_t)g * C + c] = (float)p[1]; }
+            if (tail.k1) dz_coeff_one(tail, (size_t)g * C + c, c, (float)p[0], (float)p[1]);
             t1 += p[0]; t2 += p[1];
         }
         block_sum2_d(t1, t2);
@@ -371,11 +405,26 @@ __global__ void __launch_bounds__(FIN_THREADS) dy_finalize_kernel(
             double s1 = 0.0, s2 = 0.0;
             for (int s = threadIdx.x; s < S; s += FIN_THREADS) { const double* p = partials + (((size_t)g * S + s) * C + c) * 2; s1 += p[0]; s2 += p[1]; }
             block_sum2_d(s1, s2);
-            if (S1 && threadIdx.x == 0) { S1[(size_t)g * C + c] = (float)s1; S2[(size_t)g * C + c] = (float)s2; }
+            if (threadIdx.x == 0) {
+                if (S1) { S1[(size_t)g * C + c] = (float)s1; S2[(size_t)g * C + c] = (float)s2; }
+                if (tail.k1) dz_coeff_one(tail, (size_t)g * C + c, c, (float)s1, (float)s2);
+            }
             t1 += s1; t2 += s2;
         }
     }
-    if (threadIdx.x == 0) { T1[c] = (float)t1; if (T2) T2[c] = (float)t2; }
+    if (threadIdx.x == 0) {
+        const float f1 = (float)t1, f2 = (float)t2;
+        if (T1) T1[c] = f1;
+        if (T2) T2[c] = f2;
+        const NormRef& nr = tail.nr;
+        const float ga = nr.gamma ? nr.gamma[c] : 1.0f, be = nr.beta ? nr.beta[c] : 0.0f;
+        const float w = nr.aff_w ? nr.aff_w[c] : 1.0f;
+        if (tail.dgamma) tail.dgamma[c] = w * f2;
+        if (tail.dbeta) tail.dbeta[c] = w * f1;
+        if (tail.daff_w) tail.daff_w[c] = ga * f2 + be * f1;
+        if (tail.daff_b) tail.daff_b[c] = f1;
+        if (tail.bias_grad) tail.bias_grad[c] = tail.bias_mode == 1 ? 0.0f : f1;
+    }
 }
 
 // coefficients of the folded normalisation backward: dZ = k1*dY + k3*z + k0 with
@@ -856,38 +905,36 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
             float* dY = dbuf[flip]; flip ^= 1;
             launch_colstat<STAT_DY>(st, "colstat_dy", Z, dA, dY, nr, part, p.G, bS, p.gr, lp.d_out, bslice, r1);
             r1.w = nullptr;
-            PTRB200_LAUNCH(dy_finalize_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)part,
-                           lp.has_norm ? S1 : (float*)nullptr, lp.has_norm ? S2 : (float*)nullptr, T1, T2, p.G, lp.d_out, bS);
+            // one finalize launch: channel sums -> norm-parameter gradients, bias gradient, folded-dZ coefficients
+            DyTail tail{};
+            tail.nr = nr; tail.gr = p.gr;
+            tail.bias_grad = grads->bias[l];
+            // A Linear bias feeding a normalisation has an exactly-zero gradient (the norm removes every
+            // per-channel shift); the reference's autograd produces rounding noise there.
+            tail.bias_mode = lp.has_norm ? 1 : 2;
             if (lp.has_norm) {
-                float *dg = nullptr, *db = nullptr, *dw = nullptr, *dbw = nullptr;
-                if (net->norm == PTRB200_NORM_BN) { if (net->norm_affine) { dg = grads->gamma[l]; db = grads->beta[l]; } }
-                else { dg = grads->gamma[l]; db = grads->beta[l]; if (net->norm_affine) { dw = grads->aff_w[l]; dbw = grads->aff_b[l]; } }
-                PTRB200_LAUNCH(norm_param_grad_kernel, (lp.d_out + 127) / 128, 128, 0, st, nr, (const float*)T1, (const float*)T2, dg, db, dw, dbw, lp.d_out);
+                if (net->norm == PTRB200_NORM_BN) { if (net->norm_affine) { tail.dgamma = grads->gamma[l]; tail.dbeta = grads->beta[l]; } }
+                else { tail.dgamma = grads->gamma[l]; tail.dbeta = grads->beta[l]; if (net->norm_affine) { tail.daff_w = grads->aff_w[l]; tail.daff_b = grads->aff_b[l]; } }
                 // fold dZ = a*rstd*(dY - S1/N - xhat*S2/N) into the operand staging of dgrad and wgrad when both can take it
                 // (saves one 12-bytes-per-element pass); otherwise materialise dZ in place
-                {
-                    int Rf = 32, stf = 0;
-                    const int KPl = ((lp.d_in + 15) / 16) * 16;
-                    fuse_dz = lp.d_out % 4 == 0 && lp.d_out <= 128 && lp.d_in <= 256 && (l == 0 || rows_ws_fits(lp.d_out, lp.d_in, p.passes)) &&
-                              wgrad_smem(lp.d_out, lp.d_in, KPl, Rf, p.passes, stf, true, 32) <= (size_t)227 * 1024;
-                }
+                int Rf = 32, stf = 0;
+                const int KPl = ((lp.d_in + 15) / 16) * 16;
+                fuse_dz = lp.d_out % 4 == 0 && lp.d_out <= 128 && lp.d_in <= 256 && (l == 0 || rows_ws_fits(lp.d_out, lp.d_in, p.passes)) &&
+                          wgrad_smem(lp.d_out, lp.d_in, KPl, Rf, p.passes, stf, true, 32) <= (size_t)227 * 1024;
+                if (fuse_dz) { tail.k1 = reinterpret_cast<float*>(ws + p.k1_off); tail.k3 = reinterpret_cast<float*>(ws + p.k3_off); tail.k0 = reinterpret_cast<float*>(ws + p.k0_off); }
+            }
+            PTRB200_LAUNCH(dy_finalize_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)part,
+                           (lp.has_norm && !fuse_dz) ? S1 : (float*)nullptr, (lp.has_norm && !fuse_dz) ? S2 : (float*)nullptr,
+                           (float*)nullptr, (float*)nullptr, p.G, lp.d_out, bS, tail);
+            if (lp.has_norm) {
                 if (fuse_dz) {
-                    const int cnt = p.G * lp.d_out;
-                    PTRB200_LAUNCH(dz_coeff_kernel, (cnt + 255) / 256, 256, 0, st, nr, (const float*)S1, (const float*)S2,
-                                   reinterpret_cast<float*>(ws + p.k1_off), reinterpret_cast<float*>(ws + p.k3_off), reinterpret_cast<float*>(ws + p.k0_off),
-                                   p.G, lp.d_out, p.gr);
                 } else if (lp.d_out % 4 == 0) PTRB200_LAUNCH(norm_bwd_apply4_kernel, elementwise_blocks(total / 4), 256, 0, st, Z, dY, nr, (const float*)S1, (const float*)S2, total / 4, lp.d_out, p.gr);
                 else PTRB200_LAUNCH(norm_bwd_apply_kernel, elementwise_blocks(total), 256, 0, st, Z, dY, nr, (const float*)S1, (const float*)S2, total, lp.d_out, p.gr);
-                // A Linear bias feeding a normalisation has an exactly-zero gradient (the norm removes every
-                // per-channel shift); the reference's autograd produces rounding noise there.
-                cudaMemsetAsync(grads->bias[l], 0, (size_t)lp.d_out * 4, st);
-            } else {
-                cudaMemcpyAsync(grads->bias[l], T1, (size_t)lp.d_out * 4, cudaMemcpyDeviceToDevice, st);
             }
             dZ = dY;
         } else {
             PTRB200_LAUNCH(colstat_kernel<STAT_COLSUM>, sgrid, dim3(32, 8), 0, st, dA, (const float*)nullptr, (float*)nullptr, nr, part, p.gr, lp.d_out, p.S_stat, p.slice_rows);
-            PTRB200_LAUNCH(dy_finalize_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)part, (float*)nullptr, (float*)nullptr, grads->bias[l], (float*)nullptr, p.G, lp.d_out, p.S_stat);
+            PTRB200_LAUNCH(dy_finalize_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)part, (float*)nullptr, (float*)nullptr, grads->bias[l], (float*)nullptr, p.G, lp.d_out, p.S_stat, DyTail{});
         }
         const float layer_drop = last ? 0.0f : drop;
         // ---- dW on tensor cores: sum_rows dZ^T (x) rebuilt layer input ----
@@ -917,7 +964,7 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
             if (p.passes == 3) { if ((rc = opt_in_smem(wgrad_tc_kernel<3>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<3>, grid, WG_THREADS, smem, st, w); }
             else { if ((rc = opt_in_smem(wgrad_tc_kernel<1>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<1>, grid, WG_THREADS, smem, st, w); }
             const int cnt = lp.d_in * lp.d_out;
-            PTRB200_LAUNCH(reduce_splits_kernel, (cnt + 255) / 256, 256, 0, st, (const float*)wpart, grads->weight[l], wb.gx, cnt);
+            PTRB200_LAUNCH(reduce_splits_kernel, (cnt + 63) / 64, 256, 0, st, (const float*)wpart, grads->weight[l], wb.gx, cnt);
         }
         // ---- dIn = dropmask(dZ * W) ----
         if (l > 0 || dX) {
@@ -986,7 +1033,7 @@ int ptrb200_tc_wgrad(const float* dZ, const float* P, float* dW, float* partials
     cudaStream_t st = (cudaStream_t)stream;
     if (passes == 3) { if ((rc = opt_in_smem(wgrad_tc_kernel<3>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<3>, grid, WG_THREADS, smem, st, w); }
     else { if ((rc = opt_in_smem(wgrad_tc_kernel<1>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<1>, grid, WG_THREADS, smem, st, w); }
-    PTRB200_LAUNCH(reduce_splits_kernel, (N * K + 255) / 256, 256, 0, st, (const float*)partials, dW, grid, N * K);
+    PTRB200_LAUNCH(reduce_splits_kernel, (N * K + 63) / 64, 256, 0, st, (const float*)partials, dW, grid, N * K);
     return check_launch("tc_wgrad");
 }
 
@@ -1076,7 +1123,7 @@ int ptrb200_ffnet_backward(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* 
             dim3 grid(p.G, p.S_stat);
             PTRB200_LAUNCH(colstat_kernel<STAT_DY>, grid, dim3(32, 8), 0, st, Z, dA, dY, nr, part, p.gr, lp.d_out, p.S_stat, p.slice_rows);
             PTRB200_LAUNCH(dy_finalize_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)part,
-                           lp.has_norm ? S1 : (float*)nullptr, lp.has_norm ? S2 : (float*)nullptr, T1, T2, p.G, lp.d_out, p.S_stat);
+                           lp.has_norm ? S1 : (float*)nullptr, lp.has_norm ? S2 : (float*)nullptr, T1, T2, p.G, lp.d_out, p.S_stat, DyTail{});
             if (lp.has_norm) {
                 float *dg = nullptr, *db = nullptr, *dw = nullptr, *dbw = nullptr;
                 if (net->norm == PTRB200_NORM_BN) { if (net->norm_affine) { dg = grads->gamma[l]; db = grads->beta[l]; } }
@@ -1085,7 +1132,7 @@ int ptrb200_ffnet_backward(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* 
                 PTRB200_LAUNCH(norm_bwd_apply_kernel, elementwise_blocks(total), 256, 0, st, Z, dY, nr, (const float*)S1, (const float*)S2, total, lp.d_out, p.gr);
                 // bias gradient = column sums of dZ (zero up to rounding under a norm, as in the reference)
                 PTRB200_LAUNCH(colstat_kernel<STAT_COLSUM>, grid, dim3(32, 8), 0, st, (const float*)dY, (const float*)nullptr, (float*)nullptr, nr, part, p.gr, lp.d_out, p.S_stat, p.slice_rows);
-                PTRB200_LAUNCH(dy_finalize_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)part, (float*)nullptr, (float*)nullptr, grads->bias[l], (float*)nullptr, p.G, lp.d_out, p.S_stat);
+                PTRB200_LAUNCH(dy_finalize_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)part, (float*)nullptr, (float*)nullptr, grads->bias[l], (float*)nullptr, p.G, lp.d_out, p.S_stat, DyTail{});
             } else {
                 cudaMemcpyAsync(grads->bias[l], T1, (size_t)lp.d_out * 4, cudaMemcpyDeviceToDevice, st);
             }
@@ -1093,7 +1140,7 @@ int ptrb200_ffnet_backward(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* 
         } else {
             dim3 grid(p.G, p.S_stat);
             PTRB200_LAUNCH(colstat_kernel<STAT_COLSUM>, grid, dim3(32, 8), 0, st, dA, (const float*)nullptr, (float*)nullptr, nr, part, p.gr, lp.d_out, p.S_stat, p.slice_rows);
-            PTRB200_LAUNCH(dy_finalize_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)part, (float*)nullptr, (float*)nullptr, grads->bias[l], (float*)nullptr, p.G, lp.d_out, p.S_stat);
+            PTRB200_LAUNCH(dy_finalize_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)part, (float*)nullptr, (float*)nullptr, grads->bias[l], (float*)nullptr, p.G, lp.d_out, p.S_stat, DyTail{});
         }
         const bool last = l == p.L - 1;
         const float layer_drop = last ? 0.0f : drop;
@@ -1106,7 +1153,7 @@ int ptrb200_ffnet_backward(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* 
             g.drop = make_drop(layer_drop, seed, offset * 64 + (uint64_t)l);
             launch_gemm<GEMM_BWD_WEIGHT>(g, p.S_w, st);
             const int cnt = lp.d_in * lp.d_out;
-            PTRB200_LAUNCH(reduce_splits_kernel, (cnt + 255) / 256, 256, 0, st, (const float*)wpart, grads->weight[l], p.S_w, cnt);
+            PTRB200_LAUNCH(reduce_splits_kernel, (cnt + 63) / 64, 256, 0, st, (const float*)wpart, grads->weight[l], p.S_w, cnt);
         }
         // dIn = dropout'(dZ * W)
         if (l > 0 || dX) {
