@@ -702,7 +702,7 @@ struct WgradArgs {
     int stages;            // raw-tile ring depth (2..WG_MAX_STAGES), chosen by the host to fit shared memory
 };
 
-constexpr int WG_PRODUCERS = 256;      // 8 warps split raw fp32 tiles into hi/lo TF32 operand buffers
+constexpr int WG_PRODUCERS = 512;      // 16 warps split raw fp32 tiles into hi/lo TF32 operand buffers: 8 take dZ, 8 the layer input
 constexpr int WG_THREADS = WG_PRODUCERS + 32;   // + 1 control warp: TMA bulk loads and tcgen05.mma issue
 constexpr int WG_MAX_STAGES = 4;      // raw-tile ring depth bound (TMA bulk copies in flight)
 
@@ -831,9 +831,10 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
         RowsGemmArgs pg{};
         pg.scale = g.scale; pg.shift = g.shift; pg.act = g.act; pg.gr_prev = g.gr_prev; pg.K = g.K_full; pg.drop = g.drop;
         const bool plain_p = !g.scale && g.act == PTRB200_AF_NONE && !g.drop.thr;   // layer input already materialised
-        const int r = tid >> 3, j = tid & 7;              // one 16-byte unit per thread per 32-column chunk (R*8 <= 256)
+        const int ptid = tid & 255, role = tid >> 8;      // role 0 stages the dZ operand, role 1 the layer-input operand
+        const int r = ptid >> 3, j = ptid & 7;            // one 16-byte unit per thread per 32-column chunk (R*8 <= 256)
         const bool vec_z = (N & 3) == 0;
-        const bool active = tid < R * 8;
+        const bool active = ptid < R * 8;
         const uint32_t sw = tc::swz32_offset(r, j);       // this thread's slot inside every operand chunk
         const int zoff = r * N + j * 4, poff = r * K + j * 4;
         int s = 0;
@@ -855,8 +856,8 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
                 asm volatile("bar.sync 1, %0;" ::"n"(WG_PRODUCERS) : "memory");
             }
             tc::mbar_wait(fbar, fpar);
-            if (active) {
-                const bool row_ok = r < nrows;
+            const bool row_ok = r < nrows;
+            if (active && role == 0) {
                 const float* zsrc = rz + zoff;
 #pragma unroll
                 for (int ch = 0; ch < z_chunks; ++ch) {
@@ -877,6 +878,8 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
                     }
                     store_split(z_hi + ch * chunk_bytes, z_lo + ch * chunk_bytes, 0, v, PASSES == 3);
                 }
+            }
+            if (active && role == 1) {
                 const float* psrc = rp + poff;
                 for (int ch = 0; ch < p_chunks; ++ch) {
                     const int k = ch * 32 + j * 4;
@@ -898,11 +901,12 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
     if (warp < WG_PRODUCERS / 32) {
         if (my_tiles >= 1) { const int it = my_tiles - 1; tc::mbar_wait(opfree + (it & 1), (it >> 1) & 1); }
         tc::fence_after_sync();
-        const int q = warp & 3, half = warp >> 2;
+        constexpr int NSPLIT = WG_PRODUCERS / 128;           // warps per TMEM lane quarter: each takes a column range
+        const int q = warp & 3, part = warp >> 2;
         const int n = q * 32 + lane;
         float* dst = g.partials + (size_t)blockIdx.x * g.N_full * g.K_full + (size_t)m0 * g.K_full + kk0;
-        const int cols_half = ((KP / 8 + 1) / 2) * 8;
-        const int c_begin = half == 0 ? 0 : cols_half, c_end = half == 0 ? min(cols_half, KP) : KP;
+        const int cols_part = ((KP / 8 + NSPLIT - 1) / NSPLIT) * 8;
+        const int c_begin = min(part * cols_part, KP), c_end = min(c_begin + cols_part, KP);
         for (int c0 = c_begin; c0 < c_end; c0 += 8) {
             float v[8];
             if (my_tiles > 0) tc::tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
