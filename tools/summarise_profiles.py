@@ -16,8 +16,7 @@ hdr = rows[0]
 ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
 launches = [(r[ki], float(r[vi].replace(",", "")) / 1e3) for r in rows[1:]]
 # steps start at the first forward layer kernel
-starts = [i for i, (n, _) in enumerate(launches) if "pack_b_image_kernel<0>" in n]
-step_starts = [s for j, s in enumerate(starts) if j % 6 == 0]
+step_starts = [i for i, (n, _) in enumerate(launches) if "pack_b_images_kernel" in n]     # one packing launch opens every step
 a, b = (step_starts[-2], step_starts[-1]) if len(step_starts) >= 2 else (0, len(launches))
 step = launches[a:b]
 acc = collections.OrderedDict()
