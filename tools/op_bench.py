@@ -89,6 +89,14 @@ for L in (3, 6):
     ms_s = timeit(lambda: rl.train_op(X, y, presort=True, label_type=LABEL_TYPE.MultiLabel, epoch_k=1), iters=5, warm=2)
     flops = 3 * n * (865280 + L * (147968 + 4 * n * 136)) * B
     rows.append((f"ApproxNDCG + listsf DASALC L={L} train step", f"B={B} n={n}", ms_s, B / ms_s * 1e3, flops / ms_s / 1e9, float('nan')))
+    if L == 3:      # per-kernel breakdown of this step (CUDA events around every launch of the library; serialised)
+        from ptranking_b200 import _lib
+        _lib.kernel_timings(enable=True)
+        for _ in range(2):
+            rl.train_op(X, y, presort=True, label_type=LABEL_TYPE.MultiLabel, epoch_k=1)
+        torch.cuda.synchronize()
+        listsf_kernels = {k: (v[0] / 2, v[1] / 2) for k, v in _lib.kernel_timings().items()}
+        _lib.kernel_timings(enable=False)
 
 os.makedirs("profiles", exist_ok=True)
 with open(f"profiles/{tag}_op_table.md", "w") as f:
@@ -98,4 +106,7 @@ with open(f"profiles/{tag}_op_table.md", "w") as f:
     f.write("| op | shape | ms | queries/s | GB/s (GFLOP/s) | frac of HBM |\n|---|---|---|---|---|---|\n")
     for name, shape, ms, qps, gbs, frac in rows:
         f.write(f"| {name} | {shape} | {ms:.4f} | {qps:,.0f} | {gbs:,.1f} | {frac:.4f} |\n")
+    f.write("\n## kernels of one ApproxNDCG + listsf DASALC L=3 step (B=64, n=512; launches and ms per step)\n\n| kernel | launches | ms |\n|---|---|---|\n")
+    for k, (c, ms) in sorted(listsf_kernels.items(), key=lambda kv: -kv[1][1]):
+        f.write(f"| `{k}` | {c:.0f} | {ms:.4f} |\n")
 print(open(f"profiles/{tag}_op_table.md").read())
