@@ -5,8 +5,9 @@
 // and its autograd.  Round-1 design ("materialised S"): the five contractions of forward + backward
 //     S = Q K^T,   O = A_d V,   dA_d = dO V^T,   dQ = dS K,   dK = dS^T Q,   dV = A_d^T dO
 // all run through ONE batched, strided  C[z] = alpha * op(A[z]) * B[z]^T  kernel (kind::tf32, 3xTF32 split, fp32
-// accumulation in TMEM); row softmax / softmax-backward are streaming SIMT kernels over the [n,n] score tensor, and
-// operands that are needed transposed are transposed explicitly.  The [n,n] tensors live in HBM (n <= 1024 per
+// accumulation in TMEM); row softmax / softmax-backward are streaming SIMT kernels over the [n,n] score tensor.  A factor that
+// enters a contraction transposed (V, K, Q, dO as [key|query, d]; dS and A_d as [query, key] for dK / dV) is consumed in place
+// as an MN-major tcgen05 operand, never transposed in memory.  The [n,n] tensors live in HBM (n <= 1024 per
 // list: 134 MB per layer at B=64, n=512, 2 heads) -- the fully fused flash variant is the follow-up.
 #include "common.cuh"
 #include "tc.cuh"
@@ -25,6 +26,10 @@ struct BGemmArgs {
     // the attention matrix): id = (z*K + col)*M + row
     int drop_mode;
     DropCfg drop;
+    // operand storage: 0 = K-major as written above (A[M,K], B[N,K] row-major); 1 = MN-major, the operand is stored
+    // transposed ([K,M] resp. [K,N] row-major, pitch lda/ldb between k-rows) and consumed as an MN-major tcgen05 operand
+    // (SWIZZLE_128B_BASE32B), so a transposed factor never has to be materialised.  drop_mode 2 goes with a_mn.
+    int a_mn, b_mn;
 };
 
 constexpr int BG_THREADS = 256, BG_NT = 128;
@@ -62,7 +67,7 @@ __global__ void __launch_bounds__(BG_THREADS) bgemm_nt_tc_kernel(BGemmArgs g) {
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = *slot;
-    const uint32_t idesc = tc::instr_desc(2, 128, NP);
+    const uint32_t idesc = tc::instr_desc(2, 128, NP) | (g.a_mn ? (1u << 15) : 0u) | (g.b_mn ? (1u << 16) : 0u);
     const bool vecA = (g.lda & 3) == 0 && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
     const bool vecB = (g.ldb & 3) == 0 && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
 
@@ -75,46 +80,68 @@ __global__ void __launch_bounds__(BG_THREADS) bgemm_nt_tc_kernel(BGemmArgs g) {
         if (k + 3 < K) v.w = p[k + 3];
         return v;
     };
+    auto load4m = [&](const float* p, int c0, int lim, bool vec) -> float4 {   // guarded 4-wide load at column c0 (< lim) of a row
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + 3 < lim && vec) return __ldg(reinterpret_cast<const float4*>(p + c0));
+        if (c0 < lim) v.x = p[c0];
+        if (c0 + 1 < lim) v.y = p[c0 + 1];
+        if (c0 + 2 < lim) v.z = p[c0 + 2];
+        if (c0 + 3 < lim) v.w = p[c0 + 3];
+        return v;
+    };
     for (int c = 0; c < nchunks; ++c) {
         const int k0 = c * 32;
         float4 av[4], bv[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int u = tid + i * BG_THREADS, r = u >> 3, j = u & 7, k = k0 + j * 4;
-            av[i] = (m0 + r < g.M) ? load4(A + (size_t)(m0 + r) * g.lda, k, vecA) : make_float4(0.f, 0.f, 0.f, 0.f);
-            bv[i] = (r < N) ? load4(B + (size_t)(n0 + r) * g.ldb, k, vecB) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int u = tid + i * BG_THREADS, r = u >> 3, j = u & 7, k = k0 + j * 4;      // K-major: row r, 16-byte unit j
+            const int kr = u >> 5, mu = (u & 31) * 4;                                       // MN-major: k-row kr, columns mu..mu+3
+            if (g.a_mn) av[i] = (k0 + kr < K) ? load4m(A + (size_t)(k0 + kr) * g.lda, m0 + mu, g.M, vecA) : make_float4(0.f, 0.f, 0.f, 0.f);
+            else av[i] = (m0 + r < g.M) ? load4(A + (size_t)(m0 + r) * g.lda, k, vecA) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g.b_mn) bv[i] = (k0 + kr < K) ? load4m(B + (size_t)(k0 + kr) * g.ldb, n0 + mu, n0 + N, vecB) : make_float4(0.f, 0.f, 0.f, 0.f);
+            else bv[i] = (r < N) ? load4(B + (size_t)(n0 + r) * g.ldb, k, vecB) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (c > 0) tc::mbar_wait(mbar, (c - 1) & 1);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int u = tid + i * BG_THREADS, r = u >> 3, j = u & 7, k = k0 + j * 4;
+            const int kr = u >> 5, mu = (u & 31) * 4;
+            const uint32_t off_k = tc::swz_offset(r, j);                                             // K-major slot
+            const uint32_t off_mn = (uint32_t)((u & 31) >> 3) * 4096u + tc::swz32_offset(kr, u & 7);   // MN-major: 32-column chunk, k-row, unit
             float4 v = av[i];
-            if (g.drop_mode && g.drop.thr && m0 + r < g.M) {
+            if (g.drop_mode && g.drop.thr) {
                 float* e = &v.x;
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    const uint64_t id = g.drop_mode == 1 ? ((uint64_t)z * g.M + (m0 + r)) * K + (k + t)
-                                                         : ((uint64_t)z * K + (k + t)) * g.M + (m0 + r);
-                    e[t] = (k + t < K && dropout_keep(g.drop.key, id, g.drop.thr)) ? e[t] * g.drop.scale : 0.0f;
+                    // element ids follow the row-major order of the stored attention matrix in both views
+                    const uint64_t id = g.a_mn ? ((uint64_t)z * K + (k0 + kr)) * g.M + (m0 + mu + t)
+                                               : ((uint64_t)z * g.M + (m0 + r)) * K + (k + t);
+                    e[t] = dropout_keep(g.drop.key, id, g.drop.thr) ? e[t] * g.drop.scale : 0.0f;      // (out-of-range elements are already 0)
                 }
             }
             float4 h, l;
             tc::split_tf32_rn(v.x, h.x, l.x); tc::split_tf32_rn(v.y, h.y, l.y); tc::split_tf32_rn(v.z, h.z, l.z); tc::split_tf32_rn(v.w, h.w, l.w);
-            const uint32_t off = tc::swz_offset(r, j);
-            *reinterpret_cast<float4*>(a_hi + off) = PASSES == 3 ? h : v;
-            if (PASSES == 3) *reinterpret_cast<float4*>(a_lo + off) = l;
+            const uint32_t offa = g.a_mn ? off_mn : off_k;
+            *reinterpret_cast<float4*>(a_hi + offa) = PASSES == 3 ? h : v;
+            if (PASSES == 3) *reinterpret_cast<float4*>(a_lo + offa) = l;
             const float4 w = bv[i];
             tc::split_tf32_rn(w.x, h.x, l.x); tc::split_tf32_rn(w.y, h.y, l.y); tc::split_tf32_rn(w.z, h.z, l.z); tc::split_tf32_rn(w.w, h.w, l.w);
-            *reinterpret_cast<float4*>(b_hi + off) = PASSES == 3 ? h : w;
-            if (PASSES == 3) *reinterpret_cast<float4*>(b_lo + off) = l;
+            const uint32_t offb = g.b_mn ? off_mn : off_k;
+            *reinterpret_cast<float4*>(b_hi + offb) = PASSES == 3 ? h : w;
+            if (PASSES == 3) *reinterpret_cast<float4*>(b_lo + offb) = l;
         }
         tc::fence_proxy_async();
         __syncthreads();
         if (warp == 0) {
             tc::fence_after_sync();
             const int ksteps = min(4, (K - k0 + 7) / 8);
-            uint64_t ah = tc::smem_desc_sw128(tc::smem_u32(a_hi), 1024), al = tc::smem_desc_sw128(tc::smem_u32(a_lo), 1024);
-            uint64_t bh = tc::smem_desc_sw128(tc::smem_u32(b_hi), 1024), bl = tc::smem_desc_sw128(tc::smem_u32(b_lo), 1024);
+            // K-major: 8-row atoms 1024 B apart, +32 B per K-step; MN-major: 32-column chunks 4096 B apart, 4-row groups 512 B
+            // apart, +1024 B per K-step (descriptor addresses count 16-byte units)
+            uint64_t ah = g.a_mn ? tc::smem_desc_sw128_mn(tc::smem_u32(a_hi), 4096, 512) : tc::smem_desc_sw128(tc::smem_u32(a_hi), 1024);
+            uint64_t al = g.a_mn ? tc::smem_desc_sw128_mn(tc::smem_u32(a_lo), 4096, 512) : tc::smem_desc_sw128(tc::smem_u32(a_lo), 1024);
+            uint64_t bh = g.b_mn ? tc::smem_desc_sw128_mn(tc::smem_u32(b_hi), 4096, 512) : tc::smem_desc_sw128(tc::smem_u32(b_hi), 1024);
+            uint64_t bl = g.b_mn ? tc::smem_desc_sw128_mn(tc::smem_u32(b_lo), 4096, 512) : tc::smem_desc_sw128(tc::smem_u32(b_lo), 1024);
+            const uint64_t da = g.a_mn ? 64 : 2, db = g.b_mn ? 64 : 2;
             if (tc::elect_one()) {
                 const uint32_t t_main = tmem + (uint32_t)((c % nmain) * NP), t_corr = tmem + (uint32_t)(nmain * NP);
                 for (int s = 0; s < ksteps; ++s) {
@@ -124,7 +151,7 @@ __global__ void __launch_bounds__(BG_THREADS) bgemm_nt_tc_kernel(BGemmArgs g) {
                         tc::mma_tf32(t_corr, ah, bl, idesc, 1u);
                     }
                     tc::mma_tf32(t_main, ah, bh, idesc, acc_m);
-                    ah += 2; al += 2; bh += 2; bl += 2;
+                    ah += da; al += da; bh += db; bl += db;
                 }
                 tc::mma_commit(mbar);
             }
@@ -201,25 +228,6 @@ __global__ void softmax_bwd_rows_kernel(const float* __restrict__ P, float* __re
     for (int j = lane; j < n; j += 32) d[j] = p[j] * (d[j] - acc) * inv_scale;
 }
 
-// out[z][c][r] = in[z][r][c] for in with row pitch ld_in and a column window of `cols` columns (32x32 tiles)
-__global__ void btranspose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols, int ld_in,
-                                  long long s_in_b, long long s_in_h, int H, long long s_out) {
-    __shared__ float tile[32][33];
-    const int z = blockIdx.z;
-    const float* src = in + (z / H) * s_in_b + (z % H) * s_in_h;
-    float* dst = out + (size_t)z * s_out;
-    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int r = r0 + i, c = c0 + threadIdx.x;
-        tile[i][threadIdx.x] = (r < rows && c < cols) ? src[(size_t)r * ld_in + c] : 0.0f;
-    }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int c = c0 + i, r = r0 + threadIdx.x;
-        if (c < cols && r < rows) dst[(size_t)c * rows + r] = tile[threadIdx.x][i];
-    }
-}
-
 static int launch_bgemm(BGemmArgs& g, int Z, int passes, cudaStream_t st, const char* tag) {
     const size_t smem = 1024 + 4 * 16384 + 64;
     dim3 grid((g.M + 127) / 128, (g.N + BG_NT - 1) / BG_NT, Z);
@@ -236,21 +244,17 @@ static int launch_bgemm(BGemmArgs& g, int Z, int passes, cudaStream_t st, const 
     return PTRB200_OK;
 }
 
-static void launch_transpose(const float* in, float* out, int rows, int cols, int ld_in, long long sb, long long sh, int H, int Z, cudaStream_t st) {
-    dim3 grid((cols + 31) / 32, (rows + 31) / 32, Z);
-    PTRB200_LAUNCH(btranspose_kernel, grid, dim3(32, 8), 0, st, in, out, rows, cols, ld_in, sb, sh, H, (long long)rows * cols);
-}
-
 }  // namespace ptrb200
 
 using namespace ptrb200;
 
 extern "C" {
 
-// workspace (floats): forward keeps P[Z,n,n]; scratch Vt[Z,D,n]
+// scratch (floats): the backward pass needs dS[Z,n,n]; the forward pass none (a 4-float minimum keeps allocations non-empty)
 int64_t ptrb200_attention_tc_workspace_floats(int B, int n, int H, int D, int backward) {
-    const int64_t Z = (int64_t)B * H, nn = (int64_t)n * n, dn = (int64_t)D * n;
-    return backward ? Z * (2 * nn + 2 * dn) : Z * dn;
+    const int64_t Z = (int64_t)B * H, nn = (int64_t)n * n;
+    (void)D;
+    return backward ? Z * nn : 4;
 }
 
 // P_out[B*H, n, n] receives the (un-dropped) attention probabilities and must be kept for the backward pass.
@@ -269,12 +273,11 @@ int ptrb200_attention_tc_fwd(const float* Q, const float* K, const float* V, flo
     if ((rc = launch_bgemm(g, Z, passes, st, "attn_tc_qk"))) return rc;
     const size_t rows = (size_t)Z * n;
     PTRB200_LAUNCH(softmax_rows_kernel, (unsigned)((rows + 7) / 8), 256, 0, st, P_out, (float*)nullptr, rows, n);
-    // O = dropout(P) V  ==  dropout(P) (V^T)^T
-    float* Vt = scratch;
-    launch_transpose(V, Vt, n, D, HD, sb, sh, H, Z, st);
+    // O = dropout(P) V : V is the [K = key, N = d] row-major factor, consumed MN-major
+    (void)scratch;
     BGemmArgs o{};
-    o.A = P_out; o.B = Vt; o.C = O; o.M = n; o.N = D; o.K = n; o.lda = n; o.ldb = n; o.ldc = HD;
-    o.sAb = nn * H; o.sAh = nn; o.sBb = (long long)D * n * H; o.sBh = (long long)D * n; o.sCb = sb; o.sCh = sh; o.H = H; o.alpha = 1.0f;
+    o.A = P_out; o.B = V; o.C = O; o.M = n; o.N = D; o.K = n; o.lda = n; o.ldb = HD; o.ldc = HD; o.b_mn = 1;
+    o.sAb = nn * H; o.sAh = nn; o.sBb = sb; o.sBh = sh; o.sCb = sb; o.sCh = sh; o.H = H; o.alpha = 1.0f;
     o.drop_mode = 1; o.drop = make_drop(dropout_p, seed, offset);
     if ((rc = launch_bgemm(o, Z, passes, st, "attn_tc_pv"))) return rc;
     return check_launch("attention_tc_fwd");
@@ -287,11 +290,8 @@ int ptrb200_attention_tc_bwd(const float* Q, const float* K, const float* V, con
     if (!Q || !K || !V || !P || !dO || !dQ || !dK || !dV || !scratch || B <= 0 || n <= 0 || H <= 0 || D <= 0) { set_error("attention_tc_bwd: bad arguments"); return PTRB200_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
     const int Z = B * H, HD = H * D;
-    const long long sb = (long long)n * HD, sh = D, nn = (long long)n * n, dn = (long long)D * n;
+    const long long sb = (long long)n * HD, sh = D, nn = (long long)n * n;
     float* dS = scratch;                    // [Z,n,n]
-    float* T = dS + (size_t)Z * nn;         // [Z,n,n] transposed views (dS^T, then P^T)
-    float* t1 = T + (size_t)Z * nn;         // [Z,D,n]
-    float* t2 = t1 + (size_t)Z * dn;        // [Z,D,n]
     const DropCfg drop = make_drop(dropout_p, seed, offset);
     const float inv_scale = 1.0f / sqrtf((float)D);
     int rc;
@@ -302,25 +302,20 @@ int ptrb200_attention_tc_bwd(const float* Q, const float* K, const float* V, con
     if ((rc = launch_bgemm(a, Z, passes, st, "attn_tc_dp"))) return rc;
     const size_t rows = (size_t)Z * n;
     PTRB200_LAUNCH(softmax_bwd_rows_kernel, (unsigned)((rows + 7) / 8), 256, 0, st, P, dS, rows, n, inv_scale, drop);
-    // dQ = dS K = dS (K^T)^T
-    launch_transpose(K, t1, n, D, HD, sb, sh, H, Z, st);
+    // dQ = dS K : K is the [K = key, N = d] factor (MN-major B)
     BGemmArgs q{};
-    q.A = dS; q.B = t1; q.C = dQ; q.M = n; q.N = D; q.K = n; q.lda = n; q.ldb = n; q.ldc = HD;
-    q.sAb = nn * H; q.sAh = nn; q.sBb = dn * H; q.sBh = dn; q.sCb = sb; q.sCh = sh; q.H = H; q.alpha = 1.0f;
+    q.A = dS; q.B = K; q.C = dQ; q.M = n; q.N = D; q.K = n; q.lda = n; q.ldb = HD; q.ldc = HD; q.b_mn = 1;
+    q.sAb = nn * H; q.sAh = nn; q.sBb = sb; q.sBh = sh; q.sCb = sb; q.sCh = sh; q.H = H; q.alpha = 1.0f;
     if ((rc = launch_bgemm(q, Z, passes, st, "attn_tc_dq"))) return rc;
-    // dK = dS^T Q = dS^T (Q^T)^T
-    launch_transpose(dS, T, n, n, n, nn * H, nn, H, Z, st);
-    launch_transpose(Q, t2, n, D, HD, sb, sh, H, Z, st);
+    // dK = dS^T Q : dS itself is the [K = query, M = key] factor (MN-major A), Q the [K = query, N = d] factor (MN-major B)
     BGemmArgs k{};
-    k.A = T; k.B = t2; k.C = dK; k.M = n; k.N = D; k.K = n; k.lda = n; k.ldb = n; k.ldc = HD;
-    k.sAb = nn * H; k.sAh = nn; k.sBb = dn * H; k.sBh = dn; k.sCb = sb; k.sCh = sh; k.H = H; k.alpha = 1.0f;
+    k.A = dS; k.B = Q; k.C = dK; k.M = n; k.N = D; k.K = n; k.lda = n; k.ldb = HD; k.ldc = HD; k.a_mn = 1; k.b_mn = 1;
+    k.sAb = nn * H; k.sAh = nn; k.sBb = sb; k.sBh = sh; k.sCb = sb; k.sCh = sh; k.H = H; k.alpha = 1.0f;
     if ((rc = launch_bgemm(k, Z, passes, st, "attn_tc_dk"))) return rc;
-    // dV = dropout(P)^T dO : A = P^T with the dropout mask indexed through the transpose
-    launch_transpose(P, T, n, n, n, nn * H, nn, H, Z, st);
-    launch_transpose(dO, t1, n, D, HD, sb, sh, H, Z, st);
+    // dV = dropout(P)^T dO : same shapes, the dropout mask regenerated through the transposed view
     BGemmArgs v{};
-    v.A = T; v.B = t1; v.C = dV; v.M = n; v.N = D; v.K = n; v.lda = n; v.ldb = n; v.ldc = HD;
-    v.sAb = nn * H; v.sAh = nn; v.sBb = dn * H; v.sBh = dn; v.sCb = sb; v.sCh = sh; v.H = H; v.alpha = 1.0f;
+    v.A = P; v.B = dO; v.C = dV; v.M = n; v.N = D; v.K = n; v.lda = n; v.ldb = HD; v.ldc = HD; v.a_mn = 1; v.b_mn = 1;
+    v.sAb = nn * H; v.sAh = nn; v.sBb = sb; v.sBh = sh; v.sCb = sb; v.sCh = sh; v.H = H; v.alpha = 1.0f;
     v.drop_mode = 2; v.drop = drop;
     if ((rc = launch_bgemm(v, Z, passes, st, "attn_tc_dv"))) return rc;
     return check_launch("attention_tc_bwd");

@@ -735,11 +735,6 @@ static size_t wgrad_smem(int N, int K, int KP, int& R, int passes, int& stages, 
     return limit + 1;        // does not fit
 }
 
-static size_t rows_gemm_smem(int N, int NP) {
-    const size_t operands = 32768 + (size_t)NP * 256, otile = (size_t)128 * N * 4;
-    return 1024 + (operands > otile ? operands : otile) + 64;
-}
-
 static bool rows_ws_fits(int K, int N, int passes) {
     const int NP = ((N + 15) / 16) * 16, nchunks = (K + 31) / 32;
     const size_t ws_smem = 1024 + (size_t)nchunks * NP * 128 * (passes == 3 ? 2 : 1) + 65536 + (size_t)4 * NP * 8 + 128;
@@ -881,8 +876,6 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
     double* part = reinterpret_cast<double*>(ws + p.partials_off);
     float* S1 = reinterpret_cast<float*>(ws + p.s1_off);
     float* S2 = reinterpret_cast<float*>(ws + p.s2_off);
-    float* T1 = reinterpret_cast<float*>(ws + p.t1_off);
-    float* T2 = reinterpret_cast<float*>(ws + p.t2_off);
     float* dbuf[2] = {reinterpret_cast<float*>(ws + p.dbuf0_off), reinterpret_cast<float*>(ws + p.dbuf1_off)};
     float* wpart = reinterpret_cast<float*>(ws + p.wpart_off);
     const float* dA = dOut;
