@@ -306,12 +306,55 @@ __global__ void __launch_bounds__(256, 4) colstat4_kernel(const float* __restric
     }
 }
 
+static __device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// single-channel case (the scorer's output layer): a plain strided reduction, one row per thread per step
+template <int WHAT>
+__global__ void __launch_bounds__(128) colstat_c1_kernel(const float* __restrict__ Z, const float* __restrict__ dA, float* __restrict__ dY_out,
+                                                          NormRef nr, double* __restrict__ partials, int gr, int S, int slice_rows) {
+    __shared__ double sh[2][4];
+    const int g = blockIdx.x, sl = blockIdx.y;
+    const int r0 = sl * slice_rows, r1 = min(gr, r0 + slice_rows);
+    float a = 1.0f, cc = 0.0f, mu = 0.0f, rs = 1.0f;
+    if (WHAT == STAT_DY) {
+        norm_coeffs(nr, 0, a, cc);
+        if (nr.mean) { mu = nr.mean[g]; rs = nr.rstd[g]; }
+    }
+    double s1 = 0.0, s2 = 0.0;
+    for (int r = r0 + threadIdx.x; r < r1; r += 128) {
+        const size_t off = (size_t)g * gr + r;
+        const float z = Z[off];
+        if (WHAT == STAT_MOMENTS) { s1 += (double)z; s2 += (double)z * (double)z; }
+        else if (WHAT == STAT_COLSUM) { s1 += (double)z; }
+        else {
+            const float xh = nr.mean ? (z - mu) * rs : z;
+            const float dy = dA[off] * activate(nr.act, a * xh + cc).dy;
+            dY_out[off] = dy;
+            s1 += (double)dy; s2 += (double)dy * (double)xh;
+        }
+    }
+    s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s1; sh[1][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double* p = partials + ((size_t)g * S + sl) * 2;
+        p[0] = (sh[0][0] + sh[0][1]) + (sh[0][2] + sh[0][3]);
+        p[1] = (sh[1][0] + sh[1][1]) + (sh[1][2] + sh[1][3]);
+    }
+}
+
 static bool colstat_vectorised(int C) { return C % 4 == 0 && C / 4 <= 256; }
 template <int WHAT>
 static void launch_colstat(cudaStream_t st, const char* tag, const float* Z, const float* dA, float* dY, const NormRef& nr,
                            double* part, int G, int S, int gr, int C, int slice_rows, Rank1Src r1 = Rank1Src{nullptr, DropCfg{0, 1.0f, 0}}) {
     dim3 grid(G, S);
-    if (colstat_vectorised(C)) {
+    if (C == 1 && !r1.w) {
+        PTRB200_LAUNCH_TAG(tag, colstat_c1_kernel<WHAT>, grid, 128, 0, st, Z, dA, dY, nr, part, gr, S, slice_rows);
+    } else if (colstat_vectorised(C)) {
         const int Q = C / 4;
         int RY = 256 / Q; if (RY < 1) RY = 1; if (RY > 16) RY = 16;
         PTRB200_LAUNCH_TAG(tag, colstat4_kernel<WHAT>, grid, dim3(Q, RY), (size_t)RY * Q * 8 * sizeof(double), st, Z, dA, dY, nr, part, gr, C, S, slice_rows, r1);
@@ -323,11 +366,6 @@ static void launch_colstat(cudaStream_t st, const char* tag, const float* Z, con
 // Finalize kernels: one CTA of FIN_THREADS per (group, channel) [moments] or per channel [dY sums]; threads
 // stride over the partial slots and a fixed-shape tree combines them (deterministic).
 constexpr int FIN_THREADS = 128;
-static __device__ __forceinline__ double warp_sum_d(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 static __device__ __forceinline__ void block_sum2_d(double& a, double& b) {
     __shared__ double sh[2][FIN_THREADS / 32];
     a = warp_sum_d(a); b = warp_sum_d(b);
@@ -926,7 +964,7 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
             }
             dZ = dY;
         } else {
-            PTRB200_LAUNCH(colstat_kernel<STAT_COLSUM>, sgrid, dim3(32, 8), 0, st, dA, (const float*)nullptr, (float*)nullptr, nr, part, p.gr, lp.d_out, p.S_stat, p.slice_rows);
+            launch_colstat<STAT_COLSUM>(st, "colstat_colsum", dA, nullptr, nullptr, nr, part, p.G, p.S_stat, p.gr, lp.d_out, p.slice_rows);
             PTRB200_LAUNCH(dy_finalize_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)part, (float*)nullptr, (float*)nullptr, grads->bias[l], (float*)nullptr, p.G, lp.d_out, p.S_stat, DyTail{});
         }
         const float layer_drop = last ? 0.0f : drop;
