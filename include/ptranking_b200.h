@@ -144,6 +144,10 @@ int ptrb200_adhoc_metrics_at_ks(const float* scores, const float* labels, const 
 #define PTRB200_MATH_SIMT   0   /* fp32 FMA on the SIMT pipes (any shape)                              */
 #define PTRB200_MATH_3XTF32 1   /* tcgen05 kind::tf32, error-compensated 3-pass split: fp32-equivalent */
 #define PTRB200_MATH_TF32   2   /* tcgen05 kind::tf32, single pass (10-bit mantissa operands)           */
+#define PTRB200_MATH_BF16   3   /* every GEMM operand (features, activations, weights, gradients) rounded to bf16
+                                   (round-to-nearest-even), products exact, fp32 accumulation: the numerics of a bf16
+                                   tensor-core GEMM, issued as one kind::tf32 pass (bf16 values are tf32 values);
+                                   tensors stay fp32 in memory.  Needs tensor-core-eligible widths (no SIMT fallback) */
 
 typedef struct ptrb200_ffnet {
     int num_linear;                        /* linear layers, output layer included            */
@@ -153,8 +157,7 @@ typedef struct ptrb200_ffnet {
     int norm;                              /* PTRB200_NORM_* on every layer that has an activation */
     int norm_affine;                       /* bn_affine                                       */
     float dropout_p;                       /* Dropout before every hidden Linear; 0 disables  */
-    int math_mode;                         /* PTRB200_MATH_*: tensor-core modes fall back to SIMT when a width is
-                                              not a multiple of 4 or exceeds 256                              */
+    int math_mode;                         /* PTRB200_MATH_*: the TF32 modes fall back to SIMT when a width is not a multiple of 4 */
     /* parameters, one pointer per linear layer l = 0..num_linear-1 (nn.Linear layout [out,in]) */
     const float* weight[PTRB200_MAX_FF_LAYERS];
     const float* bias[PTRB200_MAX_FF_LAYERS];

@@ -17,7 +17,7 @@ MAX_LIST_LEN = 4096
 
 AF_CODES = {None: 0, "R": 1, "GE": 2, "S": 3, "T": 4, "CE": 5, "E": 6, "LR": 7, "SE": 8}
 NORM_CODES = {None: 0, "BN": 1, "BN2": 2}
-MATH_MODES = {"simt": 0, "3xtf32": 1, "tf32": 2}
+MATH_MODES = {"simt": 0, "3xtf32": 1, "tf32": 2, "bf16": 3}
 LAMBDALOSS_TYPES = {"NDCG_Loss1": 0, "NDCG_Loss2": 1, "NDCG_Loss2++": 2}
 
 _fp = C.c_void_p   # device pointers travel as integers

@@ -219,7 +219,7 @@ __global__ void colstat_kernel(const float* __restrict__ Z, const float* __restr
 // as colstat_kernel.  blockDim = (Q = C/4, RY); dynamic smem = RY*Q*8 doubles.
 // STAT_DY can take dA in factored form: the scorer's last Linear has one output, so its data gradient is the outer
 // product dA[r,c] = dropmask(dz[r] * w[c]) -- built on the fly here instead of being written and re-read.
-struct Rank1Src { const float* w; DropCfg drop; };     // w == NULL: dA is a dense [rows, C] tensor
+struct Rank1Src { const float* w; DropCfg drop; int round_bf16; };     // w == NULL: dA is a dense [rows, C] tensor
 
 // (4 resident CTAs per SM = 64 registers: measured best for this latency-bound sweep -- 0.51 ms per step against 0.58 at
 // 3 CTAs/72 registers and 0.62 at 5-6 CTAs with their spills)
@@ -256,8 +256,9 @@ __global__ void __launch_bounds__(256, 4) colstat4_kernel(const float* __restric
         } else {
             float4 d4;
             if (rk.w) {
-                const float dz = __ldg(dA + (size_t)g * gr + r);
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(rk.w + c));
+                float dz = __ldg(dA + (size_t)g * gr + r);
+                float4 w4 = __ldg(reinterpret_cast<const float4*>(rk.w + c));
+                if (rk.round_bf16) { dz = bf16_rn(dz); w4 = make_float4(bf16_rn(w4.x), bf16_rn(w4.y), bf16_rn(w4.z), bf16_rn(w4.w)); }
                 d4 = make_float4(dz * w4.x, dz * w4.y, dz * w4.z, dz * w4.w);
                 if (rk.drop.thr) {
                     const uint64_t dd = dropout_draw4(rk.drop.key, off >> 2);
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(128) colstat_c1_kernel(const float* __restrict
 static bool colstat_vectorised(int C) { return C % 4 == 0 && C / 4 <= 256; }
 template <int WHAT>
 static void launch_colstat(cudaStream_t st, const char* tag, const float* Z, const float* dA, float* dY, const NormRef& nr,
-                           double* part, int G, int S, int gr, int C, int slice_rows, Rank1Src r1 = Rank1Src{nullptr, DropCfg{0, 1.0f, 0}}) {
+                           double* part, int G, int S, int gr, int C, int slice_rows, Rank1Src r1 = Rank1Src{nullptr, DropCfg{0, 1.0f, 0}, 0}) {
     dim3 grid(G, S);
     if (C == 1 && !r1.w) {
         PTRB200_LAUNCH_TAG(tag, colstat_c1_kernel<WHAT>, grid, 128, 0, st, Z, dA, dY, nr, part, gr, S, slice_rows);
@@ -582,6 +583,7 @@ struct LayerPlan {
 struct Plan {
     bool use_tc;                                 // every layer fits the tcgen05 kernels (else the SIMT path runs)
     int passes;                                  // 3 = 3xTF32 (fp32-equivalent), 1 = TF32
+    bool bf16;                                   // single pass with every operand rounded to bf16 first
     int tile_rows, seg_len, group_rows, tiles_per_group, ntiles, wg_grid, wg_rows;
     int L, G, gr, S_stat, slice_rows, S_w, k_chunk;
     size_t rows;
@@ -610,14 +612,18 @@ static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p) {
     p.rows = (size_t)B * n;
     p.G = net->norm == PTRB200_NORM_BN2 ? B : 1;
     p.gr = net->norm == PTRB200_NORM_BN2 ? n : (int)p.rows;
-    if (net->math_mode < PTRB200_MATH_SIMT || net->math_mode > PTRB200_MATH_TF32) { set_error("ffnet: bad math_mode %d", net->math_mode); return PTRB200_ERR_INVALID; }
+    if (net->math_mode < PTRB200_MATH_SIMT || net->math_mode > PTRB200_MATH_BF16) { set_error("ffnet: bad math_mode %d", net->math_mode); return PTRB200_ERR_INVALID; }
     p.use_tc = net->math_mode != PTRB200_MATH_SIMT;
-    p.passes = net->math_mode == PTRB200_MATH_TF32 ? 1 : 3;
+    p.passes = net->math_mode == PTRB200_MATH_3XTF32 ? 3 : 1;
+    p.bf16 = net->math_mode == PTRB200_MATH_BF16;
     for (int l = 0; l < net->num_linear && p.use_tc; ++l) {
         const int di = net->dims[l], dn = net->dims[l + 1];
         // float4 row access needs widths % 4; wider layers are tiled over output columns / weight-gradient blocks
         if (di % 4 != 0 || di > 1024 || dn > 1024 || (dn % 4 != 0 && dn > 4)) p.use_tc = false;
     }
+    for (int l = 0; l < net->num_linear && p.bf16; ++l)
+        if (net->dims[l + 1] != 1 && net->dims[l + 1] % 4 != 0) p.use_tc = false;       // such a layer's data gradient would run unrounded on SIMT
+    if (p.bf16 && !p.use_tc) { set_error("ffnet: math_mode bf16 needs layer widths the tensor-core kernels take (multiples of 4, <= 1024)"); return PTRB200_ERR_UNSUPPORTED; }
     // statistics slices: one CTA per (group, slice); aim for ~4 CTAs per SM when there is a single group
     if (p.G == 1) { p.slice_rows = 512; p.S_stat = (int)((p.rows + 511) / 512); if (p.S_stat > 1024) { p.S_stat = 1024; p.slice_rows = (int)((p.rows + 1023) / 1024); p.S_stat = (int)((p.rows + p.slice_rows - 1) / p.slice_rows); } }
     else { p.slice_rows = p.gr; p.S_stat = 1; }
@@ -723,13 +729,14 @@ static int elementwise_blocks(size_t total) {
 
 // data gradient of a Linear with a single output: dIn[r,k] = dropmask(dz[r] * W[0,k])  (the scorer's last layer)
 __global__ void dgrad_rank1_kernel(const float* __restrict__ dz, const float* __restrict__ W, float* __restrict__ dIn,
-                                   size_t units, int K, DropCfg drop) {
+                                   size_t units, int K, DropCfg drop, int round_bf16) {
     const int Q = K >> 2;
     for (size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (size_t)gridDim.x * blockDim.x) {
         const size_t row = u / Q;
         const int k = (int)(u % Q) * 4;
-        const float d = __ldg(dz + row);
-        const float4 w = __ldg(reinterpret_cast<const float4*>(W + k));
+        float d = __ldg(dz + row);
+        float4 w = __ldg(reinterpret_cast<const float4*>(W + k));
+        if (round_bf16) { d = bf16_rn(d); w = make_float4(bf16_rn(w.x), bf16_rn(w.y), bf16_rn(w.z), bf16_rn(w.w)); }
         float4 v = make_float4(d * w.x, d * w.y, d * w.z, d * w.w);
         if (drop.thr) {
             const uint64_t dd = dropout_draw4(drop.key, (row * K + k) >> 2);
@@ -863,6 +870,7 @@ static int forward_tc(const ptrb200_ffnet* net, const Plan& p, const float* X, f
             for (int tr = 0; tr < (fwd_only ? 1 : 2); ++tr) {
                 if (tr == 1 && (l == 0 || lp.d_out % 4 != 0)) continue;     // dgrad images: only where backward_tc runs the tensor-core dgrad
                 PackJob& j = jobs.job[nj++];
+                j.round_bf16 = p.bf16;
                 j.src = net->weight[l]; j.src_cols = lp.d_in; j.transpose = tr;
                 j.N = tr ? lp.d_in : lp.d_out; j.K = tr ? lp.d_out : lp.d_in;
                 j.NP = ((j.N + 15) / 16) * 16; j.nchunks = (j.K + 31) / 32;
@@ -879,6 +887,7 @@ static int forward_tc(const ptrb200_ffnet* net, const Plan& p, const float* X, f
         const bool last = l == p.L - 1;
         float* Z = (last && !lp.has_act && !lp.has_norm) ? out : reinterpret_cast<float*>(ws + lp.z_off);
         RowsGemmArgs g{};
+        g.round_bf16 = p.bf16;
         set_prologue(net, p, l, ws, X, g.P, g.scale, g.shift, g.act);
         g.gr_prev = p.gr;
         g.drop = make_drop(last ? 0.0f : drop, seed, offset * 64 + (uint64_t)l);
@@ -918,7 +927,7 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
     float* wpart = reinterpret_cast<float*>(ws + p.wpart_off);
     const float* dA = dOut;
     int flip = 0;
-    Rank1Src r1{nullptr, DropCfg{0, 1.0f, 0}};   // pending outer-product data gradient of the single-output last layer
+    Rank1Src r1{nullptr, DropCfg{0, 1.0f, 0}, 0};   // pending outer-product data gradient of the single-output last layer
     for (int l = p.L - 1; l >= 0; --l) {
         const LayerPlan& lp = p.layer[l];
         const bool last = l == p.L - 1;
@@ -971,6 +980,7 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
         // ---- dW on tensor cores: sum_rows dZ^T (x) rebuilt layer input ----
         {
             WgradArgs w{};
+            w.round_bf16 = p.bf16;
             w.dZ = dZ;
             if (l == 0) {          // layer 0 input = dropout(X): rebuilt on the fly
                 w.P = X; w.scale = w.shift = nullptr; w.act = PTRB200_AF_NONE;
@@ -1006,8 +1016,9 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
                 unsigned char* ih = reinterpret_cast<unsigned char*>(ws + lp.img_d_hi);
                 unsigned char* il = p.passes == 3 ? reinterpret_cast<unsigned char*>(ws + lp.img_d_lo) : nullptr;
                 if (l == 0)     // (layer 0's transpose image is only needed when dX is requested; deeper layers were packed by the forward call)
-                    PTRB200_LAUNCH(pack_b_image_kernel<true>, (nch * NPl * 8 + 255) / 256, 256, 0, st, net->weight[l], lp.d_out, lp.d_in, ih, il, lp.d_in, NPl, lp.d_out, nch);
+                    PTRB200_LAUNCH(pack_b_image_kernel<true>, (nch * NPl * 8 + 255) / 256, 256, 0, st, net->weight[l], lp.d_out, lp.d_in, ih, il, lp.d_in, NPl, lp.d_out, nch, (int)p.bf16);
                 RowsGemmArgs g{};
+                g.round_bf16 = p.bf16;
                 g.P = dZ; g.scale = g.shift = nullptr; g.act = PTRB200_AF_NONE; g.gr_prev = (int)p.rows;
                 if (fuse_dz) {
                     g.P2 = Z; g.gr_cur = p.gr;
@@ -1022,13 +1033,14 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
                 // the next iteration's statistics pass rebuilds dIn = dropmask(dz (x) w) on the fly
                 r1.w = net->weight[l];
                 r1.drop = make_drop(layer_drop, seed, offset * 64 + (uint64_t)l);
+                r1.round_bf16 = p.bf16;
                 flip ^= 1;                         // dIn's buffer stays unused; dZ (in the other one) must survive the next pass
                 dA = dZ;
                 continue;
             } else if (lp.d_out == 1 && lp.d_in % 4 == 0) {
                 const size_t units = p.rows * (lp.d_in / 4);
                 PTRB200_LAUNCH(dgrad_rank1_kernel, elementwise_blocks(units), 256, 0, st, dZ, net->weight[l], dIn, units, lp.d_in,
-                               make_drop(layer_drop, seed, offset * 64 + (uint64_t)l));
+                               make_drop(layer_drop, seed, offset * 64 + (uint64_t)l), (int)p.bf16);
             } else {
                 GemmArgs g{};
                 g.A = dZ; g.Bm = net->weight[l]; g.C = dIn;

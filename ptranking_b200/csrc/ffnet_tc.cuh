@@ -47,6 +47,7 @@ struct RowsGemmArgs {
     int seg_len;           // rows per statistics segment inside a tile
     int group_rows;        // BN2 with n > 128: rows per group (tiles restart at every group), else 0
     int tiles_per_group;
+    int round_bf16;        // PTRB200_MATH_BF16: the A operand is rounded to bf16 on its way into shared memory
 };
 
 enum { RG_FWD = 0, RG_DGRAD = 1 };
@@ -73,7 +74,13 @@ static __device__ __forceinline__ float4 prologue4(const RowsGemmArgs& g, float4
     return v;
 }
 
-static __device__ __forceinline__ void store_split(unsigned char* hi, unsigned char* lo, uint32_t off, float4 v, bool split) {
+// round-to-nearest-even onto the bf16 grid (the result is still an fp32 / tf32 value)
+static __device__ __forceinline__ float bf16_rn(float x) {
+    const uint32_t u = __float_as_uint(x);
+    return __uint_as_float((u + 0x7fffu + ((u >> 16) & 1u)) & 0xffff0000u);
+}
+static __device__ __forceinline__ void store_split(unsigned char* hi, unsigned char* lo, uint32_t off, float4 v, bool split, bool to_bf16 = false) {
+    if (to_bf16) v = make_float4(bf16_rn(v.x), bf16_rn(v.y), bf16_rn(v.z), bf16_rn(v.w));
     if (split) {
         float4 h, l;
         tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y);
@@ -97,7 +104,7 @@ static __device__ __forceinline__ float4 ldg4_guard(const float* p, int k, int K
 struct PackJob {
     const float* src;
     unsigned char *img_hi, *img_lo;
-    int src_cols, N, NP, K, nchunks, transpose;
+    int src_cols, N, NP, K, nchunks, transpose, round_bf16;
 };
 constexpr int PACK_MAX_JOBS = 2 * PTRB200_MAX_FF_LAYERS;
 struct PackJobs { PackJob job[PACK_MAX_JOBS]; };
@@ -119,6 +126,10 @@ __global__ void pack_b_images_kernel(const __grid_constant__ PackJobs jobs) {
                 if (k + e < K) v[e] = TRANSPOSE ? src[(size_t)(k + e) * src_cols + r] : src[(size_t)r * src_cols + k + e];
         }
         const size_t off = (size_t)c * NP * 128 + tc::swz_offset(r, j);
+        if (jb.round_bf16) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = bf16_rn(v[e]);
+        }
         float4 h, l;
         tc::split_tf32(v[0], h.x, l.x); tc::split_tf32(v[1], h.y, l.y); tc::split_tf32(v[2], h.z, l.z); tc::split_tf32(v[3], h.w, l.w);
         if (img_lo) {
@@ -133,7 +144,7 @@ __global__ void pack_b_images_kernel(const __grid_constant__ PackJobs jobs) {
 template <bool TRANSPOSE>
 __global__ void pack_b_image_kernel(const float* __restrict__ src, int src_rows, int src_cols,
                                     unsigned char* __restrict__ img_hi, unsigned char* __restrict__ img_lo,
-                                    int N, int NP, int K, int nchunks) {
+                                    int N, int NP, int K, int nchunks, int round_bf16 = 0) {
     const int total = nchunks * NP * 8;                        // 16-byte units
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < total; u += gridDim.x * blockDim.x) {
         const int c = u / (NP * 8), rem = u % (NP * 8), r = rem >> 3, j = rem & 7, k = c * 32 + j * 4;
@@ -142,6 +153,10 @@ __global__ void pack_b_image_kernel(const float* __restrict__ src, int src_rows,
 #pragma unroll
             for (int e = 0; e < 4; ++e)
                 if (k + e < K) v[e] = TRANSPOSE ? src[(size_t)(k + e) * src_cols + r] : src[(size_t)r * src_cols + k + e];
+        }
+        if (round_bf16) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = bf16_rn(v[e]);
         }
         const size_t off = (size_t)c * NP * 128 + tc::swz_offset(r, j);
         float4 h, l;
@@ -237,7 +252,7 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
                 v = prologue4(g, v, row0 + r, k, MODE == RG_FWD, coef_off[i]);
                 if (MODE == RG_FWD && g.a_out && blockIdx.y == 0) *reinterpret_cast<float4*>(g.a_out + (size_t)(row0 + r) * K + k) = v;
             } else v = make_float4(0.f, 0.f, 0.f, 0.f);
-            store_split(a_hi, a_lo, tc::swz_offset(r, j), v, PASSES == 3);
+            store_split(a_hi, a_lo, tc::swz_offset(r, j), v, PASSES == 3, g.round_bf16 != 0);
         }
         tc::fence_proxy_async();
         __syncthreads();
@@ -570,7 +585,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rows_gemm_ws_kernel(RowsGemmArg
                         }
                         if (MODE == RG_FWD && aout[i]) *reinterpret_cast<float4*>(aout[i] + c * 32) = v;
                     } else v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    store_split(a_hi, a_hi + 16384, sw_[i], v, PASSES == 3);
+                    store_split(a_hi, a_hi + 16384, sw_[i], v, PASSES == 3, g.round_bf16 != 0);
                 }
                 tc::fence_proxy_async();
                 __syncwarp();
@@ -700,6 +715,7 @@ struct WgradArgs {
     int kb;                // CTA (x, y, z) owns dZ columns [128*y, +N) and input columns [kb*z, +K)
     int tile_rows;         // R: rows per tile (multiple of 8, <= 32)
     int stages;            // raw-tile ring depth (2..WG_MAX_STAGES), chosen by the host to fit shared memory
+    int round_bf16;        // PTRB200_MATH_BF16: both operands rounded to bf16
 };
 
 constexpr int WG_PRODUCERS = 512;      // 16 warps split raw fp32 tiles into hi/lo TF32 operand buffers: 8 take dZ, 8 the layer input
@@ -876,7 +892,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
                             v.z = fmaf(a1.z, v.z, fmaf(a3.z, z.z, a0.z)); v.w = fmaf(a1.w, v.w, fmaf(a3.w, z.w, a0.w));
                         }
                     }
-                    store_split(z_hi + ch * chunk_bytes, z_lo + ch * chunk_bytes, 0, v, PASSES == 3);
+                    store_split(z_hi + ch * chunk_bytes, z_lo + ch * chunk_bytes, 0, v, PASSES == 3, g.round_bf16 != 0);
                 }
             }
             if (active && role == 1) {
@@ -888,7 +904,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
                         v = *reinterpret_cast<const float4*>(psrc + ch * 32);
                         if (!plain_p) v = prologue4(pg, v, row0 + r, kk0 + k, true, (g.scale && g.gr_prev < g.rows) ? (size_t)((row0 + r) / g.gr_prev) * g.K_full : 0);
                     }
-                    store_split(p_hi + ch * chunk_bytes, p_lo + ch * chunk_bytes, 0, v, PASSES == 3);
+                    store_split(p_hi + ch * chunk_bytes, p_lo + ch * chunk_bytes, 0, v, PASSES == 3, g.round_bf16 != 0);
                 }
             }
             tc::fence_proxy_async();                       // this thread's operand stores -> visible to the MMA (async proxy)

@@ -238,3 +238,89 @@ def test_ranker_parameters_live_in_one_flat_buffer():
     sd = {k: v.clone() for k, v in r.point_sf.state_dict().items()}
     r.point_sf.load_state_dict(sd)                      # in-place copies keep the parameters inside the flat buffer
     assert b.params_are_flat()
+
+
+def _bf16r(t):
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+class _Bf16Linear(torch.autograd.Function):
+    """nn.Linear whose three GEMMs take bf16-rounded operands and accumulate in float64 (the semantics of math_mode='bf16')."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return (_bf16r(x).double() @ _bf16r(w).double().t() + b.double()).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        gr = _bf16r(g).double()
+        return (gr @ _bf16r(w).double()).float(), (gr.t() @ _bf16r(x).double()).float(), g.sum(0)
+
+
+def test_bf16_math_mode_is_a_bf16_gemm_with_fp32_accumulation():
+    """bf16 feature / GEMM inputs.  Every operand of every contraction is rounded to bf16, products are
+    exact, accumulation fp32 -- checked against a float64-accumulating emulation with the same roundings; it must also
+    differ measurably from (and stay near) the fp32-grade default."""
+    from ptranking_b200 import ops
+    dims = [136, 100, 100, 1]
+    torch.manual_seed(11)
+    B, n = 4, 96
+    X = torch.randn(B, n, dims[0], device=DEV)
+    dO = torch.randn(B, n, 1, device=DEV)
+    params = []
+    for l in range(3):
+        params += [torch.randn(dims[l + 1], dims[l], device=DEV) / np.sqrt(dims[l]), 0.1 * torch.randn(dims[l + 1], device=DEV)]
+    res = {}
+    for mode in ("bf16", "3xtf32"):
+        pm = [q.clone().requires_grad_(True) for q in params]
+        Xm = X.clone().requires_grad_(True)
+        out = ops.ffnet_apply(Xm, ops.FFNetSpec(dims, "R", None, None, False, 0.0, math_mode=mode), pm, training=False)
+        (out * dO).sum().backward()
+        res[mode] = [out.detach()] + [q.grad for q in pm] + [Xm.grad]
+    pe = [q.clone().requires_grad_(True) for q in params]
+    Xe = X.clone().requires_grad_(True)
+    h = Xe.reshape(-1, dims[0])
+    for l in range(3):
+        h = _Bf16Linear.apply(h, pe[2 * l], pe[2 * l + 1])
+        if l < 2:
+            h = torch.relu(h)
+    (h.reshape(B, n, 1) * dO).sum().backward()
+    emu = [h.reshape(B, n, 1).detach()] + [q.grad for q in pe] + [Xe.grad]
+    for i, (a, e, f) in enumerate(zip(res["bf16"], emu, res["3xtf32"])):
+        a, e, f = (t.cpu().numpy() for t in (a, e, f))
+        # an fp32-vs-fp64 accumulation difference occasionally flips one downstream bf16 rounding (2^-8 of one operand)
+        assert rel_err(a, e) <= 2e-3, (i, rel_err(a, e))
+        # ... and bf16 really is coarser than the default: scores move by ~1e-2, gradients (ReLU gates flip) by more
+        assert 1e-4 < rel_err(a, f) <= (3e-2 if i == 0 else 0.5), (i, rel_err(a, f))
+
+
+@pytest.mark.parametrize("n", [32, 256, 1024])
+def test_listmle_with_bf16_scorer_tracks_the_fp32_scorer(n, monkeypatch):
+    """Config (e) end to end: ListMLE over a bf16-input scorer vs the fp32-grade scorer on the same weights and batch --
+    loss within bf16 tolerance, ranks compared (top-10 overlap reported through the assertion)."""
+    import ptranking_b200
+    from ptranking_b200 import LABEL_TYPE
+    rng = np.random.default_rng(n)
+    B = 8
+    X = torch.from_numpy(rng.standard_normal((B, n, 136)).astype(np.float32)).to(DEV)
+    y = torch.from_numpy(np.sort(rng.integers(0, 5, size=(B, n)).astype(np.float32), axis=1)[:, ::-1].copy()).to(DEV)
+    out = {}
+    for mode in ("3xtf32", "bf16"):
+        monkeypatch.setenv("PTRANKING_B200_MATH", mode)
+        torch.manual_seed(3)
+        r = _point_ranker("ListMLE", 136, dropout=0.0)
+        r.eval_mode()
+        with torch.no_grad():
+            s = r.forward(X)
+        r.train_mode()
+        loss = float(r.train_op(X, y, presort=True, label_type=LABEL_TYPE.MultiLabel, epoch_k=1)[0])
+        out[mode] = (s.cpu().numpy(), loss)
+    s32, l32 = out["3xtf32"]
+    s16, l16 = out["bf16"]
+    assert np.isfinite(l16) and abs(l16 - l32) <= 2e-2 * abs(l32), (l16, l32)
+    assert rel_err(s16, s32) <= 5e-2
+    top = lambda s: np.argsort(-s, axis=1, kind="stable")[:, :10]
+    overlap = np.mean([len(set(a) & set(b)) / 10.0 for a, b in zip(top(s16), top(s32))])
+    assert overlap >= 0.6, overlap
