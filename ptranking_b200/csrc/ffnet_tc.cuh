@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
                 v = prologue4(g, v, row0 + r, k, MODE == RG_FWD, coef_off[i]);
                 if (MODE == RG_FWD && g.a_out && blockIdx.y == 0) *reinterpret_cast<float4*>(g.a_out + (size_t)(row0 + r) * K + k) = v;
             } else v = make_float4(0.f, 0.f, 0.f, 0.f);
-            store_split(a_hi, a_lo, tc::swz_offset(r, j), v, PASSES == 3, g.round_bf16 != 0);
+            store_split(a_hi, a_lo, tc::swz_offset(r, j), v, PASSES == 3, PASSES == 1 && g.round_bf16 != 0);
         }
         tc::fence_proxy_async();
         __syncthreads();
@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rows_gemm_ws_kernel(RowsGemmArg
                         }
                         if (MODE == RG_FWD && aout[i]) *reinterpret_cast<float4*>(aout[i] + c * 32) = v;
                     } else v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    store_split(a_hi, a_hi + 16384, sw_[i], v, PASSES == 3, g.round_bf16 != 0);
+                    store_split(a_hi, a_hi + 16384, sw_[i], v, PASSES == 3, PASSES == 1 && g.round_bf16 != 0);
                 }
                 tc::fence_proxy_async();
                 __syncwarp();
@@ -892,7 +892,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
                             v.z = fmaf(a1.z, v.z, fmaf(a3.z, z.z, a0.z)); v.w = fmaf(a1.w, v.w, fmaf(a3.w, z.w, a0.w));
                         }
                     }
-                    store_split(z_hi + ch * chunk_bytes, z_lo + ch * chunk_bytes, 0, v, PASSES == 3, g.round_bf16 != 0);
+                    store_split(z_hi + ch * chunk_bytes, z_lo + ch * chunk_bytes, 0, v, PASSES == 3, PASSES == 1 && g.round_bf16 != 0);
                 }
             }
             if (active && role == 1) {
@@ -904,7 +904,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
                         v = *reinterpret_cast<const float4*>(psrc + ch * 32);
                         if (!plain_p) v = prologue4(pg, v, row0 + r, kk0 + k, true, (g.scale && g.gr_prev < g.rows) ? (size_t)((row0 + r) / g.gr_prev) * g.K_full : 0);
                     }
-                    store_split(p_hi + ch * chunk_bytes, p_lo + ch * chunk_bytes, 0, v, PASSES == 3, g.round_bf16 != 0);
+                    store_split(p_hi + ch * chunk_bytes, p_lo + ch * chunk_bytes, 0, v, PASSES == 3, PASSES == 1 && g.round_bf16 != 0);
                 }
             }
             tc::fence_proxy_async();                       // this thread's operand stores -> visible to the MMA (async proxy)

@@ -291,9 +291,12 @@ def test_bf16_math_mode_is_a_bf16_gemm_with_fp32_accumulation():
     for i, (a, e, f) in enumerate(zip(res["bf16"], emu, res["3xtf32"])):
         a, e, f = (t.cpu().numpy() for t in (a, e, f))
         # an fp32-vs-fp64 accumulation difference occasionally flips one downstream bf16 rounding (2^-8 of one operand)
-        assert rel_err(a, e) <= 2e-3, (i, rel_err(a, e))
+        assert rel_err(a, e) <= (2e-3 if i == 0 else 5e-3), (i, rel_err(a, e))
         # ... and bf16 really is coarser than the default: scores move by ~1e-2, gradients (ReLU gates flip) by more
-        assert 1e-4 < rel_err(a, f) <= (3e-2 if i == 0 else 0.5), (i, rel_err(a, f))
+        # (the last bias gradient is sum(dO) in every mode, hence no lower bound on the gradients)
+        assert rel_err(a, f) <= (3e-2 if i == 0 else 0.5), (i, rel_err(a, f))
+        if i == 0:
+            assert rel_err(a, f) > 1e-4, rel_err(a, f)
 
 
 @pytest.mark.parametrize("n", [32, 256, 1024])
