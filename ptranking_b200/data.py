@@ -1,0 +1,114 @@
+"""Length-bucketed batching: the input side of the hot path.
+
+The reference batches whole queries and asks every batch to hold lists of ONE length: ``LETORSampler`` draws
+``batch_size`` queries of equal ``num_docs`` (ptranking/data/data_utils.py:683-742), and with the default settings a
+query of 100+ documents travels alone (B = 1), which leaves a GPU launch-bound.  ``LengthBucketedBatches`` keeps the
+contract the kernels rely on -- uniform n per batch, labels presorted descending per query (data_utils.py:205-232) --
+but sizes B per bucket so that every batch carries about ``docs_per_batch`` documents (2^18 fills one B200; one step of
+the default scorer then runs at its large-batch rate).  Batches are assembled once into pinned host memory, so
+``NeuralRanker.train`` can stream them with asynchronous copies.  Host-side only: no device work happens here.
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+from typing import Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+Query = Tuple[str, np.ndarray, np.ndarray]        # (qid, features [n, F], labels [n])
+
+
+def presort_query(features: np.ndarray, labels: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """Order one query's documents by label, descending and stable -- the ``presort=True`` contract
+    (data_utils.py:221-232) every loss kernel assumes."""
+    order = np.argsort(-labels, kind="stable")
+    return features[order], labels[order]
+
+
+class LengthBucketedBatches:
+    """Iterable of ``(qids, X[B,n,F], y[B,n])`` CPU batches (pinned when CUDA is available).
+
+    queries         : iterable of (qid, features [n,F] float32, labels [n])
+    docs_per_batch  : target B*n per batch; B = max(1, docs_per_batch // n), capped by ``max_queries``
+    presort         : sort each query's documents by label first (set False when the data already is)
+    shuffle_seed    : None keeps dataset order inside each bucket; an int reshuffles buckets and batch order per epoch
+    drop_ragged     : drop the last, smaller batch of each length instead of emitting it
+    rank / world    : data-parallel sharding -- every rank walks the same batch list and keeps batches rank::world,
+                      so all ranks see the same number of batches per epoch (the last ``len % world`` are dropped)
+    """
+
+    def __init__(self, queries: Iterable[Query], docs_per_batch: int = 1 << 18, max_queries: Optional[int] = None,
+                 presort: bool = True, shuffle_seed: Optional[int] = None, drop_ragged: bool = False,
+                 rank: int = 0, world: int = 1, pin_memory: Optional[bool] = None):
+        if docs_per_batch < 1 or world < 1 or not (0 <= rank < world):
+            raise ValueError("docs_per_batch >= 1 and 0 <= rank < world are required")
+        self.docs_per_batch, self.max_queries = int(docs_per_batch), max_queries
+        self.shuffle_seed, self.drop_ragged, self.rank, self.world = shuffle_seed, drop_ragged, rank, world
+        self.pin = torch.cuda.is_available() if pin_memory is None else bool(pin_memory)
+        self.epoch = 0
+        self.buckets = defaultdict(list)                 # n -> [(qid, X, y)]
+        self.num_features = None
+        for qid, X, y in queries:
+            X = np.ascontiguousarray(X, dtype=np.float32)
+            y = np.ascontiguousarray(y, dtype=np.float32)
+            if X.ndim != 2 or y.shape != (X.shape[0],):
+                raise ValueError(f"query {qid}: features {X.shape} / labels {y.shape} do not describe one list")
+            if X.shape[0] == 0:
+                continue                                 # the reference skips empty queries as well (data_utils.py:150-155)
+            if self.num_features is None:
+                self.num_features = X.shape[1]
+            elif X.shape[1] != self.num_features:
+                raise ValueError(f"query {qid}: {X.shape[1]} features, expected {self.num_features}")
+            if presort:
+                X, y = presort_query(X, y)
+            self.buckets[X.shape[0]].append((str(qid), X, y))
+
+    def batch_size(self, n: int) -> int:
+        B = max(1, self.docs_per_batch // n)
+        return min(B, self.max_queries) if self.max_queries else B
+
+    def _plan(self) -> List[Tuple[int, List[int]]]:
+        rng = np.random.default_rng(self.shuffle_seed + self.epoch) if self.shuffle_seed is not None else None
+        plan = []
+        for n in sorted(self.buckets):
+            idx = np.arange(len(self.buckets[n]))
+            if rng is not None:
+                rng.shuffle(idx)
+            B = self.batch_size(n)
+            for s in range(0, len(idx), B):
+                chunk = idx[s: s + B]
+                if len(chunk) < B and self.drop_ragged:
+                    continue
+                plan.append((n, chunk.tolist()))
+        if rng is not None:
+            rng.shuffle(plan)
+        usable = len(plan) - len(plan) % self.world
+        return plan[:usable][self.rank:: self.world]
+
+    def __len__(self) -> int:
+        return len(self._plan())
+
+    def __iter__(self) -> Iterator[Tuple[List[str], torch.Tensor, torch.Tensor]]:
+        plan = self._plan()
+        self.epoch += 1
+        for n, members in plan:
+            qs = [self.buckets[n][i] for i in members]
+            X = torch.empty((len(qs), n, self.num_features), dtype=torch.float32, pin_memory=self.pin)
+            y = torch.empty((len(qs), n), dtype=torch.float32, pin_memory=self.pin)
+            for b, (_, Xq, yq) in enumerate(qs):
+                X[b] = torch.from_numpy(Xq)
+                y[b] = torch.from_numpy(yq)
+            yield [q[0] for q in qs], X, y
+
+    def stats(self) -> dict:
+        """Fill statistics: queries, documents, batches, and the share of batches that reach the document target."""
+        plan = self._plan() if self.world == 1 else None
+        nq = sum(len(v) for v in self.buckets.values())
+        nd = sum(n * len(v) for n, v in self.buckets.items())
+        out = dict(queries=nq, docs=nd, lengths=len(self.buckets))
+        if plan is not None:
+            docs = [n * len(m) for n, m in plan]
+            out.update(batches=len(plan), mean_docs_per_batch=float(np.mean(docs)) if docs else 0.0,
+                       full_batches=float(np.mean([d >= 0.5 * self.docs_per_batch for d in docs])) if docs else 0.0)
+        return out
