@@ -39,6 +39,10 @@ MSLR_P /= MSLR_P.sum()
 SEED = 137                                   # ptranking/ltr_global.py:5
 
 
+WORKLOAD = ("LambdaRank + pointwise-MLP (5x100 GELU, BN affine, sigmoid tail, dropout 0.1, Adam), "
+            "136 feat x 256 docs (BASELINE.json configs[1])")
+
+
 def default_sf(dropout=0.1):
     """The reference's default pointwise scorer (ptranking/ltr_adhoc/eval/parameter.py:142-146)."""
     return dict(sf_id="pointsf", opt="Adam", lr=1e-4,
@@ -144,15 +148,16 @@ def run_reference(args):
     if rank != 0:
         return
     B_cpu = args.cpu_batch
-    r = cpu_reference_run(args.steps, args.warmup, B_cpu, budget_s=120.0)
+    r = cpu_reference_run(args.steps, args.warmup, B_cpu, budget_s=240.0)
     sample = f"{r['steps']} steps x {B_cpu} queries x {N_DOCS} docs x {N_FEAT} feat, oracle/ref_port.py train_op"
     line = {
         "impl": "reference", "metric": "queries/sec (LambdaRank train step, 256-doc lists)", "value": r["qps"],
         "unit": "queries/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "LambdaRank + pointwise-MLP (5x100 GELU, BN affine, sigmoid tail), 136 feat x 256 docs",
-                   "queries_per_step": B_cpu, "n_docs": N_DOCS, "n_features": N_FEAT, "device": "cpu"},
+        "config": {"workload": WORKLOAD, "queries_per_step": B_cpu, "n_docs": N_DOCS, "n_features": N_FEAT, "device": "cpu",
+                   "sample": "each step is a bounded sample of the workload: one batch of %d queries (the GPU arm steps %d per GPU)" % (B_cpu, args.batch),
+                   "normalisation": "BN (reference default, batch statistics)", "math": "fp32 ATen CPU kernels"},
         "cpu_baseline": {"value": r["qps"], "unit": "queries/s", "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": r["qps"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -301,8 +306,7 @@ def run_b200(args):
             "metric": "queries/sec (LambdaRank train step, 256-doc lists)", "value": value, "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "LambdaRank + pointwise-MLP (5x100 GELU, BN affine, sigmoid tail, dropout 0.1, Adam), "
-                                   "136 feat x 256 docs (BASELINE.json configs[1])",
+            "config": {"workload": WORKLOAD,
                        "queries_per_gpu_per_step": B, "n_docs": N_DOCS, "n_features": N_FEAT,
                        "parallelism": f"dp{world}", "l2": "inputs (2 x 143 MB rotating batches) larger than the 126 MB L2",
                        "normalisation": "BN (reference default, batch statistics per rank)",
