@@ -78,3 +78,31 @@ def test_grad_bucket_views_survive_zero():
     assert torch.allclose(b.flat, torch.cat([torch.full((12,), 2.0), torch.full((5,), 3.0)]))
     b.zero()
     assert float(b.flat.abs().sum()) == 0.0 and p[0].grad.data_ptr() == b.flat.data_ptr()
+
+
+def test_aligned_bucket_and_flat_parameters_share_one_layout():
+    """align=4 keeps every tensor 16-byte aligned; flatten_params re-homes the parameters into a buffer with the same
+    offsets, keeps their values and identity, and gradients keep flowing into the flat gradient buffer."""
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(5, 3)                       # weight 15 elements, bias 3: neither is a multiple of 4
+    extra = torch.nn.Parameter(torch.randn(1))
+    params = list(lin.parameters()) + [extra]
+    before = [p.detach().clone() for p in params]
+    b = b200dist.GradBucket(params, align=4)
+    assert b.offsets == [0, 16, 20] and b.flat.numel() == 24
+    assert not b.params_are_flat()
+    flat = b.flatten_params()
+    assert b.params_are_flat() and flat.numel() == b.flat.numel()
+    assert all(torch.equal(p.detach(), q) for p, q in zip(params, before))
+    assert list(lin.parameters())[0] is params[0]                      # same Parameter objects, new storage
+    assert all(p.data_ptr() == flat.data_ptr() + 4 * o for p, o in zip(params, b.offsets))
+    assert float(flat[15]) == 0.0 and float(flat[19:20].abs().sum()) == 0.0      # padding stays zero
+    (lin(torch.ones(2, 5)).sum() + 3 * extra.sum()).backward()
+    assert torch.allclose(b.flat[16:19], torch.full((3,), 2.0)) and float(b.flat[20]) == 3.0
+    # an in-place update of the flat buffer is an update of every parameter (what the fused optimizer does)
+    flat.add_(1.0)
+    assert all(torch.allclose(p.detach(), q + 1.0) for p, q in zip(params, before))
+    lin.load_state_dict({k: v.clone() for k, v in lin.state_dict().items()})
+    assert b.params_are_flat()
+    params[0].data = params[0].data.clone()                              # re-allocation is detected
+    assert not b.params_are_flat()
