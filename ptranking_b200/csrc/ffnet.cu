@@ -466,22 +466,6 @@ __global__ void __launch_bounds__(FIN_THREADS) dy_finalize_kernel(
     }
 }
 
-// coefficients of the folded normalisation backward: dZ = k1*dY + k3*z + k0 with
-//   k1 = a*rstd,  k3 = -a*rstd^2*S2/N,  k0 = -a*rstd*S1/N + a*rstd^2*S2/N*mean      (a = gamma*aff_w)
-__global__ void dz_coeff_kernel(NormRef nr, const float* __restrict__ S1, const float* __restrict__ S2,
-                                float* __restrict__ k1, float* __restrict__ k3, float* __restrict__ k0, int G, int C, int gr) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= G * C) return;
-    const int c = i % C;
-    float a, cc;
-    norm_coeffs(nr, c, a, cc);
-    const float rs = nr.rstd[i], mu = nr.mean[i], invN = 1.0f / (float)gr;
-    const float ar = a * rs, t = ar * rs * (S2[i] * invN);
-    k1[i] = ar;
-    k3[i] = -t;
-    k0[i] = t * mu - ar * (S1[i] * invN);
-}
-
 // ------------------------------------------------------------------ elementwise passes
 // A = act(a * (z - mean) * rstd + c)
 __global__ void norm_act_fwd_kernel(const float* __restrict__ Z, float* __restrict__ A, NormRef nr,
@@ -750,12 +734,6 @@ __global__ void dgrad_rank1_kernel(const float* __restrict__ dz, const float* __
 }
 
 // ------------------------------------------------------------------ tensor-core host paths
-__global__ void transpose_kernel(const float* __restrict__ W, float* __restrict__ Wt, int rows, int cols) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;       // Wt[c][r] = W[r][c]
-    if (i >= rows * cols) return;
-    const int c = i / rows, r = i % rows;
-    Wt[i] = W[(size_t)r * cols + c];
-}
 
 template <typename K>
 static int opt_in_smem(K kernel, size_t bytes) {

@@ -26,7 +26,7 @@ struct RowsGemmArgs {
     int gr_prev;           // rows per statistics group of P's normalisation
     DropCfg drop;          // dropout stream: FWD masks A elements (row*K+k), DGRAD masks outputs (row*N+n)
     // DGRAD with the normalisation backward folded in: A = k1*P + k3*P2 + k0 (P = dY, P2 = Z of this layer,
-    // coefficients per (statistics group, column) from dz_coeff_kernel).  P2 == NULL: A = P.
+    // coefficients per (statistics group, column) from dy_finalize_kernel).  P2 == NULL: A = P.
     const float* P2;
     const float *kc1, *kc3, *kc0;
     int gr_cur;            // rows per statistics group of kc*
