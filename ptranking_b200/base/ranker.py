@@ -54,7 +54,11 @@ class Evaluator:
 
     def _scores_and_labels(self, batch_q_doc_vectors, batch_std_labels):
         dev = self.device
-        preds = self.predict(batch_q_doc_vectors.to(dev, non_blocking=True))
+        # no autograd tape in evaluation: the scorer then runs forward-only (no backward by-products written, no
+        # activation workspace kept alive).  The reference never disables grad here (ranker.py:623-630), which only
+        # matters for its BN2 train/eval switch; these kernels use per-query statistics in both modes.
+        with torch.no_grad():
+            preds = self.predict(batch_q_doc_vectors.to(dev, non_blocking=True))
         return preds.detach(), batch_std_labels.to(dev, non_blocking=True)
 
     def ndcg_at_k(self, test_data=None, k=10, label_type=LABEL_TYPE.MultiLabel, presort=False, device='cpu'):
@@ -182,12 +186,17 @@ class NeuralRanker(Evaluator):
         else:
             raise NotImplementedError
         self.scheduler = StepLR(self.optimizer, step_size=20, gamma=0.5)
+        # data parallel: every replica must start from rank 0's weights (xavier_normal_ draws from the per-process
+        # torch seed); the all-reduced gradient is only meaningful when applied to identical replicas
+        b200dist.broadcast_parameters(self.grad_bucket, src=0)
 
     def backward_and_step(self, batch_loss):
         """The tail every reference loss class ends with (e.g. lambdarank.py:58-60), plus the
         data-parallel gradient all-reduce (sum: every reference loss is a sum over queries)."""
         self.grad_bucket.zero(skip_memset=getattr(self, 'grad_bucket_overwritten', False))
-        batch_loss.backward()
+        if getattr(self, '_unit_grad', None) is None or self._unit_grad.device != batch_loss.device:
+            self._unit_grad = torch.ones((), dtype=torch.float32, device=batch_loss.device)
+        batch_loss.backward(gradient=self._unit_grad)       # cached root gradient: no fill kernel per step
         self.grad_bucket.all_reduce()
         self.optimizer.step()
 

@@ -98,6 +98,18 @@ class GradBucket:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
 
 
+def broadcast_parameters(bucket: "GradBucket", src: int = 0) -> None:
+    """Make every replica's parameters equal to rank ``src``'s (no-op when not distributed): one broadcast of the flat
+    parameter buffer when the parameters were re-homed into it, else one per tensor."""
+    if not is_distributed():
+        return
+    if bucket.flat_param is not None and bucket.params_are_flat():
+        dist.broadcast(bucket.flat_param, src=src)
+    else:
+        for p in bucket.params:
+            dist.broadcast(p.data, src=src)
+
+
 def all_reduce_sum_(t: torch.Tensor) -> torch.Tensor:
     if is_distributed():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)

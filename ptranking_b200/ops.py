@@ -7,9 +7,10 @@ arithmetic of the hot path happens in Python/ATen here.
 from __future__ import annotations
 
 import ctypes as C
+import functools
+import os
 from typing import Optional, Sequence
 
-import os
 import torch
 
 from . import _lib
@@ -17,6 +18,25 @@ from . import _lib
 
 def _stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def _on_tensor_device(fn):
+    """Run ``fn`` with the CUDA device of its first CUDA tensor argument current.
+
+    The C library launches on the *current* device and ``_stream_ptr`` returns the current device's current stream, so a
+    tensor on ``cuda:1`` while ``cuda:0`` is current would be dereferenced by a kernel on the wrong GPU (the reference
+    driver avoids this only because it calls ``torch.cuda.set_device``, ltr.py:48).  Every entry point that reaches the
+    C ABI is wrapped with this guard."""
+    @functools.wraps(fn)
+    def guarded(*args, **kw):
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kw)
+                break
+        return fn(*args, **kw)
+    return guarded
 
 
 def _dev_f32(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -36,6 +56,7 @@ def _check_pair(scores: torch.Tensor, labels: torch.Tensor):
 # --------------------------------------------------------------------------- #
 # ranking losses
 # --------------------------------------------------------------------------- #
+@_on_tensor_device
 def _loss_call(name: str, scores: torch.Tensor, labels: torch.Tensor, params: dict):
     """-> (loss_per_query[B], grad[B,n]) from one fused kernel launch."""
     lib = _lib.load()
@@ -78,6 +99,7 @@ def _loss_call(name: str, scores: torch.Tensor, labels: torch.Tensor, params: di
     return loss_q, grad
 
 
+@_on_tensor_device
 def sum_f32(x: torch.Tensor) -> torch.Tensor:
     """Fixed-order device sum -> 0-dim tensor."""
     lib = _lib.load()
@@ -87,6 +109,7 @@ def sum_f32(x: torch.Tensor) -> torch.Tensor:
     return out.reshape(())
 
 
+@_on_tensor_device
 def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
               lr: float, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0) -> None:
     """In-place torch.optim.Adam update of flat fp32 device buffers with identical layouts (one kernel)."""
@@ -103,16 +126,22 @@ class _RankLoss(torch.autograd.Function):
     """batch loss = sum of per-query losses; backward hands the fused gradient to the scorer."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, scores, labels, name, params):
         loss_q, grad = _loss_call(name, scores.detach(), labels, params)
         ctx.save_for_backward(grad)
         ctx.mark_non_differentiable(loss_q)
+        ctx.set_materialize_grads(False)        # no zero-filled gradient for the per-query by-product
         return sum_f32(loss_q), loss_q
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, g_loss, _g_lq):
         (grad,) = ctx.saved_tensors
-        return grad * g_loss, None, None, None
+        if g_loss is None:
+            return None, None, None, None
+        # d(sum_q loss_q)/d scores scaled by the incoming scalar gradient -- our elementwise kernel, not an ATen launch
+        return _ew(EW_MUL_SCALAR, grad, g_loss.reshape(1)), None, None, None
 
 
 def rank_loss(name: str, scores: torch.Tensor, labels: torch.Tensor, **params) -> torch.Tensor:
@@ -130,6 +159,7 @@ def rank_loss_and_grad(name: str, scores: torch.Tensor, labels: torch.Tensor, **
 _tie_offset = 0
 
 
+@_on_tensor_device
 def shuffle_ties_perm(labels: torch.Tensor, seed: Optional[int] = None, offset: Optional[int] = None) -> torch.Tensor:
     """int32 [B,n] ordering of each row's labels, descending, ties in random order."""
     global _tie_offset
@@ -150,6 +180,7 @@ def shuffle_ties_perm(labels: torch.Tensor, seed: Optional[int] = None, offset: 
 # --------------------------------------------------------------------------- #
 # metric
 # --------------------------------------------------------------------------- #
+@_on_tensor_device
 def ndcg_at_ks(scores: torch.Tensor, labels: torch.Tensor, ks: Sequence[int], presort: bool = False,
                return_order: bool = False):
     """Per-query nDCG at the cutoffs ``ks`` -> [B, len(ks)] (zero where k > n)."""
@@ -172,6 +203,7 @@ def ndcg_at_ks(scores: torch.Tensor, labels: torch.Tensor, ks: Sequence[int], pr
     return (out, order) if return_order else out
 
 
+@_on_tensor_device
 def adhoc_metrics_at_ks(scores: torch.Tensor, labels: torch.Tensor, ks: Sequence[int], presort: bool = False,
                         max_label: Optional[float] = None):
     """(nDCG, nERR, AP, P) per query at the cutoffs ``ks`` -> four [B, len(ks)] tensors from one kernel."""
@@ -265,7 +297,8 @@ class FFNetSpec:
 
 class _FFNetFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, X, spec: FFNetSpec, training: bool, seed: int, offset: int, grad_targets, *params):
+    @_on_tensor_device
+    def forward(ctx, X, spec: FFNetSpec, training: bool, seed: int, offset: int, grad_targets, need_backward, *params):
         lib = _lib.load()
         X = _dev_f32(X, "X")
         B, n, F = X.shape
@@ -278,18 +311,20 @@ class _FFNetFn(torch.autograd.Function):
             _lib.check(int(nbytes), "ffnet_workspace_bytes")
         ws = torch.empty(int(nbytes), dtype=torch.uint8, device=X.device)
         out = torch.empty((B, n, spec.dims[-1]), dtype=torch.float32, device=X.device)
-        # bit 1 = forward only (PTRB200_FFNET_FORWARD_ONLY): nothing requires grad, skip the backward by-products
-        flags = int(training) | (0 if any(ctx.needs_input_grad) else 2)
+        # bit 1 = forward only (PTRB200_FFNET_FORWARD_ONLY): no backward will follow (nothing requires grad, or the
+        # caller runs under torch.no_grad()), so the by-products the backward pass reads are not written
+        flags = int(training) | (0 if need_backward else 2)
         _lib.check(lib.ptrb200_ffnet_forward(C.byref(desc), X.data_ptr(), out.data_ptr(), ws.data_ptr(), int(nbytes),
                                              B, n, flags, seed, offset, _stream_ptr()), "ffnet_forward")
         ctx.spec, ctx.training, ctx.seed, ctx.offset = spec, training, seed, offset
         ctx.grad_targets = grad_targets
-        ctx.ws, ctx.nbytes = ws, int(nbytes)
+        ctx.ws, ctx.nbytes = (ws if need_backward else None), int(nbytes)
         ctx.need_dx = X.requires_grad
         ctx.save_for_backward(X, *params)
         return out
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, d_out):
         lib = _lib.load()
         X, *params = ctx.saved_tensors
@@ -305,8 +340,8 @@ class _FFNetFn(torch.autograd.Function):
                    "ffnet_backward")
         ctx.ws = None
         if ctx.grad_targets is not None:            # written straight into the parameters' .grad storage
-            return (dX, None, None, None, None, None, *([None] * len(gouts)))
-        return (dX, None, None, None, None, None, *gouts)
+            return (dX, None, None, None, None, None, None, *([None] * len(gouts)))
+        return (dX, None, None, None, None, None, None, *gouts)
 
 
 def ffnet_apply(X: torch.Tensor, spec: FFNetSpec, params: Sequence[torch.Tensor], training: bool,
@@ -317,7 +352,8 @@ def ffnet_apply(X: torch.Tensor, spec: FFNetSpec, params: Sequence[torch.Tensor]
         seed = torch.initial_seed() & (2 ** 64 - 1)
     if offset is None:
         offset = next_dropout_offset()
-    return _FFNetFn.apply(X, spec, bool(training), int(seed), int(offset), grad_targets, *params)
+    need_backward = torch.is_grad_enabled() and (X.requires_grad or any(p.requires_grad for p in params))
+    return _FFNetFn.apply(X, spec, bool(training), int(seed), int(offset), grad_targets, bool(need_backward), *params)
 
 
 # --------------------------------------------------------------------------- #
@@ -336,6 +372,7 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, math_mode:
 
 class _Attention(torch.autograd.Function):
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, Q, K, V, n_heads, dropout_p, seed, offset):
         lib = _lib.load()
         Q, K, V = _dev_f32(Q, "Q"), _dev_f32(K, "K"), _dev_f32(V, "V")
@@ -350,6 +387,7 @@ class _Attention(torch.autograd.Function):
         return O
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dO):
         lib = _lib.load()
         Q, K, V, O, lse = ctx.saved_tensors
@@ -368,6 +406,7 @@ class _AttentionTC(torch.autograd.Function):
     """Tensor-core attention: batched tcgen05 GEMMs around a materialised [B*H,n,n] probability tensor."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, Q, K, V, n_heads, dropout_p, seed, offset, passes):
         lib = _lib.load()
         Q, K, V = _dev_f32(Q, "Q"), _dev_f32(K, "K"), _dev_f32(V, "V")
@@ -384,6 +423,7 @@ class _AttentionTC(torch.autograd.Function):
         return O
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dO):
         lib = _lib.load()
         Q, K, V, P = ctx.saved_tensors
@@ -419,6 +459,7 @@ def attention(Q, K, V, n_heads: int, dropout_p: float = 0.0, seed: Optional[int]
 
 class _LayerNormRef(torch.autograd.Function):
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x, a2, b2, eps):
         lib = _lib.load()
         x = _dev_f32(x, "x")
@@ -435,6 +476,7 @@ class _LayerNormRef(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dy):
         lib = _lib.load()
         x, a2, mean, std = ctx.saved_tensors
@@ -455,9 +497,10 @@ def layernorm_ref(x, a2, b2, eps: float = 1e-6):
     return _LayerNormRef.apply(x, a2, b2, eps)
 
 
-EW_ADD, EW_LATENT_CROSS, EW_MUL, EW_RELU, EW_RELU_BWD, EW_DROPOUT, EW_SCALE_ADD1 = range(7)
+EW_ADD, EW_LATENT_CROSS, EW_MUL, EW_RELU, EW_RELU_BWD, EW_DROPOUT, EW_SCALE_ADD1, EW_MUL_SCALAR = range(8)
 
 
+@_on_tensor_device
 def _ew(op, a, b=None, p=0.0, seed=0, offset=0):
     lib = _lib.load()
     a = _dev_f32(a, "a")
@@ -470,10 +513,12 @@ def _ew(op, a, b=None, p=0.0, seed=0, offset=0):
 
 class _Add(torch.autograd.Function):
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, a, b):
         return _ew(EW_ADD, a, b)
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, g):
         return g, g
 
@@ -482,11 +527,13 @@ class _LatentCross(torch.autograd.Function):
     """(enc + 1) * head -- DASALC's latent cross (list_ranker.py:366)."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, enc, head):
         ctx.save_for_backward(enc, head)
         return _ew(EW_LATENT_CROSS, enc, head)
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, g):
         enc, head = ctx.saved_tensors
         return _ew(EW_MUL, g, head), _ew(EW_SCALE_ADD1, g, enc)
@@ -494,11 +541,13 @@ class _LatentCross(torch.autograd.Function):
 
 class _Relu(torch.autograd.Function):
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x):
         ctx.save_for_backward(x)
         return _ew(EW_RELU, x)
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, g):
         (x,) = ctx.saved_tensors
         return _ew(EW_RELU_BWD, g, x)
@@ -506,11 +555,13 @@ class _Relu(torch.autograd.Function):
 
 class _Dropout(torch.autograd.Function):
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x, p, seed, offset):
         ctx.cfg = (p, seed, offset)
         return _ew(EW_DROPOUT, x, None, p, seed, offset)
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, g):
         p, seed, offset = ctx.cfg
         return _ew(EW_DROPOUT, g, None, p, seed, offset), None, None, None
