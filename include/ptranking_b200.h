@@ -207,6 +207,16 @@ int ptrb200_adam_step(float* param, const float* grad, float* exp_avg, float* ex
                       double lr, double beta1, double beta2, double eps, double weight_decay, int step,
                       ptrb200_stream_t stream);
 
+/* torch.optim.Adagrad.step() (the list scorer's default optimizer, ltr_adhoc/eval/parameter.py:157-162; PyTorch defaults
+ * lr_decay=0, eps=1e-10, initial_accumulator_value=0) and torch.optim.RMSprop.step() (alpha=0.99, eps=1e-8, momentum=0,
+ * centered=False) as configured at ranker.py:517-520, over the same flat fp32 layout with one state buffer. */
+int ptrb200_adagrad_step(float* param, const float* grad, float* state_sum, int64_t count,
+                         double lr, double lr_decay, double eps, double weight_decay, int step,
+                         ptrb200_stream_t stream);
+int ptrb200_rmsprop_step(float* param, const float* grad, float* square_avg, int64_t count,
+                         double lr, double alpha, double eps, double weight_decay,
+                         ptrb200_stream_t stream);
+
 /* ---- multi-head self-attention list scorer ------------------------------------------------ */
 /* MultiheadAttention.forward, ptranking/base/list_ranker.py:226-248: for every (query b, head h)
  * O = dropout(softmax(Q K^T / sqrt(D))) V, flash-style (no [n,n] tensor in HBM).  Q,K,V,O: [B,n,H*D] with head h

@@ -69,6 +69,8 @@ SIGNATURES = {
     "ptrb200_adhoc_metrics_at_ks": (_I, [_fp, _fp, C.POINTER(C.c_int32), _I, _fp, _I, _I, _I, _F, _fp]),
     "ptrb200_attention_fwd": (_I, [_fp, _fp, _fp, _fp, _fp, _I, _I, _I, _I, _F, _U64, _U64, _fp]),
     "ptrb200_adam_step": (_I, [_fp, _fp, _fp, _fp, _I64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _I, _fp]),
+    "ptrb200_adagrad_step": (_I, [_fp, _fp, _fp, _I64, C.c_double, C.c_double, C.c_double, C.c_double, _I, _fp]),
+    "ptrb200_rmsprop_step": (_I, [_fp, _fp, _fp, _I64, C.c_double, C.c_double, C.c_double, C.c_double, _fp]),
     "ptrb200_attention_tc_workspace_floats": (_I64, [_I, _I, _I, _I, _I]),
     "ptrb200_attention_tc_fwd": (_I, [_fp] * 6 + [_I, _I, _I, _I, _F, _U64, _U64, _I, _fp]),
     "ptrb200_attention_tc_bwd": (_I, [_fp] * 9 + [_I, _I, _I, _I, _F, _U64, _U64, _I, _fp]),

@@ -38,6 +38,42 @@ class FlatAdam(optim.Optimizer):
                       lr=g['lr'], betas=g['betas'], eps=g['eps'], weight_decay=g['weight_decay'])
 
 
+class FlatAdagrad(optim.Optimizer):
+    """torch.optim.Adagrad(lr, weight_decay) -- the list scorer's default (parameter.py:157-162) -- as one kernel."""
+
+    def __init__(self, params, bucket, lr=1e-2, lr_decay=0.0, eps=1e-10, weight_decay=0.0):
+        super().__init__(params, dict(lr=lr, lr_decay=lr_decay, eps=eps, weight_decay=weight_decay))
+        self.bucket = bucket
+        self.state_sum = torch.zeros_like(bucket.flat_param)
+        self.num_steps = 0
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if not self.bucket.params_are_flat():
+            raise RuntimeError("FlatAdagrad: a parameter was re-allocated outside the flat buffer (use copy_ / load_state_dict)")
+        g = self.param_groups[0]
+        self.num_steps += 1
+        ops.adagrad_step(self.bucket.flat_param, self.bucket.flat, self.state_sum, self.num_steps, lr=g['lr'],
+                         lr_decay=g['lr_decay'], eps=g['eps'], weight_decay=g['weight_decay'])
+
+
+class FlatRMSprop(optim.Optimizer):
+    """torch.optim.RMSprop(lr, weight_decay) (alpha=0.99, eps=1e-8, no momentum, not centered) as one kernel."""
+
+    def __init__(self, params, bucket, lr=1e-2, alpha=0.99, eps=1e-8, weight_decay=0.0):
+        super().__init__(params, dict(lr=lr, alpha=alpha, eps=eps, weight_decay=weight_decay))
+        self.bucket = bucket
+        self.square_avg = torch.zeros_like(bucket.flat_param)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if not self.bucket.params_are_flat():
+            raise RuntimeError("FlatRMSprop: a parameter was re-allocated outside the flat buffer (use copy_ / load_state_dict)")
+        g = self.param_groups[0]
+        ops.rmsprop_step(self.bucket.flat_param, self.bucket.flat, self.square_avg, lr=g['lr'], alpha=g['alpha'],
+                         eps=g['eps'], weight_decay=g['weight_decay'])
+
+
 @unique
 class LABEL_TYPE(Enum):
     """Same members as ptranking.data.data_utils.LABEL_TYPE (data_utils.py:88-91)."""
@@ -176,15 +212,16 @@ class NeuralRanker(Evaluator):
         """ranker.py:512-525: Adam | RMS | Adagrad with L2-in-gradient weight decay + StepLR(20, 0.5)."""
         params = list(self.get_parameters())
         self.grad_bucket = b200dist.GradBucket(params, align=4)     # one flat fp32 gradient buffer (one all-reduce per step)
-        if 'Adam' == self.opt:      # the reference default: one fused kernel over the flat buffers
-            self.grad_bucket.flatten_params()
+        # every optimizer the reference offers is ONE fused kernel over the flat parameter / gradient / state buffers
+        if self.opt not in ('Adam', 'RMS', 'Adagrad'):
+            raise NotImplementedError
+        self.grad_bucket.flatten_params()
+        if 'Adam' == self.opt:      # the pointwise scorer's default
             self.optimizer = FlatAdam(params, self.grad_bucket, lr=self.lr, weight_decay=self.weight_decay)
         elif 'RMS' == self.opt:
-            self.optimizer = optim.RMSprop(params, lr=self.lr, weight_decay=self.weight_decay)
-        elif 'Adagrad' == self.opt:
-            self.optimizer = optim.Adagrad(params, lr=self.lr, weight_decay=self.weight_decay)
-        else:
-            raise NotImplementedError
+            self.optimizer = FlatRMSprop(params, self.grad_bucket, lr=self.lr, weight_decay=self.weight_decay)
+        else:                       # 'Adagrad': the list scorer's default (parameter.py:157-162)
+            self.optimizer = FlatAdagrad(params, self.grad_bucket, lr=self.lr, weight_decay=self.weight_decay)
         self.scheduler = StepLR(self.optimizer, step_size=20, gamma=0.5)
         # data parallel: every replica must start from rank 0's weights (xavier_normal_ draws from the per-process
         # torch seed); the all-reduced gradient is only meaningful when applied to identical replicas

@@ -33,9 +33,74 @@ __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict_
     for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) adam1(p[i], g[i], m[i], v[i], c);
 }
 
+// ---- Adagrad / RMSprop: the other two optimizers config_optimizer offers (ranker.py:517-520; Adagrad is the listsf
+// default, ltr_adhoc/eval/parameter.py:157-162).  One state buffer each, same flat layout.  Operation order follows
+// torch's _multi_tensor_adagrad / _multi_tensor_rmsprop (PyTorch defaults: Adagrad lr_decay=0, eps=1e-10,
+// initial_accumulator_value=0; RMSprop alpha=0.99, eps=1e-8, momentum=0, centered=False):
+//   Adagrad: g += wd*p; sum += g*g;                    p += -clr * g / (sqrt(sum) + eps)
+//   RMSprop: g += wd*p; sq = alpha*sq + (1-alpha)*g*g; p += -lr  * g / (sqrt(sq)  + eps)
+struct AccCfg { float lr, decay, one_minus_decay, eps, weight_decay; };
+
+template <bool RMS>
+static __device__ __forceinline__ void acc1(float& p, float g, float& st, const AccCfg& c) {
+    if (c.weight_decay != 0.0f) g = fmaf(c.weight_decay, p, g);
+    if (RMS) st = fmaf(c.one_minus_decay * g, g, st * c.decay);
+    else st = fmaf(g, g, st);
+    const float denom = sqrtf(st) + c.eps;
+    p = fmaf(-c.lr, g / denom, p);
+}
+
+template <bool RMS>
+__global__ void accum_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ st, size_t n, AccCfg c) {
+    const size_t n4 = n >> 2;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 P = reinterpret_cast<float4*>(p)[i], S = reinterpret_cast<float4*>(st)[i];
+        const float4 G = reinterpret_cast<const float4*>(g)[i];
+        acc1<RMS>(P.x, G.x, S.x, c); acc1<RMS>(P.y, G.y, S.y, c); acc1<RMS>(P.z, G.z, S.z, c); acc1<RMS>(P.w, G.w, S.w, c);
+        reinterpret_cast<float4*>(p)[i] = P; reinterpret_cast<float4*>(st)[i] = S;
+    }
+    for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc1<RMS>(p[i], g[i], st[i], c);
+}
+
+static int check_flat(const char* who, const void* a, const void* b, const void* c, int64_t count) {
+    if (!a || !b || !c || count <= 0) { set_error("%s: bad arguments", who); return PTRB200_ERR_INVALID; }
+    if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) {
+        set_error("%s: buffers must be 16-byte aligned", who);
+        return PTRB200_ERR_INVALID;
+    }
+    return PTRB200_OK;
+}
+static unsigned flat_blocks(int64_t count) {
+    const size_t n4 = (size_t)count / 4 + 1;
+    return (unsigned)((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184);
+}
+
 }  // namespace ptrb200
 
 using namespace ptrb200;
+
+extern "C" int ptrb200_adagrad_step(float* param, const float* grad, float* state_sum, int64_t count,
+                                    double lr, double lr_decay, double eps, double weight_decay, int step,
+                                    ptrb200_stream_t stream) {
+    int rc = check_flat("adagrad_step", param, grad, state_sum, count);
+    if (rc) return rc;
+    if (step < 1) { set_error("adagrad_step: step must be >= 1"); return PTRB200_ERR_INVALID; }
+    const double clr = lr / (1.0 + (double)(step - 1) * lr_decay);
+    AccCfg c{(float)clr, 1.0f, 0.0f, (float)eps, (float)weight_decay};
+    PTRB200_LAUNCH_TAG("adagrad_step_kernel", accum_step_kernel<false>, flat_blocks(count), 256, 0, stream, param, grad, state_sum, (size_t)count, c);
+    return check_launch("adagrad_step");
+}
+
+extern "C" int ptrb200_rmsprop_step(float* param, const float* grad, float* square_avg, int64_t count,
+                                    double lr, double alpha, double eps, double weight_decay,
+                                    ptrb200_stream_t stream) {
+    int rc = check_flat("rmsprop_step", param, grad, square_avg, count);
+    if (rc) return rc;
+    AccCfg c{(float)lr, (float)alpha, (float)(1.0 - alpha), (float)eps, (float)weight_decay};
+    PTRB200_LAUNCH_TAG("rmsprop_step_kernel", accum_step_kernel<true>, flat_blocks(count), 256, 0, stream, param, grad, square_avg, (size_t)count, c);
+    return check_launch("rmsprop_step");
+}
 
 extern "C" int ptrb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count,
                                  double lr, double beta1, double beta2, double eps, double weight_decay, int step,

@@ -122,6 +122,32 @@ def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, ex
                                      _stream_ptr()), "adam_step")
 
 
+def _check_flat(who, param, *others):
+    for t in (param, *others):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == param.numel()):
+            raise ValueError(f"{who}: every buffer must be a contiguous fp32 CUDA tensor of {param.numel()} elements")
+
+
+@_on_tensor_device
+def adagrad_step(param: torch.Tensor, grad: torch.Tensor, state_sum: torch.Tensor, step: int, lr: float,
+                 lr_decay: float = 0.0, eps: float = 1e-10, weight_decay: float = 0.0) -> None:
+    """In-place torch.optim.Adagrad update of flat fp32 device buffers (one kernel)."""
+    _check_flat("adagrad_step", param, grad, state_sum)
+    _lib.check(_lib.load().ptrb200_adagrad_step(param.data_ptr(), grad.data_ptr(), state_sum.data_ptr(), param.numel(),
+                                                float(lr), float(lr_decay), float(eps), float(weight_decay), int(step),
+                                                _stream_ptr()), "adagrad_step")
+
+
+@_on_tensor_device
+def rmsprop_step(param: torch.Tensor, grad: torch.Tensor, square_avg: torch.Tensor, lr: float, alpha: float = 0.99,
+                 eps: float = 1e-8, weight_decay: float = 0.0) -> None:
+    """In-place torch.optim.RMSprop (momentum=0, centered=False) update of flat fp32 device buffers (one kernel)."""
+    _check_flat("rmsprop_step", param, grad, square_avg)
+    _lib.check(_lib.load().ptrb200_rmsprop_step(param.data_ptr(), grad.data_ptr(), square_avg.data_ptr(), param.numel(),
+                                                float(lr), float(alpha), float(eps), float(weight_decay),
+                                                _stream_ptr()), "rmsprop_step")
+
+
 class _RankLoss(torch.autograd.Function):
     """batch loss = sum of per-query losses; backward hands the fused gradient to the scorer."""
 

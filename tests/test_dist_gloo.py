@@ -106,3 +106,30 @@ def test_aligned_bucket_and_flat_parameters_share_one_layout():
     assert b.params_are_flat()
     params[0].data = params[0].data.clone()                              # re-allocation is detected
     assert not b.params_are_flat()
+
+
+def _bcast_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    b200dist.init_from_env(backend="gloo")
+    for flat in (False, True):
+        net, _, _ = _make(seed=100 + rank)              # every rank draws different initial weights
+        bucket = b200dist.GradBucket(list(net.parameters()), align=4)
+        if flat:
+            bucket.flatten_params()
+        b200dist.broadcast_parameters(bucket, src=0)
+        out[(rank, flat)] = torch.cat([p.detach().reshape(-1) for p in net.parameters()]).numpy()
+    dist.destroy_process_group()
+
+
+def test_replicas_start_from_rank0_weights():
+    """ranks seeded differently must hold identical parameters after the optimizer is configured
+    (NeuralRanker.config_optimizer ends with dist.broadcast_parameters)."""
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_bcast_worker, args=(2, port, out), nprocs=2, join=True)
+    ref, _, _ = _make(seed=100)
+    want = torch.cat([p.detach().reshape(-1) for p in ref.parameters()]).numpy()
+    for flat in (False, True):
+        assert np.array_equal(out[(0, flat)], want)
+        assert np.array_equal(out[(1, flat)], want)

@@ -230,6 +230,63 @@ def test_flat_adam_matches_torch_adam(wd):
     assert rel_err(v.cpu().numpy(), st["exp_avg_sq"].cpu().numpy()) <= 1e-6
 
 
+@pytest.mark.parametrize("wd", [0.0, 1e-3])
+@pytest.mark.parametrize("which", ["Adagrad", "RMS"])
+def test_flat_adagrad_rmsprop_match_torch(which, wd):
+    """ops.adagrad_step / ops.rmsprop_step (one kernel over the flat buffers) against torch.optim.Adagrad /
+    torch.optim.RMSprop as ranker.py:517-520 configures them, over several steps with the StepLR schedule."""
+    from ptranking_b200 import ops
+    torch.manual_seed(6)
+    n = 883370                                           # the default list scorer's parameter count (+1: tail loop)
+    p0 = torch.randn(n, device=DEV)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = (torch.optim.Adagrad if which == "Adagrad" else torch.optim.RMSprop)([ref], lr=1e-2, weight_decay=wd)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=3, gamma=0.5)
+    p, st = p0.clone(), torch.zeros(n, device=DEV)
+    for step in range(1, 8):
+        g = torch.randn(n, device=DEV) * (10.0 ** float(torch.randint(-3, 2, (1,))))
+        ref.grad = g.clone()
+        opt.step()
+        if which == "Adagrad":
+            ops.adagrad_step(p, g, st, step, lr=opt.param_groups[0]["lr"], weight_decay=wd)
+        else:
+            ops.rmsprop_step(p, g, st, lr=opt.param_groups[0]["lr"], weight_decay=wd)
+        sched.step()
+        assert rel_err(p.cpu().numpy(), ref.detach().cpu().numpy()) <= 1e-6, step
+    key = "sum" if which == "Adagrad" else "square_avg"
+    assert rel_err(st.cpu().numpy(), opt.state[ref][key].cpu().numpy()) <= 1e-6
+
+
+@pytest.mark.parametrize("opt_id", ["Adagrad", "RMS"])
+def test_ranker_steps_with_fused_adagrad_rmsprop(opt_id):
+    """Three LambdaRank train steps with the fused optimizer against the same steps with torch.optim over the same flat
+    gradient bucket (identical kernels upstream of the optimizer, dropout off): parameters agree to fp32 rounding."""
+    import ptranking_b200
+    from ptranking_b200 import LABEL_TYPE
+    from ptranking_b200.base import ranker as rk
+    F = 136
+    sf = dict(sf_id="pointsf", opt=opt_id, lr=1e-3, pointsf=point_cfg(F))
+    sf["pointsf"]["dropout"] = 0.0
+    torch.manual_seed(11)
+    a = ptranking_b200.LambdaRank(sf_para_dict=sf, model_para_dict=dict(model_id="LambdaRank", sigma=1.0), gpu=True, device=DEV)
+    a.init()
+    assert isinstance(a.optimizer, rk.FlatAdagrad if opt_id == "Adagrad" else rk.FlatRMSprop)
+    b = ptranking_b200.LambdaRank(sf_para_dict=sf, model_para_dict=dict(model_id="LambdaRank", sigma=1.0), gpu=True, device=DEV)
+    b.init()
+    b.point_sf.load_state_dict({k: v.clone() for k, v in a.point_sf.state_dict().items()})
+    cls = torch.optim.Adagrad if opt_id == "Adagrad" else torch.optim.RMSprop
+    b.optimizer = cls(list(b.get_parameters()), lr=1e-3, weight_decay=b.weight_decay)
+    g = torch.Generator().manual_seed(3)
+    X = torch.randn(8, 64, F, generator=g).to(DEV)
+    y = torch.sort(torch.randint(0, 5, (8, 64), generator=g).float(), dim=1, descending=True)[0].to(DEV)
+    for _ in range(3):
+        la, _ = a.train_op(X, y, presort=True, label_type=LABEL_TYPE.MultiLabel)
+        lb, _ = b.train_op(X, y, presort=True, label_type=LABEL_TYPE.MultiLabel)
+        assert abs(float(la) - float(lb)) <= 1e-5 * abs(float(lb))
+    for (k, va), (_, vb) in zip(a.point_sf.state_dict().items(), b.point_sf.state_dict().items()):
+        assert rel_err(va.cpu().numpy(), vb.cpu().numpy()) <= 2e-6, k
+
+
 def test_ranker_parameters_live_in_one_flat_buffer():
     r = _point_ranker("ListNet", 136)
     b = r.grad_bucket
