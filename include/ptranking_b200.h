@@ -105,6 +105,32 @@ int ptrb200_approxndcg_fwd_bwd(const float* scores, const float* labels, float* 
                                float* scratch, int B, int n, float alpha, int presort, int batch_coupled,
                                ptrb200_stream_t stream);
 
+/* ---- sibling losses ----------------------------------------------------------
+ * Same contract as above.  `offsets` (device, B+1 int32 prefix offsets into the flat score / label / grad arrays) makes
+ * the batch ragged -- query b owns [offsets[b], offsets[b+1]) and `n` is then the longest list; NULL = dense [B,n]. */
+
+/* RankMSE.custom_loss_function, ptranking/ltr_adhoc/pointwise/rank_mse.py:13-22: the MEAN over queries of the per-query
+ * summed squared error; loss_per_query[b] already carries the 1/B so that their sum is the reference's value. */
+int ptrb200_rankmse_fwd_bwd(const float* scores, const float* labels, const int32_t* offsets, float* grad, float* loss_per_query,
+                            int B, int n, ptrb200_stream_t stream);
+/* RankCosine.custom_loss_function, ptranking/ltr_adhoc/listwise/rank_cosine.py:33 (nn.CosineSimilarity(dim=1), eps 1e-8). */
+int ptrb200_rankcosine_fwd_bwd(const float* scores, const float* labels, const int32_t* offsets, float* grad, float* loss_per_query,
+                               int B, int n, ptrb200_stream_t stream);
+/* STListNet.custom_loss_function, ptranking/ltr_adhoc/listwise/st_listnet.py:41-49.  unif (optional, same layout as
+ * scores) supplies the U[0,1) draw behind the Gumbel noise; NULL draws it from Philox4x32-10 keyed by (seed, offset, doc). */
+int ptrb200_stlistnet_fwd_bwd(const float* scores, const float* labels, const int32_t* offsets, const float* unif,
+                              float* grad, float* loss_per_query, int B, int n, float temperature,
+                              uint64_t seed, uint64_t offset, ptrb200_stream_t stream);
+/* SoftRank.custom_loss_function (metric nDCG), ptranking/ltr_adhoc/listwise/softrank.py:46-72; labels presorted
+ * descending (:40).  top_k <= 0 means the whole list (the reference's top_k=None). */
+int ptrb200_softrank_fwd_bwd(const float* scores, const float* labels, const int32_t* offsets, float* grad, float* loss_per_query,
+                             int B, int n, float delta, int top_k, ptrb200_stream_t stream);
+/* sinkstep, ptranking/ltr_adhoc/listwise/wassrank/pytorch_wasserstein.py:132-224 (the reference's one CUDA kernel,
+ * CPU form :277-291): log_v[b][j] = log_nu[b][j] - logsumexp_i(-dist[i][j]/lambda + log_u[b][i]).
+ * dist[d1,d2], log_nu[B,d2], log_u[B,d1], log_v[B,d2]. */
+int ptrb200_sinkstep(const float* dist, const float* log_nu, const float* log_u, float* log_v,
+                     int B, int d1, int d2, float lambda, ptrb200_stream_t stream);
+
 /* deterministic (fixed-order) sum of n floats into out[0] -- the `torch.sum` over queries
  * that ends every reference loss (e.g. lambdarank.py:56). */
 int ptrb200_sum_f32(const float* x, float* out, int n, ptrb200_stream_t stream);

@@ -207,6 +207,58 @@ def approxndcg(s, y, alpha=10.0, presort=True, batch_coupled=True):
     return loss, grad
 
 
+def rankmse(s, y):
+    """pointwise/rank_mse.py:13-22: mean over queries of the summed squared error."""
+    s = s.astype(np.float64); y = y.astype(np.float64)
+    B = s.shape[0]
+    return ((s - y) ** 2).sum() / B, 2.0 * (s - y) / B
+
+
+def rankcosine(s, y, eps=1e-8):
+    """listwise/rank_cosine.py:33 with ATen's cosine_similarity (each vector divided by max(norm, eps))."""
+    s = s.astype(np.float64); y = y.astype(np.float64)
+    ns = np.sqrt((s * s).sum(1, keepdims=True)); ny = np.sqrt((y * y).sum(1, keepdims=True))
+    S = np.maximum(ns, eps); Y = np.maximum(ny, eps)
+    sy = (s * y).sum(1, keepdims=True)
+    cos = sy / (S * Y)
+    dcos = y / (S * Y) - np.where(ns > eps, sy * s / (S * S * np.maximum(ns, 1e-300) * Y), 0.0)
+    return (2.0 * (1.0 - cos)).sum(), -2.0 * dcos
+
+
+def stlistnet(s, y, unif, temperature=1.0):
+    """listwise/st_listnet.py:41-49 with the uniform draw given.  The Gumbel transform is evaluated in fp32 like the
+    reference (its 1e-20 guards are below float64's resolution of u but not of fp32's)."""
+    u = unif.astype(np.float32)
+    g = -np.log(-np.log(u + np.float32(1e-20)) + np.float32(1e-20))
+    z = (s.astype(np.float64) + g.astype(np.float64)) / temperature
+    y = y.astype(np.float64)
+    logsm = z - z.max(1, keepdims=True)
+    logsm = logsm - np.log(np.exp(logsm).sum(1, keepdims=True))
+    return -(_softmax(y) * logsm).sum(), (_softmax(z) - _softmax(y)) / temperature
+
+
+def softrank(s, y, delta=2.0, top_k=None):
+    """listwise/softrank.py:46-72 (nDCG, labels presorted)."""
+    from math import erfc, pi, sqrt
+    s = s.astype(np.float64); y = y.astype(np.float64)
+    B, n = s.shape
+    den = sqrt(2.0 * 2.0 * delta * delta)
+    x = (s[:, :, None] - s[:, None, :]) / den                       # [b,i,j]
+    phi = 0.5 * np.vectorize(erfc)(x)
+    off = 1.0 - np.eye(n)[None]
+    r = (phi * off).sum(2) + 1.0
+    G = _gain(y)
+    K = n if top_k is None else min(top_k, n)
+    mask = (np.arange(n) < K)[None, :]
+    lg = np.log2(r + 1.0)
+    idcg = _idcg(y)[:, None]
+    loss = -((G / lg) * mask / idcg).sum()
+    c = mask * G / (idcg * lg ** 2 * (r + 1.0) * LN2)
+    e = -np.exp(-x * x) / (sqrt(pi) * den) * off
+    grad = (e * (c[:, :, None] - c[:, None, :])).sum(2)
+    return loss, grad
+
+
 def ndcg_at_ks(scores, labels, ks, presort=True):
     """metric/adhoc/adhoc_metric.py:219-260 over the ranking base/ranker.py:50-56 builds."""
     s = scores.astype(np.float64); y = labels.astype(np.float64)

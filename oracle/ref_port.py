@@ -244,7 +244,73 @@ def approxndcg_loss(preds, labels, alpha=10.0, presort=True):
     return -torch.sum(dcg / idcg)
 
 
+# --------------------------------------------------------------------------- #
+# sibling losses
+# --------------------------------------------------------------------------- #
+def rankmse_loss(preds, labels):
+    """ltr_adhoc/pointwise/rank_mse.py:13-22: MEAN over the batch of the per-query summed squared error."""
+    return torch.mean(torch.sum(F.mse_loss(preds, labels, reduction='none'), dim=1))
+
+
+def rankcosine_loss(preds, labels):
+    """ltr_adhoc/listwise/rank_cosine.py:15,33."""
+    return torch.sum((1.0 - F.cosine_similarity(preds, labels, dim=1)) / 0.5)
+
+
+def stlistnet_loss(preds, labels, temperature=1.0, unif: Optional[torch.Tensor] = None):
+    """ltr_adhoc/listwise/st_listnet.py:41-49.  ``unif`` injects the uniform draw (the reference calls torch.rand, :41)."""
+    if unif is None:
+        unif = torch.rand(preds.size())
+    gumbel = -torch.log(-torch.log(unif + 1e-20) + 1e-20)
+    z = (preds + gumbel) / temperature
+    return torch.sum(-torch.sum(F.softmax(labels, dim=1) * F.log_softmax(z, dim=1), dim=1))
+
+
+def softrank_loss(preds, labels, delta=2.0, top_k=None):
+    """ltr_adhoc/listwise/softrank.py:46-72 (metric nDCG, labels presorted descending)."""
+    delta_t = torch.tensor([delta])
+    pairsub = torch.unsqueeze(preds, dim=2) - torch.unsqueeze(preds, dim=1)
+    pairsub_vars = 2 * delta_t ** 2
+    phi0 = 0.5 * torch.erfc(pairsub / torch.sqrt(2 * pairsub_vars))
+    phi0_offdiag = torch.triu(phi0, diagonal=1) + torch.tril(phi0, diagonal=-1)
+    expt_ranks = torch.sum(phi0_offdiag, dim=2) + 1.0
+    g = torch.pow(2.0, labels) - 1.0
+    dists = 1.0 / torch.log2(expt_ranks + 1.0)
+    idcgs = dcg_at_k(labels)
+    if top_k is None:
+        dcgs = dists * g
+    else:
+        k = min(top_k, labels.size(1))
+        dcgs = dists[:, 0:k] * g[:, 0:k]
+    return -torch.sum(torch.sum(dcgs / idcgs, dim=1))
+
+
+def sinkstep(dist, log_nu, log_u, lam: float):
+    """ltr_adhoc/listwise/wassrank/pytorch_wasserstein.py:277-291 (the CPU form of the CUDA kernel at :132-224)."""
+    log_v = log_nu.clone()
+    for b in range(log_u.size(0)):
+        log_v[b] -= torch.logsumexp(-dist / lam + log_u[b, :, None], 0)
+    return log_v
+
+
+def sinkhorn_ot(mu, nu, dist, lam=1e-3, N=100):
+    """SinkhornOT.forward / backward, pytorch_wasserstein.py:294-324 -> (distances[B], d/dmu per unit grad, d/dnu)."""
+    d1, d2 = dist.size()
+    log_mu, log_nu = mu.log(), nu.log()
+    log_u = torch.full_like(mu, -math.log(d1))
+    log_v = torch.full_like(nu, -math.log(d2))
+    for _ in range(N):
+        log_v = sinkstep(dist, log_nu, log_u, lam)
+        log_u = sinkstep(dist.t(), log_mu, log_v, lam)
+    distances = (-sinkstep(-dist.log() + dist / lam, -log_v, log_u, 1.0)).logsumexp(1).exp()
+    return distances, log_u * lam, log_v * lam
+
+
 LOSSES = {
+    "RankMSE": rankmse_loss,
+    "RankCosine": rankcosine_loss,
+    "STListNet": stlistnet_loss,
+    "SoftRank": softrank_loss,
     "RankNet": ranknet_loss,
     "LambdaRank": lambdarank_loss,
     "LambdaLoss": lambdaloss_loss,
@@ -259,8 +325,8 @@ def loss_and_grad(name: str, scores: torch.Tensor, labels: torch.Tensor, **param
     s = scores.detach().clone().float().requires_grad_(True)
     if name == "ListMLE":
         loss = listmle_loss(s, labels, perm=params.get("perm"))
-    elif name == "ListNet":
-        loss = listnet_loss(s, labels)
+    elif name in ("ListNet", "RankMSE", "RankCosine"):
+        loss = LOSSES[name](s, labels)
     else:
         loss = LOSSES[name](s, labels, **params)
     loss.backward()

@@ -64,6 +64,11 @@ SIGNATURES = {
     "ptrb200_listmle_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _I, _I, _fp]),
     "ptrb200_shuffle_ties_perm": (_I, [_fp, _fp, _I, _I, _U64, _U64, _fp]),
     "ptrb200_approxndcg_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _fp, _I, _I, _F, _I, _I, _fp]),
+    "ptrb200_rankmse_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _fp, _I, _I, _fp]),
+    "ptrb200_rankcosine_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _fp, _I, _I, _fp]),
+    "ptrb200_stlistnet_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _fp, _fp, _I, _I, _F, _U64, _U64, _fp]),
+    "ptrb200_softrank_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _fp, _I, _I, _F, _I, _fp]),
+    "ptrb200_sinkstep": (_I, [_fp, _fp, _fp, _fp, _I, _I, _I, _F, _fp]),
     "ptrb200_sum_f32": (_I, [_fp, _fp, _I, _fp]),
     "ptrb200_ndcg_at_ks": (_I, [_fp, _fp, C.POINTER(C.c_int32), _I, _fp, _fp, _I, _I, _I, _fp]),
     "ptrb200_adhoc_metrics_at_ks": (_I, [_fp, _fp, C.POINTER(C.c_int32), _I, _fp, _I, _I, _I, _F, _fp]),

@@ -93,10 +93,82 @@ def _loss_call(name: str, scores: torch.Tensor, labels: torch.Tensor, params: di
                                                 scratch.data_ptr(), B, n, float(params.get("alpha", 10.0)),
                                                 int(bool(params.get("presort", True))),
                                                 int(bool(params.get("batch_coupled", True))), st)
+        elif name == "RankMSE":
+            rc = lib.ptrb200_rankmse_fwd_bwd(s.data_ptr(), y.data_ptr(), None, grad.data_ptr(), loss_q.data_ptr(), B, n, st)
+        elif name == "RankCosine":
+            rc = lib.ptrb200_rankcosine_fwd_bwd(s.data_ptr(), y.data_ptr(), None, grad.data_ptr(), loss_q.data_ptr(), B, n, st)
+        elif name == "STListNet":
+            unif = params.get("unif")
+            if unif is not None:
+                unif = _dev_f32(unif, "unif")
+                _check_pair(s, unif)
+            seed, offset = params.get("seed"), params.get("offset")
+            if seed is None:
+                seed = torch.initial_seed()
+            if offset is None:
+                offset = next_noise_offset()
+            rc = lib.ptrb200_stlistnet_fwd_bwd(s.data_ptr(), y.data_ptr(), None, unif.data_ptr() if unif is not None else None,
+                                               grad.data_ptr(), loss_q.data_ptr(), B, n, float(params.get("temperature", 1.0)),
+                                               seed & (2 ** 64 - 1), offset & (2 ** 64 - 1), st)
+        elif name == "SoftRank":
+            top_k = params.get("top_k")
+            rc = lib.ptrb200_softrank_fwd_bwd(s.data_ptr(), y.data_ptr(), None, grad.data_ptr(), loss_q.data_ptr(), B, n,
+                                              float(params.get("delta", 2.0)), int(top_k) if top_k else 0, st)
         else:
             raise NotImplementedError(name)
     _lib.check(rc, f"{name} loss kernel")
     return loss_q, grad
+
+
+_noise_offset = 0
+
+
+def next_noise_offset() -> int:
+    """Counter that keys the Gumbel draw of successive STListNet calls (same role as the tie-shuffle counter)."""
+    global _noise_offset
+    _noise_offset += 1
+    return _noise_offset
+
+
+@_on_tensor_device
+def sinkstep(dist: torch.Tensor, log_nu: torch.Tensor, log_u: torch.Tensor, lam: float) -> torch.Tensor:
+    """log_v[b,j] = log_nu[b,j] - logsumexp_i(-dist[i,j]/lam + log_u[b,i]) (pytorch_wasserstein.py:277-291)."""
+    lib = _lib.load()
+    dist, log_nu, log_u = _dev_f32(dist, "dist"), _dev_f32(log_nu, "log_nu"), _dev_f32(log_u, "log_u")
+    if dist.dim() != 2 or log_nu.dim() != 2 or log_u.dim() != 2 or dist.size(0) != log_u.size(1) or \
+            dist.size(1) != log_nu.size(1) or log_u.size(0) != log_nu.size(0):
+        raise ValueError("sinkstep: expected dist[d1,d2], log_nu[B,d2], log_u[B,d1]")
+    log_v = torch.empty_like(log_nu)
+    _lib.check(lib.ptrb200_sinkstep(dist.data_ptr(), log_nu.data_ptr(), log_u.data_ptr(), log_v.data_ptr(),
+                                    log_u.size(0), dist.size(0), dist.size(1), float(lam), _stream_ptr()), "sinkstep")
+    return log_v
+
+
+class SinkhornOT(torch.autograd.Function):
+    """SinkhornOT of pytorch_wasserstein.py:294-324 with every half-step on the sinkstep kernel: entropic OT distances
+    between batches of histograms mu[B,d1], nu[B,d2] under the cost matrix dist[d1,d2]; backward returns
+    lam * log_u / lam * log_v like the reference."""
+
+    @staticmethod
+    def forward(ctx, mu, nu, dist, lam=1e-3, N=100):
+        import math
+        d1, d2 = dist.shape
+        log_mu, log_nu = mu.log(), nu.log()
+        log_u = torch.full_like(mu, -math.log(d1))
+        log_v = torch.full_like(nu, -math.log(d2))
+        dist_t = dist.t().contiguous()
+        for _ in range(N):
+            log_v = sinkstep(dist, log_nu, log_u, lam)
+            log_u = sinkstep(dist_t, log_mu, log_v, lam)
+        distances = (-sinkstep(-dist.log() + dist / lam, -log_v, log_u, 1.0)).logsumexp(1).exp()
+        ctx.save_for_backward(log_u, log_v)
+        ctx.lam = lam
+        return distances
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        log_u, log_v = ctx.saved_tensors
+        return grad_out[:, None] * log_u * ctx.lam, grad_out[:, None] * log_v * ctx.lam, None, None, None
 
 
 @_on_tensor_device

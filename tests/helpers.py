@@ -46,3 +46,39 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
     denom = max(np.abs(b).max(), 1e-30)
     return float(np.abs(a - b).max() / denom)
+
+
+def sibling_cases():
+    """tests/golden/siblings.npz -> list of (loss_key, case, dict) for RankMSE / RankCosine / STListNet / SoftRank."""
+    z = load("siblings.npz")
+    groups = {}
+    for k in z.files:
+        head, case, field = k.split("__")
+        if head in ("sinkstep", "sinkhorn"):
+            continue
+        groups.setdefault((head, case), {})[field] = z[k]
+    return [(h, c, v) for (h, c), v in sorted(groups.items())]
+
+
+def sinkhorn_cases(kind):
+    z = load("siblings.npz")
+    groups = {}
+    for k in z.files:
+        head, case, field = k.split("__")
+        if head == kind:
+            groups.setdefault(case, {})[field] = z[k]
+    return sorted(groups.items())
+
+
+def parse_sibling_key(head):
+    """'SoftRank_delta2.0_kNone' -> ('SoftRank', dict(delta=2.0, top_k=None))."""
+    name = head.split("_")[0]
+    params = {}
+    m = re.search(r"_T([0-9.]+)", head)
+    if m:
+        params["temperature"] = float(m.group(1))
+    m = re.search(r"delta([0-9.]+)_k(\w+)", head)
+    if m:
+        params["delta"] = float(m.group(1))
+        params["top_k"] = None if m.group(2) == "None" else int(m.group(2))
+    return name, params
