@@ -60,17 +60,22 @@ int                ptrb200_timing_report(char* buf_host, int buflen);
 /* ---- ranking losses: loss value per query + d(sum loss)/d(scores) ---------- */
 /* Each call writes loss_per_query[B] (the reference returns their sum) and
  * grad[B,n] = d(sum_b loss_b)/d scores -- the tensor autograd would hand back
- * to the scorer after the reference's `batch_loss.backward()`. */
+ * to the scorer after the reference's `batch_loss.backward()`.
+ *
+ * `offsets`: NULL for the reference's dense batches (every query has n documents, scores/labels/grad are [B,n]:
+ * data_utils.py:683-718).  Non-NULL (device, B+1 int32 prefix offsets) makes the batch RAGGED: scores /
+ * labels / grad are flat [offsets[B]] arrays, query b owns [offsets[b], offsets[b+1]) and `n` is the longest list of the
+ * batch (it sizes the CTA and its shared memory).  Empty lists are allowed and contribute a zero loss. */
 
 /* RankNet.custom_loss_function, ptranking/ltr_adhoc/pairwise/ranknet.py:25-36
  * (+ get_pairwise_comp_probs, ltr_adhoc/util/lambda_utils.py:5-23). */
-int ptrb200_ranknet_fwd_bwd(const float* scores, const float* labels, float* grad, float* loss_per_query,
+int ptrb200_ranknet_fwd_bwd(const float* scores, const float* labels, const int32_t* offsets, float* grad, float* loss_per_query,
                             int B, int n, float sigma, ptrb200_stream_t stream);
 
 /* LambdaRank.custom_loss_function, ptranking/ltr_adhoc/listwise/lambdarank.py:27-56
  * (+ get_delta_ndcg, metric/metric_utils.py:19-45).  Labels must be presorted
  * descending (lambdarank.py:36). */
-int ptrb200_lambdarank_fwd_bwd(const float* scores, const float* labels, float* grad, float* loss_per_query,
+int ptrb200_lambdarank_fwd_bwd(const float* scores, const float* labels, const int32_t* offsets, float* grad, float* loss_per_query,
                                int B, int n, float sigma, ptrb200_stream_t stream);
 
 #define PTRB200_NDCG_LOSS1    0
@@ -78,36 +83,34 @@ int ptrb200_lambdarank_fwd_bwd(const float* scores, const float* labels, float* 
 #define PTRB200_NDCG_LOSS2PP  2
 /* LambdaLoss.custom_loss_function, ptranking/ltr_adhoc/listwise/lambdaloss.py:73-132.
  * NDCG_Loss1 is evaluated per query (the reference's broadcast only works for B==1). */
-int ptrb200_lambdaloss_fwd_bwd(const float* scores, const float* labels, float* grad, float* loss_per_query,
+int ptrb200_lambdaloss_fwd_bwd(const float* scores, const float* labels, const int32_t* offsets, float* grad, float* loss_per_query,
                                int B, int n, int k, float sigma, float mu, int loss_type, int presort,
                                ptrb200_stream_t stream);
 
 /* ListNet.custom_loss_function, ptranking/ltr_adhoc/listwise/listnet.py:39. */
-int ptrb200_listnet_fwd_bwd(const float* scores, const float* labels, float* grad, float* loss_per_query,
+int ptrb200_listnet_fwd_bwd(const float* scores, const float* labels, const int32_t* offsets, float* grad, float* loss_per_query,
                             int B, int n, ptrb200_stream_t stream);
 
 /* ListMLE.custom_loss_function, ptranking/ltr_adhoc/listwise/listmle.py:83-97, with the
- * tie-shuffled ordering `perm[B,n]` (int32 doc indices, labels descending) supplied. */
-int ptrb200_listmle_fwd_bwd(const float* scores, const int32_t* perm, float* grad, float* loss_per_query,
+ * tie-shuffled ordering `perm[B,n]` (int32 doc positions within each query's own list, labels descending) supplied. */
+int ptrb200_listmle_fwd_bwd(const float* scores, const int32_t* perm, const int32_t* offsets, float* grad, float* loss_per_query,
                             int B, int n, ptrb200_stream_t stream);
 
 /* arg_shuffle_ties, ptranking/ltr_adhoc/util/sampling_utils.py:13-28: perm[B,n] orders each
  * row's labels descending with ties broken uniformly at random (Philox4x32-10 keyed by
  * (seed, offset, b, doc); not the torch RNG stream). */
-int ptrb200_shuffle_ties_perm(const float* labels, int32_t* perm, int B, int n,
+int ptrb200_shuffle_ties_perm(const float* labels, const int32_t* offsets, int32_t* perm, int B, int n,
                               uint64_t seed, uint64_t offset, ptrb200_stream_t stream);
 
 /* ApproxNDCG.custom_loss_function, ptranking/ltr_adhoc/listwise/approxNDCG.py:83-101
  * (+ get_approx_ranks :19-28, approxNDCG_loss :45-62, Robust_Sigmoid base/utils.py:57-92).
  * batch_coupled != 0 keeps the reference's [B]/[B,1] broadcast (every query scaled by
  * sum_a 1/iDCG_a, :58-61).  scratch: B+1 floats. */
-int ptrb200_approxndcg_fwd_bwd(const float* scores, const float* labels, float* grad, float* loss_per_query,
+int ptrb200_approxndcg_fwd_bwd(const float* scores, const float* labels, const int32_t* offsets, float* grad, float* loss_per_query,
                                float* scratch, int B, int n, float alpha, int presort, int batch_coupled,
                                ptrb200_stream_t stream);
 
-/* ---- sibling losses ----------------------------------------------------------
- * Same contract as above.  `offsets` (device, B+1 int32 prefix offsets into the flat score / label / grad arrays) makes
- * the batch ragged -- query b owns [offsets[b], offsets[b+1]) and `n` is then the longest list; NULL = dense [B,n]. */
+/* ---- sibling losses: same contract as above, `offsets` included ---------------- */
 
 /* RankMSE.custom_loss_function, ptranking/ltr_adhoc/pointwise/rank_mse.py:13-22: the MEAN over queries of the per-query
  * summed squared error; loss_per_query[b] already carries the 1/B so that their sum is the reference's value. */
@@ -139,15 +142,24 @@ int ptrb200_sum_f32(const float* x, float* out, int n, ptrb200_stream_t stream);
 /* Evaluator.ndcg_at_ks ranking + torch_ndcg_at_ks, ptranking/base/ranker.py:67-95 and
  * metric/adhoc/adhoc_metric.py:219-260.  out[B,nks]; cutoffs > n yield 0 (the reference's
  * zero padding).  order[B,n] (optional, may be NULL) receives the doc indices in predicted
- * rank order (score descending, index ascending among equal scores).  ks: host pointer. */
-int ptrb200_ndcg_at_ks(const float* scores, const float* labels, const int32_t* ks_host, int nks,
+ * rank order (score descending, index ascending among equal scores).  ks: host pointer.  offsets: as for the losses. */
+int ptrb200_ndcg_at_ks(const float* scores, const float* labels, const int32_t* offsets, const int32_t* ks_host, int nks,
                        float* out, int32_t* order, int B, int n, int presort, ptrb200_stream_t stream);
 
 /* adhoc_performance_at_ks, ptranking/base/ranker.py:202-263 with torch_ndcg_at_ks / torch_nerr_at_ks / torch_ap_at_ks /
  * torch_precision_at_ks (metric/adhoc/adhoc_metric.py:36-64, 95-128, 132-193, 243-260): out[B][4][nks] in the order
  * nDCG, nERR, AP, P from one in-CTA sort per query; cutoffs > n yield 0; max_label as the evaluator passes it. */
-int ptrb200_adhoc_metrics_at_ks(const float* scores, const float* labels, const int32_t* ks_host, int nks,
+int ptrb200_adhoc_metrics_at_ks(const float* scores, const float* labels, const int32_t* offsets, const int32_t* ks_host, int nks,
                                 float* out, int B, int n, int presort, float max_label, ptrb200_stream_t stream);
+
+/* ---- input side: per-query feature scaling -------------------------------------------------- */
+/* sklearn StandardScaler().fit_transform applied per query as the loader does for MSLR-WEB / Istella
+ * (ptranking/data/data_utils.py:482-487; selection :205-218): out = (x - mean_q) / std_q per feature column with the
+ * population standard deviation, statistics in float64, constant columns divided by 1.  X/out: [B,n,F] dense, or flat
+ * [offsets[B], F] with per-query offsets (ragged).  clip != 0 first clamps features at clip_max (the ISTELLA_MAX clip,
+ * :484-485).  In-place (out == X) is allowed. */
+int ptrb200_standard_scale(const float* X, const int32_t* offsets, float* out, int B, int n, int F,
+                           int clip, float clip_max, ptrb200_stream_t stream);
 
 /* ---- stacked feed-forward scorer (pointwise MLP; also the head/tail nets of listsf) ---- */
 /* get_stacked_FFNet, ptranking/base/utils.py:288-356; PointNeuralRanker.forward,

@@ -306,6 +306,17 @@ def sinkhorn_ot(mu, nu, dist, lam=1e-3, N=100):
     return distances, log_u * lam, log_v * lam
 
 
+def per_query_standard_scale(feature_mat, clip_max=None):
+    """ptranking/data/data_utils.py:482-487: sklearn StandardScaler().fit_transform on ONE query's [n,F] feature matrix
+    (float64, as np.vstack of the parsed rows gives), ISTELLA clip first when asked (:484-485)."""
+    import numpy as np
+    from sklearn.preprocessing import StandardScaler
+    x = np.asarray(feature_mat, dtype=np.float64)
+    if clip_max is not None:
+        x = np.clip(x, a_min=None, a_max=clip_max)
+    return StandardScaler().fit_transform(x)
+
+
 LOSSES = {
     "RankMSE": rankmse_loss,
     "RankCosine": rankcosine_loss,

@@ -57,21 +57,22 @@ SIGNATURES = {
     "ptrb200_device_ok": (_I, []),
     "ptrb200_timing_enable": (_I, [_I]),
     "ptrb200_timing_report": (_I, [C.c_char_p, _I]),
-    "ptrb200_ranknet_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _I, _I, _F, _fp]),
-    "ptrb200_lambdarank_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _I, _I, _F, _fp]),
-    "ptrb200_lambdaloss_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _I, _I, _I, _F, _F, _I, _I, _fp]),
-    "ptrb200_listnet_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _I, _I, _fp]),
-    "ptrb200_listmle_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _I, _I, _fp]),
-    "ptrb200_shuffle_ties_perm": (_I, [_fp, _fp, _I, _I, _U64, _U64, _fp]),
-    "ptrb200_approxndcg_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _fp, _I, _I, _F, _I, _I, _fp]),
+    "ptrb200_ranknet_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _fp, _I, _I, _F, _fp]),
+    "ptrb200_lambdarank_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _fp, _I, _I, _F, _fp]),
+    "ptrb200_lambdaloss_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _fp, _I, _I, _I, _F, _F, _I, _I, _fp]),
+    "ptrb200_listnet_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _fp, _I, _I, _fp]),
+    "ptrb200_listmle_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _fp, _I, _I, _fp]),
+    "ptrb200_shuffle_ties_perm": (_I, [_fp, _fp, _fp, _I, _I, _U64, _U64, _fp]),
+    "ptrb200_approxndcg_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _fp, _fp, _I, _I, _F, _I, _I, _fp]),
     "ptrb200_rankmse_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _fp, _I, _I, _fp]),
     "ptrb200_rankcosine_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _fp, _I, _I, _fp]),
     "ptrb200_stlistnet_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _fp, _fp, _I, _I, _F, _U64, _U64, _fp]),
     "ptrb200_softrank_fwd_bwd": (_I, [_fp, _fp, _fp, _fp, _fp, _I, _I, _F, _I, _fp]),
     "ptrb200_sinkstep": (_I, [_fp, _fp, _fp, _fp, _I, _I, _I, _F, _fp]),
+    "ptrb200_standard_scale": (_I, [_fp, _fp, _fp, _I, _I, _I, _I, _F, _fp]),
     "ptrb200_sum_f32": (_I, [_fp, _fp, _I, _fp]),
-    "ptrb200_ndcg_at_ks": (_I, [_fp, _fp, C.POINTER(C.c_int32), _I, _fp, _fp, _I, _I, _I, _fp]),
-    "ptrb200_adhoc_metrics_at_ks": (_I, [_fp, _fp, C.POINTER(C.c_int32), _I, _fp, _I, _I, _I, _F, _fp]),
+    "ptrb200_ndcg_at_ks": (_I, [_fp, _fp, _fp, C.POINTER(C.c_int32), _I, _fp, _fp, _I, _I, _I, _fp]),
+    "ptrb200_adhoc_metrics_at_ks": (_I, [_fp, _fp, _fp, C.POINTER(C.c_int32), _I, _fp, _I, _I, _I, _F, _fp]),
     "ptrb200_attention_fwd": (_I, [_fp, _fp, _fp, _fp, _fp, _I, _I, _I, _I, _F, _U64, _U64, _fp]),
     "ptrb200_adam_step": (_I, [_fp, _fp, _fp, _fp, _I64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _I, _fp]),
     "ptrb200_adagrad_step": (_I, [_fp, _fp, _fp, _I64, C.c_double, C.c_double, C.c_double, C.c_double, _I, _fp]),

@@ -42,6 +42,11 @@ class PointNeuralRanker(NeuralRanker):
         num_docs = batch_q_doc_vectors.size(1)
         return self.point_sf(batch_q_doc_vectors).view(-1, num_docs)
 
+    def forward_ragged(self, flat_q_doc_vectors, offsets, max_len):
+        """[total_docs, F] -> [total_docs]: the pointwise scorer acts per document, so a ragged batch is one long list
+        to it; only per-query normalisation (BN2) needs the offsets."""
+        return self.point_sf(flat_q_doc_vectors, offsets=offsets, max_len=max_len).view(-1)
+
     def eval_mode(self):
         self.point_sf.eval()
 

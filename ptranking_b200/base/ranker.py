@@ -88,14 +88,37 @@ def _is_multilabel(label_type) -> bool:
 class Evaluator:
     """nDCG evaluation API of ptranking.base.ranker.Evaluator."""
 
-    def _scores_and_labels(self, batch_q_doc_vectors, batch_std_labels):
+    def _scores_and_labels(self, batch_q_doc_vectors, batch_std_labels, offsets=None, max_len=None):
         dev = self.device
         # no autograd tape in evaluation: the scorer then runs forward-only (no backward by-products written, no
         # activation workspace kept alive).  The reference never disables grad here (ranker.py:623-630), which only
         # matters for its BN2 train/eval switch (SURVEY B4); these kernels use per-query statistics in both modes.
         with torch.no_grad():
-            preds = self.predict(batch_q_doc_vectors.to(dev, non_blocking=True))
+            X = batch_q_doc_vectors.to(dev, non_blocking=True)
+            preds = self.predict(X) if offsets is None else self.forward_ragged(X, offsets, max_len)
         return preds.detach(), batch_std_labels.to(dev, non_blocking=True)
+
+    def _eval_batches(self, test_data, k=None):
+        """-> (num_queries counted, preds, labels, ragged kwargs) per batch.  Dense batches are the reference's
+        (ids, X[B,n,F], y[B,n]); ragged ones are data.RaggedBatches' (ids, X[total,F], y[total], offsets, max_len).
+        With ``k`` given, lists shorter than k do not count (ranker.py:41-42 skips such batches; in a ragged batch the
+        rule applies per query -- the kernel reports 0 for them)."""
+        for batch in test_data:
+            if len(batch) == 5:
+                ids, X, y, offsets, max_len = batch
+                lens = (offsets[1:] - offsets[:-1]).cpu()
+                counted = int((lens >= k).sum()) if k is not None else len(ids)
+                if counted == 0:
+                    continue
+                off_d = offsets.to(self.device, non_blocking=True)
+                preds, labels = self._scores_and_labels(X, y, off_d, max_len)
+                yield counted, preds, labels, dict(offsets=off_d, max_len=max_len)
+            else:
+                ids, X, y = batch
+                if k is not None and y.size(1) < k:
+                    continue
+                preds, labels = self._scores_and_labels(X, y)
+                yield len(ids), preds, labels, {}
 
     def ndcg_at_k(self, test_data=None, k=10, label_type=LABEL_TYPE.MultiLabel, presort=False, device='cpu'):
         """ranker.py:31-65: average nDCG@k; batches with fewer than k documents are skipped (:41-42)."""
@@ -103,12 +126,9 @@ class Evaluator:
         self.eval_mode()
         num_queries = 0
         total = torch.zeros(1, device=self.device)
-        for batch_ids, X, y in test_data:
-            if y.size(1) < k:
-                continue
-            num_queries += len(batch_ids)
-            preds, labels = self._scores_and_labels(X, y)
-            total += ops.sum_f32(ops.ndcg_at_ks(preds, labels, [k], presort=presort))
+        for counted, preds, labels, rk in self._eval_batches(test_data, k=k):
+            num_queries += counted
+            total += ops.sum_f32(ops.ndcg_at_ks(preds, labels, [k], presort=presort, **rk))
         return (total / num_queries).cpu()
 
     def ndcg_at_ks(self, test_data=None, ks=[1, 5, 10], label_type=LABEL_TYPE.MultiLabel, presort=False, device='cpu'):
@@ -117,10 +137,9 @@ class Evaluator:
         self.eval_mode()
         num_queries = 0
         total = torch.zeros(len(ks), device=self.device)
-        for batch_ids, X, y in test_data:
-            preds, labels = self._scores_and_labels(X, y)
-            total += ops.ndcg_at_ks(preds, labels, ks, presort=presort).sum(dim=0)
-            num_queries += len(batch_ids)
+        for counted, preds, labels, rk in self._eval_batches(test_data):
+            total += ops.ndcg_at_ks(preds, labels, ks, presort=presort, **rk).sum(dim=0)
+            num_queries += counted
         return (total / num_queries).cpu()
 
     def _metric_at_k(self, which, test_data, k, presort, max_label=None, skip_short=True):
@@ -129,12 +148,9 @@ class Evaluator:
         self.eval_mode()
         num_queries = 0
         total = torch.zeros(1, device=self.device)
-        for batch_ids, X, y in test_data:
-            if skip_short and y.size(1) < k:
-                continue
-            num_queries += len(batch_ids)
-            preds, labels = self._scores_and_labels(X, y)
-            vals = ops.adhoc_metrics_at_ks(preds, labels, [k], presort=presort, max_label=max_label)[which]
+        for counted, preds, labels, rk in self._eval_batches(test_data, k=k if skip_short else None):
+            num_queries += counted
+            vals = ops.adhoc_metrics_at_ks(preds, labels, [k], presort=presort, max_label=max_label, **rk)[which]
             total += ops.sum_f32(vals)
         return (total / num_queries).cpu()
 
@@ -170,14 +186,13 @@ class Evaluator:
         num_queries = 0
         sums = [torch.zeros(len(ks), device=self.device) for _ in range(4)]
         per_q = [[] for _ in range(4)]
-        for batch_ids, X, y in test_data:
-            preds, labels = self._scores_and_labels(X, y)
-            vals = ops.adhoc_metrics_at_ks(preds, labels, ks, presort=presort, max_label=max_label)
+        for counted, preds, labels, rk in self._eval_batches(test_data):
+            vals = ops.adhoc_metrics_at_ks(preds, labels, ks, presort=presort, max_label=max_label, **rk)
             for m in range(4):
                 sums[m] += vals[m].sum(dim=0)
                 if need_per_q:
                     per_q[m].append(vals[m].cpu())
-            num_queries += len(batch_ids)
+            num_queries += counted
         avgs = [(s_ / num_queries).cpu() for s_ in sums]
         if need_per_q:
             return (*avgs, *per_q)
@@ -278,25 +293,30 @@ class NeuralRanker(Evaluator):
         copier = self._copy_stream()
 
         def upload(batch):
-            ids, X, y = batch
+            # dense (ids, X[B,n,F], y[B,n]) as the reference's loaders yield, or ragged
+            # (ids, X[total,F], y[total], offsets[B+1], max_len) from data.RaggedBatches
+            ids, X, y = batch[0], batch[1], batch[2]
             with torch.cuda.stream(copier):
                 Xd, yd = X.to(self.device, non_blocking=True), y.to(self.device, non_blocking=True)
+                ragged = dict(offsets=batch[3].to(self.device, non_blocking=True), max_len=int(batch[4])) if len(batch) == 5 else {}
                 ready = torch.cuda.Event()
                 ready.record(copier)
-            return ids, Xd, yd, ready
+            return ids, Xd, yd, ready, ragged
 
         it = iter(train_data)
         nxt = next(it, None)
         pending = upload(nxt) if nxt is not None else None
         while pending is not None:
-            batch_ids, X, y, ready = pending
+            batch_ids, X, y, ready, ragged = pending
             nxt = next(it, None)
             pending = upload(nxt) if nxt is not None else None       # overlaps with the step below
             compute.wait_event(ready)
             X.record_stream(compute); y.record_stream(compute)
+            if ragged:
+                ragged['offsets'].record_stream(compute)
             num_queries += len(batch_ids)
             batch_loss, stop_training = self.train_op(X, y, batch_ids=batch_ids, epoch_k=epoch_k,
-                                                      presort=presort, label_type=label_type)
+                                                      presort=presort, label_type=label_type, **ragged)
             if stop_training:
                 break
             ring[filled].copy_(batch_loss.detach(), non_blocking=True)
@@ -323,7 +343,10 @@ class NeuralRanker(Evaluator):
     def train_op(self, batch_q_doc_vectors, batch_std_labels, **kwargs):
         """ranker.py:589-603."""
         stop_training = False
-        batch_preds = self.forward(batch_q_doc_vectors)
+        if kwargs.get('offsets') is not None:     # ragged batch: flat [total_docs, F] features, per-query offsets
+            batch_preds = self.forward_ragged(batch_q_doc_vectors, kwargs['offsets'], kwargs['max_len'])
+        else:
+            batch_preds = self.forward(batch_q_doc_vectors)
         if 'epoch_k' in kwargs and kwargs['epoch_k'] is not None and kwargs['epoch_k'] % self.stop_check_freq == 0:
             stop_training = self.stop_training(batch_preds)
         return self.custom_loss_function(batch_preds, batch_std_labels, **kwargs), stop_training
@@ -334,6 +357,18 @@ class NeuralRanker(Evaluator):
     def forward(self, batch_q_doc_vectors):
         pass
 
+    def forward_ragged(self, flat_q_doc_vectors, offsets, max_len):
+        """[total_docs, F] + int32 offsets[B+1] -> flat scores [total_docs] (no counterpart in the reference, whose
+        batches are dense)."""
+        raise NotImplementedError("this scorer has no ragged-batch path")
+
     def predict(self, batch_q_doc_vectors):
         """ranker.py:623-630."""
         return self.forward(batch_q_doc_vectors)
+
+    @staticmethod
+    def ragged_kwargs(kwargs):
+        """The ragged-batch description a loss kernel needs, out of custom_loss_function's kwargs."""
+        if kwargs.get('offsets') is None:
+            return {}
+        return dict(offsets=kwargs['offsets'], max_len=kwargs['max_len'])

@@ -80,8 +80,11 @@ class StackedFFNet(nn.Module):
     def ordered_parameters(self):
         return list(self._order)
 
-    def forward(self, X):
-        """[B,n,F] (or [rows,F]) -> [B,n,out]."""
+    def forward(self, X, offsets=None, max_len=None):
+        """[B,n,F] (or [rows,F]) -> [B,n,out].  ``offsets``/``max_len`` describe a ragged batch ([total_docs,F] rows cut
+        into queries): batch-level BN and norm-free nets see one long list; per-query BN2 needs the query boundaries."""
+        if offsets is not None and self.spec.norm == "BN2":
+            raise NotImplementedError("ragged batches with per-query BN2 normalisation: use BN / no norm, or dense batches")
         squeeze = X.dim() == 2
         if squeeze:
             X = X.unsqueeze(0)

@@ -1,0 +1,50 @@
+// data.cu -- the input side of the hot path on the device.
+//
+// Reference functions replaced (wildltr/ptranking @ f1d366c):
+//   per-query feature scaling  ptranking/data/data_utils.py:482-487 (sklearn StandardScaler().fit_transform per query,
+//                              ISTELLA clip at :484-485; which datasets are scaled: :205-218)
+#include "losses_common.cuh"
+
+namespace ptrb200 {
+
+// One CTA per query; thread t owns feature columns t, t+blockDim, ... so every row read is coalesced.
+// sklearn semantics: mean over the query's documents, POPULATION variance (ddof = 0), both accumulated in float64
+// (two passes: the variance is the mean squared deviation from the computed mean); a constant column -- variance not
+// above sklearn's _is_constant_feature bound n*eps*var + (n*mean*eps)^2 -- is divided by 1 instead of 0.
+__global__ void standard_scale_kernel(const float* __restrict__ X, const int32_t* __restrict__ offsets, float* __restrict__ out,
+                                      int n_uniform, int F, float clip_max, int clip) {
+    const int b = blockIdx.x;
+    const ListSpan sp = list_span(offsets, b, n_uniform);
+    const int n = sp.n;
+    if (n == 0) return;
+    const float* x = X + sp.base * (size_t)F;
+    float* o = out + sp.base * (size_t)F;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < n; ++r) { float v = x[(size_t)r * F + f]; if (clip) v = fminf(v, clip_max); s += (double)v; }
+        const double mean = s / n;
+        double q = 0.0;
+        for (int r = 0; r < n; ++r) { float v = x[(size_t)r * F + f]; if (clip) v = fminf(v, clip_max); const double d = (double)v - mean; q += d * d; }
+        const double var = q / n;
+        const double eps = 2.220446049250313e-16;
+        const double bound = n * eps * var + (n * mean * eps) * (n * mean * eps);
+        const double scale = (var <= bound) ? 1.0 : sqrt(var);
+        for (int r = 0; r < n; ++r) {
+            float v = x[(size_t)r * F + f];
+            if (clip) v = fminf(v, clip_max);
+            o[(size_t)r * F + f] = (float)(((double)v - mean) / scale);
+        }
+    }
+}
+
+}  // namespace ptrb200
+
+using namespace ptrb200;
+
+extern "C" int ptrb200_standard_scale(const float* X, const int32_t* offsets, float* out, int B, int n, int F,
+                                      int clip, float clip_max, ptrb200_stream_t stream) {
+    if (!X || !out || B <= 0 || n <= 0 || F <= 0) { set_error("standard_scale: bad arguments (B=%d n=%d F=%d)", B, n, F); return PTRB200_ERR_INVALID; }
+    int threads = ((F + 31) / 32) * 32; if (threads > 256) threads = 256;
+    PTRB200_LAUNCH(standard_scale_kernel, B, threads, 0, stream, X, offsets, out, n, F, clip_max, clip);
+    return check_launch("standard_scale");
+}

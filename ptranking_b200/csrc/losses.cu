@@ -25,21 +25,24 @@ namespace ptrb200 {
 // ---------------------------------------------------------------------------
 template <bool LAMBDA>
 __global__ void pairwise_bce_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
-                                    float* __restrict__ grad, float* __restrict__ loss_q,
-                                    int n, int npow2, float sigma) {
+                                    float* __restrict__ grad, float* __restrict__ loss_q, const int32_t* __restrict__ offsets,
+                                    int nmax, int npow2max, float sigma) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* keys = reinterpret_cast<u64*>(smem_raw);
-    float* ss = reinterpret_cast<float*>(keys + (LAMBDA ? npow2 : 0));
-    float* ys = ss + n;
-    float* ng = ys + n;
-    float* dinv = ng + n;
-    float* gout = dinv + n;
-    int* idx = reinterpret_cast<int*>(gout + n);
-    float* red = reinterpret_cast<float*>(idx + n);
+    float* ss = reinterpret_cast<float*>(keys + (LAMBDA ? npow2max : 0));
+    float* ys = ss + nmax;
+    float* ng = ys + nmax;
+    float* dinv = ng + nmax;
+    float* gout = dinv + nmax;
+    int* idx = reinterpret_cast<int*>(gout + nmax);
+    float* red = reinterpret_cast<float*>(idx + nmax);
 
     const int b = blockIdx.x;
-    const float* s = scores + (size_t)b * n;
-    const float* y = labels + (size_t)b * n;
+    const ListSpan sp = list_span(offsets, b, nmax);
+    const int n = sp.n, npow2 = offsets ? next_pow2(n) : npow2max;
+    if (n == 0) { if (threadIdx.x == 0) loss_q[b] = 0.0f; return; }
+    const float* s = scores + sp.base;
+    const float* y = labels + sp.base;
 
     if (LAMBDA) {
         const float idcg = block_idcg(y, n, npow2, /*presort=*/true, keys, red);
@@ -87,7 +90,7 @@ __global__ void pairwise_bce_kernel(const float* __restrict__ scores, const floa
         gout[idx[i]] = acc;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) grad[(size_t)b * n + i] = gout[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) grad[sp.base + i] = gout[i];
     loss = block_sum(loss, red);
     if (threadIdx.x == 0) loss_q[b] = loss;
 }
@@ -122,22 +125,25 @@ static __device__ __forceinline__ float pair_term(float sa, float sb, float ya, 
 
 template <bool LAMBDA>
 __global__ void pairwise_bce_circ_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
-                                         float* __restrict__ grad, float* __restrict__ loss_q,
-                                         int n, int npow2, float sigma) {
+                                         float* __restrict__ grad, float* __restrict__ loss_q, const int32_t* __restrict__ offsets,
+                                         int nmax, int npow2max, float sigma) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* keys = reinterpret_cast<u64*>(smem_raw);
-    float* ss = reinterpret_cast<float*>(keys + (LAMBDA ? npow2 : 0));
-    float* ys = ss + n;
-    float* ng = ys + n;
-    float* dinv = ng + n;
-    float* gout = dinv + n;
-    int* idx = reinterpret_cast<int*>(gout + n);
-    float* red = reinterpret_cast<float*>(idx + n);
-    float* xch = red + 33;                              // [2][PAIR_KB][n] partner mailbox
+    float* ss = reinterpret_cast<float*>(keys + (LAMBDA ? npow2max : 0));
+    float* ys = ss + nmax;
+    float* ng = ys + nmax;
+    float* dinv = ng + nmax;
+    float* gout = dinv + nmax;
+    int* idx = reinterpret_cast<int*>(gout + nmax);
+    float* red = reinterpret_cast<float*>(idx + nmax);
+    float* xch = red + 33;                              // [2][PAIR_KB][nmax] partner mailbox
 
     const int b = blockIdx.x, i = threadIdx.x;
-    const float* s = scores + (size_t)b * n;
-    const float* y = labels + (size_t)b * n;
+    const ListSpan sp = list_span(offsets, b, nmax);
+    const int n = sp.n, npow2 = offsets ? next_pow2(n) : npow2max;
+    if (n == 0) { if (threadIdx.x == 0) loss_q[b] = 0.0f; return; }
+    const float* s = scores + sp.base;
+    const float* y = labels + sp.base;
     if (LAMBDA) {
         const float idcg = block_idcg(y, n, npow2, /*presort=*/true, keys, red);
         for (int t = threadIdx.x; t < npow2; t += blockDim.x) keys[t] = t < n ? desc_key(s[t], t) : 0ull;
@@ -173,31 +179,31 @@ __global__ void pairwise_bce_circ_kernel(const float* __restrict__ scores, const
     const int half = (n - 1) / 2;
     int buf = 0;
     for (int k0 = 1; k0 <= half; k0 += PAIR_KB) {
-        float* xb = xch + (size_t)buf * PAIR_KB * n;
+        float* xb = xch + (size_t)buf * PAIR_KB * nmax;
 #pragma unroll
         for (int kk = 0; kk < PAIR_KB; ++kk) {
             const int k = k0 + kk;
             if (mine && k <= half) {
                 int j = i + k;
                 if (j >= n) j -= n;
-                visit(j, xb + kk * n);
+                visit(j, xb + kk * nmax);
             }
         }
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < PAIR_KB; ++kk)
-            if (mine && k0 + kk <= half) own += xb[kk * n + i];
+            if (mine && k0 + kk <= half) own += xb[kk * nmax + i];
         buf ^= 1;
     }
     if ((n & 1) == 0 && n >= 2) {                       // the diameter pairs (i, i + n/2)
-        float* xb = xch + (size_t)buf * PAIR_KB * n;
+        float* xb = xch + (size_t)buf * PAIR_KB * nmax;
         if (i < n / 2) visit(i + n / 2, xb);
         __syncthreads();
         if (mine && i >= n / 2) own += xb[i];
     }
     if (mine) gout[idx[i]] = own;
     __syncthreads();
-    for (int t = threadIdx.x; t < n; t += blockDim.x) grad[(size_t)b * n + t] = gout[t];
+    for (int t = threadIdx.x; t < n; t += blockDim.x) grad[sp.base + t] = gout[t];
     loss = block_sum(loss, red);
     if (threadIdx.x == 0) loss_q[b] = loss;
 }
@@ -226,20 +232,24 @@ static __device__ __forceinline__ LLTerm lambdaloss_term(float sa, float sb, flo
 }
 
 __global__ void lambdaloss_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
-                                  float* __restrict__ grad, float* __restrict__ loss_q,
-                                  int n, int npow2, int K, float sigma, float mu, int loss_type, int presort) {
+                                  float* __restrict__ grad, float* __restrict__ loss_q, const int32_t* __restrict__ offsets,
+                                  int nmax, int npow2max, int k, float sigma, float mu, int loss_type, int presort) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* keys = reinterpret_cast<u64*>(smem_raw);
-    float* ss = reinterpret_cast<float*>(keys + npow2);
-    float* ys = ss + n;
-    float* ng = ys + n;
-    float* gout = ng + n;
-    int* idx = reinterpret_cast<int*>(gout + n);
-    float* red = reinterpret_cast<float*>(idx + n);
+    float* ss = reinterpret_cast<float*>(keys + npow2max);
+    float* ys = ss + nmax;
+    float* ng = ys + nmax;
+    float* gout = ng + nmax;
+    int* idx = reinterpret_cast<int*>(gout + nmax);
+    float* red = reinterpret_cast<float*>(idx + nmax);
 
     const int b = blockIdx.x;
-    const float* s = scores + (size_t)b * n;
-    const float* y = labels + (size_t)b * n;
+    const ListSpan sp = list_span(offsets, b, nmax);
+    const int n = sp.n, npow2 = offsets ? next_pow2(n) : npow2max;
+    if (n == 0) { if (threadIdx.x == 0) loss_q[b] = 0.0f; return; }
+    const int K = k < n ? k : n;                          // truncation at the top-k predicted positions (lambdaloss.py:122-123)
+    const float* s = scores + sp.base;
+    const float* y = labels + sp.base;
 
     const float idcg = block_idcg(y, n, npow2, presort != 0, keys, red);
     __syncthreads();
@@ -292,7 +302,7 @@ __global__ void lambdaloss_kernel(const float* __restrict__ scores, const float*
     }
     __syncthreads();
     // scatter back to document order
-    for (int r = threadIdx.x; r < n; r += blockDim.x) grad[(size_t)b * n + idx[r]] = gout[r];
+    for (int r = threadIdx.x; r < n; r += blockDim.x) grad[sp.base + idx[r]] = gout[r];
     loss = block_sum(loss, red);
     if (threadIdx.x == 0) loss_q[b] = loss;
 }
@@ -301,15 +311,18 @@ __global__ void lambdaloss_kernel(const float* __restrict__ scores, const float*
 // ListNet: cross entropy between softmax(labels) and softmax(scores)
 // ---------------------------------------------------------------------------
 __global__ void listnet_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
-                               float* __restrict__ grad, float* __restrict__ loss_q, int n) {
+                               float* __restrict__ grad, float* __restrict__ loss_q, const int32_t* __restrict__ offsets, int nmax) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* ss = reinterpret_cast<float*>(smem_raw);
-    float* ys = ss + n;
-    float* red = ys + n;
+    float* ys = ss + nmax;
+    float* red = ys + nmax;
     const int b = blockIdx.x;
+    const ListSpan sp = list_span(offsets, b, nmax);
+    const int n = sp.n;
+    if (n == 0) { if (threadIdx.x == 0) loss_q[b] = 0.0f; return; }
     float ms = -INFINITY, my = -INFINITY;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const float a = scores[(size_t)b * n + i], c = labels[(size_t)b * n + i];
+        const float a = scores[sp.base + i], c = labels[sp.base + i];
         ss[i] = a; ys[i] = c;
         ms = fmaxf(ms, a); my = fmaxf(my, c);
     }
@@ -325,7 +338,7 @@ __global__ void listnet_kernel(const float* __restrict__ scores, const float* __
         const float py = expf(ys[i] - my) / zy;
         const float lsm = (ss[i] - ms) - log_zs;
         loss -= py * lsm;
-        grad[(size_t)b * n + i] = expf(lsm) - py;
+        grad[sp.base + i] = expf(lsm) - py;
     }
     loss = block_sum(loss, red);
     if (threadIdx.x == 0) loss_q[b] = loss;
@@ -335,19 +348,22 @@ __global__ void listnet_kernel(const float* __restrict__ scores, const float* __
 // ListMLE: Plackett-Luce likelihood of the (tie-shuffled) ideal ordering
 // ---------------------------------------------------------------------------
 __global__ void listmle_kernel(const float* __restrict__ scores, const int32_t* __restrict__ perm,
-                               float* __restrict__ grad, float* __restrict__ loss_q, int n) {
+                               float* __restrict__ grad, float* __restrict__ loss_q, const int32_t* __restrict__ offsets, int nmax) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* z = reinterpret_cast<float*>(smem_raw);
-    float* e = z + n;
-    float* c = e + n;
-    int* pid = reinterpret_cast<int*>(c + n);
-    float* red = reinterpret_cast<float*>(pid + n);
+    float* e = z + nmax;
+    float* c = e + nmax;
+    int* pid = reinterpret_cast<int*>(c + nmax);
+    float* red = reinterpret_cast<float*>(pid + nmax);
     const int b = blockIdx.x;
+    const ListSpan sp = list_span(offsets, b, nmax);
+    const int n = sp.n;
+    if (n == 0) { if (threadIdx.x == 0) loss_q[b] = 0.0f; return; }
     float m = -INFINITY;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int id = clampi(perm[(size_t)b * n + i], 0, n - 1);
+        const int id = clampi(perm[sp.base + i], 0, n - 1);      // perm holds positions within the query's own list
         pid[i] = id;
-        const float v = scores[(size_t)b * n + id];
+        const float v = scores[sp.base + id];
         z[i] = v;
         m = fmaxf(m, v);
     }
@@ -363,29 +379,32 @@ __global__ void listmle_kernel(const float* __restrict__ scores, const int32_t* 
     }
     __syncthreads();
     block_scan_inclusive<false>(c, n, red);              // c_k = sum_{i<=k} 1/C_i
-    for (int i = threadIdx.x; i < n; i += blockDim.x) grad[(size_t)b * n + pid[i]] = e[i] * c[i] - 1.0f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) grad[sp.base + pid[i]] = e[i] * c[i] - 1.0f;
     loss = block_sum(loss, red);
     if (threadIdx.x == 0) loss_q[b] = loss;
 }
 
 // perm for ListMLE: labels descending, ties broken by Philox noise (sampling_utils.py:13-28)
-__global__ void shuffle_ties_kernel(const float* __restrict__ labels, int32_t* __restrict__ perm,
-                                    int n, int npow2, uint64_t seed, uint64_t offset) {
+__global__ void shuffle_ties_kernel(const float* __restrict__ labels, int32_t* __restrict__ perm, const int32_t* __restrict__ offsets,
+                                    int nmax, int npow2max, uint64_t seed, uint64_t offset) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* keys = reinterpret_cast<u64*>(smem_raw);
     const int b = blockIdx.x;
+    const ListSpan sp = list_span(offsets, b, nmax);
+    const int n = sp.n, npow2 = offsets ? next_pow2(n) : npow2max;
+    if (n == 0) return;
     for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
         u64 k = 0ull;
         if (i < n) {
-            const u64 hi = desc_key(labels[(size_t)b * n + i], 0) >> 32;
-            const uint32_t rnd = dropout_bits(seed, offset, (uint64_t)b * (uint64_t)n + (uint64_t)i);
+            const u64 hi = desc_key(labels[sp.base + i], 0) >> 32;
+            const uint32_t rnd = dropout_bits(seed, offset, (uint64_t)sp.base + (uint64_t)i);
             // [label order : 32][random : 19][1][doc index : 12]  (n <= 4096); low field never 0
             k = (hi << 32) | ((u64)(rnd >> 13) << 13) | (1ull << 12) | (u64)i;
         }
         keys[i] = k;
     }
     block_sort_desc(keys, npow2);
-    for (int r = threadIdx.x; r < n; r += blockDim.x) perm[(size_t)b * n + r] = (int32_t)(keys[r] & 0xfffull);
+    for (int r = threadIdx.x; r < n; r += blockDim.x) perm[sp.base + r] = (int32_t)(keys[r] & 0xfffull);
 }
 
 // ---------------------------------------------------------------------------
@@ -399,26 +418,32 @@ static __device__ __forceinline__ float robust_sigmoid(float in, float alpha) {
     return 0.5f;
 }
 
-__global__ void inv_idcg_kernel(const float* __restrict__ labels, float* __restrict__ inv_idcg,
-                                int n, int npow2, int presort) {
+__global__ void inv_idcg_kernel(const float* __restrict__ labels, float* __restrict__ inv_idcg, const int32_t* __restrict__ offsets,
+                                int nmax, int npow2max, int presort) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* keys = reinterpret_cast<u64*>(smem_raw);
-    float* red = reinterpret_cast<float*>(keys + npow2);
+    float* red = reinterpret_cast<float*>(keys + npow2max);
     const int b = blockIdx.x;
-    const float idcg = block_idcg(labels + (size_t)b * n, n, npow2, presort != 0, keys, red);
+    const ListSpan sp = list_span(offsets, b, nmax);
+    const int n = sp.n, npow2 = offsets ? next_pow2(n) : npow2max;
+    if (n == 0) { if (threadIdx.x == 0) inv_idcg[b] = 0.0f; return; }      // an empty list adds nothing to sum_a 1/iDCG_a
+    const float idcg = block_idcg(labels + sp.base, n, npow2, presort != 0, keys, red);
     if (threadIdx.x == 0) inv_idcg[b] = 1.0f / idcg;
 }
 
 __global__ void approxndcg_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
-                                  float* __restrict__ grad, float* __restrict__ loss_q,
-                                  const float* __restrict__ scratch, int B, int n, float alpha, int batch_coupled) {
+                                  float* __restrict__ grad, float* __restrict__ loss_q, const int32_t* __restrict__ offsets,
+                                  const float* __restrict__ scratch, int B, int nmax, float alpha, int batch_coupled) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* ss = reinterpret_cast<float*>(smem_raw);
-    float* cc = ss + n;
-    float* red = cc + n;
+    float* cc = ss + nmax;
+    float* red = cc + nmax;
     const int b = blockIdx.x;
+    const ListSpan sp = list_span(offsets, b, nmax);
+    const int n = sp.n;
+    if (n == 0) { if (threadIdx.x == 0) loss_q[b] = 0.0f; return; }
     const float scale = batch_coupled ? scratch[B] : scratch[b];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) ss[i] = scores[(size_t)b * n + i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) ss[i] = scores[sp.base + i];
     __syncthreads();
     float dcg = 0.0f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -426,7 +451,7 @@ __global__ void approxndcg_kernel(const float* __restrict__ scores, const float*
         float pi = 0.0f;
         for (int j = 0; j < n; ++j) pi += robust_sigmoid(ss[j] - si, alpha);
         pi += 0.5f;
-        const float G = gain_of(labels[(size_t)b * n + i]);
+        const float G = gain_of(labels[sp.base + i]);
         const float lg = log2f(pi + 1.0f);
         dcg += G / lg;
         cc[i] = scale * G / (lg * lg * (pi + 1.0f) * 0.6931471805599453f);
@@ -439,7 +464,7 @@ __global__ void approxndcg_kernel(const float* __restrict__ scores, const float*
             const float sg = robust_sigmoid(sj - ss[i], alpha);
             acc += (alpha * sg * (1.0f - sg)) * (cc[i] - cj);
         }
-        grad[(size_t)b * n + j] = acc;
+        grad[sp.base + j] = acc;
     }
     dcg = block_sum(dcg, red);
     if (threadIdx.x == 0) loss_q[b] = -scale * dcg;
@@ -459,15 +484,18 @@ __global__ void sum_kernel(const float* __restrict__ x, float* __restrict__ out,
 struct Cutoffs { int k[PTRB200_MAX_CUTOFFS]; int n; };
 
 __global__ void ndcg_at_ks_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
-                                  Cutoffs ks, float* __restrict__ out, int32_t* __restrict__ order,
-                                  int n, int npow2, int presort) {
+                                  Cutoffs ks, float* __restrict__ out, int32_t* __restrict__ order, const int32_t* __restrict__ offsets,
+                                  int nmax, int npow2max, int presort) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* keys = reinterpret_cast<u64*>(smem_raw);
-    float* tsys = reinterpret_cast<float*>(keys + npow2);   // gain/discount in predicted order
-    float* tide = tsys + n;                                 // gain/discount in ideal order
+    float* tsys = reinterpret_cast<float*>(keys + npow2max);   // gain/discount in predicted order
+    float* tide = tsys + nmax;                                 // gain/discount in ideal order
     const int b = blockIdx.x;
-    const float* s = scores + (size_t)b * n;
-    const float* y = labels + (size_t)b * n;
+    const ListSpan sp = list_span(offsets, b, nmax);
+    const int n = sp.n, npow2 = offsets ? next_pow2(n) : npow2max;
+    if (n == 0) { if (threadIdx.x < ks.n) out[(size_t)b * ks.n + threadIdx.x] = 0.0f; return; }
+    const float* s = scores + sp.base;
+    const float* y = labels + sp.base;
     if (presort) {
         for (int r = threadIdx.x; r < n; r += blockDim.x) tide[r] = gain_of(y[r]) / log2_rank(r);
     } else {
@@ -480,7 +508,7 @@ __global__ void ndcg_at_ks_kernel(const float* __restrict__ scores, const float*
     block_sort_desc(keys, npow2);
     for (int r = threadIdx.x; r < n; r += blockDim.x) {
         const int id = key_index(keys[r]);
-        if (order) order[(size_t)b * n + r] = id;
+        if (order) order[sp.base + r] = id;
         tsys[r] = gain_of(y[id]) / log2_rank(r);
     }
     __syncthreads();
@@ -501,14 +529,18 @@ __global__ void ndcg_at_ks_kernel(const float* __restrict__ scores, const float*
 // nDCG, nERR, AP and P at every cutoff from ONE sort per query (adhoc_performance_at_ks,
 // base/ranker.py:202-263 + metric/adhoc/adhoc_metric.py:18-260).  out[B][4][nks], metric order nDCG,nERR,AP,P.
 __global__ void adhoc_metrics_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
-                                     Cutoffs ks, float* __restrict__ out, int n, int npow2, int presort, float max_label) {
+                                     Cutoffs ks, float* __restrict__ out, const int32_t* __restrict__ offsets,
+                                     int nmax, int npow2max, int presort, float max_label) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* keys = reinterpret_cast<u64*>(smem_raw);
-    float* ysys = reinterpret_cast<float*>(keys + npow2);   // labels in predicted order
-    float* yide = ysys + n;                                 // labels in ideal order
+    float* ysys = reinterpret_cast<float*>(keys + npow2max);   // labels in predicted order
+    float* yide = ysys + nmax;                                 // labels in ideal order
     const int b = blockIdx.x;
-    const float* s = scores + (size_t)b * n;
-    const float* y = labels + (size_t)b * n;
+    const ListSpan sp = list_span(offsets, b, nmax);
+    const int n = sp.n, npow2 = offsets ? next_pow2(n) : npow2max;
+    if (n == 0) { if (threadIdx.x < 4 * ks.n) out[(size_t)b * 4 * ks.n + threadIdx.x] = 0.0f; return; }
+    const float* s = scores + sp.base;
+    const float* y = labels + sp.base;
     if (presort) {
         for (int r = threadIdx.x; r < n; r += blockDim.x) yide[r] = y[r];
     } else {
@@ -576,7 +608,7 @@ __global__ void adhoc_metrics_kernel(const float* __restrict__ scores, const flo
 // host launchers
 // ---------------------------------------------------------------------------
 template <bool LAMBDA>
-static int launch_pairwise(const float* scores, const float* labels, float* grad, float* loss_q,
+static int launch_pairwise(const float* scores, const float* labels, const int32_t* offsets, float* grad, float* loss_q,
                            int B, int n, float sigma, ptrb200_stream_t stream) {
     int rc = check_list_args(scores, labels, grad, loss_q, B, n);
     if (rc) return rc;
@@ -586,11 +618,11 @@ static int launch_pairwise(const float* scores, const float* labels, float* grad
         const size_t smem_c = smem + (size_t)2 * PAIR_KB * n * 4;
         if ((rc = allow_smem(pairwise_bce_circ_kernel<LAMBDA>, smem_c))) return rc;
         PTRB200_LAUNCH_TAG(LAMBDA ? "pairwise_bce_kernel<LAMBDA>" : "pairwise_bce_kernel<RANKNET>", pairwise_bce_circ_kernel<LAMBDA>, B, block_threads(n), smem_c, stream,
-                           scores, labels, grad, loss_q, n, npow2, sigma);
+                           scores, labels, grad, loss_q, offsets, n, npow2, sigma);
         return check_launch(LAMBDA ? "lambdarank" : "ranknet");
     }
     if ((rc = allow_smem(pairwise_bce_kernel<LAMBDA>, smem))) return rc;
-    PTRB200_LAUNCH(pairwise_bce_kernel<LAMBDA>, B, block_threads(n), smem, stream, scores, labels, grad, loss_q, n, npow2, sigma);
+    PTRB200_LAUNCH(pairwise_bce_kernel<LAMBDA>, B, block_threads(n), smem, stream, scores, labels, grad, loss_q, offsets, n, npow2, sigma);
     return check_launch(LAMBDA ? "lambdarank" : "ranknet");
 }
 
@@ -600,17 +632,17 @@ using namespace ptrb200;
 
 extern "C" {
 
-int ptrb200_ranknet_fwd_bwd(const float* scores, const float* labels, float* grad, float* loss_per_query,
+int ptrb200_ranknet_fwd_bwd(const float* scores, const float* labels, const int32_t* offsets, float* grad, float* loss_per_query,
                             int B, int n, float sigma, ptrb200_stream_t stream) {
-    return launch_pairwise<false>(scores, labels, grad, loss_per_query, B, n, sigma, stream);
+    return launch_pairwise<false>(scores, labels, offsets, grad, loss_per_query, B, n, sigma, stream);
 }
 
-int ptrb200_lambdarank_fwd_bwd(const float* scores, const float* labels, float* grad, float* loss_per_query,
+int ptrb200_lambdarank_fwd_bwd(const float* scores, const float* labels, const int32_t* offsets, float* grad, float* loss_per_query,
                                int B, int n, float sigma, ptrb200_stream_t stream) {
-    return launch_pairwise<true>(scores, labels, grad, loss_per_query, B, n, sigma, stream);
+    return launch_pairwise<true>(scores, labels, offsets, grad, loss_per_query, B, n, sigma, stream);
 }
 
-int ptrb200_lambdaloss_fwd_bwd(const float* scores, const float* labels, float* grad, float* loss_per_query,
+int ptrb200_lambdaloss_fwd_bwd(const float* scores, const float* labels, const int32_t* offsets, float* grad, float* loss_per_query,
                                int B, int n, int k, float sigma, float mu, int loss_type, int presort,
                                ptrb200_stream_t stream) {
     int rc = check_list_args(scores, labels, grad, loss_per_query, B, n);
@@ -620,53 +652,54 @@ int ptrb200_lambdaloss_fwd_bwd(const float* scores, const float* labels, float* 
         return PTRB200_ERR_INVALID;
     }
     const int npow2 = next_pow2(n);
-    const int K = k < n ? k : n;
     const size_t smem = (size_t)npow2 * 8 + (size_t)n * 4 * 5 + 33 * 4;
     if ((rc = allow_smem(lambdaloss_kernel, smem))) return rc;
     PTRB200_LAUNCH(lambdaloss_kernel, B, block_threads(n), smem, stream, scores, labels, grad, loss_per_query,
-                   n, npow2, K, sigma, mu, loss_type, presort);
+                   offsets, n, npow2, k, sigma, mu, loss_type, presort);
     return check_launch("lambdaloss");
 }
 
-int ptrb200_listnet_fwd_bwd(const float* scores, const float* labels, float* grad, float* loss_per_query,
+int ptrb200_listnet_fwd_bwd(const float* scores, const float* labels, const int32_t* offsets, float* grad, float* loss_per_query,
                             int B, int n, ptrb200_stream_t stream) {
     int rc = check_list_args(scores, labels, grad, loss_per_query, B, n);
     if (rc) return rc;
     const size_t smem = (size_t)n * 4 * 2 + 33 * 4;
-    PTRB200_LAUNCH(listnet_kernel, B, block_threads(n), smem, stream, scores, labels, grad, loss_per_query, n);
+    if ((rc = allow_smem(listnet_kernel, smem))) return rc;
+    PTRB200_LAUNCH(listnet_kernel, B, block_threads(n), smem, stream, scores, labels, grad, loss_per_query, offsets, n);
     return check_launch("listnet");
 }
 
-int ptrb200_listmle_fwd_bwd(const float* scores, const int32_t* perm, float* grad, float* loss_per_query,
+int ptrb200_listmle_fwd_bwd(const float* scores, const int32_t* perm, const int32_t* offsets, float* grad, float* loss_per_query,
                             int B, int n, ptrb200_stream_t stream) {
     int rc = check_list_args(scores, perm, grad, loss_per_query, B, n);
     if (rc) return rc;
     const size_t smem = (size_t)n * 4 * 4 + 72 * 4;
     if ((rc = allow_smem(listmle_kernel, smem))) return rc;
-    PTRB200_LAUNCH(listmle_kernel, B, block_threads(n), smem, stream, scores, perm, grad, loss_per_query, n);
+    PTRB200_LAUNCH(listmle_kernel, B, block_threads(n), smem, stream, scores, perm, grad, loss_per_query, offsets, n);
     return check_launch("listmle");
 }
 
-int ptrb200_shuffle_ties_perm(const float* labels, int32_t* perm, int B, int n,
+int ptrb200_shuffle_ties_perm(const float* labels, const int32_t* offsets, int32_t* perm, int B, int n,
                               uint64_t seed, uint64_t offset, ptrb200_stream_t stream) {
     int rc = check_list_args(labels, perm, labels, perm, B, n);
     if (rc) return rc;
     const int npow2 = next_pow2(n);
-    PTRB200_LAUNCH(shuffle_ties_kernel, B, block_threads(n), (size_t)npow2 * 8, stream, labels, perm, n, npow2, seed, offset);
+    PTRB200_LAUNCH(shuffle_ties_kernel, B, block_threads(n), (size_t)npow2 * 8, stream, labels, perm, offsets, n, npow2, seed, offset);
     return check_launch("shuffle_ties");
 }
 
-int ptrb200_approxndcg_fwd_bwd(const float* scores, const float* labels, float* grad, float* loss_per_query,
+int ptrb200_approxndcg_fwd_bwd(const float* scores, const float* labels, const int32_t* offsets, float* grad, float* loss_per_query,
                                float* scratch, int B, int n, float alpha, int presort, int batch_coupled,
                                ptrb200_stream_t stream) {
     int rc = check_list_args(scores, labels, grad, loss_per_query, B, n);
     if (rc) return rc;
     if (!scratch) { set_error("approxndcg: scratch (B+1 floats) is NULL"); return PTRB200_ERR_INVALID; }
     const int npow2 = next_pow2(n);
-    PTRB200_LAUNCH(inv_idcg_kernel, B, block_threads(n), (size_t)npow2 * 8 + 33 * 4, stream, labels, scratch, n, npow2, presort);
+    PTRB200_LAUNCH(inv_idcg_kernel, B, block_threads(n), (size_t)npow2 * 8 + 33 * 4, stream, labels, scratch, offsets, n, npow2, presort);
     PTRB200_LAUNCH(sum_kernel, 1, 256, 0, stream, (const float*)scratch, scratch + B, B);
     const size_t smem = (size_t)n * 4 * 2 + 33 * 4;
-    PTRB200_LAUNCH(approxndcg_kernel, B, block_threads(n), smem, stream, scores, labels, grad, loss_per_query,
+    if ((rc = allow_smem(approxndcg_kernel, smem))) return rc;
+    PTRB200_LAUNCH(approxndcg_kernel, B, block_threads(n), smem, stream, scores, labels, grad, loss_per_query, offsets,
                    (const float*)scratch, B, n, alpha, batch_coupled);
     return check_launch("approxndcg");
 }
@@ -677,7 +710,7 @@ int ptrb200_sum_f32(const float* x, float* out, int n, ptrb200_stream_t stream) 
     return check_launch("sum_f32");
 }
 
-int ptrb200_ndcg_at_ks(const float* scores, const float* labels, const int32_t* ks_host, int nks,
+int ptrb200_ndcg_at_ks(const float* scores, const float* labels, const int32_t* offsets, const int32_t* ks_host, int nks,
                        float* out, int32_t* order, int B, int n, int presort, ptrb200_stream_t stream) {
     int rc = check_list_args(scores, labels, out, ks_host, B, n);
     if (rc) return rc;
@@ -691,11 +724,11 @@ int ptrb200_ndcg_at_ks(const float* scores, const float* labels, const int32_t* 
     const int npow2 = next_pow2(n);
     const size_t smem = (size_t)npow2 * 8 + (size_t)n * 4 * 2;
     if ((rc = allow_smem(ndcg_at_ks_kernel, smem))) return rc;
-    PTRB200_LAUNCH(ndcg_at_ks_kernel, B, block_threads(n), smem, stream, scores, labels, ks, out, order, n, npow2, presort);
+    PTRB200_LAUNCH(ndcg_at_ks_kernel, B, block_threads(n), smem, stream, scores, labels, ks, out, order, offsets, n, npow2, presort);
     return check_launch("ndcg_at_ks");
 }
 
-int ptrb200_adhoc_metrics_at_ks(const float* scores, const float* labels, const int32_t* ks_host, int nks,
+int ptrb200_adhoc_metrics_at_ks(const float* scores, const float* labels, const int32_t* offsets, const int32_t* ks_host, int nks,
                                 float* out, int B, int n, int presort, float max_label, ptrb200_stream_t stream) {
     int rc = check_list_args(scores, labels, out, ks_host, B, n);
     if (rc) return rc;
@@ -710,7 +743,7 @@ int ptrb200_adhoc_metrics_at_ks(const float* scores, const float* labels, const 
     const size_t smem = (size_t)npow2 * 8 + (size_t)n * 4 * 2;
     if ((rc = allow_smem(adhoc_metrics_kernel, smem))) return rc;
     int threads = block_threads(n); if (threads < 128) threads = 128;
-    PTRB200_LAUNCH(adhoc_metrics_kernel, B, threads, smem, stream, scores, labels, ks, out, n, npow2, presort, max_label);
+    PTRB200_LAUNCH(adhoc_metrics_kernel, B, threads, smem, stream, scores, labels, ks, out, offsets, n, npow2, presort, max_label);
     return check_launch("adhoc_metrics_at_ks");
 }
 

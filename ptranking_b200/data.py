@@ -112,3 +112,91 @@ class LengthBucketedBatches:
             out.update(batches=len(plan), mean_docs_per_batch=float(np.mean(docs)) if docs else 0.0,
                        full_batches=float(np.mean([d >= 0.5 * self.docs_per_batch for d in docs])) if docs else 0.0)
         return out
+
+
+class RaggedBatches:
+    """Iterable of ragged batches ``(qids, X[total,F], y[total], offsets[B+1] int32, max_len)`` -- variable-length
+    lists inside ONE launch.
+
+    The reference batches only queries of identical length (data_utils.py:683-742); on real collections (MSLR-WEB30K:
+    1..1251 documents per query, mean 119.6, testing/data/testing_data_utils.py:318-326) equal-length buckets hold a
+    handful of queries each and cannot fill a GPU.  Here queries are packed in dataset (or shuffled) order until about
+    ``docs_per_batch`` documents are reached, whatever their lengths; the kernels address each query through the prefix
+    offsets.  Same presort contract as :class:`LengthBucketedBatches`; rank-disjoint shards with equal batch counts.
+    """
+
+    def __init__(self, queries: Iterable[Query], docs_per_batch: int = 1 << 18, max_queries: Optional[int] = None,
+                 presort: bool = True, shuffle_seed: Optional[int] = None, rank: int = 0, world: int = 1,
+                 pin_memory: Optional[bool] = None, max_list_len: int = 4096):
+        if docs_per_batch < 1 or world < 1 or not (0 <= rank < world):
+            raise ValueError("docs_per_batch >= 1 and 0 <= rank < world are required")
+        self.docs_per_batch, self.max_queries = int(docs_per_batch), max_queries
+        self.shuffle_seed, self.rank, self.world = shuffle_seed, rank, world
+        self.pin = torch.cuda.is_available() if pin_memory is None else bool(pin_memory)
+        self.epoch = 0
+        self.queries: List[Tuple[str, np.ndarray, np.ndarray]] = []
+        self.num_features = None
+        for qid, X, y in queries:
+            X = np.ascontiguousarray(X, dtype=np.float32)
+            y = np.ascontiguousarray(y, dtype=np.float32)
+            if X.ndim != 2 or y.shape != (X.shape[0],):
+                raise ValueError(f"query {qid}: features {X.shape} / labels {y.shape} do not describe one list")
+            if X.shape[0] == 0:
+                continue
+            if X.shape[0] > max_list_len:
+                raise ValueError(f"query {qid}: {X.shape[0]} documents exceed the per-list kernel limit {max_list_len}")
+            if self.num_features is None:
+                self.num_features = X.shape[1]
+            elif X.shape[1] != self.num_features:
+                raise ValueError(f"query {qid}: {X.shape[1]} features, expected {self.num_features}")
+            if presort:
+                X, y = presort_query(X, y)
+            self.queries.append((str(qid), X, y))
+
+    def _plan(self) -> List[List[int]]:
+        idx = np.arange(len(self.queries))
+        if self.shuffle_seed is not None:
+            np.random.default_rng(self.shuffle_seed + self.epoch).shuffle(idx)
+        plan, cur, docs = [], [], 0
+        for i in idx:
+            n = self.queries[i][1].shape[0]
+            if cur and (docs + n > self.docs_per_batch or (self.max_queries and len(cur) >= self.max_queries)):
+                plan.append(cur)
+                cur, docs = [], 0
+            cur.append(int(i))
+            docs += n
+        if cur:
+            plan.append(cur)
+        usable = len(plan) - len(plan) % self.world
+        return plan[:usable][self.rank:: self.world]
+
+    def __len__(self) -> int:
+        return len(self._plan())
+
+    def __iter__(self):
+        plan = self._plan()
+        self.epoch += 1
+        for members in plan:
+            qs = [self.queries[i] for i in members]
+            lens = np.array([q[1].shape[0] for q in qs], dtype=np.int64)
+            total = int(lens.sum())
+            X = torch.empty((total, self.num_features), dtype=torch.float32, pin_memory=self.pin)
+            y = torch.empty((total,), dtype=torch.float32, pin_memory=self.pin)
+            offsets = torch.zeros(len(qs) + 1, dtype=torch.int32, pin_memory=self.pin)
+            offsets[1:] = torch.from_numpy(np.cumsum(lens)).to(torch.int32)
+            o = 0
+            for _, Xq, yq in qs:
+                X[o: o + Xq.shape[0]] = torch.from_numpy(Xq)
+                y[o: o + Xq.shape[0]] = torch.from_numpy(yq)
+                o += Xq.shape[0]
+            yield [q[0] for q in qs], X, y, offsets, int(lens.max())
+
+    def stats(self) -> dict:
+        lens = np.array([q[1].shape[0] for q in self.queries])
+        out = dict(queries=len(lens), docs=int(lens.sum()), min_len=int(lens.min()) if len(lens) else 0,
+                   max_len=int(lens.max()) if len(lens) else 0, mean_len=float(lens.mean()) if len(lens) else 0.0)
+        if self.world == 1:
+            plan = self._plan()
+            docs = [int(sum(self.queries[i][1].shape[0] for i in m)) for m in plan]
+            out.update(batches=len(plan), mean_docs_per_batch=float(np.mean(docs)) if docs else 0.0)
+        return out

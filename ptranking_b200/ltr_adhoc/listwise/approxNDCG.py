@@ -21,6 +21,6 @@ class ApproxNDCG(AdhocNeuralRanker):
         assert _is_multilabel(kwargs['label_type'])
         presort = bool(kwargs.get('presort', False))
         batch_loss = ops.rank_loss('ApproxNDCG', batch_preds, batch_std_labels, alpha=self.alpha,
-                                   presort=presort, batch_coupled=self.batch_coupled)
+                                   presort=presort, batch_coupled=self.batch_coupled, **self.ragged_kwargs(kwargs))
         self.backward_and_step(batch_loss)
         return batch_loss

@@ -18,6 +18,6 @@ class LambdaLoss(AdhocNeuralRanker):
         assert _is_multilabel(kwargs['label_type'])
         presort = bool(kwargs.get('presort', False))
         batch_loss = ops.rank_loss('LambdaLoss', batch_preds, batch_std_labels, k=self.k, sigma=self.sigma,
-                                   mu=self.mu, loss_type=self.loss_type, presort=presort)
+                                   mu=self.mu, loss_type=self.loss_type, presort=presort, **self.ragged_kwargs(kwargs))
         self.backward_and_step(batch_loss)
         return batch_loss

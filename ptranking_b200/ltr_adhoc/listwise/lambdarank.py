@@ -14,6 +14,6 @@ class LambdaRank(AdhocNeuralRanker):
         reference (lambdarank.py:34-36): MultiLabel labels, presorted descending."""
         assert 'label_type' in kwargs and _is_multilabel(kwargs['label_type'])
         assert 'presort' in kwargs and kwargs['presort'] is True
-        batch_loss = ops.rank_loss('LambdaRank', batch_preds, batch_std_labels, sigma=self.sigma)
+        batch_loss = ops.rank_loss('LambdaRank', batch_preds, batch_std_labels, sigma=self.sigma, **self.ragged_kwargs(kwargs))
         self.backward_and_step(batch_loss)
         return batch_loss

@@ -13,7 +13,7 @@ class ListMLE(AdhocNeuralRanker):
         ``perm=`` (int [B,n]) injects a fixed ordering (parity tests)."""
         perm = kwargs.get('perm')
         if perm is None:
-            perm = ops.shuffle_ties_perm(batch_std_labels)
-        batch_loss = ops.rank_loss('ListMLE', batch_preds, batch_std_labels, perm=perm)
+            perm = ops.shuffle_ties_perm(batch_std_labels, **self.ragged_kwargs(kwargs))
+        batch_loss = ops.rank_loss('ListMLE', batch_preds, batch_std_labels, perm=perm, **self.ragged_kwargs(kwargs))
         self.backward_and_step(batch_loss)
         return batch_loss

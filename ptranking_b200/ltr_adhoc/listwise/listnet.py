@@ -9,6 +9,6 @@ class ListNet(AdhocNeuralRanker):
 
     def custom_loss_function(self, batch_preds, batch_std_labels, **kwargs):
         """Top-1 ListNet: cross entropy of softmax(scores) against softmax(labels)."""
-        batch_loss = ops.rank_loss('ListNet', batch_preds, batch_std_labels)
+        batch_loss = ops.rank_loss('ListNet', batch_preds, batch_std_labels, **self.ragged_kwargs(kwargs))
         self.backward_and_step(batch_loss)
         return batch_loss

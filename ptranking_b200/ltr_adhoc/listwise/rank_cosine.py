@@ -9,6 +9,6 @@ class RankCosine(AdhocNeuralRanker):
 
     def custom_loss_function(self, batch_preds, batch_std_labels, **kwargs):
         """sum_q (1 - cos(preds_q, labels_q)) / 0.5 (rank_cosine.py:33)."""
-        batch_loss = ops.rank_loss('RankCosine', batch_preds, batch_std_labels)
+        batch_loss = ops.rank_loss('RankCosine', batch_preds, batch_std_labels, **self.ragged_kwargs(kwargs))
         self.backward_and_step(batch_loss)
         return batch_loss

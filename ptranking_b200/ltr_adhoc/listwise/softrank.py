@@ -16,6 +16,6 @@ class SoftRank(AdhocNeuralRanker):
         assert 'presort' in kwargs and kwargs['presort'] is True
         assert 'nDCG' == self.metric
         assert _is_multilabel(kwargs['label_type'])
-        batch_loss = ops.rank_loss('SoftRank', batch_preds, batch_std_labels, delta=self.delta, top_k=self.top_k)
+        batch_loss = ops.rank_loss('SoftRank', batch_preds, batch_std_labels, delta=self.delta, top_k=self.top_k, **self.ragged_kwargs(kwargs))
         self.backward_and_step(batch_loss)
         return batch_loss

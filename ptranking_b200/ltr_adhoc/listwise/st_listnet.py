@@ -12,6 +12,6 @@ class STListNet(AdhocNeuralRanker):
         """ListNet's top-1 cross entropy on Gumbel-perturbed scores (st_listnet.py:41-49).  The uniform draw comes from
         the kernel's counter-based generator (the reference calls torch.rand); ``unif=`` injects one (parity tests)."""
         batch_loss = ops.rank_loss('STListNet', batch_preds, batch_std_labels, temperature=self.temperature,
-                                   unif=kwargs.get('unif'))
+                                   unif=kwargs.get('unif'), **self.ragged_kwargs(kwargs))
         self.backward_and_step(batch_loss)
         return batch_loss

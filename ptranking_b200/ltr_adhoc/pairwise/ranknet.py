@@ -10,6 +10,6 @@ class RankNet(AdhocNeuralRanker):
 
     def custom_loss_function(self, batch_preds, batch_std_labels, **kwargs):
         """BCE over all pairs i<j of sigmoid(sigma (s_i - s_j)) vs 1/2 (1 + sign(y_i - y_j)); one fused kernel."""
-        batch_loss = ops.rank_loss('RankNet', batch_preds, batch_std_labels, sigma=self.sigma)
+        batch_loss = ops.rank_loss('RankNet', batch_preds, batch_std_labels, sigma=self.sigma, **self.ragged_kwargs(kwargs))
         self.backward_and_step(batch_loss)
         return batch_loss

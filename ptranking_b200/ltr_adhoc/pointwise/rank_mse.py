@@ -9,6 +9,6 @@ class RankMSE(AdhocNeuralRanker):
 
     def custom_loss_function(self, batch_preds, batch_std_labels, **kwargs):
         """Mean over the batch of the per-query summed squared error (rank_mse.py:20-21)."""
-        batch_loss = ops.rank_loss('RankMSE', batch_preds, batch_std_labels)
+        batch_loss = ops.rank_loss('RankMSE', batch_preds, batch_std_labels, **self.ragged_kwargs(kwargs))
         self.backward_and_step(batch_loss)
         return batch_loss

@@ -47,10 +47,22 @@ def _dev_f32(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
-def _check_pair(scores: torch.Tensor, labels: torch.Tensor):
-    if scores.dim() != 2 or scores.shape != labels.shape:
-        raise ValueError(f"expected scores/labels of identical shape [B,n], got {tuple(scores.shape)} / {tuple(labels.shape)}")
-    return scores.shape
+def _list_layout(s: torch.Tensor, offsets, max_len):
+    """-> (B, n, offsets tensor or None, offsets pointer or None).  Dense batches: ``s`` is [B,n] and offsets is None.
+    Ragged batches: ``s`` is the flat [total_docs] array, ``offsets`` the int32 [B+1] prefix offsets on the
+    same device, ``max_len`` the longest list (host int: it sizes the CTAs, so no device read-back is needed)."""
+    if offsets is None:
+        if s.dim() != 2:
+            raise ValueError(f"expected [B,n] scores, got {tuple(s.shape)} (pass offsets= and max_len= for a ragged batch)")
+        return s.shape[0], s.shape[1], None, None
+    if s.dim() != 1:
+        raise ValueError(f"ragged batches are flat [total_docs] arrays, got {tuple(s.shape)}")
+    if max_len is None:
+        raise ValueError("ragged batches need max_len= (longest list of the batch)")
+    if not (offsets.is_cuda and offsets.device == s.device):
+        raise _lib.B200LibraryError("offsets must live on the device of the scores")
+    offsets = offsets.to(torch.int32).contiguous()
+    return offsets.numel() - 1, max(int(max_len), 1), offsets, offsets.data_ptr()
 
 
 # --------------------------------------------------------------------------- #
@@ -61,58 +73,62 @@ def _loss_call(name: str, scores: torch.Tensor, labels: torch.Tensor, params: di
     """-> (loss_per_query[B], grad[B,n]) from one fused kernel launch."""
     lib = _lib.load()
     s = _dev_f32(scores, "scores")
-    B, n = s.shape
+    B, n, offsets, op = _list_layout(s, params.get("offsets"), params.get("max_len"))
     grad = torch.empty_like(s)
     loss_q = torch.empty(B, dtype=torch.float32, device=s.device)
     st = _stream_ptr()
     if name == "ListMLE":
         perm = params.get("perm")
         if perm is None:
-            perm = shuffle_ties_perm(labels)
+            perm = shuffle_ties_perm(labels, offsets=offsets, max_len=n if offsets is not None else None)
         perm = perm.to(device=s.device, dtype=torch.int32).contiguous()
-        rc = lib.ptrb200_listmle_fwd_bwd(s.data_ptr(), perm.data_ptr(), grad.data_ptr(), loss_q.data_ptr(), B, n, st)
+        if perm.shape != s.shape:
+            raise ValueError(f"perm {tuple(perm.shape)} does not match scores {tuple(s.shape)}")
+        rc = lib.ptrb200_listmle_fwd_bwd(s.data_ptr(), perm.data_ptr(), op, grad.data_ptr(), loss_q.data_ptr(), B, n, st)
     else:
         y = _dev_f32(labels, "labels")
-        _check_pair(s, y)
+        if y.shape != s.shape:
+            raise ValueError(f"expected scores/labels of identical shape, got {tuple(s.shape)} / {tuple(y.shape)}")
         if name == "RankNet":
-            rc = lib.ptrb200_ranknet_fwd_bwd(s.data_ptr(), y.data_ptr(), grad.data_ptr(), loss_q.data_ptr(), B, n,
+            rc = lib.ptrb200_ranknet_fwd_bwd(s.data_ptr(), y.data_ptr(), op, grad.data_ptr(), loss_q.data_ptr(), B, n,
                                              float(params.get("sigma", 1.0)), st)
         elif name == "LambdaRank":
-            rc = lib.ptrb200_lambdarank_fwd_bwd(s.data_ptr(), y.data_ptr(), grad.data_ptr(), loss_q.data_ptr(), B, n,
+            rc = lib.ptrb200_lambdarank_fwd_bwd(s.data_ptr(), y.data_ptr(), op, grad.data_ptr(), loss_q.data_ptr(), B, n,
                                                 float(params.get("sigma", 1.0)), st)
         elif name == "LambdaLoss":
             lt = _lib.LAMBDALOSS_TYPES[params.get("loss_type", "NDCG_Loss2++")]
-            rc = lib.ptrb200_lambdaloss_fwd_bwd(s.data_ptr(), y.data_ptr(), grad.data_ptr(), loss_q.data_ptr(), B, n,
+            rc = lib.ptrb200_lambdaloss_fwd_bwd(s.data_ptr(), y.data_ptr(), op, grad.data_ptr(), loss_q.data_ptr(), B, n,
                                                 int(params.get("k", 5)), float(params.get("sigma", 1.0)),
                                                 float(params.get("mu", 5.0)), lt, int(bool(params.get("presort", True))), st)
         elif name == "ListNet":
-            rc = lib.ptrb200_listnet_fwd_bwd(s.data_ptr(), y.data_ptr(), grad.data_ptr(), loss_q.data_ptr(), B, n, st)
+            rc = lib.ptrb200_listnet_fwd_bwd(s.data_ptr(), y.data_ptr(), op, grad.data_ptr(), loss_q.data_ptr(), B, n, st)
         elif name == "ApproxNDCG":
             scratch = torch.empty(B + 1, dtype=torch.float32, device=s.device)
-            rc = lib.ptrb200_approxndcg_fwd_bwd(s.data_ptr(), y.data_ptr(), grad.data_ptr(), loss_q.data_ptr(),
+            rc = lib.ptrb200_approxndcg_fwd_bwd(s.data_ptr(), y.data_ptr(), op, grad.data_ptr(), loss_q.data_ptr(),
                                                 scratch.data_ptr(), B, n, float(params.get("alpha", 10.0)),
                                                 int(bool(params.get("presort", True))),
                                                 int(bool(params.get("batch_coupled", True))), st)
         elif name == "RankMSE":
-            rc = lib.ptrb200_rankmse_fwd_bwd(s.data_ptr(), y.data_ptr(), None, grad.data_ptr(), loss_q.data_ptr(), B, n, st)
+            rc = lib.ptrb200_rankmse_fwd_bwd(s.data_ptr(), y.data_ptr(), op, grad.data_ptr(), loss_q.data_ptr(), B, n, st)
         elif name == "RankCosine":
-            rc = lib.ptrb200_rankcosine_fwd_bwd(s.data_ptr(), y.data_ptr(), None, grad.data_ptr(), loss_q.data_ptr(), B, n, st)
+            rc = lib.ptrb200_rankcosine_fwd_bwd(s.data_ptr(), y.data_ptr(), op, grad.data_ptr(), loss_q.data_ptr(), B, n, st)
         elif name == "STListNet":
             unif = params.get("unif")
             if unif is not None:
                 unif = _dev_f32(unif, "unif")
-                _check_pair(s, unif)
+                if unif.shape != s.shape:
+                    raise ValueError("unif must have the shape of scores")
             seed, offset = params.get("seed"), params.get("offset")
             if seed is None:
                 seed = torch.initial_seed()
             if offset is None:
                 offset = next_noise_offset()
-            rc = lib.ptrb200_stlistnet_fwd_bwd(s.data_ptr(), y.data_ptr(), None, unif.data_ptr() if unif is not None else None,
+            rc = lib.ptrb200_stlistnet_fwd_bwd(s.data_ptr(), y.data_ptr(), op, unif.data_ptr() if unif is not None else None,
                                                grad.data_ptr(), loss_q.data_ptr(), B, n, float(params.get("temperature", 1.0)),
                                                seed & (2 ** 64 - 1), offset & (2 ** 64 - 1), st)
         elif name == "SoftRank":
             top_k = params.get("top_k")
-            rc = lib.ptrb200_softrank_fwd_bwd(s.data_ptr(), y.data_ptr(), None, grad.data_ptr(), loss_q.data_ptr(), B, n,
+            rc = lib.ptrb200_softrank_fwd_bwd(s.data_ptr(), y.data_ptr(), op, grad.data_ptr(), loss_q.data_ptr(), B, n,
                                               float(params.get("delta", 2.0)), int(top_k) if top_k else 0, st)
         else:
             raise NotImplementedError(name)
@@ -258,21 +274,49 @@ _tie_offset = 0
 
 
 @_on_tensor_device
-def shuffle_ties_perm(labels: torch.Tensor, seed: Optional[int] = None, offset: Optional[int] = None) -> torch.Tensor:
-    """int32 [B,n] ordering of each row's labels, descending, ties in random order."""
+def shuffle_ties_perm(labels: torch.Tensor, seed: Optional[int] = None, offset: Optional[int] = None,
+                      offsets: Optional[torch.Tensor] = None, max_len: Optional[int] = None) -> torch.Tensor:
+    """int32 ordering (positions within each query's list) of each query's labels, descending, ties in random order;
+    same layout as ``labels`` ([B,n], or flat with ``offsets``/``max_len`` for a ragged batch)."""
     global _tie_offset
     lib = _lib.load()
     y = _dev_f32(labels, "labels")
-    B, n = y.shape
-    perm = torch.empty((B, n), dtype=torch.int32, device=y.device)
+    B, n, offsets, op = _list_layout(y, offsets, max_len)
+    perm = torch.empty(y.shape, dtype=torch.int32, device=y.device)
     if seed is None:
         seed = torch.initial_seed()
     if offset is None:
         _tie_offset += 1
         offset = _tie_offset
-    _lib.check(lib.ptrb200_shuffle_ties_perm(y.data_ptr(), perm.data_ptr(), B, n, seed & (2 ** 64 - 1),
+    _lib.check(lib.ptrb200_shuffle_ties_perm(y.data_ptr(), op, perm.data_ptr(), B, n, seed & (2 ** 64 - 1),
                                              offset & (2 ** 64 - 1), _stream_ptr()), "shuffle_ties_perm")
     return perm
+
+
+# --------------------------------------------------------------------------- #
+# input side
+# --------------------------------------------------------------------------- #
+@_on_tensor_device
+def standard_scale(X: torch.Tensor, offsets: Optional[torch.Tensor] = None, max_len: Optional[int] = None,
+                   clip_max: Optional[float] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-query StandardScaler (data_utils.py:482-487) on the device.  X: [B,n,F], or flat [total_docs,F] with
+    ``offsets``/``max_len``.  ``clip_max``: clamp features first (the loader's ISTELLA_MAX clip)."""
+    lib = _lib.load()
+    X = _dev_f32(X, "X")
+    if offsets is None:
+        if X.dim() != 3:
+            raise ValueError(f"expected [B,n,F] features, got {tuple(X.shape)}")
+        B, n, F, op = X.shape[0], X.shape[1], X.shape[2], None
+    else:
+        if X.dim() != 2 or max_len is None:
+            raise ValueError("ragged features are [total_docs, F] with offsets= and max_len=")
+        offsets = offsets.to(device=X.device, dtype=torch.int32).contiguous()
+        B, n, F, op = offsets.numel() - 1, max(int(max_len), 1), X.shape[1], offsets.data_ptr()
+    if out is None:
+        out = torch.empty_like(X)
+    _lib.check(lib.ptrb200_standard_scale(X.data_ptr(), op, out.data_ptr(), B, n, F, int(clip_max is not None),
+                                          float(clip_max if clip_max is not None else 0.0), _stream_ptr()), "standard_scale")
+    return out
 
 
 # --------------------------------------------------------------------------- #
@@ -280,18 +324,20 @@ def shuffle_ties_perm(labels: torch.Tensor, seed: Optional[int] = None, offset: 
 # --------------------------------------------------------------------------- #
 @_on_tensor_device
 def ndcg_at_ks(scores: torch.Tensor, labels: torch.Tensor, ks: Sequence[int], presort: bool = False,
-               return_order: bool = False):
-    """Per-query nDCG at the cutoffs ``ks`` -> [B, len(ks)] (zero where k > n)."""
+               return_order: bool = False, offsets: Optional[torch.Tensor] = None, max_len: Optional[int] = None):
+    """Per-query nDCG at the cutoffs ``ks`` -> [B, len(ks)] (zero where k > n).  ``offsets``/``max_len``: ragged batch."""
     lib = _lib.load()
     s, y = _dev_f32(scores, "scores"), _dev_f32(labels, "labels")
-    B, n = _check_pair(s, y)
+    if s.shape != y.shape:
+        raise ValueError(f"expected scores/labels of identical shape, got {tuple(s.shape)} / {tuple(y.shape)}")
+    B, n, offsets, op = _list_layout(s, offsets, max_len)
     ks = [int(k) for k in ks]
     order_ix = sorted(range(len(ks)), key=lambda i: ks[i])
     ks_sorted = [ks[i] for i in order_ix]
     arr = (C.c_int32 * len(ks))(*ks_sorted)
     out = torch.empty((B, len(ks)), dtype=torch.float32, device=s.device)
-    order = torch.empty((B, n), dtype=torch.int32, device=s.device) if return_order else None
-    _lib.check(lib.ptrb200_ndcg_at_ks(s.data_ptr(), y.data_ptr(), arr, len(ks), out.data_ptr(),
+    order = torch.empty(s.shape, dtype=torch.int32, device=s.device) if return_order else None
+    _lib.check(lib.ptrb200_ndcg_at_ks(s.data_ptr(), y.data_ptr(), op, arr, len(ks), out.data_ptr(),
                                       order.data_ptr() if return_order else None, B, n, int(bool(presort)),
                                       _stream_ptr()), "ndcg_at_ks")
     if order_ix != list(range(len(ks))):
@@ -303,18 +349,21 @@ def ndcg_at_ks(scores: torch.Tensor, labels: torch.Tensor, ks: Sequence[int], pr
 
 @_on_tensor_device
 def adhoc_metrics_at_ks(scores: torch.Tensor, labels: torch.Tensor, ks: Sequence[int], presort: bool = False,
-                        max_label: Optional[float] = None):
+                        max_label: Optional[float] = None, offsets: Optional[torch.Tensor] = None,
+                        max_len: Optional[int] = None):
     """(nDCG, nERR, AP, P) per query at the cutoffs ``ks`` -> four [B, len(ks)] tensors from one kernel."""
     lib = _lib.load()
     s, y = _dev_f32(scores, "scores"), _dev_f32(labels, "labels")
-    B, n = _check_pair(s, y)
+    if s.shape != y.shape:
+        raise ValueError(f"expected scores/labels of identical shape, got {tuple(s.shape)} / {tuple(y.shape)}")
+    B, n, offsets, op = _list_layout(s, offsets, max_len)
     ks = [int(k) for k in ks]
     order_ix = sorted(range(len(ks)), key=lambda i: ks[i])
     arr = (C.c_int32 * len(ks))(*[ks[i] for i in order_ix])
     if max_label is None:                       # the reference falls back to the maximum over the batch
         max_label = float(y.max())
     out = torch.empty((B, 4, len(ks)), dtype=torch.float32, device=s.device)
-    _lib.check(lib.ptrb200_adhoc_metrics_at_ks(s.data_ptr(), y.data_ptr(), arr, len(ks), out.data_ptr(), B, n,
+    _lib.check(lib.ptrb200_adhoc_metrics_at_ks(s.data_ptr(), y.data_ptr(), op, arr, len(ks), out.data_ptr(), B, n,
                                                int(bool(presort)), float(max_label), _stream_ptr()), "adhoc_metrics_at_ks")
     if order_ix != list(range(len(ks))):
         inv = torch.empty(len(ks), dtype=torch.long)
