@@ -196,6 +196,9 @@ typedef struct ptrb200_ffnet {
     int norm_affine;                       /* bn_affine                                       */
     float dropout_p;                       /* Dropout before every hidden Linear; 0 disables  */
     int math_mode;                         /* PTRB200_MATH_*: the TF32 modes fall back to SIMT when a width is not a multiple of 4 */
+    int sync_bn;                           /* != 0 with PTRB200_NORM_BN: the batch statistics (forward moments and the two backward
+                                              sums) span every data-parallel rank -- the library folds its partial sums into
+                                              2*C+1 doubles per layer and asks the hook below to all-reduce them (SUM) */
     /* parameters, one pointer per linear layer l = 0..num_linear-1 (nn.Linear layout [out,in]) */
     const float* weight[PTRB200_MAX_FF_LAYERS];
     const float* bias[PTRB200_MAX_FF_LAYERS];
@@ -215,6 +218,18 @@ typedef struct ptrb200_ffnet_grads {       /* same layout as the parameter point
     float* aff_w[PTRB200_MAX_FF_LAYERS];
     float* aff_b[PTRB200_MAX_FF_LAYERS];
 } ptrb200_ffnet_grads;
+
+/* Host hook for the two things a data-parallel caller has to do in the middle of a forward / backward call; the library
+ * itself holds no communicator.  Called on the launching host thread, between kernel launches on `stream`:
+ *   PTRB200_HOOK_ALLREDUCE_F64      all-reduce (SUM) `count` doubles at device pointer `ptr`, ordered on `stream`
+ *                                   (sync_bn statistics of layer `layer`: 2*C sums + the row count)
+ *   PTRB200_HOOK_LAYER_GRADS_READY  every parameter gradient of layer `layer` has been enqueued on `stream`
+ *                                   (ptr NULL, count 0): the caller may start its gradient all-reduce for that layer
+ * Return 0; anything else aborts the call with PTRB200_ERR_INVALID.  fn == NULL removes the hook. */
+#define PTRB200_HOOK_ALLREDUCE_F64      1
+#define PTRB200_HOOK_LAYER_GRADS_READY  2
+typedef int (*ptrb200_hook_fn)(int what, int layer, void* ptr, int64_t count, void* stream, void* user);
+int ptrb200_set_hook(ptrb200_hook_fn fn, void* user);
 
 /* bytes of activation workspace the forward pass fills for the backward pass
  * (rows = B*n documents) */

@@ -34,6 +34,7 @@ class FFNetDesc(C.Structure):
         ("norm_affine", C.c_int),
         ("dropout_p", C.c_float),
         ("math_mode", C.c_int),
+        ("sync_bn", C.c_int),
         ("weight", _fp * MAX_FF_LAYERS),
         ("bias", _fp * MAX_FF_LAYERS),
         ("gamma", _fp * MAX_FF_LAYERS),
@@ -92,7 +93,26 @@ SIGNATURES = {
                                     _I, _I, _I, _U64, _U64, _fp]),
 }
 
+HOOK_ALLREDUCE_F64, HOOK_LAYER_GRADS_READY = 1, 2
+# int hook(int what, int layer, void* ptr, int64_t count, void* stream, void* user)
+HOOK_T = C.CFUNCTYPE(C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
+SIGNATURES["ptrb200_set_hook"] = (_I, [HOOK_T, C.c_void_p])
+
 _lib = None
+_hook_keepalive = None
+
+
+def set_hook(pyfunc):
+    """Install ``pyfunc(what, layer, ptr, count, stream) -> int`` as the library's host hook (None removes it)."""
+    global _hook_keepalive
+    lib = load()
+    if pyfunc is None:
+        _hook_keepalive = None
+        check(lib.ptrb200_set_hook(C.cast(None, HOOK_T), None), "set_hook")
+        return
+    cb = HOOK_T(lambda what, layer, ptr, count, stream, user: int(pyfunc(what, layer, ptr or 0, count, stream or 0)))
+    _hook_keepalive = cb          # ctypes callbacks must outlive their registration
+    check(lib.ptrb200_set_hook(cb, None), "set_hook")
 
 
 class B200LibraryError(RuntimeError):

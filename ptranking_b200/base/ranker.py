@@ -248,6 +248,8 @@ class NeuralRanker(Evaluator):
         self.grad_bucket.zero(skip_memset=getattr(self, 'grad_bucket_overwritten', False))
         if getattr(self, '_unit_grad', None) is None or self._unit_grad.device != batch_loss.device:
             self._unit_grad = torch.ones((), dtype=torch.float32, device=batch_loss.device)
+        if getattr(self, 'grad_bucket_overwritten', False):
+            self.grad_bucket.begin_overlap()               # layers' gradient slices go out as they complete
         batch_loss.backward(gradient=self._unit_grad)       # cached root gradient: no fill kernel per step
         self.grad_bucket.all_reduce()
         self.optimizer.step()

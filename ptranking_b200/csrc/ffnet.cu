@@ -383,14 +383,17 @@ static __device__ __forceinline__ void block_sum2_d(double& a, double& b) {
 // coefficients  y = a*(z-mean)*rstd + c  ==  z*scale + shift.   grid = G*C
 __global__ void __launch_bounds__(FIN_THREADS) moments_finalize_kernel(
         const double* __restrict__ partials, float* __restrict__ mean, float* __restrict__ rstd,
-        float* __restrict__ scale, float* __restrict__ shift, NormRef nr, int G, int C, int S, int gr) {
+        float* __restrict__ scale, float* __restrict__ shift, NormRef nr, int G, int C, int S, int gr,
+        const double* __restrict__ gcount = nullptr) {
+    // gcount (sync-BN): the statistics group spans every rank's rows; its size arrives all-reduced on the device
+    const double grd = gcount ? *gcount : (double)gr;
     const int i = blockIdx.x, g = i / C, c = i % C;
     double s1 = 0.0, s2 = 0.0;
     for (int s = threadIdx.x; s < S; s += FIN_THREADS) { const double* p = partials + (((size_t)g * S + s) * C + c) * 2; s1 += p[0]; s2 += p[1]; }
     block_sum2_d(s1, s2);
     if (threadIdx.x == 0) {
-        const double m = s1 / gr;
-        double var = s2 / gr - m * m;
+        const double m = s1 / grd;
+        double var = s2 / grd - m * m;
         if (var < 0.0) var = 0.0;
         const float mf = (float)m, rf = (float)(1.0 / sqrt(var + 1e-5));
         mean[i] = mf;
@@ -415,11 +418,15 @@ struct DyTail {
     int gr;
     float* bias_grad;                           // [C] or NULL
     int bias_mode;                              // 1: exact zero (the bias feeds a normalisation), 2: T1
+    // sync-BN: counts[0] = rows of the statistics group over all ranks, counts[1] = this rank's rows.  The sums are
+    // global then; parameter gradients are scaled by counts[1]/counts[0] so that the gradient all-reduce (SUM over
+    // ranks) restores them exactly once.
+    const double* counts;
 };
 static __device__ __forceinline__ void dz_coeff_one(const DyTail& t, size_t i, int c, float s1, float s2) {
     float a, cc;
     norm_coeffs(t.nr, c, a, cc);
-    const float rs = t.nr.rstd[i], mu = t.nr.mean[i], invN = 1.0f / (float)t.gr;
+    const float rs = t.nr.rstd[i], mu = t.nr.mean[i], invN = t.counts ? (float)(1.0 / t.counts[0]) : 1.0f / (float)t.gr;
     const float ar = a * rs, q = ar * rs * (s2 * invN);
     t.k1[i] = ar;
     t.k3[i] = -q;
@@ -452,6 +459,7 @@ __global__ void __launch_bounds__(FIN_THREADS) dy_finalize_kernel(
         }
     }
     if (threadIdx.x == 0) {
+        if (tail.counts) { const double w = tail.counts[1] / tail.counts[0]; t1 *= w; t2 *= w; }
         const float f1 = (float)t1, f2 = (float)t2;
         if (T1) T1[c] = f1;
         if (T2) T2[c] = f2;
@@ -464,6 +472,32 @@ __global__ void __launch_bounds__(FIN_THREADS) dy_finalize_kernel(
         if (tail.daff_b) tail.daff_b[c] = f1;
         if (tail.bias_grad) tail.bias_grad[c] = tail.bias_mode == 1 ? 0.0f : f1;
     }
+}
+
+// sync-BN: fold the per-slot partials [S][C][2] of the single statistics group into buf[c][2]; buf[2C] and buf[2C+1]
+// both receive this rank's row count.  The caller all-reduces buf[0 .. 2C] (sums and the first count) across ranks, so
+// afterwards buf[2C] is the global group size while buf[2C+1] stays local.   grid = C
+__global__ void __launch_bounds__(FIN_THREADS) partials_fold_kernel(const double* __restrict__ partials, double* __restrict__ buf,
+                                                                     int S, int C, double local_rows) {
+    const int c = blockIdx.x;
+    double s1 = 0.0, s2 = 0.0;
+    for (int s = threadIdx.x; s < S; s += FIN_THREADS) { const double* p = partials + ((size_t)s * C + c) * 2; s1 += p[0]; s2 += p[1]; }
+    block_sum2_d(s1, s2);
+    if (threadIdx.x == 0) {
+        buf[c * 2] = s1; buf[c * 2 + 1] = s2;
+        if (c == 0) { buf[2 * C] = local_rows; buf[2 * C + 1] = local_rows; }
+    }
+}
+
+// host hook (ptrb200_set_hook): collectives and gradient-ready notifications are the caller's business (the library
+// holds no communicator); the hook runs on the launching host thread between kernel launches of the same stream.
+static ptrb200_hook_fn g_hook = nullptr;
+static void* g_hook_user = nullptr;
+static int call_hook(int what, int layer, void* ptr, int64_t count, cudaStream_t st) {
+    if (!g_hook) return PTRB200_OK;
+    const int rc = g_hook(what, layer, ptr, count, (void*)st, g_hook_user);
+    if (rc) { set_error("hook(%d, layer %d) returned %d", what, layer, rc); return PTRB200_ERR_INVALID; }
+    return PTRB200_OK;
 }
 
 // ------------------------------------------------------------------ elementwise passes
@@ -502,9 +536,10 @@ __global__ void norm_act_fwd4_kernel(const float* __restrict__ Z, float* __restr
     }
 }
 __global__ void norm_bwd_apply4_kernel(const float* __restrict__ Z, float* __restrict__ dY, NormRef nr,
-                                       const float* __restrict__ S1, const float* __restrict__ S2, size_t units, int C, int gr) {
+                                       const float* __restrict__ S1, const float* __restrict__ S2, size_t units, int C, int gr,
+                                       const double* __restrict__ gcount = nullptr) {
     const int Q = C >> 2;
-    const float invN = 1.0f / (float)gr;
+    const float invN = gcount ? (float)(1.0 / *gcount) : 1.0f / (float)gr;
     for (size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(u % Q) * 4;
         const size_t g = (u / Q) / gr;
@@ -527,8 +562,8 @@ __global__ void norm_bwd_apply4_kernel(const float* __restrict__ Z, float* __res
 // dZ = a * rstd * (dY - S1/N - xhat * S2/N)     (in place over dY)
 __global__ void norm_bwd_apply_kernel(const float* __restrict__ Z, float* __restrict__ dY, NormRef nr,
                                       const float* __restrict__ S1, const float* __restrict__ S2,
-                                      size_t total, int C, int gr) {
-    const float invN = 1.0f / (float)gr;
+                                      size_t total, int C, int gr, const double* __restrict__ gcount = nullptr) {
+    const float invN = gcount ? (float)(1.0 / *gcount) : 1.0f / (float)gr;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
         const size_t g = (i / C) / gr;
@@ -572,7 +607,8 @@ struct Plan {
     int L, G, gr, S_stat, slice_rows, S_w, k_chunk;
     size_t rows;
     LayerPlan layer[PTRB200_MAX_FF_LAYERS];
-    size_t partials_off, s1_off, s2_off, t1_off, t2_off, dbuf0_off, dbuf1_off, wpart_off, k1_off, k3_off, k0_off, total;
+    size_t partials_off, s1_off, s2_off, t1_off, t2_off, dbuf0_off, dbuf1_off, wpart_off, k1_off, k3_off, k0_off, sync_off, total;
+    bool sync_bn;                                // batch-level BN statistics all-reduced across data-parallel ranks
 };
 
 // column blocking of the weight gradient: dZ columns in blocks of 128 (MMA M), input columns in blocks of <= 256 (MMA N)
@@ -598,6 +634,7 @@ static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p) {
     p.gr = net->norm == PTRB200_NORM_BN2 ? n : (int)p.rows;
     if (net->math_mode < PTRB200_MATH_SIMT || net->math_mode > PTRB200_MATH_BF16) { set_error("ffnet: bad math_mode %d", net->math_mode); return PTRB200_ERR_INVALID; }
     p.use_tc = net->math_mode != PTRB200_MATH_SIMT;
+    p.sync_bn = net->sync_bn != 0 && net->norm == PTRB200_NORM_BN;
     p.passes = net->math_mode == PTRB200_MATH_3XTF32 ? 3 : 1;
     p.bf16 = net->math_mode == PTRB200_MATH_BF16;
     for (int l = 0; l < net->num_linear && p.use_tc; ++l) {
@@ -621,6 +658,8 @@ static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p) {
         p.ntiles = p.group_rows > 0 ? B * p.tiles_per_group : (int)((p.rows + p.tile_rows - 1) / p.tile_rows);
         p.wg_rows = 32; p.wg_grid = 444;
     }
+    if (p.sync_bn && !p.use_tc) { set_error("ffnet: sync_bn needs the tensor-core path (layer widths multiples of 4)"); return PTRB200_ERR_UNSUPPORTED; }
+    if (p.sync_bn && !g_hook) { set_error("ffnet: sync_bn needs an all-reduce hook (ptrb200_set_hook)"); return PTRB200_ERR_INVALID; }
     p.k_chunk = 2048; p.S_w = (int)((p.rows + 2047) / 2048);
     if (p.S_w > 592) { p.S_w = 592; p.k_chunk = (int)((p.rows + 591) / 592); p.S_w = (int)((p.rows + p.k_chunk - 1) / p.k_chunk); }
     size_t off = 0;
@@ -660,6 +699,7 @@ static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p) {
     p.k1_off = off; off = align_up(off + (size_t)p.G * maxd * 4, 256);
     p.k3_off = off; off = align_up(off + (size_t)p.G * maxd * 4, 256);
     p.k0_off = off; off = align_up(off + (size_t)p.G * maxd * 4, 256);
+    p.sync_off = off; off = align_up(off + ((size_t)2 * maxd + 2) * 8, 256);
     p.dbuf0_off = off; off = align_up(off + p.rows * maxd * 4, 256);
     p.dbuf1_off = off; off = align_up(off + p.rows * maxd * 4, 256);
     {
@@ -882,10 +922,18 @@ static int forward_tc(const ptrb200_ffnet* net, const Plan& p, const float* X, f
         NormRef nr = norm_ref(net, p, l, ws);
         if (lp.has_norm) {
             const int cnt = p.G * lp.d_out;
-            PTRB200_LAUNCH(moments_finalize_kernel, cnt, FIN_THREADS, 0, st, (const double*)g.partials,
+            const double* part = g.partials;
+            const double* gcount = nullptr;
+            if (p.sync_bn) {       // LTRBatchNorm over the GLOBAL batch: per-channel (sum, sum of squares, rows) summed over ranks
+                double* buf = reinterpret_cast<double*>(ws + p.sync_off);
+                PTRB200_LAUNCH(partials_fold_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)g.partials, buf, S_fwd, lp.d_out, (double)p.rows);
+                if ((rc = call_hook(PTRB200_HOOK_ALLREDUCE_F64, l, buf, 2 * lp.d_out + 1, st))) return rc;
+                part = buf; gcount = buf + 2 * lp.d_out; S_fwd = 1;
+            }
+            PTRB200_LAUNCH(moments_finalize_kernel, cnt, FIN_THREADS, 0, st, part,
                            reinterpret_cast<float*>(ws + lp.mean_off), reinterpret_cast<float*>(ws + lp.rstd_off),
                            reinterpret_cast<float*>(ws + lp.scale_off), reinterpret_cast<float*>(ws + lp.shift_off),
-                           nr, p.G, lp.d_out, S_fwd, p.gr);
+                           nr, p.G, lp.d_out, S_fwd, p.gr, gcount);
         }
         if (last && (lp.has_act || lp.has_norm)) {
             const size_t total = p.rows * lp.d_out;
@@ -941,13 +989,22 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
                           wgrad_smem(lp.d_out, lp.d_in, KPl, Rf, p.passes, stf, true, 32) <= (size_t)227 * 1024;
                 if (fuse_dz) { tail.k1 = reinterpret_cast<float*>(ws + p.k1_off); tail.k3 = reinterpret_cast<float*>(ws + p.k3_off); tail.k0 = reinterpret_cast<float*>(ws + p.k0_off); }
             }
-            PTRB200_LAUNCH(dy_finalize_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)part,
+            const double* fin_part = part;
+            const double* gcount = nullptr;
+            if (lp.has_norm && p.sync_bn) {   // S1 = sum dY, S2 = sum dY*xhat over the GLOBAL batch (same exchange as the forward moments)
+                double* buf = reinterpret_cast<double*>(ws + p.sync_off);
+                PTRB200_LAUNCH(partials_fold_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)part, buf, bS, lp.d_out, (double)p.rows);
+                if ((rc = call_hook(PTRB200_HOOK_ALLREDUCE_F64, l, buf, 2 * lp.d_out + 1, st))) return rc;
+                fin_part = buf; bS = 1; gcount = buf + 2 * lp.d_out;
+                tail.counts = gcount;
+            }
+            PTRB200_LAUNCH(dy_finalize_kernel, lp.d_out, FIN_THREADS, 0, st, fin_part,
                            (lp.has_norm && !fuse_dz) ? S1 : (float*)nullptr, (lp.has_norm && !fuse_dz) ? S2 : (float*)nullptr,
                            (float*)nullptr, (float*)nullptr, p.G, lp.d_out, bS, tail);
             if (lp.has_norm) {
                 if (fuse_dz) {
-                } else if (lp.d_out % 4 == 0) PTRB200_LAUNCH(norm_bwd_apply4_kernel, elementwise_blocks(total / 4), 256, 0, st, Z, dY, nr, (const float*)S1, (const float*)S2, total / 4, lp.d_out, p.gr);
-                else PTRB200_LAUNCH(norm_bwd_apply_kernel, elementwise_blocks(total), 256, 0, st, Z, dY, nr, (const float*)S1, (const float*)S2, total, lp.d_out, p.gr);
+                } else if (lp.d_out % 4 == 0) PTRB200_LAUNCH(norm_bwd_apply4_kernel, elementwise_blocks(total / 4), 256, 0, st, Z, dY, nr, (const float*)S1, (const float*)S2, total / 4, lp.d_out, p.gr, gcount);
+                else PTRB200_LAUNCH(norm_bwd_apply_kernel, elementwise_blocks(total), 256, 0, st, Z, dY, nr, (const float*)S1, (const float*)S2, total, lp.d_out, p.gr, gcount);
             }
             dZ = dY;
         } else {
@@ -984,6 +1041,9 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
             else { if ((rc = opt_in_smem(wgrad_tc_kernel<1>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<1>, grid, WG_THREADS, smem, st, w); }
             const int cnt = lp.d_in * lp.d_out;
             PTRB200_LAUNCH(reduce_splits_kernel, (cnt + 63) / 64, 256, 0, st, (const float*)wpart, grads->weight[l], wb.gx, cnt);
+            // every parameter gradient of layer l is now enqueued: a data-parallel caller can start reducing it while the
+            // layers below are still running (dist.GradBucket's overlapped all-reduce)
+            if ((rc = call_hook(PTRB200_HOOK_LAYER_GRADS_READY, l, nullptr, 0, st))) return rc;
         }
         // ---- dIn = dropmask(dZ * W) ----
         if (l > 0 || dX) {
@@ -1038,6 +1098,12 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
 using namespace ptrb200;
 
 extern "C" {
+
+int ptrb200_set_hook(ptrb200_hook_fn fn, void* user) {
+    g_hook = fn;
+    g_hook_user = user;
+    return PTRB200_OK;
+}
 
 int ptrb200_tc_wgrad(const float* dZ, const float* P, float* dW, float* partials, int rows, int N, int K, int passes,
                      ptrb200_stream_t stream) {

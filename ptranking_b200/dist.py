@@ -10,8 +10,9 @@ with the gloo backend on CPU.
 """
 from __future__ import annotations
 
+import contextlib
 import os
-from typing import Iterable, List, Sequence
+from typing import Iterable, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
@@ -39,6 +40,71 @@ def init_from_env(backend: str = "nccl") -> tuple:
     return rank, local, world
 
 
+# --------------------------------------------------------------------------- #
+# host hook of the C library: collectives in the middle of a forward / backward call
+# --------------------------------------------------------------------------- #
+_sync_bn = os.environ.get("PTRANKING_B200_SYNC_BN", "0") == "1"
+_call = {"ws": None, "layer_targets": None}
+_active_bucket: Optional["GradBucket"] = None
+_hook_installed = False
+
+
+def set_sync_bn(on: bool) -> None:
+    """Batch-level ``BN`` statistics over the GLOBAL batch (sum over data-parallel ranks) instead of per rank: with it a
+    sharded step computes exactly what one GPU would on the concatenated batch (LTRBatchNorm, base/utils.py:201-223,
+    normalises over every document it is handed).  Costs one 2*C+1-double all-reduce per normalised layer in the forward
+    pass and one in the backward pass; off by default (PTRANKING_B200_SYNC_BN=1 turns it on)."""
+    global _sync_bn
+    _sync_bn = bool(on)
+
+
+def sync_bn_active() -> bool:
+    if _sync_bn and is_distributed():
+        _install_hook()
+        return True
+    return False
+
+
+def _install_hook() -> None:
+    global _hook_installed
+    if not _hook_installed:
+        from . import _lib
+        _lib.set_hook(_hook)
+        _hook_installed = True
+
+
+def _hook(what, layer, ptr, count, stream) -> int:
+    """Runs on the launching thread between kernel launches (include/ptranking_b200.h: ptrb200_set_hook)."""
+    from . import _lib
+    try:
+        if what == _lib.HOOK_ALLREDUCE_F64:
+            ws = _call["ws"]
+            if ws is None:
+                return 1
+            off = ptr - ws.data_ptr()
+            if off < 0 or off + 8 * count > ws.numel():
+                return 1
+            dist.all_reduce(ws[off: off + 8 * count].view(torch.float64), op=dist.ReduceOp.SUM)
+        elif what == _lib.HOOK_LAYER_GRADS_READY:
+            if _active_bucket is not None and _call["layer_targets"] is not None:
+                _active_bucket.layer_ready(layer, _call["layer_targets"])
+        return 0
+    except Exception as e:      # never let an exception cross the C boundary
+        print(f"ptranking_b200.dist hook failed: {e!r}", flush=True)
+        return 1
+
+
+@contextlib.contextmanager
+def call_context(ws, layer_targets):
+    """Tells the hook which workspace tensor / per-layer gradient tensors the running C call uses."""
+    prev = dict(_call)
+    _call["ws"], _call["layer_targets"] = ws, layer_targets
+    try:
+        yield
+    finally:
+        _call.update(prev)
+
+
 def shard_queries(num_queries: int, rank: int, world: int) -> range:
     """Contiguous block of query indices owned by ``rank`` (sizes differ by at most one)."""
     base, rem = divmod(num_queries, world)
@@ -62,6 +128,10 @@ class GradBucket:
         dev = self.params[0].device if self.params else torch.device("cpu")
         self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
         self.flat_param = None
+        self.distributed = True            # False: a purely local bucket even inside an initialised process group
+        self._reduced_from = None          # overlapped all-reduce: flat[_reduced_from:] is already on the side stream
+        self._side = None
+        self.overlap_from_layer = 1        # start reducing when this layer's gradients are complete (layers above it too)
         for p, v in zip(self.params, self._views()):
             p.grad = v
 
@@ -94,14 +164,51 @@ class GradBucket:
             yield self.flat[off: off + p.numel()].view_as(p)
 
     def all_reduce(self) -> None:
-        if is_distributed():
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        """Finish the step's gradient reduction: whatever :meth:`layer_ready` has not already put on the side stream is
+        reduced now; then the compute stream waits for the side stream."""
+        global _active_bucket
+        _active_bucket = None
+        if not (is_distributed() and self.distributed):
+            return
+        upto = self._reduced_from if self._reduced_from is not None else self.flat.numel()
+        if upto > 0:
+            dist.all_reduce(self.flat[:upto], op=dist.ReduceOp.SUM)
+        if self._reduced_from is not None:
+            torch.cuda.current_stream(self.flat.device).wait_stream(self._side)
+            self._reduced_from = None
+
+    def begin_overlap(self) -> None:
+        """Arm the overlapped reduction for the backward pass that follows (CUDA + NCCL only): the scorer's backward
+        call reports each layer's gradients complete (last layer first) and the tail of the flat buffer goes onto a side
+        stream while the layers below are still computing."""
+        global _active_bucket
+        self._reduced_from = None
+        if is_distributed() and self.distributed and self.flat.is_cuda and os.environ.get("PTRANKING_B200_OVERLAP", "1") == "1":
+            _install_hook()
+            _active_bucket = self
+
+    def layer_ready(self, layer: int, layer_targets) -> None:
+        if layer != self.overlap_from_layer or self._reduced_from is not None or layer >= len(layer_targets):
+            return
+        tens = layer_targets[layer]
+        if not tens:
+            return
+        start = min((t.data_ptr() - self.flat.data_ptr()) // 4 for t in tens)
+        if not (0 < start < self.flat.numel()):
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.flat.device)
+        cur = torch.cuda.current_stream(self.flat.device)
+        self._side.wait_stream(cur)                       # everything enqueued so far (layers >= `layer`) is complete
+        with torch.cuda.stream(self._side):
+            dist.all_reduce(self.flat[start:], op=dist.ReduceOp.SUM)
+        self._reduced_from = int(start)
 
 
 def broadcast_parameters(bucket: "GradBucket", src: int = 0) -> None:
     """Make every replica's parameters equal to rank ``src``'s (no-op when not distributed): one broadcast of the flat
     parameter buffer when the parameters were re-homed into it, else one per tensor."""
-    if not is_distributed():
+    if not (is_distributed() and bucket.distributed):
         return
     if bucket.flat_param is not None and bucket.params_are_flat():
         dist.broadcast(bucket.flat_param, src=src)

@@ -384,6 +384,11 @@ def next_dropout_offset() -> int:
     return _dropout_offset
 
 
+def _b200dist():
+    from . import dist as b200dist          # late import: dist imports nothing from ops, ops only needs it at call time
+    return b200dist
+
+
 class FFNetSpec:
     """Static description of one stacked FF net + the order its parameters are passed in."""
 
@@ -419,6 +424,7 @@ class FFNetSpec:
         d.norm_affine = int(self.norm_affine)
         d.dropout_p = self.dropout_p
         d.math_mode = _lib.MATH_MODES[self.math_mode]
+        d.sync_bn = int(self.norm == "BN" and _b200dist().sync_bn_active())
         it = iter(params)
         for l, names in enumerate(self.slots):
             for nm in names:
@@ -461,8 +467,9 @@ class _FFNetFn(torch.autograd.Function):
         # bit 1 = forward only (PTRB200_FFNET_FORWARD_ONLY): no backward will follow (nothing requires grad, or the
         # caller runs under torch.no_grad()), so the by-products the backward pass reads are not written
         flags = int(training) | (0 if need_backward else 2)
-        _lib.check(lib.ptrb200_ffnet_forward(C.byref(desc), X.data_ptr(), out.data_ptr(), ws.data_ptr(), int(nbytes),
-                                             B, n, flags, seed, offset, _stream_ptr()), "ffnet_forward")
+        with _b200dist().call_context(ws, None):
+            _lib.check(lib.ptrb200_ffnet_forward(C.byref(desc), X.data_ptr(), out.data_ptr(), ws.data_ptr(), int(nbytes),
+                                                 B, n, flags, seed, offset, _stream_ptr()), "ffnet_forward")
         ctx.spec, ctx.training, ctx.seed, ctx.offset = spec, training, seed, offset
         ctx.grad_targets = grad_targets
         ctx.ws, ctx.nbytes = (ws if need_backward else None), int(nbytes)
@@ -481,10 +488,19 @@ class _FFNetFn(torch.autograd.Function):
         gdesc, gouts = spec.grads(params, ctx.grad_targets)
         d_out = _dev_f32(d_out, "d_out")
         dX = torch.empty_like(X) if ctx.need_dx else None
-        _lib.check(lib.ptrb200_ffnet_backward(C.byref(desc), C.byref(gdesc), X.data_ptr(), d_out.data_ptr(),
-                                              dX.data_ptr() if dX is not None else None, ctx.ws.data_ptr(), ctx.nbytes,
-                                              B, n, int(ctx.training), ctx.seed, ctx.offset, _stream_ptr()),
-                   "ffnet_backward")
+        # per-layer gradient tensors (write-through targets only): lets a data-parallel bucket start reducing a layer's
+        # slice as soon as the library reports it complete
+        layer_targets = None
+        if ctx.grad_targets is not None:
+            layer_targets, i = [], 0
+            for names in spec.slots:
+                layer_targets.append(gouts[i: i + len(names)])
+                i += len(names)
+        with _b200dist().call_context(ctx.ws, layer_targets):
+            _lib.check(lib.ptrb200_ffnet_backward(C.byref(desc), C.byref(gdesc), X.data_ptr(), d_out.data_ptr(),
+                                                  dX.data_ptr() if dX is not None else None, ctx.ws.data_ptr(), ctx.nbytes,
+                                                  B, n, int(ctx.training), ctx.seed, ctx.offset, _stream_ptr()),
+                       "ffnet_backward")
         ctx.ws = None
         if ctx.grad_targets is not None:            # written straight into the parameters' .grad storage
             return (dX, None, None, None, None, None, None, *([None] * len(gouts)))

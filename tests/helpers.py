@@ -82,3 +82,12 @@ def parse_sibling_key(head):
         params["delta"] = float(m.group(1))
         params["top_k"] = None if m.group(2) == "None" else int(m.group(2))
     return name, params
+
+
+def sampled(arr, limit=16384, target=8192):
+    """Flattened tensor, or every k-th element of it when it has more than ``limit`` elements (k = size // target) --
+    the storage rule of tests/golden/make_golden_r2.py for large gradients / weights."""
+    flat = np.asarray(arr).reshape(-1)
+    if flat.size <= limit:
+        return flat.copy()
+    return flat[:: flat.size // target].copy()
