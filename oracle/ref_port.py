@@ -45,14 +45,14 @@ def dcg_at_k(rankings: torch.Tensor, cutoff: Optional[int] = None) -> torch.Tens
     """[B,n] labels in rank order -> [B,1] DCG@cutoff (adhoc_metric.py:197-217)."""
     k = rankings.size(1) if cutoff is None else cutoff
     num = gains(rankings[:, :k])
-    disc = torch.log2(torch.arange(k, dtype=torch.float).expand_as(num) + 2.0)
+    disc = torch.log2(torch.arange(k, dtype=torch.float, device=num.device).expand_as(num) + 2.0)
     return torch.sum(num / disc, dim=1, keepdim=True)
 
 
 def dcg_at_ks(rankings: torch.Tensor, max_cutoff: int) -> torch.Tensor:
     """[B,n] -> [B,max_cutoff] running DCG (adhoc_metric.py:219-235)."""
     num = gains(rankings[:, :max_cutoff])
-    disc = torch.log2(torch.arange(max_cutoff, dtype=torch.float).expand_as(num) + 2.0)
+    disc = torch.log2(torch.arange(max_cutoff, dtype=torch.float, device=num.device).expand_as(num) + 2.0)
     return torch.cumsum(num / disc, dim=1)
 
 
@@ -107,7 +107,7 @@ def _delta_ndcg(ideal_rankings, predict_rankings):
     idcg = dcg_at_k(ideal_rankings)
     ng = gains(predict_rankings) / idcg
     ng_diff = ng.unsqueeze(2) - ng.unsqueeze(1)
-    ranks = torch.arange(predict_rankings.size(1), dtype=torch.float)
+    ranks = torch.arange(predict_rankings.size(1), dtype=torch.float, device=predict_rankings.device)
     disc = (1.0 / torch.log2(ranks + 2.0)).unsqueeze(0)
     disc_diff = disc.unsqueeze(2) - disc.unsqueeze(1)
     return torch.abs(ng_diff) * torch.abs(disc_diff)
@@ -210,7 +210,7 @@ class _RobustSigmoid(torch.autograd.Function):
     @staticmethod
     def forward(ctx, inp, sigma):
         x = inp if 1.0 == sigma else sigma * inp
-        half = torch.tensor([0.5], dtype=torch.float)
+        half = torch.tensor([0.5], dtype=torch.float, device=inp.device)
         pos = torch.where(inp > 0, 1.0 / (1.0 + torch.exp(-x)), half)
         ex = torch.exp(x)
         out = torch.where(inp < 0, ex / (1.0 + ex), pos)
@@ -462,7 +462,7 @@ class RefMHSA(nn.Module):
         d = self.width // self.n_heads
         split = lambda t: t.view(B, -1, self.n_heads, d).permute(0, 2, 1, 3)
         Q, K, V = split(self.w_q(x)), split(self.w_k(x)), split(self.w_v(x))
-        att = torch.matmul(Q, K.permute(0, 1, 3, 2)) / torch.sqrt(torch.tensor([float(d)]))
+        att = torch.matmul(Q, K.permute(0, 1, 3, 2)) / torch.sqrt(torch.tensor([float(d)], device=Q.device))
         att = self.do_dropout(torch.softmax(att, dim=-1))
         out = torch.matmul(att, V).permute(0, 2, 1, 3).contiguous().view(B, -1, self.width)
         return self.fc(out)

@@ -6,7 +6,8 @@ mkdir -p gpurun_out
 stages="${*:-tests bench}"
 for s in $stages; do
   case "$s" in
-    tests)    timeout 600 python -m pytest tests -q -m gpu --timeout 100 --tb=short 2>&1 | grep -v "^  \|Warning" | tail -15 ;;
+    tests)    timeout 900 python -m pytest tests -q -m gpu --timeout 200 --tb=short -x --maxfail=25 > gpurun_out/pytest_gpu.log 2>&1; grep -v "Warning" gpurun_out/pytest_gpu.log | tail -60 ;;
+    testsall) timeout 1200 python -m pytest tests -q -m gpu --timeout 200 --tb=short --maxfail=40 > gpurun_out/pytest_gpu.log 2>&1; grep -v "Warning" gpurun_out/pytest_gpu.log | tail -150 ;;
     smoke)    timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 ;;
     bench)    timeout 200 python bench.py 2>gpurun_out/bench_n1.err | tail -1 > gpurun_out/bench_n1.json
               python -c "import json; d=json.loads(open('gpurun_out/bench_n1.json').read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches']); print(d['roofline']['kernels_ms_per_step'])" ;;

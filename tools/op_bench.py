@@ -11,7 +11,7 @@ import bench
 import ptranking_b200
 from ptranking_b200 import ops, LABEL_TYPE
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 dev = "cuda:0"
 rng = np.random.default_rng(137)
 rows = []
@@ -45,6 +45,10 @@ for name, params, shapes in [
     ("ListNet", {}, [(1024, 256), (256, 1024)]),
     ("ListMLE", {}, [(4096, 32), (1024, 256), (256, 1024)]),
     ("ApproxNDCG", dict(alpha=10.0), [(1024, 256), (512, 512)]),
+    ("SoftRank", dict(delta=2.0, top_k=None), [(1024, 256), (256, 1024)]),
+    ("STListNet", dict(temperature=1.0), [(1024, 256), (4096, 32)]),
+    ("RankCosine", {}, [(1024, 256)]),
+    ("RankMSE", {}, [(1024, 256)]),
 ]:
     for (B, n) in shapes:
         s = torch.sigmoid(torch.randn(B, n, device=dev))
@@ -52,6 +56,8 @@ for name, params, shapes in [
         kw = dict(params)
         if name == "ListMLE":
             kw["perm"] = ops.shuffle_ties_perm(y, seed=1, offset=1)
+        if name == "STListNet":
+            kw.update(seed=1, offset=1)
         ms = timeit(lambda: ops.rank_loss_and_grad(name, s, y, **kw))
         algo = (16 if name == "ListMLE" else 12) * n * B
         rows.append((f"{name} {params.get('loss_type', '')} {('k=%d' % params['k']) if 'k' in params else ''}".strip(), f"B={B} n={n}",
@@ -62,12 +68,29 @@ for (B, n) in [(1024, 256), (256, 1024)]:
     ms = timeit(lambda: ops.adhoc_metrics_at_ks(s, y, [1, 3, 5, 10, 20, 50], presort=True, max_label=4.0))
     rows.append(("nDCG+nERR+AP+P @6 cutoffs", f"B={B} n={n}", ms, B / ms * 1e3, 8 * n * B / ms / 1e6, 8 * n * B / ms / 1e6 / HBM))
 
+# ragged batches: an MSLR-WEB30K-shaped length distribution (1..1251 documents, mean ~120) against uniform lists with
+# the same number of documents, loss kernel alone and the whole training step
+lens = np.clip(rng.lognormal(mean=4.45, sigma=0.85, size=4096), 1, 1251).astype(np.int64)
+take = int(np.searchsorted(np.cumsum(lens), 1 << 18))
+lens = lens[:take]
+off = np.zeros(len(lens) + 1, dtype=np.int32); off[1:] = np.cumsum(lens)
+total = int(off[-1])
+yr = np.concatenate([-np.sort(-np.maximum(rng.choice(5, size=n_, p=bench.MSLR_P), (np.arange(n_) == 0).astype(np.int64)).astype(np.float32)) for n_ in lens])
+s_r = torch.sigmoid(torch.randn(total, device=dev)); y_r = torch.from_numpy(yr).to(dev); off_d = torch.from_numpy(off).to(dev)
+for name, params in [("LambdaRank", dict(sigma=1.0)), ("ListNet", {}), ("ApproxNDCG", dict(alpha=10.0))]:
+    ms = timeit(lambda: ops.rank_loss_and_grad(name, s_r, y_r, offsets=off_d, max_len=int(lens.max()), **params))
+    rows.append((f"{name} RAGGED (lens 1..{int(lens.max())}, mean {lens.mean():.0f})", f"B={len(lens)} docs={total}", ms, len(lens) / ms * 1e3,
+                 12 * total / ms / 1e6, 12 * total / ms / 1e6 / HBM))
+Xs = torch.randn(total, 136, device=dev)
+ms = timeit(lambda: ops.standard_scale(Xs, offsets=off_d, max_len=int(lens.max())))
+rows.append(("per-query StandardScaler (ragged)", f"B={len(lens)} docs={total}", ms, len(lens) / ms * 1e3, 8 * 136 * total / ms / 1e6, 8 * 136 * total / ms / 1e6 / HBM))
+
 # scorer forward / forward+backward (default pointsf) and full step
-sf = bench.default_sf()
+sf = bench.point_sf(136)
 r = ptranking_b200.LambdaRank(sf_para_dict=sf, model_para_dict=dict(model_id="LambdaRank", sigma=1.0), gpu=True, device=dev)
 r.init(); r.train_mode()
 for (B, n) in [(1024, 256), (256, 1024), (4096, 32)]:
-    X, y = bench.synth_batch(rng, B, n)
+    X, y = bench.synth_batch(rng, B, n, 136, bench.MSLR_P)
     X, y = X.to(dev), y.to(dev)
     with torch.no_grad():
         ms_f = timeit(lambda: r.forward(X))
@@ -75,6 +98,12 @@ for (B, n) in [(1024, 256), (256, 1024), (4096, 32)]:
     algo = n * B * (136 * 4 + 8)
     rows.append(("pointsf forward (5x100 GELU BN)", f"B={B} n={n}", ms_f, B / ms_f * 1e3, algo / ms_f / 1e6, algo / ms_f / 1e6 / HBM))
     rows.append(("LambdaRank train step (fwd+loss+bwd+Adam)", f"B={B} n={n}", ms_s, B / ms_s * 1e3, algo / ms_s / 1e6, algo / ms_s / 1e6 / HBM))
+# the same step on the ragged batch (batch-level BN: one long list to the scorer, per-query offsets to the loss)
+Xr = torch.randn(total, 136, device=dev)
+ms_s = timeit(lambda: r.train_op(Xr, y_r, presort=True, label_type=LABEL_TYPE.MultiLabel, epoch_k=1, offsets=off_d, max_len=int(lens.max())))
+algo = total * (136 * 4 + 8)
+rows.append((f"LambdaRank train step RAGGED (lens 1..{int(lens.max())})", f"B={len(lens)} docs={total}", ms_s, len(lens) / ms_s * 1e3, algo / ms_s / 1e6, algo / ms_s / 1e6 / HBM))
+rows.append(("   -> documents/s ragged vs uniform 1024x256", "", float('nan'), total / ms_s * 1e3, float('nan'), float('nan')))
 
 # list scorer (DASALC, 2 heads) forward + step, config (c) shape
 for L in (3, 6):
@@ -84,7 +113,7 @@ for L in (3, 6):
     rl = ptranking_b200.ApproxNDCG(sf_para_dict=sfl, model_para_dict=dict(model_id="ApproxNDCG", alpha=10.0), gpu=True, device=dev)
     rl.init(); rl.train_mode()
     B, n = 64, 512
-    X, y = bench.synth_batch(rng, B, n)
+    X, y = bench.synth_batch(rng, B, n, 136, bench.MSLR_P)
     X, y = X.to(dev), y.to(dev)
     ms_s = timeit(lambda: rl.train_op(X, y, presort=True, label_type=LABEL_TYPE.MultiLabel, epoch_k=1), iters=5, warm=2)
     flops = 3 * n * (865280 + L * (147968 + 4 * n * 136)) * B
