@@ -304,7 +304,9 @@ int ptrb200_layernorm_bwd(const float* x, const float* a2, const float* dy, cons
                           int rows, int F, float eps, ptrb200_stream_t stream);
 /* elementwise glue of the encoder variants (list_ranker.py:138-149, 357-373) and of PositionwiseFeedForward (:269-277):
  * op 0: a+b   1: (a+1)*b (DASALC latent cross)   2: a*b   3: relu(a)   4: b>0 ? a : 0   5: dropout(a)   6: a*(b+1)
- * 7: a*b[0] (b = one device scalar: the incoming gradient of the summed batch loss, e.g. lambdarank.py:56-59) */
+ * 7: a*b[0] (b = one device scalar: the incoming gradient of the summed batch loss, e.g. lambdarank.py:56-59)
+ * 8 / 9: act(a) / act'(a) of get_AF (base/utils.py:101-143) with the PTRB200_AF_* code passed in `seed` -- the scorer's
+ *        own activation routine, exposed so its accuracy can be tested element by element */
 #define PTRB200_EW_ADD 0
 #define PTRB200_EW_LATENT_CROSS 1
 #define PTRB200_EW_MUL 2
@@ -313,6 +315,8 @@ int ptrb200_layernorm_bwd(const float* x, const float* a2, const float* dy, cons
 #define PTRB200_EW_DROPOUT 5
 #define PTRB200_EW_SCALE_ADD1 6
 #define PTRB200_EW_MUL_SCALAR 7
+#define PTRB200_EW_ACT 8
+#define PTRB200_EW_ACT_GRAD 9
 int ptrb200_elementwise(int op, const float* a, const float* b, float* out, int64_t count,
                         float dropout_p, uint64_t seed, uint64_t offset, ptrb200_stream_t stream);
 

@@ -13,6 +13,7 @@
 // saved per-row log-sum-exp.  Q, K, V, O are the [B, n, H*D] projection outputs, head h = columns
 // [h*D, (h+1)*D) -- the reference's view/permute (list_ranker.py:222-224) is pure indexing here.
 #include "common.cuh"
+#include "ffnet_act.cuh"
 
 namespace ptrb200 {
 
@@ -262,7 +263,7 @@ __global__ void reduce_rows_kernel(const float* __restrict__ partials, float* __
 }
 
 // ---------------------------------------------------------------- elementwise glue
-enum { EW_ADD = 0, EW_LATENT_CROSS = 1, EW_MUL = 2, EW_RELU = 3, EW_RELU_BWD = 4, EW_DROPOUT = 5, EW_SCALE_ADD1 = 6, EW_MUL_SCALAR = 7 };
+enum { EW_ADD = 0, EW_LATENT_CROSS = 1, EW_MUL = 2, EW_RELU = 3, EW_RELU_BWD = 4, EW_DROPOUT = 5, EW_SCALE_ADD1 = 6, EW_MUL_SCALAR = 7, EW_ACT = 8, EW_ACT_GRAD = 9 };
 // out = a + b | (a + 1) * b | a * b | relu(a) | (b > 0) ? a : 0 | dropout(a) | a*(b+1) | a * b[0]
 __global__ void elementwise_kernel(int op, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
                                    size_t n, DropCfg drop) {
@@ -276,6 +277,8 @@ __global__ void elementwise_kernel(int op, const float* __restrict__ a, const fl
             case EW_RELU_BWD: v = b[i] > 0.0f ? a[i] : 0.0f; break;
             case EW_DROPOUT: v = (!drop.thr || dropout_keep(drop.key, i, drop.thr)) ? a[i] * drop.scale : 0.0f; break;
             case EW_MUL_SCALAR: v = a[i] * b[0]; break;
+            case EW_ACT: v = activate((int)drop.thr, a[i]).y; break;          // activation code travels in drop.thr
+            case EW_ACT_GRAD: v = activate((int)drop.thr, a[i]).dy; break;
             default: v = a[i] * (b[i] + 1.0f); break;
         }
         out[i] = v;
@@ -359,10 +362,12 @@ int ptrb200_layernorm_bwd(const float* x, const float* a2, const float* dy, cons
 
 int ptrb200_elementwise(int op, const float* a, const float* b, float* out, int64_t count,
                         float dropout_p, uint64_t seed, uint64_t offset, ptrb200_stream_t stream) {
-    if (!a || !out || count <= 0 || op < EW_ADD || op > EW_MUL_SCALAR) { set_error("elementwise: bad arguments"); return PTRB200_ERR_INVALID; }
-    if (!b && op != EW_RELU && op != EW_DROPOUT) { set_error("elementwise: op %d needs two inputs", op); return PTRB200_ERR_INVALID; }
+    if (!a || !out || count <= 0 || op < EW_ADD || op > EW_ACT_GRAD) { set_error("elementwise: bad arguments"); return PTRB200_ERR_INVALID; }
+    if (!b && op != EW_RELU && op != EW_DROPOUT && op != EW_ACT && op != EW_ACT_GRAD) { set_error("elementwise: op %d needs two inputs", op); return PTRB200_ERR_INVALID; }
     size_t blocks = ((size_t)count + 255) / 256; if (blocks > 148 * 16) blocks = 148 * 16;
-    PTRB200_LAUNCH(elementwise_kernel, (unsigned)blocks, 256, 0, stream, op, a, b, out, (size_t)count, make_drop(dropout_p, seed, offset));
+    DropCfg dc = make_drop(dropout_p, seed, offset);
+    if (op == EW_ACT || op == EW_ACT_GRAD) dc.thr = (uint32_t)seed;           // seed = PTRB200_AF_* code
+    PTRB200_LAUNCH(elementwise_kernel, (unsigned)blocks, 256, 0, stream, op, a, b, out, (size_t)count, dc);
     return check_launch("elementwise");
 }
 

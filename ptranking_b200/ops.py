@@ -660,7 +660,7 @@ def layernorm_ref(x, a2, b2, eps: float = 1e-6):
     return _LayerNormRef.apply(x, a2, b2, eps)
 
 
-EW_ADD, EW_LATENT_CROSS, EW_MUL, EW_RELU, EW_RELU_BWD, EW_DROPOUT, EW_SCALE_ADD1, EW_MUL_SCALAR = range(8)
+EW_ADD, EW_LATENT_CROSS, EW_MUL, EW_RELU, EW_RELU_BWD, EW_DROPOUT, EW_SCALE_ADD1, EW_MUL_SCALAR, EW_ACT, EW_ACT_GRAD = range(10)
 
 
 @_on_tensor_device
@@ -672,6 +672,11 @@ def _ew(op, a, b=None, p=0.0, seed=0, offset=0):
     _lib.check(lib.ptrb200_elementwise(op, a.data_ptr(), bb.data_ptr() if bb is not None else None, out.data_ptr(),
                                        a.numel(), float(p), seed, offset, _stream_ptr()), "elementwise")
     return out
+
+
+def activation(x: torch.Tensor, code: str, grad: bool = False) -> torch.Tensor:
+    """act(x) (or act'(x)) exactly as the scorer kernels evaluate get_AF's activation ``code`` -- for accuracy tests."""
+    return _ew(EW_ACT_GRAD if grad else EW_ACT, x, None, 0.0, _lib.AF_CODES[code], 0)
 
 
 class _Add(torch.autograd.Function):

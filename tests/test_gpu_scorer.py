@@ -384,3 +384,29 @@ def test_listmle_with_bf16_scorer_tracks_the_fp32_scorer(n, monkeypatch):
     top = lambda s: np.argsort(-s, axis=1, kind="stable")[:, :10]
     overlap = np.mean([len(set(a) & set(b)) / 10.0 for a, b in zip(top(s16), top(s32))])
     assert overlap >= 0.6, overlap
+
+
+def test_gelu_matches_exact_erf_gelu_to_fp32_rounding():
+    """The scorer's GELU evaluates the normal CDF directly (csrc/ffnet_act.cuh::normal_cdf) instead of calling erff; it must
+    be as close to the exact-erf GELU of nn.GELU() (get_AF 'GE', base/utils.py:125) as a correctly rounded erff would be:
+    dense grid over [-8, 8] plus normal samples, value and derivative, against float64."""
+    from ptranking_b200 import ops
+    x = torch.cat([torch.linspace(-8.0, 8.0, 2_000_001), torch.randn(1_000_000) * 1.5,
+                   torch.tensor([0.0, -0.0, 5.75, -5.75, 6.0, -6.0, 30.0, -30.0, 1e-30, -1e-30, 1e30, -1e30])]).to(DEV)
+    y = ops.activation(x, "GE").double().cpu()
+    dy = ops.activation(x, "GE", grad=True).double().cpu()
+    x64 = x.double().cpu()
+    cdf = 0.5 * torch.erfc(-x64 / 2 ** 0.5)
+    want = x64 * cdf
+    dwant = cdf + x64 * torch.exp(-0.5 * x64 * x64) / (2 * torch.pi) ** 0.5
+    fin = x64.abs() <= 8.0
+    # torch's own fp32 GELU (erff based) as the yardstick
+    base = torch.nn.functional.gelu(x.cpu()).double()
+    err, err_base = (y - want).abs()[fin].max().item(), (base - want).abs()[fin].max().item()
+    assert err <= max(1.25 * err_base, 6e-7), (err, err_base)
+    rms, rms_base = ((y - want)[fin] ** 2).mean().sqrt().item(), ((base - want)[fin] ** 2).mean().sqrt().item()
+    assert rms <= 1.25 * rms_base, (rms, rms_base)
+    assert (dy - dwant).abs()[fin].max().item() <= 6e-7
+    # far tails: exact limits, no NaN from the flushed half
+    assert y[-1].item() == 0.0 and y[-2].item() == 1e30 and torch.isfinite(y).all()
+    assert ops.activation(torch.tensor([float("nan")], device=DEV), "GE").isnan().all()
