@@ -231,9 +231,13 @@ typedef struct ptrb200_ffnet_grads {       /* same layout as the parameter point
 typedef int (*ptrb200_hook_fn)(int what, int layer, void* ptr, int64_t count, void* stream, void* user);
 int ptrb200_set_hook(ptrb200_hook_fn fn, void* user);
 
-/* bytes of activation workspace the forward pass fills for the backward pass
- * (rows = B*n documents) */
-int64_t ptrb200_ffnet_workspace_bytes(const ptrb200_ffnet* net, int B, int n);
+/* Batch shape of the three calls below.  Dense (the reference's contract): B queries of n documents, X is [B,n,dims[0]],
+ * offsets = NULL, total_rows = 0.  Ragged: B queries cut out of total_rows documents by the device prefix
+ * offsets[B+1], n = the longest list, X is [total_rows, dims[0]].  Batch-level BN and norm-free nets treat a ragged batch as
+ * one long list; per-query BN2 (LTRBatchNorm2) normalises every query over its own documents. */
+
+/* bytes of activation workspace the forward pass fills for the backward pass */
+int64_t ptrb200_ffnet_workspace_bytes(const ptrb200_ffnet* net, int B, int n, int total_rows);
 
 /* `training` argument of the two calls below: bit 0 = training mode (dropout active); bit 1 (forward only) tells
  * ptrb200_ffnet_forward that no backward call will follow, so the by-products the backward pass reads are not written. */
@@ -242,14 +246,14 @@ int64_t ptrb200_ffnet_workspace_bytes(const ptrb200_ffnet* net, int B, int n);
 /* forward: X[B,n,dims[0]] -> out[B,n,dims[last]].  `workspace` keeps pre-activations and
  * statistics for ptrb200_ffnet_backward.  dropout uses Philox keyed by (seed, offset). */
 int ptrb200_ffnet_forward(const ptrb200_ffnet* net, const float* X, float* out, void* workspace,
-                          int64_t workspace_bytes, int B, int n, int training,
+                          int64_t workspace_bytes, int B, int n, const int32_t* offsets, int total_rows, int training,
                           uint64_t seed, uint64_t offset, ptrb200_stream_t stream);
 
 /* backward: dOut[B,n,dims[last]] -> parameter grads (+ dX[B,n,dims[0]] when dX != NULL).
  * Must follow a forward call with the same net/X/workspace/seed/offset. */
 int ptrb200_ffnet_backward(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grads, const float* X,
                            const float* dOut, float* dX, void* workspace, int64_t workspace_bytes,
-                           int B, int n, int training, uint64_t seed, uint64_t offset,
+                           int B, int n, const int32_t* offsets, int total_rows, int training, uint64_t seed, uint64_t offset,
                            ptrb200_stream_t stream);
 
 /* ---- optimizer step ---------------------------------------------------------------------- */

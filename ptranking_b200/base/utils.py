@@ -83,9 +83,8 @@ class StackedFFNet(nn.Module):
     def forward(self, X, offsets=None, max_len=None):
         """[B,n,F] (or [rows,F]) -> [B,n,out].  ``offsets``/``max_len`` describe a ragged batch ([total_docs,F] rows cut
         into queries): batch-level BN and norm-free nets see one long list; per-query BN2 needs the query boundaries."""
-        if offsets is not None and self.spec.norm == "BN2":
-            raise NotImplementedError("ragged batches with per-query BN2 normalisation: use BN / no norm, or dense batches")
-        squeeze = X.dim() == 2
+        ragged_bn2 = offsets is not None and self.spec.norm == "BN2"       # per-query statistics need the boundaries
+        squeeze = X.dim() == 2 and not ragged_bn2
         if squeeze:
             X = X.unsqueeze(0)
         # when every parameter already owns gradient storage (the ranker's flat bucket), the backward kernels write
@@ -94,6 +93,11 @@ class StackedFFNet(nn.Module):
         if torch.is_grad_enabled() and all(p.grad is not None and p.grad.is_contiguous() for p in self._order) \
                 and getattr(self, "write_through_grads", False):
             targets = [p.grad for p in self._order]
+        if ragged_bn2:
+            if X.dim() != 2:
+                raise ValueError("a ragged batch is [total_docs, F]")
+            return ops.ffnet_apply(X, self.spec, self._order, training=self.training, grad_targets=targets,
+                                   offsets=offsets, max_len=max_len)
         out = ops.ffnet_apply(X, self.spec, self._order, training=self.training, grad_targets=targets)
         return out.squeeze(0) if squeeze else out
 

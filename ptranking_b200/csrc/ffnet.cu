@@ -609,6 +609,7 @@ struct Plan {
     LayerPlan layer[PTRB200_MAX_FF_LAYERS];
     size_t partials_off, s1_off, s2_off, t1_off, t2_off, dbuf0_off, dbuf1_off, wpart_off, k1_off, k3_off, k0_off, sync_off, total;
     bool sync_bn;                                // batch-level BN statistics all-reduced across data-parallel ranks
+    bool ragged;                                 // per-query BN2 over a ragged batch (query boundaries from prefix offsets)
 };
 
 // column blocking of the weight gradient: dZ columns in blocks of 128 (MMA M), input columns in blocks of <= 256 (MMA N)
@@ -623,13 +624,17 @@ static WgBlocks wgrad_blocks(int N, int K) {
     return b;
 }
 
-static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p) {
-    if (!net || B <= 0 || n <= 0) { set_error("ffnet: null net or non-positive B/n"); return PTRB200_ERR_INVALID; }
+static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p, int total_rows = 0) {
+    if (!net || B <= 0 || n <= 0 || total_rows < 0) { set_error("ffnet: null net or non-positive B/n"); return PTRB200_ERR_INVALID; }
     if (net->num_linear < 1 || net->num_linear > PTRB200_MAX_FF_LAYERS) { set_error("ffnet: num_linear=%d outside 1..%d", net->num_linear, PTRB200_MAX_FF_LAYERS); return PTRB200_ERR_INVALID; }
     if (net->norm < PTRB200_NORM_NONE || net->norm > PTRB200_NORM_BN2) { set_error("ffnet: bad norm %d", net->norm); return PTRB200_ERR_INVALID; }
     if (!(net->dropout_p >= 0.0f && net->dropout_p < 1.0f)) { set_error("ffnet: dropout_p must be in [0,1)"); return PTRB200_ERR_INVALID; }
     p.L = net->num_linear;
-    p.rows = (size_t)B * n;
+    // total_rows > 0: a ragged batch -- B queries cut out of total_rows documents by prefix offsets, n = longest list.
+    // Batch-level BN and norm-free nets see one long list of total_rows documents (the dense code path as is); per-query
+    // BN2 needs the query boundaries and takes the ragged path (forward_ragged / backward_ragged below).
+    p.ragged = total_rows > 0 && net->norm == PTRB200_NORM_BN2;
+    p.rows = total_rows > 0 ? (size_t)total_rows : (size_t)B * n;
     p.G = net->norm == PTRB200_NORM_BN2 ? B : 1;
     p.gr = net->norm == PTRB200_NORM_BN2 ? n : (int)p.rows;
     if (net->math_mode < PTRB200_MATH_SIMT || net->math_mode > PTRB200_MATH_BF16) { set_error("ffnet: bad math_mode %d", net->math_mode); return PTRB200_ERR_INVALID; }
@@ -658,6 +663,8 @@ static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p) {
         p.ntiles = p.group_rows > 0 ? B * p.tiles_per_group : (int)((p.rows + p.tile_rows - 1) / p.tile_rows);
         p.wg_rows = 32; p.wg_grid = 444;
     }
+    if (p.ragged && !p.use_tc) { set_error("ffnet: ragged BN2 batches need the tensor-core path (layer widths multiples of 4)"); return PTRB200_ERR_UNSUPPORTED; }
+    if (p.ragged) { p.tile_rows = 128; p.seg_len = 128; p.group_rows = 0; p.tiles_per_group = 0; p.ntiles = (int)((p.rows + 127) / 128); p.S_stat = 1; p.slice_rows = (int)p.rows; }
     if (p.sync_bn && !p.use_tc) { set_error("ffnet: sync_bn needs the tensor-core path (layer widths multiples of 4)"); return PTRB200_ERR_UNSUPPORTED; }
     if (p.sync_bn && !g_hook) { set_error("ffnet: sync_bn needs an all-reduce hook (ptrb200_set_hook)"); return PTRB200_ERR_INVALID; }
     p.k_chunk = 2048; p.S_w = (int)((p.rows + 2047) / 2048);
@@ -674,7 +681,7 @@ static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p) {
         lp.has_norm = lp.has_act && net->norm != PTRB200_NORM_NONE;
         if (lp.has_norm && net->norm == PTRB200_NORM_BN2 && (!net->gamma[l] || !net->beta[l])) { set_error("ffnet: BN2 layer %d needs gamma/beta", l); return PTRB200_ERR_INVALID; }
         lp.z_off = off; off = align_up(off + p.rows * lp.d_out * 4, 256);
-        lp.a_off = off; if (l < p.L - 1 && !p.use_tc) off = align_up(off + p.rows * lp.d_out * 4, 256);
+        lp.a_off = off; if (l < p.L - 1 && (!p.use_tc || p.ragged)) off = align_up(off + p.rows * lp.d_out * 4, 256);
         lp.mean_off = off; lp.rstd_off = off; lp.scale_off = off; lp.shift_off = off;
         lp.img_f_hi = lp.img_f_lo = lp.img_d_hi = lp.img_d_lo = lp.ain_off = off;
         if (lp.has_norm) {
@@ -809,6 +816,7 @@ static bool rows_ws_fits(int K, int N, int passes) {
 static int launch_rows_gemm(int mode, int passes, RowsGemmArgs& g, int ntiles, cudaStream_t st,
                             int stats_kind = 0, int* S_out = nullptr, int S_default = 1) {
     g.NP = ((g.N + 15) / 16) * 16;
+    { static const int no_partial = getenv("PTRB200_NO_PARTIAL") ? 1 : 0; g.no_partial = no_partial; }
     int rc;
     const int nchunks = (g.K + 31) / 32;
     // ---- persistent warp-specialised kernel when the whole weight image fits beside the A ring ----
@@ -875,6 +883,249 @@ static void set_prologue(const ptrb200_ffnet* net, const Plan& p, int l, char* w
     scale = prev.has_norm ? reinterpret_cast<const float*>(ws + prev.scale_off) : nullptr;
     shift = prev.has_norm ? reinterpret_cast<const float*>(ws + prev.shift_off) : nullptr;
     act = prev.has_act ? prev.act : PTRB200_AF_NONE;
+}
+
+// ------------------------------------------------------------------ per-query BN2 over a ragged batch
+// LTRBatchNorm2 (base/utils.py:227-282) normalises every query over its own documents.  With per-query offsets one CTA
+// owns one query (32 channel lanes x 8 row lanes), so moments, dY sums and the normalisation backward need no cross-CTA
+// reduction; the Linear contractions run on the same tcgen05 kernels in their plain (no fused prologue) form.
+__global__ void __launch_bounds__(256) bn2_ragged_moments_kernel(const float* __restrict__ Z, const int32_t* __restrict__ offsets,
+                                                                  float* __restrict__ mean, float* __restrict__ rstd, int C) {
+    __shared__ double sh1[8][33], sh2[8][33];
+    const int g = blockIdx.x, r0 = offsets[g], n = offsets[g + 1] - r0;
+    for (int cb = 0; cb < C; cb += 32) {
+        const int c = cb + threadIdx.x;
+        double s1 = 0.0, s2 = 0.0;
+        if (c < C)
+            for (int r = threadIdx.y; r < n; r += 8) { const double z = (double)Z[(size_t)(r0 + r) * C + c]; s1 += z; s2 += z * z; }
+        sh1[threadIdx.y][threadIdx.x] = s1; sh2[threadIdx.y][threadIdx.x] = s2;
+        __syncthreads();
+        if (threadIdx.y == 0 && c < C) {
+            for (int y = 1; y < 8; ++y) { s1 += sh1[y][threadIdx.x]; s2 += sh2[y][threadIdx.x]; }
+            const double cnt = n > 0 ? (double)n : 1.0, m = s1 / cnt;
+            double var = s2 / cnt - m * m;
+            if (var < 0.0) var = 0.0;
+            mean[(size_t)g * C + c] = (float)m;
+            rstd[(size_t)g * C + c] = (float)(1.0 / sqrt(var + 1e-5));
+        }
+        __syncthreads();
+    }
+}
+
+// A = act(a * (z - mean_g) * rstd_g + c) for the documents of query g
+__global__ void __launch_bounds__(256) bn2_ragged_act_kernel(const float* __restrict__ Z, float* __restrict__ A, NormRef nr,
+                                                              const int32_t* __restrict__ offsets, int C) {
+    const int g = blockIdx.x, r0 = offsets[g], n = offsets[g + 1] - r0;
+    for (int c = threadIdx.x; c < C; c += 32) {
+        float a, cc;
+        norm_coeffs(nr, c, a, cc);
+        const float mu = nr.mean[(size_t)g * C + c], rs = nr.rstd[(size_t)g * C + c];
+        for (int r = threadIdx.y; r < n; r += 8) {
+            const size_t off = (size_t)(r0 + r) * C + c;
+            A[off] = activate(nr.act, a * ((Z[off] - mu) * rs) + cc).y;
+        }
+    }
+}
+
+// dY = dA * act'(Y) (written) and, per (query, channel), S1 = sum dY, S2 = sum dY * xhat -> partials[g][c][2]
+__global__ void __launch_bounds__(256) bn2_ragged_dy_kernel(const float* __restrict__ Z, const float* __restrict__ dA, float* __restrict__ dY,
+                                                             NormRef nr, const int32_t* __restrict__ offsets, double* __restrict__ partials, int C) {
+    __shared__ double sh1[8][33], sh2[8][33];
+    const int g = blockIdx.x, r0 = offsets[g], n = offsets[g + 1] - r0;
+    for (int cb = 0; cb < C; cb += 32) {
+        const int c = cb + threadIdx.x;
+        double s1 = 0.0, s2 = 0.0;
+        if (c < C) {
+            float a, cc;
+            norm_coeffs(nr, c, a, cc);
+            const float mu = nr.mean[(size_t)g * C + c], rs = nr.rstd[(size_t)g * C + c];
+            for (int r = threadIdx.y; r < n; r += 8) {
+                const size_t off = (size_t)(r0 + r) * C + c;
+                const float xh = (Z[off] - mu) * rs;
+                const float dy = dA[off] * activate(nr.act, a * xh + cc).dy;
+                dY[off] = dy;
+                s1 += (double)dy; s2 += (double)dy * (double)xh;
+            }
+        }
+        sh1[threadIdx.y][threadIdx.x] = s1; sh2[threadIdx.y][threadIdx.x] = s2;
+        __syncthreads();
+        if (threadIdx.y == 0 && c < C) {
+            for (int y = 1; y < 8; ++y) { s1 += sh1[y][threadIdx.x]; s2 += sh2[y][threadIdx.x]; }
+            double* p = partials + ((size_t)g * C + c) * 2;
+            p[0] = s1; p[1] = s2;
+        }
+        __syncthreads();
+    }
+}
+
+// dZ = a * rstd_g * (dY - S1_g / n_g - xhat * S2_g / n_g), in place over dY
+__global__ void __launch_bounds__(256) bn2_ragged_apply_kernel(const float* __restrict__ Z, float* __restrict__ dY, NormRef nr,
+                                                                const float* __restrict__ S1, const float* __restrict__ S2,
+                                                                const int32_t* __restrict__ offsets, int C) {
+    const int g = blockIdx.x, r0 = offsets[g], n = offsets[g + 1] - r0;
+    const float invN = n > 0 ? 1.0f / (float)n : 0.0f;
+    for (int c = threadIdx.x; c < C; c += 32) {
+        float a, cc;
+        norm_coeffs(nr, c, a, cc);
+        const float mu = nr.mean[(size_t)g * C + c], rs = nr.rstd[(size_t)g * C + c];
+        const float s1 = S1[(size_t)g * C + c] * invN, s2 = S2[(size_t)g * C + c] * invN;
+        for (int r = threadIdx.y; r < n; r += 8) {
+            const size_t off = (size_t)(r0 + r) * C + c;
+            const float xh = (Z[off] - mu) * rs;
+            dY[off] = a * rs * (dY[off] - s1 - xh * s2);
+        }
+    }
+}
+
+static int forward_ragged(const ptrb200_ffnet* net, const Plan& p, const float* X, const int32_t* offsets, float* out, char* ws,
+                          float drop, uint64_t seed, uint64_t offset, cudaStream_t st, bool fwd_only) {
+    int rc;
+    {   // operand images of every weight matrix (forward W, and W^T for the data gradients)
+        PackJobs jobs{};
+        int nj = 0, max_units = 0;
+        for (int l = 0; l < p.L; ++l) {
+            const LayerPlan& lp = p.layer[l];
+            for (int tr = 0; tr < (fwd_only ? 1 : 2); ++tr) {
+                if (tr == 1 && (l == 0 || lp.d_out % 4 != 0)) continue;
+                PackJob& j = jobs.job[nj++];
+                j.round_bf16 = p.bf16;
+                j.src = net->weight[l]; j.src_cols = lp.d_in; j.transpose = tr;
+                j.N = tr ? lp.d_in : lp.d_out; j.K = tr ? lp.d_out : lp.d_in;
+                j.NP = ((j.N + 15) / 16) * 16; j.nchunks = (j.K + 31) / 32;
+                j.img_hi = reinterpret_cast<unsigned char*>(ws + (tr ? lp.img_d_hi : lp.img_f_hi));
+                j.img_lo = p.passes == 3 ? reinterpret_cast<unsigned char*>(ws + (tr ? lp.img_d_lo : lp.img_f_lo)) : nullptr;
+                const int units = j.nchunks * j.NP * 8;
+                max_units = units > max_units ? units : max_units;
+            }
+        }
+        PTRB200_LAUNCH(pack_b_images_kernel, dim3((max_units + 255) / 256, nj), 256, 0, st, jobs);
+    }
+    const float* in = X;
+    for (int l = 0; l < p.L; ++l) {
+        const LayerPlan& lp = p.layer[l];
+        const bool last = l == p.L - 1;
+        const bool bare = !lp.has_act && !lp.has_norm;
+        float* Z = (last && bare) ? out : reinterpret_cast<float*>(ws + lp.z_off);
+        RowsGemmArgs g{};
+        g.round_bf16 = p.bf16;
+        g.P = in; g.scale = g.shift = nullptr; g.act = PTRB200_AF_NONE; g.gr_prev = (int)p.rows;
+        g.drop = make_drop(last ? 0.0f : drop, seed, offset * 64 + (uint64_t)l);
+        g.bias = net->bias[l]; g.Out = Z;
+        g.a_out = (l > 0 && !fwd_only) ? reinterpret_cast<float*>(ws + lp.ain_off) : nullptr;     // dropout(A_{l-1}) for the weight gradient
+        g.partials = nullptr;
+        g.rows = (int)p.rows; g.K = lp.d_in; g.N = lp.d_out;
+        g.b_img_hi = reinterpret_cast<unsigned char*>(ws + lp.img_f_hi);
+        g.b_img_lo = p.passes == 3 ? reinterpret_cast<unsigned char*>(ws + lp.img_f_lo) : nullptr;
+        g.tile_rows = 128; g.seg_len = 128; g.group_rows = 0; g.tiles_per_group = 0;
+        if ((rc = launch_rows_gemm(RG_FWD, p.passes, g, p.ntiles, st, 0, nullptr, 1))) return rc;
+        if (bare) { in = Z; continue; }
+        NormRef nr = norm_ref(net, p, l, ws);
+        if (lp.has_norm)
+            PTRB200_LAUNCH(bn2_ragged_moments_kernel, p.G, dim3(32, 8), 0, st, (const float*)Z, offsets,
+                           reinterpret_cast<float*>(ws + lp.mean_off), reinterpret_cast<float*>(ws + lp.rstd_off), lp.d_out);
+        float* A = last ? out : reinterpret_cast<float*>(ws + lp.a_off);
+        if (lp.has_norm) PTRB200_LAUNCH(bn2_ragged_act_kernel, p.G, dim3(32, 8), 0, st, (const float*)Z, A, nr, offsets, lp.d_out);
+        else { const size_t total = p.rows * lp.d_out; PTRB200_LAUNCH(norm_act_fwd_kernel, elementwise_blocks(total), 256, 0, st, (const float*)Z, A, nr, total, lp.d_out, (int)p.rows); }
+        in = A;
+    }
+    return check_launch("ffnet_forward(ragged)");
+}
+
+static int backward_ragged(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grads, const Plan& p, const float* X, const int32_t* offsets,
+                           const float* dOut, float* dX, char* ws, float drop, uint64_t seed, uint64_t offset, cudaStream_t st) {
+    int rc;
+    double* part = reinterpret_cast<double*>(ws + p.partials_off);
+    float* S1 = reinterpret_cast<float*>(ws + p.s1_off);
+    float* S2 = reinterpret_cast<float*>(ws + p.s2_off);
+    float* dbuf[2] = {reinterpret_cast<float*>(ws + p.dbuf0_off), reinterpret_cast<float*>(ws + p.dbuf1_off)};
+    float* wpart = reinterpret_cast<float*>(ws + p.wpart_off);
+    const float* dA = dOut;
+    int flip = 0;
+    for (int l = p.L - 1; l >= 0; --l) {
+        const LayerPlan& lp = p.layer[l];
+        const bool last = l == p.L - 1;
+        if (!grads->weight[l] || !grads->bias[l]) { set_error("ffnet_backward: layer %d grad buffers NULL", l); return PTRB200_ERR_INVALID; }
+        const float* Z = reinterpret_cast<const float*>(ws + lp.z_off);
+        const float* dZ = dA;
+        NormRef nr = norm_ref(net, p, l, ws);
+        if (lp.has_norm) {
+            float* dY = dbuf[flip]; flip ^= 1;
+            PTRB200_LAUNCH(bn2_ragged_dy_kernel, p.G, dim3(32, 8), 0, st, Z, dA, dY, nr, offsets, part, lp.d_out);
+            DyTail tail{};
+            tail.nr = nr; tail.gr = 1;
+            tail.bias_grad = grads->bias[l]; tail.bias_mode = 1;
+            tail.dgamma = grads->gamma[l]; tail.dbeta = grads->beta[l];
+            if (net->norm_affine) { tail.daff_w = grads->aff_w[l]; tail.daff_b = grads->aff_b[l]; }
+            PTRB200_LAUNCH(dy_finalize_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)part, S1, S2, (float*)nullptr, (float*)nullptr, p.G, lp.d_out, 1, tail);
+            PTRB200_LAUNCH(bn2_ragged_apply_kernel, p.G, dim3(32, 8), 0, st, Z, dY, nr, (const float*)S1, (const float*)S2, offsets, lp.d_out);
+            dZ = dY;
+        } else if (lp.has_act) {          // activation without a norm (not produced by get_stacked_FFNet with BN2, kept for completeness)
+            float* dY = dbuf[flip]; flip ^= 1;
+            launch_colstat<STAT_DY>(st, "colstat_dy", Z, dA, dY, nr, part, 1, 1, (int)p.rows, lp.d_out, (int)p.rows);
+            DyTail tail{};
+            tail.nr = nr; tail.gr = (int)p.rows; tail.bias_grad = grads->bias[l]; tail.bias_mode = 2;
+            PTRB200_LAUNCH(dy_finalize_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)part, (float*)nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr, 1, lp.d_out, 1, tail);
+            dZ = dY;
+        } else {                          // bare Linear: the bias gradient is the column sum of the incoming gradient
+            launch_colstat<STAT_COLSUM>(st, "colstat_colsum", dA, nullptr, nullptr, nr, part, 1, 1, (int)p.rows, lp.d_out, (int)p.rows);
+            PTRB200_LAUNCH(dy_finalize_kernel, lp.d_out, FIN_THREADS, 0, st, (const double*)part, (float*)nullptr, (float*)nullptr, grads->bias[l], (float*)nullptr, 1, lp.d_out, 1, DyTail{});
+        }
+        const float layer_drop = last ? 0.0f : drop;
+        {   // dW = sum_rows dZ^T (x) dropout(layer input)
+            WgradArgs w{};
+            w.round_bf16 = p.bf16;
+            w.dZ = dZ;
+            w.scale = w.shift = nullptr; w.act = PTRB200_AF_NONE; w.gr_prev = (int)p.rows;
+            if (l == 0) { w.P = X; w.drop = make_drop(layer_drop, seed, offset * 64 + (uint64_t)l); }
+            else { w.P = reinterpret_cast<const float*>(ws + lp.ain_off); w.drop = make_drop(0.0f, 0, 0); }
+            w.partials = wpart;
+            const WgBlocks wb = wgrad_blocks(lp.d_out, lp.d_in);
+            w.rows = (int)p.rows; w.N_full = lp.d_out; w.K_full = lp.d_in; w.kb = wb.kb;
+            w.N = lp.d_out < 128 ? lp.d_out : 128; w.K = wb.kb;
+            w.KP = ((w.K + 15) / 16) * 16;
+            w.tile_rows = p.wg_rows;
+            { static const int no_partial = getenv("PTRB200_NO_PARTIAL") ? 1 : 0; w.no_partial = no_partial; }
+            const size_t smem = wgrad_smem(w.N, w.K, w.KP, w.tile_rows, p.passes, w.stages, false, 8);
+            const dim3 grid(wb.gx, wb.mblocks, wb.kblocks);
+            if (p.passes == 3) { if ((rc = opt_in_smem(wgrad_tc_kernel<3>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<3>, grid, WG_THREADS, smem, st, w); }
+            else { if ((rc = opt_in_smem(wgrad_tc_kernel<1>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<1>, grid, WG_THREADS, smem, st, w); }
+            const int cnt = lp.d_in * lp.d_out;
+            PTRB200_LAUNCH(reduce_splits_kernel, (cnt + 63) / 64, 256, 0, st, (const float*)wpart, grads->weight[l], wb.gx, cnt);
+            if ((rc = call_hook(PTRB200_HOOK_LAYER_GRADS_READY, l, nullptr, 0, st))) return rc;
+        }
+        if (l > 0 || dX) {   // dIn = dropmask(dZ W)
+            float* dIn = l == 0 ? dX : dbuf[flip];
+            if (l > 0) flip ^= 1;
+            if (lp.d_out % 4 == 0) {
+                const int NPl = ((lp.d_in + 15) / 16) * 16, nch = (lp.d_out + 31) / 32;
+                unsigned char* ih = reinterpret_cast<unsigned char*>(ws + lp.img_d_hi);
+                unsigned char* il = p.passes == 3 ? reinterpret_cast<unsigned char*>(ws + lp.img_d_lo) : nullptr;
+                if (l == 0)
+                    PTRB200_LAUNCH(pack_b_image_kernel<true>, (nch * NPl * 8 + 255) / 256, 256, 0, st, net->weight[l], lp.d_out, lp.d_in, ih, il, lp.d_in, NPl, lp.d_out, nch, (int)p.bf16);
+                RowsGemmArgs g{};
+                g.round_bf16 = p.bf16;
+                g.P = dZ; g.scale = g.shift = nullptr; g.act = PTRB200_AF_NONE; g.gr_prev = (int)p.rows;
+                g.drop = make_drop(layer_drop, seed, offset * 64 + (uint64_t)l);
+                g.b_img_hi = ih; g.b_img_lo = il; g.bias = nullptr; g.Out = dIn; g.partials = nullptr;
+                g.rows = (int)p.rows; g.K = lp.d_out; g.N = lp.d_in;
+                g.tile_rows = 128; g.seg_len = 128; g.group_rows = 0; g.tiles_per_group = 0;
+                if ((rc = launch_rows_gemm(RG_DGRAD, p.passes, g, (int)((p.rows + 127) / 128), st, 0, nullptr, 1))) return rc;
+            } else if (lp.d_out == 1 && lp.d_in % 4 == 0) {
+                const size_t units = p.rows * (lp.d_in / 4);
+                PTRB200_LAUNCH(dgrad_rank1_kernel, elementwise_blocks(units), 256, 0, st, dZ, net->weight[l], dIn, units, lp.d_in,
+                               make_drop(layer_drop, seed, offset * 64 + (uint64_t)l), (int)p.bf16);
+            } else {
+                GemmArgs g{};
+                g.A = dZ; g.Bm = net->weight[l]; g.C = dIn;
+                g.rows = (int)p.rows; g.d_in = lp.d_in; g.d_out = lp.d_out;
+                g.M = (int)p.rows; g.N = lp.d_in; g.K = lp.d_out;
+                g.drop = make_drop(layer_drop, seed, offset * 64 + (uint64_t)l);
+                launch_gemm<GEMM_BWD_DATA>(g, 1, st);
+            }
+            dA = dIn;
+        }
+    }
+    return check_launch("ffnet_backward(ragged)");
 }
 
 static int forward_tc(const ptrb200_ffnet* net, const Plan& p, const float* X, float* out, char* ws,
@@ -1016,6 +1267,7 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
         {
             WgradArgs w{};
             w.round_bf16 = p.bf16;
+            { static const int no_partial = getenv("PTRB200_NO_PARTIAL") ? 1 : 0; w.no_partial = no_partial; }
             w.dZ = dZ;
             if (l == 0) {          // layer 0 input = dropout(X): rebuilt on the fly
                 w.P = X; w.scale = w.shift = nullptr; w.act = PTRB200_AF_NONE;
@@ -1124,23 +1376,25 @@ int ptrb200_tc_wgrad(const float* dZ, const float* P, float* dW, float* partials
     return check_launch("tc_wgrad");
 }
 
-int64_t ptrb200_ffnet_workspace_bytes(const ptrb200_ffnet* net, int B, int n) {
+int64_t ptrb200_ffnet_workspace_bytes(const ptrb200_ffnet* net, int B, int n, int total_rows) {
     Plan p;
-    const int rc = make_plan(net, B, n, p);
+    const int rc = make_plan(net, B, n, p, total_rows);
     return rc ? (int64_t)rc : (int64_t)p.total;
 }
 
 int ptrb200_ffnet_forward(const ptrb200_ffnet* net, const float* X, float* out, void* workspace,
-                          int64_t workspace_bytes, int B, int n, int training,
+                          int64_t workspace_bytes, int B, int n, const int32_t* offsets, int total_rows, int training,
                           uint64_t seed, uint64_t offset, ptrb200_stream_t stream) {
     Plan p;
-    int rc = make_plan(net, B, n, p);
+    if ((offsets != nullptr) != (total_rows > 0)) { set_error("ffnet_forward: offsets and total_rows go together (ragged batch) or are both absent"); return PTRB200_ERR_INVALID; }
+    int rc = make_plan(net, B, n, p, total_rows);
     if (rc) return rc;
     if (!X || !out || !workspace) { set_error("ffnet_forward: null buffer"); return PTRB200_ERR_INVALID; }
     if ((size_t)workspace_bytes < p.total) { set_error("ffnet_forward: workspace %lld < %zu bytes", (long long)workspace_bytes, p.total); return PTRB200_ERR_WORKSPACE; }
     char* ws = static_cast<char*>(workspace);
     cudaStream_t st = (cudaStream_t)stream;
     const float drop = (training & 1) ? net->dropout_p : 0.0f;
+    if (p.ragged) return forward_ragged(net, p, X, offsets, out, ws, drop, seed, offset, st, (training & PTRB200_FFNET_FORWARD_ONLY) != 0);
     if (p.use_tc) return forward_tc(net, p, X, out, ws, drop, seed, offset, st, (training & PTRB200_FFNET_FORWARD_ONLY) != 0);
     const float* in = X;
     for (int l = 0; l < p.L; ++l) {
@@ -1177,16 +1431,18 @@ int ptrb200_ffnet_forward(const ptrb200_ffnet* net, const float* X, float* out, 
 
 int ptrb200_ffnet_backward(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grads, const float* X,
                            const float* dOut, float* dX, void* workspace, int64_t workspace_bytes,
-                           int B, int n, int training, uint64_t seed, uint64_t offset,
+                           int B, int n, const int32_t* offsets, int total_rows, int training, uint64_t seed, uint64_t offset,
                            ptrb200_stream_t stream) {
     Plan p;
-    int rc = make_plan(net, B, n, p);
+    if ((offsets != nullptr) != (total_rows > 0)) { set_error("ffnet_backward: offsets and total_rows go together (ragged batch) or are both absent"); return PTRB200_ERR_INVALID; }
+    int rc = make_plan(net, B, n, p, total_rows);
     if (rc) return rc;
     if (!grads || !X || !dOut || !workspace) { set_error("ffnet_backward: null buffer"); return PTRB200_ERR_INVALID; }
     if ((size_t)workspace_bytes < p.total) { set_error("ffnet_backward: workspace %lld < %zu bytes", (long long)workspace_bytes, p.total); return PTRB200_ERR_WORKSPACE; }
     char* ws = static_cast<char*>(workspace);
     cudaStream_t st = (cudaStream_t)stream;
     const float drop = (training & 1) ? net->dropout_p : 0.0f;
+    if (p.ragged) return backward_ragged(net, grads, p, X, offsets, dOut, dX, ws, drop, seed, offset, st);
     if (p.use_tc) return backward_tc(net, grads, p, X, dOut, dX, ws, drop, seed, offset, st);
     double* part = reinterpret_cast<double*>(ws + p.partials_off);
     float* S1 = reinterpret_cast<float*>(ws + p.s1_off);

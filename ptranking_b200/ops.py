@@ -451,26 +451,36 @@ class FFNetSpec:
 class _FFNetFn(torch.autograd.Function):
     @staticmethod
     @_on_tensor_device
-    def forward(ctx, X, spec: FFNetSpec, training: bool, seed: int, offset: int, grad_targets, need_backward, *params):
+    def forward(ctx, X, spec: FFNetSpec, training: bool, seed: int, offset: int, grad_targets, need_backward, ragged, *params):
         lib = _lib.load()
         X = _dev_f32(X, "X")
-        B, n, F = X.shape
+        if ragged is None:          # dense [B,n,F]
+            B, n, F = X.shape
+            offsets, op, total = None, None, 0
+            out_shape = (B, n, spec.dims[-1])
+        else:                       # ragged: [total_docs, F] rows cut into queries by int32 prefix offsets
+            offsets, n = ragged
+            offsets = offsets.to(device=X.device, dtype=torch.int32).contiguous()
+            total, F = X.shape
+            B, op = offsets.numel() - 1, offsets.data_ptr()
+            out_shape = (total, spec.dims[-1])
         if F != spec.dims[0]:
             raise ValueError(f"feature width {F} != net input width {spec.dims[0]}")
         params = [p.detach().contiguous() for p in params]
         desc = spec.describe(params)
-        nbytes = lib.ptrb200_ffnet_workspace_bytes(C.byref(desc), B, n)
+        nbytes = lib.ptrb200_ffnet_workspace_bytes(C.byref(desc), B, n, total)
         if nbytes < 0:
             _lib.check(int(nbytes), "ffnet_workspace_bytes")
         ws = torch.empty(int(nbytes), dtype=torch.uint8, device=X.device)
-        out = torch.empty((B, n, spec.dims[-1]), dtype=torch.float32, device=X.device)
+        out = torch.empty(out_shape, dtype=torch.float32, device=X.device)
         # bit 1 = forward only (PTRB200_FFNET_FORWARD_ONLY): no backward will follow (nothing requires grad, or the
         # caller runs under torch.no_grad()), so the by-products the backward pass reads are not written
         flags = int(training) | (0 if need_backward else 2)
         with _b200dist().call_context(ws, None):
             _lib.check(lib.ptrb200_ffnet_forward(C.byref(desc), X.data_ptr(), out.data_ptr(), ws.data_ptr(), int(nbytes),
-                                                 B, n, flags, seed, offset, _stream_ptr()), "ffnet_forward")
+                                                 B, n, op, total, flags, seed, offset, _stream_ptr()), "ffnet_forward")
         ctx.spec, ctx.training, ctx.seed, ctx.offset = spec, training, seed, offset
+        ctx.shape = (B, n, offsets, total)
         ctx.grad_targets = grad_targets
         ctx.ws, ctx.nbytes = (ws if need_backward else None), int(nbytes)
         ctx.need_dx = X.requires_grad
@@ -483,7 +493,7 @@ class _FFNetFn(torch.autograd.Function):
         lib = _lib.load()
         X, *params = ctx.saved_tensors
         spec = ctx.spec
-        B, n, _ = X.shape
+        B, n, offsets, total = ctx.shape
         desc = spec.describe(params)
         gdesc, gouts = spec.grads(params, ctx.grad_targets)
         d_out = _dev_f32(d_out, "d_out")
@@ -499,24 +509,32 @@ class _FFNetFn(torch.autograd.Function):
         with _b200dist().call_context(ctx.ws, layer_targets):
             _lib.check(lib.ptrb200_ffnet_backward(C.byref(desc), C.byref(gdesc), X.data_ptr(), d_out.data_ptr(),
                                                   dX.data_ptr() if dX is not None else None, ctx.ws.data_ptr(), ctx.nbytes,
-                                                  B, n, int(ctx.training), ctx.seed, ctx.offset, _stream_ptr()),
+                                                  B, n, offsets.data_ptr() if offsets is not None else None, total,
+                                                  int(ctx.training), ctx.seed, ctx.offset, _stream_ptr()),
                        "ffnet_backward")
         ctx.ws = None
         if ctx.grad_targets is not None:            # written straight into the parameters' .grad storage
-            return (dX, None, None, None, None, None, None, *([None] * len(gouts)))
-        return (dX, None, None, None, None, None, None, *gouts)
+            return (dX, None, None, None, None, None, None, None, *([None] * len(gouts)))
+        return (dX, None, None, None, None, None, None, None, *gouts)
 
 
 def ffnet_apply(X: torch.Tensor, spec: FFNetSpec, params: Sequence[torch.Tensor], training: bool,
-                seed: Optional[int] = None, offset: Optional[int] = None, grad_targets=None) -> torch.Tensor:
+                seed: Optional[int] = None, offset: Optional[int] = None, grad_targets=None,
+                offsets: Optional[torch.Tensor] = None, max_len: Optional[int] = None) -> torch.Tensor:
     """[B,n,F] -> [B,n,out] through the fused stacked-FF kernels (differentiable).  ``grad_targets``: tensors the
-    parameter gradients are written into directly (each parameter must be used by exactly one call per step)."""
+    parameter gradients are written into directly (each parameter must be used by exactly one call per step).
+    ``offsets``/``max_len``: X is a ragged batch [total_docs, F] -> [total_docs, out] (per-query BN2 uses the boundaries)."""
     if seed is None:
         seed = torch.initial_seed() & (2 ** 64 - 1)
     if offset is None:
         offset = next_dropout_offset()
     need_backward = torch.is_grad_enabled() and (X.requires_grad or any(p.requires_grad for p in params))
-    return _FFNetFn.apply(X, spec, bool(training), int(seed), int(offset), grad_targets, bool(need_backward), *params)
+    ragged = None
+    if offsets is not None:
+        if X.dim() != 2 or max_len is None:
+            raise ValueError("a ragged batch is [total_docs, F] with offsets= and max_len=")
+        ragged = (offsets, max(int(max_len), 1))
+    return _FFNetFn.apply(X, spec, bool(training), int(seed), int(offset), grad_targets, bool(need_backward), ragged, *params)
 
 
 # --------------------------------------------------------------------------- #

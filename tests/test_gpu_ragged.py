@@ -221,3 +221,65 @@ def test_ragged_train_step_matches_oracle(model, paras):
     assert np.abs(nd.numpy() - want.numpy()).max() <= 1e-5
     nd10 = r.ndcg_at_k(test_data=loader, k=10, label_type=LABEL_TYPE.MultiLabel, presort=True)
     assert np.isfinite(nd10.numpy()).all()
+
+
+@pytest.mark.parametrize("cfg", ["bn2_relu", "bn2_aff_celu", "bn2_gelu_drop0"])
+def test_ragged_bn2_scorer_matches_oracle_per_query(cfg):
+    """Per-query BN2 (LTRBatchNorm2, base/utils.py:227-282) over a ragged batch: scores and every parameter gradient equal
+    the oracle scoring each query alone (its statistics span that query's documents only) with gradients summed."""
+    import ptranking_b200
+    from tests.test_oracle_vs_golden import POINT_CFGS, point_cfg
+    over = dict(POINT_CFGS[cfg]) if cfg in POINT_CFGS else dict(AF="GE", TL_AF="S", bn_type="BN2", bn_affine=True, num_layers=3)
+    F = 136
+    lens = [50, 7, 130, 33, 1, 64, 260]
+    off = np.zeros(len(lens) + 1, dtype=np.int32); off[1:] = np.cumsum(lens)
+    total = int(off[-1])
+    sf = dict(sf_id="pointsf", opt="Adam", lr=1e-3, pointsf=point_cfg(F, **over))
+    torch.manual_seed(2)
+    r = ptranking_b200.ListNet(sf_para_dict=sf, gpu=True, device=DEV)
+    r.init(); r.eval_mode()
+    with torch.no_grad():                      # perturb the norm parameters off their init point
+        for k, p in r.point_sf.named_parameters():
+            if "bn" in k:
+                p.add_(0.1 * torch.randn_like(p))
+    net = rp.point_scorer(**sf["pointsf"])
+    net.load_state_dict({k: v.cpu() for k, v in r.point_sf.state_dict().items()})
+    net.eval()
+    g = torch.Generator().manual_seed(5)
+    X = torch.randn(total, F, generator=g); w = torch.randn(total, generator=g)
+    offd = torch.from_numpy(off).to(DEV)
+    s = r.forward_ragged(X.to(DEV), offd, max(lens))
+    assert s.shape == (total,)
+    r.grad_bucket.zero()
+    (s * w.to(DEV)).sum().backward()
+    want = []
+    for b in range(len(lens)):
+        sq = rp.point_forward(net, X[off[b]: off[b + 1]][None]).view(-1)
+        (sq * w[off[b]: off[b + 1]]).sum().backward()          # parameter gradients accumulate over the queries
+        want.append(sq.detach())
+    want = torch.cat(want).numpy()
+    # a one-document query has zero variance: the normalised value is 0/sqrt(eps) on both sides
+    assert rel_err(s.detach().cpu().numpy(), want) <= 2e-5
+    gscale = max(float(p.grad.abs().max()) for p in net.parameters())
+    for (k, p), q in zip(r.point_sf.named_parameters(), net.parameters()):
+        err = float((p.grad.cpu() - q.grad).abs().max())
+        assert err <= 3e-5 * float(q.grad.abs().max()) + 2e-6 * gscale + 1e-9, (k, err, float(q.grad.abs().max()), gscale)
+
+
+def test_ragged_bn2_equals_dense_bn2_on_uniform_lengths():
+    import ptranking_b200
+    from tests.test_oracle_vs_golden import point_cfg
+    F, B, n = 136, 6, 96
+    sf = dict(sf_id="pointsf", opt="Adam", lr=1e-3, pointsf=point_cfg(F, bn_type="BN2", bn_affine=True, num_layers=3, dropout=0.1))
+    torch.manual_seed(2)
+    r = ptranking_b200.ListNet(sf_para_dict=sf, gpu=True, device=DEV)
+    r.init(); r.train_mode()                   # dropout ON: the ragged path must draw the same counter-based masks
+    X = torch.randn(B, n, F, generator=torch.Generator().manual_seed(1)).to(DEV)
+    off = torch.arange(0, B * n + 1, n, dtype=torch.int32, device=DEV)
+    torch.manual_seed(9)
+    from ptranking_b200 import ops
+    o0 = ops._dropout_offset
+    a = r.forward(X)
+    ops._dropout_offset = o0                   # same dropout stream for the second call
+    b = r.forward_ragged(X.reshape(B * n, F), off, n)
+    assert rel_err(b.detach().cpu().numpy(), a.detach().cpu().numpy().reshape(-1)) <= 1e-5
