@@ -7,7 +7,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 os.makedirs(P, exist_ok=True)
 
 # ---- launch list: the last full step ------------------------------------------------
@@ -43,10 +43,16 @@ WANT = [("gpu__time_duration.sum", "duration us"), ("dram__bytes_read.sum", "dra
         ("launch__shared_mem_per_block_dynamic", "dyn smem KB")]
 traffic = {}
 NAME_MAP = {"rows_gemm_ws_kernel<0,": "rows_gemm_ws_fwd", "rows_gemm_ws_kernel<1,": "rows_gemm_ws_dgrad", "wgrad_tc_kernel": "wgrad_tc",
-            "colstat4_kernel<1>": "colstat_dy", "norm_bwd_apply4_kernel": "norm_bwd_apply4_kernel", "pairwise_bce_": "pairwise_bce_kernel<LAMBDA>"}
+            "colstat4_kernel<1>": "colstat_dy", "norm_bwd_apply4_kernel": "norm_bwd_apply4_kernel", "pairwise_bce_": "pairwise_bce_kernel<LAMBDA>",
+            "approxndcg_kernel": "approxndcg_kernel", "lambdaloss_kernel": "lambdaloss_kernel", "listmle_kernel": "listmle_kernel"}
+# file-name tag -> key of traffic.json for kernels that share one C++ name (the batched attention GEMM)
+FILE_MAP = {"full_c_attn_qk": "attn_tc_qk", "full_c_attn_pv": "attn_tc_pv", "full_c_softmax": "softmax_rows_kernel",
+            "full_c_softmax_bwd": "softmax_bwd_rows_kernel", "full_c_rows_gemm_tc": "rows_gemm_tc_fwd"}
+WHAT = {"full_b": "config b (LambdaRank + pointwise MLP, B=1024 x 256 x 136)", "full_c": "config c (ApproxNDCG + list scorer L=3, B=64 x 512 x 136)",
+        "full_d": "config d (LambdaLoss, B=256 x 1024 x 136)", "full_e": "config e (ListMLE bf16, B=1024 x 256 x 136)"}
 with open(os.path.join(P, f"{tag}_kernels_full.md"), "w") as f:
     f.write(f"# {tag}: `ncu --set full --clock-control none --import-source on` of the heavy kernels\n\n")
-    f.write("One launch each from the second training step (B=1024 x 256 x 136).  dram bytes are per launch.\n\n")
+    f.write("One launch each from the second training step of the named bench configuration (`tools/profile_r02.sh`).  dram bytes are per launch.\n\n")
     for fn in sorted(os.listdir(G)):
         if not (fn.startswith("full_") and fn.endswith("_raw.csv")):
             continue
@@ -56,7 +62,8 @@ with open(os.path.join(P, f"{tag}_kernels_full.md"), "w") as f:
         h = rws[0]
         for r in rws[2:]:
             kn = r[h.index("Kernel Name")]
-            f.write(f"## `{kn[:110]}`\n\n| metric | value |\n|---|---|\n")
+            what = next((v for k, v in WHAT.items() if fn.startswith(k)), "")
+            f.write(f"## `{kn[:110]}`\n\n{fn[:-8]} -- {what}\n\n| metric | value |\n|---|---|\n")
             for m, label in WANT:
                 if m in h:
                     f.write(f"| {label} | {r[h.index(m)]} |\n")
@@ -67,8 +74,12 @@ with open(os.path.join(P, f"{tag}_kernels_full.md"), "w") as f:
                 unit_r, unit_w = rws[1][h.index("dram__bytes_read.sum")], rws[1][h.index("dram__bytes_write.sum")]
                 scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
                 tb = mb(r[h.index("dram__bytes_read.sum")]) * scale.get(unit_r, 1e6) + mb(r[h.index("dram__bytes_write.sum")]) * scale.get(unit_w, 1e6)
-                for key, nm in NAME_MAP.items():
-                    if key in kn and nm not in traffic:
-                        traffic[nm] = tb
+                fkey = next((v for k, v in FILE_MAP.items() if fn.startswith(k)), None)
+                if fkey:
+                    traffic.setdefault(fkey, tb)
+                elif fn.startswith("full_b") or not fn.startswith("full_c"):
+                    for key, nm in NAME_MAP.items():
+                        if key in kn and nm not in traffic:
+                            traffic[nm] = tb
 json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
 print(traffic)
