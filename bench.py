@@ -456,7 +456,9 @@ def build_roofline(cfg, B, tm, steps_timed, ms_per_step):
         tens_ms = sum(v[1] for v in tens.values()) / steps_timed
         achieved = flops / (tens_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": achieved / tf32_peak, "traffic": traffic_tab.get(name),
+                "frac": achieved / tf32_peak,
+                # per-launch DRAM bytes from the committed captures of THIS configuration only (wgrad_tc's entry is config b's)
+                "traffic": traffic_tab.get(name) if (name.startswith("attn_tc") or name == "rows_gemm_tc_fwd") else None,
                 "peak_source": peaks["source"] + " (bf16 sustained / 2 = dense TF32)",
                 "share_of_step": kms / total_ms, "tensor_kernels_ms_per_step": tens_ms,
                 "issued_frac_3xtf32": 3 * achieved / tf32_peak,

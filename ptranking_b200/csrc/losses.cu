@@ -13,6 +13,7 @@
 //   ListMLE     ptranking/ltr_adhoc/listwise/listmle.py:83-97
 //   ApproxNDCG  ptranking/ltr_adhoc/listwise/approxNDCG.py:19-28,45-62
 //   nDCG@ks     ptranking/base/ranker.py:67-95, metric/adhoc/adhoc_metric.py:219-260
+#include <stdlib.h>
 #include "losses_common.cuh"
 
 namespace ptrb200 {
@@ -204,6 +205,78 @@ __global__ void pairwise_bce_circ_kernel(const float* __restrict__ scores, const
     if (mine) gout[idx[i]] = own;
     __syncthreads();
     for (int t = threadIdx.x; t < n; t += blockDim.x) grad[sp.base + t] = gout[t];
+    loss = block_sum(loss, red);
+    if (threadIdx.x == 0) loss_q[b] = loss;
+}
+
+// LambdaRank with the tie pairs left out.  The pair weight |G_a - G_b| |1/D_a - 1/D_b| is exactly zero whenever the two
+// labels are equal (39 % of all pairs under the MSLR-WEB30K label marginals), and such a pair then adds exactly +-0 to the
+// loss and to both gradients.  Labels arrive presorted descending (lambdarank.py:36), so equal labels form contiguous runs of
+// the ORIGINAL document order: thread i (= document i) visits precisely the documents [0, run_start(i)) -- all strictly
+// better labelled -- which enumerates every non-tie pair once, with trip counts that are uniform inside a warp (a warp lies
+// in one run except at run boundaries).  All lanes of a warp visit the same partner in the same step, so the partner's
+// share of the gradient is one fixed-order warp sum per step, accumulated in a per-warp row of shared memory (no atomics:
+// bit-for-bit deterministic).  Each pair is oriented by predicted rank exactly like the reference's upper triangle.
+__global__ void lambdarank_runs_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
+                                       float* __restrict__ grad, float* __restrict__ loss_q, const int32_t* __restrict__ offsets,
+                                       int nmax, int npow2max, float sigma) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64* keys = reinterpret_cast<u64*>(smem_raw);
+    float* ss = reinterpret_cast<float*>(keys + npow2max);     // by ORIGINAL index
+    float* ys = ss + nmax;
+    float* ng = ys + nmax;
+    float* dinv = ng + nmax;
+    int* rk = reinterpret_cast<int*>(dinv + nmax);              // predicted rank of document i
+    float* red = reinterpret_cast<float*>(rk + nmax);
+    float* part = red + 33;                                     // [warps][nmax] partner contributions
+    const int b = blockIdx.x, i = threadIdx.x, lane = i & 31, warp = i >> 5, nwarps = blockDim.x >> 5;
+    const ListSpan sp = list_span(offsets, b, nmax);
+    const int n = sp.n, npow2 = offsets ? next_pow2(n) : npow2max;
+    if (n == 0) { if (threadIdx.x == 0) loss_q[b] = 0.0f; return; }
+    const float* s = scores + sp.base;
+    const float* y = labels + sp.base;
+    const float idcg = block_idcg(y, n, npow2, /*presort=*/true, keys, red);
+    for (int t = threadIdx.x; t < npow2; t += blockDim.x) keys[t] = t < n ? desc_key(s[t], t) : 0ull;
+    block_sort_desc(keys, npow2);
+    for (int r = threadIdx.x; r < n; r += blockDim.x) rk[key_index(keys[r])] = r;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) { ss[t] = s[t]; const float yt = y[t]; ys[t] = yt; ng[t] = gain_of(yt) / idcg; }
+    for (int t = threadIdx.x; t < nwarps * nmax; t += blockDim.x) part[t] = 0.0f;
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) dinv[t] = 1.0f / log2_rank(rk[t]);
+    __syncthreads();
+    const bool mine = i < n;
+    const float si = mine ? ss[i] : 0.0f, yi = mine ? ys[i] : 0.0f, gi = mine ? ng[i] : 0.0f, di = mine ? dinv[i] : 0.0f;
+    const int ri = mine ? rk[i] : 0;
+    int start = 0;                                              // first index carrying label yi (labels sorted descending)
+    if (mine) {
+        int lo = 0, hi = i;                                     // ys[lo..hi] is non-increasing and ys[i] == yi
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (ys[mid] > yi) lo = mid + 1; else hi = mid; }
+        start = lo;
+    }
+    int trips = start;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, o));
+    float own = 0.0f, loss = 0.0f;
+    float* prow = part + (size_t)warp * nmax;
+    for (int p = 0; p < trips; ++p) {
+        float gp = 0.0f;                                        // this lane's contribution to document p's gradient
+        if (p < start) {
+            const float sj = ss[p], yj = ys[p], gj = ng[p], dj = dinv[p];
+            const bool first = ri < rk[p];                      // the better-ranked document is the pair's first element
+            const float g = pair_term<true>(first ? si : sj, first ? sj : si, first ? yi : yj, first ? yj : yi,
+                                            first ? gi : gj, first ? gj : gi, first ? di : dj, first ? dj : di, sigma, loss);
+            own += first ? g : -g;
+            gp = first ? -g : g;
+        }
+        gp = warp_sum(gp);
+        if (lane == 0) prow[p] += gp;
+    }
+    __syncthreads();
+    if (mine) {
+        float tot = own;
+        for (int w = 0; w < nwarps; ++w) tot += part[(size_t)w * nmax + i];
+        grad[sp.base + i] = tot;
+    }
     loss = block_sum(loss, red);
     if (threadIdx.x == 0) loss_q[b] = loss;
 }
@@ -614,6 +687,15 @@ static int launch_pairwise(const float* scores, const float* labels, const int32
     if (rc) return rc;
     const int npow2 = next_pow2(n);
     const size_t smem = (LAMBDA ? (size_t)npow2 * 8 : 0) + (size_t)n * 4 * 6 + 33 * 4;
+    static const bool no_runs = getenv("PTRB200_NO_RUNS") != nullptr;      // debugging switch: keep the circulant schedule
+    if (LAMBDA && n <= 512 && !no_runs) {       // tie pairs skipped: one thread per document, partners = the better-labelled prefix
+        const int threads = block_threads(n);
+        const size_t smem_r = (size_t)npow2 * 8 + (size_t)n * 4 * 5 + 33 * 4 + (size_t)(threads / 32) * n * 4;
+        if ((rc = allow_smem(lambdarank_runs_kernel, smem_r))) return rc;
+        PTRB200_LAUNCH_TAG("pairwise_bce_kernel<LAMBDA>", lambdarank_runs_kernel, B, threads, smem_r, stream,
+                           scores, labels, grad, loss_q, offsets, n, npow2, sigma);
+        return check_launch("lambdarank");
+    }
     if (n <= 1024) {        // one thread per position: each unordered pair once
         const size_t smem_c = smem + (size_t)2 * PAIR_KB * n * 4;
         if ((rc = allow_smem(pairwise_bce_circ_kernel<LAMBDA>, smem_c))) return rc;

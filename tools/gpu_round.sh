@@ -10,7 +10,7 @@ for s in $stages; do
     testsall) timeout 1200 python -m pytest tests -q -m gpu --timeout 200 --tb=short --maxfail=40 > gpurun_out/pytest_gpu.log 2>&1; grep -v "Warning" gpurun_out/pytest_gpu.log | tail -150
               if ! tail -1 gpurun_out/pytest_gpu.log | grep -q " passed" || tail -1 gpurun_out/pytest_gpu.log | grep -q failed; then
                 echo "== bisect: scorer tests with the regular last-chunk mapping (PTRB200_NO_PARTIAL=1)"
-                PTRB200_NO_PARTIAL=1 timeout 600 python -m pytest tests/test_gpu_scorer.py tests/test_gpu_tc_gemm.py tests/test_gpu_r2_parity.py -q -m gpu --timeout 200 --tb=line 2>&1 | grep -v Warning | tail -15
+                PTRB200_NO_PARTIAL=1 PTRB200_NO_RUNS=1 timeout 600 python -m pytest tests/test_gpu_scorer.py tests/test_gpu_tc_gemm.py tests/test_gpu_r2_parity.py tests/test_gpu_losses.py -q -m gpu --timeout 200 --tb=line 2>&1 | grep -v Warning | tail -15
               fi ;;
     smoke)    timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 ;;
     bench)    timeout 200 python bench.py 2>gpurun_out/bench_n1.err | tail -1 > gpurun_out/bench_n1.json
