@@ -195,12 +195,24 @@ def reference_run(cfg, steps, warmup, B, budget_s, device="cpu"):
     return dict(qps=done * B / dt, ms_per_step=1e3 * dt / done, steps=done, B=B, cores=torch.get_num_threads())
 
 
+def host_threads():
+    """Threads for the CPU arm: every PHYSICAL core this process may run on (torchrun exports OMP_NUM_THREADS=1, and
+    oversubscribing the SMT siblings makes ATen's elementwise kernels several times slower)."""
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False) or 0
+    except Exception:
+        phys = 0
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    n = phys if phys > 0 else max(1, avail // 2)
+    return max(1, min(n, avail))
+
+
 def run_reference(args, cfg, device="cpu"):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # torchrun exports OMP_NUM_THREADS=1; the reference arm gets every host core the box has
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_threads())
     cuda = device != "cpu"
     B = (cfg["B"] if cuda else cfg["cpu_B"])
     r = reference_run(cfg, args.steps, args.warmup, B, budget_s=240.0, device=device)
@@ -363,7 +375,7 @@ def run_b200(args, cfg):
     # ---- baselines (rank 0, N=1 only) -----------------------------------------
     cpu = ref_b1 = ref_cuda = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        torch.set_num_threads(os.cpu_count() or 1)
+        torch.set_num_threads(host_threads())
         r = reference_run(cfg, steps=40, warmup=2, B=cfg["cpu_B"], budget_s=15.0)
         cpu = {"value": r["qps"], "unit": "queries/s", "cores": r["cores"], "kind": "port",
                "sample": f"{r['steps']} steps x {r['B']} queries x {n} docs (oracle/ref_port.py train_op, fp32 CPU PyTorch ops)"}

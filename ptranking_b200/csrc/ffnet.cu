@@ -1084,7 +1084,6 @@ static int backward_ragged(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* 
             w.N = lp.d_out < 128 ? lp.d_out : 128; w.K = wb.kb;
             w.KP = ((w.K + 15) / 16) * 16;
             w.tile_rows = p.wg_rows;
-            { static const int no_partial = getenv("PTRB200_NO_PARTIAL") ? 1 : 0; w.no_partial = no_partial; }
             const size_t smem = wgrad_smem(w.N, w.K, w.KP, w.tile_rows, p.passes, w.stages, false, 8);
             const dim3 grid(wb.gx, wb.mblocks, wb.kblocks);
             if (p.passes == 3) { if ((rc = opt_in_smem(wgrad_tc_kernel<3>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<3>, grid, WG_THREADS, smem, st, w); }
@@ -1267,7 +1266,6 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
         {
             WgradArgs w{};
             w.round_bf16 = p.bf16;
-            { static const int no_partial = getenv("PTRB200_NO_PARTIAL") ? 1 : 0; w.no_partial = no_partial; }
             w.dZ = dZ;
             if (l == 0) {          // layer 0 input = dropout(X): rebuilt on the fly
                 w.P = X; w.scale = w.shift = nullptr; w.act = PTRB200_AF_NONE;

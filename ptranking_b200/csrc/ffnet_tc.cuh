@@ -497,146 +497,249 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rows_gemm_ws_kernel(RowsGemmArg
             }
         }
     } else if (warp > RW_EPI_WARPS) {
-        // ================================ producer warps ================================
-        const int ptid = tid - (RW_EPI_WARPS + 1) * 32;
-        const int j4 = (ptid & 7) * 4;                              // first column of this thread's 16-byte unit inside a chunk
-        const int r_[2] = {ptid >> 3, (ptid >> 3) + 64};
-        const uint32_t sw_[2] = {tc::swz_offset(r_[0], ptid & 7), tc::swz_offset(r_[1], ptid & 7)};
-        const int total_q = my_tiles * nchunks;
-        const bool has_coef = g.scale != nullptr;
-        const bool per_group = has_coef && g.gr_prev < g.rows;
-        const bool fused_dz = MODE == RG_DGRAD && g.P2 != nullptr;
-        // A width that is not a multiple of 32 leaves the LAST K-chunk mostly empty (K = 100: 4 of its 32 columns).  With
-        // the regular mapping (8 units per row) 7 of every 8 lanes would run the whole prologue on nothing, so that chunk
-        // uses a unit-major mapping instead: unit jB = (ptid >> 7) + 4 i of row rB = ptid & 127 -- whole warps share jB
-        // and only those below `zfill` (the units the chunk's MMA K-steps read) do any work; units in [vlast, zfill) are
-        // written as zeros.  22 % of the staging work of a 100-wide layer disappears.
-        const int lastc = nchunks - 1;
-        const int vlast = (K - lastc * 32 + 3) >> 2;                // 16-byte units of the last chunk that hold data (1..8)
-        const bool partial = vlast < 8 && !g.no_partial;
-        const int zfill = 2 * min(4, (K - lastc * 32 + 7) / 8);     // units the last chunk's MMAs read
-        const int rB = ptid & 127;
-        const int jB_[2] = {ptid >> 7, (ptid >> 7) + 4};
-        float4 pre[2], pre2[2];
-        size_t soff[2], soffB[2];                                   // element offset of the thread's units in the tile being fetched
-        bool ok[2], okB[2];
-        auto point = [&](int it) {                                  // set soff/ok for tile `it`
-            int r0, nr;
-            rw_tile(g, blockIdx.x + it * gridDim.x, r0, nr);
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                ok[i] = r_[i] < nr; soff[i] = (size_t)(r0 + min(r_[i], nr - 1)) * K + j4;
-                okB[i] = rB < nr && jB_[i] < vlast; soffB[i] = (size_t)(r0 + min(rB, nr - 1)) * K + lastc * 32 + min(jB_[i], vlast - 1) * 4;
-            }
-        };
-        auto fetch = [&](int c) {
-            if (partial && c == lastc) {
-#pragma unroll
+        if constexpr (MODE == RG_DGRAD) {
+        // (the data-gradient instantiation keeps the round-1 producer loop verbatim: its fused dZ = k1*dY + k3*Z + k0 staging sits
+        //  at the 72-register cap, and the restructured loop below spills there -- measured 0.48 -> 0.63 ms per step)
+            // ================================ producer warps ================================
+            const int ptid = tid - (RW_EPI_WARPS + 1) * 32;
+            const int j4 = (ptid & 7) * 4;                              // first column of this thread's 16-byte unit inside a chunk
+            const int r_[2] = {ptid >> 3, (ptid >> 3) + 64};
+            const uint32_t sw_[2] = {tc::swz_offset(r_[0], ptid & 7), tc::swz_offset(r_[1], ptid & 7)};
+            const int total_q = my_tiles * nchunks;
+            const bool has_coef = g.scale != nullptr;
+            const bool per_group = has_coef && g.gr_prev < g.rows;
+            const bool fused_dz = MODE == RG_DGRAD && g.P2 != nullptr;
+            float4 pre[2], pre2[2];
+            size_t soff[2];                                             // row * K + j4 for the tile being fetched
+            bool ok[2];
+            auto point = [&](int it) {                                  // set soff/ok for tile `it`
+                int r0, nr;
+                rw_tile(g, blockIdx.x + it * gridDim.x, r0, nr);
+    #pragma unroll
+                for (int i = 0; i < 2; ++i) { ok[i] = r_[i] < nr; soff[i] = (size_t)(r0 + min(r_[i], nr - 1)) * K + j4; }
+            };
+            auto fetch = [&](int c) {
+                const bool kv = c * 32 + j4 < K;
+    #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    pre[i] = okB[i] ? __ldg(reinterpret_cast<const float4*>(g.P + soffB[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (MODE == RG_DGRAD) pre2[i] = (fused_dz && okB[i]) ? __ldg(reinterpret_cast<const float4*>(g.P2 + soffB[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    pre[i] = (ok[i] && kv) ? __ldg(reinterpret_cast<const float4*>(g.P + soff[i] + c * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (MODE == RG_DGRAD) pre2[i] = (fused_dz && ok[i] && kv) ? __ldg(reinterpret_cast<const float4*>(g.P2 + soff[i] + c * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                return;
-            }
-            const bool kv = c * 32 + j4 < K;
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                pre[i] = (ok[i] && kv) ? __ldg(reinterpret_cast<const float4*>(g.P + soff[i] + c * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (MODE == RG_DGRAD) pre2[i] = (fused_dz && ok[i] && kv) ? __ldg(reinterpret_cast<const float4*>(g.P2 + soff[i] + c * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        };
-        // prologue of one 16-byte unit: [dZ = k1*dY + k3*Z + k0] -> scale/shift -> activation -> dropout -> by-product store
-        auto xform = [&](float4 v, const float4 z, const float* scp, const float* shp, size_t kcoff, uint64_t dquad, float* aoutp) -> float4 {
-            if (MODE == RG_DGRAD && fused_dz) {           // dZ = k1*dY + k3*Z + k0
-                const float4 a1 = __ldg(reinterpret_cast<const float4*>(g.kc1 + kcoff));
-                const float4 a3 = __ldg(reinterpret_cast<const float4*>(g.kc3 + kcoff));
-                const float4 a0 = __ldg(reinterpret_cast<const float4*>(g.kc0 + kcoff));
-                v.x = fmaf(a1.x, v.x, fmaf(a3.x, z.x, a0.x)); v.y = fmaf(a1.y, v.y, fmaf(a3.y, z.y, a0.y));
-                v.z = fmaf(a1.z, v.z, fmaf(a3.z, z.z, a0.z)); v.w = fmaf(a1.w, v.w, fmaf(a3.w, z.w, a0.w));
-            }
-            if (has_coef) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(scp));
-                const float4 b = __ldg(reinterpret_cast<const float4*>(shp));
-                v.x = fmaf(v.x, a.x, b.x); v.y = fmaf(v.y, a.y, b.y); v.z = fmaf(v.z, a.z, b.z); v.w = fmaf(v.w, a.w, b.w);
-            }
-            if (ACT != PTRB200_AF_NONE) {
-                const int af = ACT < 0 ? g.act : ACT;
-                v.x = activate(af, v.x).y; v.y = activate(af, v.y).y; v.z = activate(af, v.z).y; v.w = activate(af, v.w).y;
-            }
-            if (MODE == RG_FWD && g.drop.thr) {
-                const uint64_t d = dropout_draw4(g.drop.key, dquad);
-                v.x = ((uint32_t)(d) & 0xffffu) >= g.drop.thr ? v.x * g.drop.scale : 0.0f;
-                v.y = ((uint32_t)(d >> 16) & 0xffffu) >= g.drop.thr ? v.y * g.drop.scale : 0.0f;
-                v.z = ((uint32_t)(d >> 32) & 0xffffu) >= g.drop.thr ? v.z * g.drop.scale : 0.0f;
-                v.w = ((uint32_t)(d >> 48)) >= g.drop.thr ? v.w * g.drop.scale : 0.0f;
-            }
-            if (MODE == RG_FWD && aoutp) *reinterpret_cast<float4*>(aoutp) = v;
-            return v;
-        };
-        if (total_q > 0) { point(0); fetch(0); }
-        int q = 0;
-        for (int it = 0; it < my_tiles; ++it) {
-            int row0, nrows;
-            rw_tile(g, blockIdx.x + it * gridDim.x, row0, nrows);
-            // per-tile invariants of this thread's two rows
-            bool live[2];
-            float* aout[2];
-            const float* sc[2];
-            const float* sh[2];
-            size_t kco[2];
-            uint64_t dq[2];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                live[i] = r_[i] < nrows;
-                const size_t e0 = (size_t)(row0 + min(r_[i], nrows - 1)) * K + j4;
-                aout[i] = (MODE == RG_FWD && g.a_out) ? g.a_out + e0 : nullptr;
-                const size_t co = per_group ? (size_t)((row0 + min(r_[i], nrows - 1)) / g.gr_prev) * K + j4 : (size_t)j4;
-                sc[i] = has_coef ? g.scale + co : nullptr;
-                sh[i] = has_coef ? g.shift + co : nullptr;
-                kco[i] = (fused_dz && g.gr_cur < g.rows) ? (size_t)((row0 + min(r_[i], nrows - 1)) / g.gr_cur) * K + j4 : (size_t)j4;
-                dq[i] = (uint64_t)e0 >> 2;
-            }
-            for (int c = 0; c < nchunks; ++c, ++q) {
-                const int s = q & 1;
-                const float4 cur[2] = {pre[0], pre[1]};
-                const float4 cur2[2] = {pre2[0], pre2[1]};
-                if (q + 1 < total_q) {                              // prefetch the next chunk (possibly of the next tile)
-                    if (c + 1 < nchunks) fetch(c + 1); else { point(it + 1); fetch(0); }
+            };
+            if (total_q > 0) { point(0); fetch(0); }
+            int q = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                int row0, nrows;
+                rw_tile(g, blockIdx.x + it * gridDim.x, row0, nrows);
+                // per-tile invariants of this thread's two rows
+                bool live[2];
+                float* aout[2];
+                const float* sc[2];
+                const float* sh[2];
+                size_t kco[2];
+                uint64_t dq[2];
+    #pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    live[i] = r_[i] < nrows;
+                    const size_t e0 = (size_t)(row0 + min(r_[i], nrows - 1)) * K + j4;
+                    aout[i] = (MODE == RG_FWD && g.a_out) ? g.a_out + e0 : nullptr;
+                    const size_t co = per_group ? (size_t)((row0 + min(r_[i], nrows - 1)) / g.gr_prev) * K + j4 : (size_t)j4;
+                    sc[i] = has_coef ? g.scale + co : nullptr;
+                    sh[i] = has_coef ? g.shift + co : nullptr;
+                    kco[i] = (fused_dz && g.gr_cur < g.rows) ? (size_t)((row0 + min(r_[i], nrows - 1)) / g.gr_cur) * K + j4 : (size_t)j4;
+                    dq[i] = (uint64_t)e0 >> 2;
                 }
-                if (q >= 2) tc::mbar_wait(afree + s, ((q - 2) >> 1) & 1);
-                unsigned char* a_hi = a_ring + s * 32768;
-                if (partial && c == lastc) {
-                    // unit-major mapping of the short last chunk: warps whose unit lies beyond `zfill` have nothing to do
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int jB = jB_[i];
-                        if (jB < zfill) {
-                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (jB < vlast && rB < nrows) {
-                                const int col = lastc * 32 + jB * 4;
-                                const size_t e0 = (size_t)(row0 + rB) * K + col;
-                                const size_t co = (per_group ? (size_t)((row0 + rB) / g.gr_prev) * K : (size_t)0) + col;
-                                const size_t kc = ((fused_dz && g.gr_cur < g.rows) ? (size_t)((row0 + rB) / g.gr_cur) * K : (size_t)0) + col;
-                                v = xform(cur[i], cur2[i], has_coef ? g.scale + co : nullptr, has_coef ? g.shift + co : nullptr, kc,
-                                          (uint64_t)e0 >> 2, (MODE == RG_FWD && g.a_out) ? g.a_out + e0 : nullptr);
-                            }
-                            store_split(a_hi, a_hi + 16384, tc::swz_offset(rB, jB), v, PASSES == 3, PASSES == 1 && g.round_bf16 != 0);
-                        }
+                for (int c = 0; c < nchunks; ++c, ++q) {
+                    const int s = q & 1;
+                    const float4 cur[2] = {pre[0], pre[1]};
+                    const float4 cur2[2] = {pre2[0], pre2[1]};
+                    if (q + 1 < total_q) {                              // prefetch the next chunk (possibly of the next tile)
+                        if (c + 1 < nchunks) fetch(c + 1); else { point(it + 1); fetch(0); }
                     }
-                } else {
+                    if (q >= 2) tc::mbar_wait(afree + s, ((q - 2) >> 1) & 1);
+                    unsigned char* a_hi = a_ring + s * 32768;
                     const bool kv = c * 32 + j4 < K;
-#pragma unroll
+    #pragma unroll
                     for (int i = 0; i < 2; ++i) {
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (live[i] && kv)
-                            v = xform(cur[i], cur2[i], has_coef ? sc[i] + c * 32 : nullptr, has_coef ? sh[i] + c * 32 : nullptr,
-                                      kco[i] + c * 32, dq[i] + c * 8, aout[i] ? aout[i] + c * 32 : nullptr);
+                        float4 v = cur[i];
+                        if (live[i] && kv) {
+                            if (MODE == RG_DGRAD && fused_dz) {           // dZ = k1*dY + k3*Z + k0
+                                const float4 a1 = __ldg(reinterpret_cast<const float4*>(g.kc1 + kco[i] + c * 32));
+                                const float4 a3 = __ldg(reinterpret_cast<const float4*>(g.kc3 + kco[i] + c * 32));
+                                const float4 a0 = __ldg(reinterpret_cast<const float4*>(g.kc0 + kco[i] + c * 32));
+                                const float4 z = cur2[i];
+                                v.x = fmaf(a1.x, v.x, fmaf(a3.x, z.x, a0.x)); v.y = fmaf(a1.y, v.y, fmaf(a3.y, z.y, a0.y));
+                                v.z = fmaf(a1.z, v.z, fmaf(a3.z, z.z, a0.z)); v.w = fmaf(a1.w, v.w, fmaf(a3.w, z.w, a0.w));
+                            }
+                            if (has_coef) {
+                                const float4 a = __ldg(reinterpret_cast<const float4*>(sc[i] + c * 32));
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(sh[i] + c * 32));
+                                v.x = fmaf(v.x, a.x, b.x); v.y = fmaf(v.y, a.y, b.y); v.z = fmaf(v.z, a.z, b.z); v.w = fmaf(v.w, a.w, b.w);
+                            }
+                            if (ACT != PTRB200_AF_NONE) {
+                                const int af = ACT < 0 ? g.act : ACT;
+                                v.x = activate(af, v.x).y; v.y = activate(af, v.y).y; v.z = activate(af, v.z).y; v.w = activate(af, v.w).y;
+                            }
+                            if (MODE == RG_FWD && g.drop.thr) {
+                                const uint64_t d = dropout_draw4(g.drop.key, dq[i] + c * 8);
+                                v.x = ((uint32_t)(d) & 0xffffu) >= g.drop.thr ? v.x * g.drop.scale : 0.0f;
+                                v.y = ((uint32_t)(d >> 16) & 0xffffu) >= g.drop.thr ? v.y * g.drop.scale : 0.0f;
+                                v.z = ((uint32_t)(d >> 32) & 0xffffu) >= g.drop.thr ? v.z * g.drop.scale : 0.0f;
+                                v.w = ((uint32_t)(d >> 48)) >= g.drop.thr ? v.w * g.drop.scale : 0.0f;
+                            }
+                            if (MODE == RG_FWD && aout[i]) *reinterpret_cast<float4*>(aout[i] + c * 32) = v;
+                        } else v = make_float4(0.f, 0.f, 0.f, 0.f);
                         store_split(a_hi, a_hi + 16384, sw_[i], v, PASSES == 3, PASSES == 1 && g.round_bf16 != 0);
                     }
+                    tc::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(aready + s);
                 }
-                tc::fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(aready + s);
+            }
+        } else {
+            // ================================ producer warps ================================
+            const int ptid = tid - (RW_EPI_WARPS + 1) * 32;
+            const int j4 = (ptid & 7) * 4;                              // first column of this thread's 16-byte unit inside a chunk
+            const int r_[2] = {ptid >> 3, (ptid >> 3) + 64};
+            const uint32_t sw_[2] = {tc::swz_offset(r_[0], ptid & 7), tc::swz_offset(r_[1], ptid & 7)};
+            const int total_q = my_tiles * nchunks;
+            const bool has_coef = g.scale != nullptr;
+            const bool per_group = has_coef && g.gr_prev < g.rows;
+            const bool fused_dz = MODE == RG_DGRAD && g.P2 != nullptr;
+            // A width that is not a multiple of 32 leaves the LAST K-chunk mostly empty (K = 100: 4 of its 32 columns).  With
+            // the regular mapping (8 units per row) 7 of every 8 lanes would run the whole prologue on nothing, so that chunk
+            // uses a unit-major mapping instead: unit jB = (ptid >> 7) + 4 i of row rB = ptid & 127 -- whole warps share jB
+            // and only those below `zfill` (the units the chunk's MMA K-steps read) do any work; units in [vlast, zfill) are
+            // written as zeros.  22 % of the staging work of a 100-wide layer disappears.
+            const int lastc = nchunks - 1;
+            const int vlast = (K - lastc * 32 + 3) >> 2;                // 16-byte units of the last chunk that hold data (1..8)
+            // (forward only: in the dgrad instantiation the extra live state pushes the producers past 72 registers -- measured
+            //  +30 % on that kernel -- so it keeps the regular mapping)
+            const bool partial = MODE == RG_FWD && vlast < 8 && !g.no_partial;
+            const int zfill = 2 * min(4, (K - lastc * 32 + 7) / 8);     // units the last chunk's MMAs read
+            const int rB = ptid & 127;
+            const int jB_[2] = {ptid >> 7, (ptid >> 7) + 4};
+            float4 pre[2], pre2[2];
+            size_t soff[2], soffB[2];                                   // element offset of the thread's units in the tile being fetched
+            bool ok[2], okB[2];
+            auto point = [&](int it) {                                  // set soff/ok for tile `it`
+                int r0, nr;
+                rw_tile(g, blockIdx.x + it * gridDim.x, r0, nr);
+    #pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    ok[i] = r_[i] < nr; soff[i] = (size_t)(r0 + min(r_[i], nr - 1)) * K + j4;
+                    okB[i] = rB < nr && jB_[i] < vlast; soffB[i] = (size_t)(r0 + min(rB, nr - 1)) * K + lastc * 32 + min(jB_[i], vlast - 1) * 4;
+                }
+            };
+            auto fetch = [&](int c) {
+                if (partial && c == lastc) {
+    #pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        pre[i] = okB[i] ? __ldg(reinterpret_cast<const float4*>(g.P + soffB[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (MODE == RG_DGRAD) pre2[i] = (fused_dz && okB[i]) ? __ldg(reinterpret_cast<const float4*>(g.P2 + soffB[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    return;
+                }
+                const bool kv = c * 32 + j4 < K;
+    #pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    pre[i] = (ok[i] && kv) ? __ldg(reinterpret_cast<const float4*>(g.P + soff[i] + c * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (MODE == RG_DGRAD) pre2[i] = (fused_dz && ok[i] && kv) ? __ldg(reinterpret_cast<const float4*>(g.P2 + soff[i] + c * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            // prologue of one 16-byte unit: [dZ = k1*dY + k3*Z + k0] -> scale/shift -> activation -> dropout -> by-product store
+            auto xform = [&](float4 v, const float4 z, const float* scp, const float* shp, size_t kcoff, uint64_t dquad, float* aoutp) -> float4 {
+                if (MODE == RG_DGRAD && fused_dz) {           // dZ = k1*dY + k3*Z + k0
+                    const float4 a1 = __ldg(reinterpret_cast<const float4*>(g.kc1 + kcoff));
+                    const float4 a3 = __ldg(reinterpret_cast<const float4*>(g.kc3 + kcoff));
+                    const float4 a0 = __ldg(reinterpret_cast<const float4*>(g.kc0 + kcoff));
+                    v.x = fmaf(a1.x, v.x, fmaf(a3.x, z.x, a0.x)); v.y = fmaf(a1.y, v.y, fmaf(a3.y, z.y, a0.y));
+                    v.z = fmaf(a1.z, v.z, fmaf(a3.z, z.z, a0.z)); v.w = fmaf(a1.w, v.w, fmaf(a3.w, z.w, a0.w));
+                }
+                if (has_coef) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(scp));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(shp));
+                    v.x = fmaf(v.x, a.x, b.x); v.y = fmaf(v.y, a.y, b.y); v.z = fmaf(v.z, a.z, b.z); v.w = fmaf(v.w, a.w, b.w);
+                }
+                if (ACT != PTRB200_AF_NONE) {
+                    const int af = ACT < 0 ? g.act : ACT;
+                    v.x = activate(af, v.x).y; v.y = activate(af, v.y).y; v.z = activate(af, v.z).y; v.w = activate(af, v.w).y;
+                }
+                if (MODE == RG_FWD && g.drop.thr) {
+                    const uint64_t d = dropout_draw4(g.drop.key, dquad);
+                    v.x = ((uint32_t)(d) & 0xffffu) >= g.drop.thr ? v.x * g.drop.scale : 0.0f;
+                    v.y = ((uint32_t)(d >> 16) & 0xffffu) >= g.drop.thr ? v.y * g.drop.scale : 0.0f;
+                    v.z = ((uint32_t)(d >> 32) & 0xffffu) >= g.drop.thr ? v.z * g.drop.scale : 0.0f;
+                    v.w = ((uint32_t)(d >> 48)) >= g.drop.thr ? v.w * g.drop.scale : 0.0f;
+                }
+                if (MODE == RG_FWD && aoutp) *reinterpret_cast<float4*>(aoutp) = v;
+                return v;
+            };
+            if (total_q > 0) { point(0); fetch(0); }
+            int q = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                int row0, nrows;
+                rw_tile(g, blockIdx.x + it * gridDim.x, row0, nrows);
+                // per-tile invariants of this thread's two rows
+                bool live[2];
+                float* aout[2];
+                const float* sc[2];
+                const float* sh[2];
+                size_t kco[2];
+                uint64_t dq[2];
+    #pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    live[i] = r_[i] < nrows;
+                    const size_t e0 = (size_t)(row0 + min(r_[i], nrows - 1)) * K + j4;
+                    aout[i] = (MODE == RG_FWD && g.a_out) ? g.a_out + e0 : nullptr;
+                    const size_t co = per_group ? (size_t)((row0 + min(r_[i], nrows - 1)) / g.gr_prev) * K + j4 : (size_t)j4;
+                    sc[i] = has_coef ? g.scale + co : nullptr;
+                    sh[i] = has_coef ? g.shift + co : nullptr;
+                    kco[i] = (fused_dz && g.gr_cur < g.rows) ? (size_t)((row0 + min(r_[i], nrows - 1)) / g.gr_cur) * K + j4 : (size_t)j4;
+                    dq[i] = (uint64_t)e0 >> 2;
+                }
+                for (int c = 0; c < nchunks; ++c, ++q) {
+                    const int s = q & 1;
+                    const float4 cur[2] = {pre[0], pre[1]};
+                    const float4 cur2[2] = {pre2[0], pre2[1]};
+                    if (q + 1 < total_q) {                              // prefetch the next chunk (possibly of the next tile)
+                        if (c + 1 < nchunks) fetch(c + 1); else { point(it + 1); fetch(0); }
+                    }
+                    if (q >= 2) tc::mbar_wait(afree + s, ((q - 2) >> 1) & 1);
+                    unsigned char* a_hi = a_ring + s * 32768;
+                    if (partial && c == lastc) {
+                        // unit-major mapping of the short last chunk: warps whose unit lies beyond `zfill` have nothing to do
+    #pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int jB = jB_[i];
+                            if (jB < zfill) {
+                                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (jB < vlast && rB < nrows) {
+                                    const int col = lastc * 32 + jB * 4;
+                                    const size_t e0 = (size_t)(row0 + rB) * K + col;
+                                    const size_t co = (per_group ? (size_t)((row0 + rB) / g.gr_prev) * K : (size_t)0) + col;
+                                    const size_t kc = ((fused_dz && g.gr_cur < g.rows) ? (size_t)((row0 + rB) / g.gr_cur) * K : (size_t)0) + col;
+                                    v = xform(cur[i], cur2[i], has_coef ? g.scale + co : nullptr, has_coef ? g.shift + co : nullptr, kc,
+                                              (uint64_t)e0 >> 2, (MODE == RG_FWD && g.a_out) ? g.a_out + e0 : nullptr);
+                                }
+                                store_split(a_hi, a_hi + 16384, tc::swz_offset(rB, jB), v, PASSES == 3, PASSES == 1 && g.round_bf16 != 0);
+                            }
+                        }
+                    } else {
+                        const bool kv = c * 32 + j4 < K;
+    #pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (live[i] && kv)
+                                v = xform(cur[i], cur2[i], has_coef ? sc[i] + c * 32 : nullptr, has_coef ? sh[i] + c * 32 : nullptr,
+                                          kco[i] + c * 32, dq[i] + c * 8, aout[i] ? aout[i] + c * 32 : nullptr);
+                            store_split(a_hi, a_hi + 16384, sw_[i], v, PASSES == 3, PASSES == 1 && g.round_bf16 != 0);
+                        }
+                    }
+                    tc::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(aready + s);
+                }
             }
         }
     } else {
@@ -763,7 +866,6 @@ struct WgradArgs {
     int tile_rows;         // R: rows per tile (multiple of 8, <= 32)
     int stages;            // raw-tile ring depth (2..WG_MAX_STAGES), chosen by the host to fit shared memory
     int round_bf16;        // PTRB200_MATH_BF16: both operands rounded to bf16
-    int no_partial;        // debugging switch (PTRB200_NO_PARTIAL=1): regular unit mapping for short last chunks
 };
 
 constexpr int WG_PRODUCERS = 512;      // 16 warps split raw fp32 tiles into hi/lo TF32 operand buffers: 8 take dZ, 8 the layer input
@@ -899,8 +1001,6 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
         const int r = ptid >> 3, j = ptid & 7;            // one 16-byte unit per thread per 32-column chunk (R*8 <= 256)
         const bool vec_z = (N & 3) == 0;
         const bool active = ptid < R * 8;
-        const bool remap_z = vec_z && (N & 31) != 0 && !g.no_partial;      // short last chunk of the dZ operand staged unit-major
-        const bool remap_p = (K & 31) != 0 && !g.no_partial;               // ... and of the layer-input operand (K % 4 == 0 always)
         const uint32_t sw = tc::swz32_offset(r, j);       // this thread's slot inside every operand chunk
         const int zoff = r * N + j * 4, poff = r * K + j * 4;
         int s = 0;
@@ -923,43 +1023,18 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
             }
             tc::mbar_wait(fbar, fpar);
             const bool row_ok = r < nrows;
-            // A width that is not a multiple of 32 leaves its last 128-byte chunk mostly empty (N = K = 100: one unit of
-            // eight).  Whole chunks use the (row, unit) = (ptid >> 3, ptid & 7) mapping; the short last chunk is staged
-            // unit-major -- unit jB = ptid / R of row rB = ptid % R -- so that only R * (valid units) threads touch it.  Units
-            // beyond the data are not written at all: they only feed accumulator rows / columns that are never stored.
-            if (role == 0) {
-                const int zfull = remap_z ? (N >> 5) : z_chunks;     // chunks staged with the regular mapping
-                if (active) {
-                    const float* zsrc = rz + zoff;
-                    for (int ch = 0; ch < zfull; ++ch) {
-                        const int n = ch * 32 + j * 4;
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (row_ok && n < N) {
-                            if (vec_z) v = *reinterpret_cast<const float4*>(zsrc + ch * 32);
-                            else { const float* p = zsrc + ch * 32; v.x = p[0]; if (n + 1 < N) v.y = p[1]; if (n + 2 < N) v.z = p[2]; if (n + 3 < N) v.w = p[3]; }
-                            if (fused_dz) {                            // host guarantees N % 4 == 0 here
-                                const float4 z = *reinterpret_cast<const float4*>(zsrc + rawz1 / 4 + ch * 32);
-                                const size_t co = (g.gr_cur < g.rows ? (size_t)((row0 + r) / g.gr_cur) * N : 0) + n;
-                                const float4 a1 = __ldg(reinterpret_cast<const float4*>(g.kc1 + co));
-                                const float4 a3 = __ldg(reinterpret_cast<const float4*>(g.kc3 + co));
-                                const float4 a0 = __ldg(reinterpret_cast<const float4*>(g.kc0 + co));
-                                v.x = fmaf(a1.x, v.x, fmaf(a3.x, z.x, a0.x)); v.y = fmaf(a1.y, v.y, fmaf(a3.y, z.y, a0.y));
-                                v.z = fmaf(a1.z, v.z, fmaf(a3.z, z.z, a0.z)); v.w = fmaf(a1.w, v.w, fmaf(a3.w, z.w, a0.w));
-                            }
-                        }
-                        store_split(z_hi + ch * chunk_bytes, z_lo + ch * chunk_bytes, 0, v, PASSES == 3, PASSES == 1 && g.round_bf16 != 0);
-                    }
-                }
-                const int vz = remap_z ? ((N & 31) >> 2) : 0;        // data units of the short last chunk (0: none)
-                if (ptid < R * vz) {
-                    const int jB = ptid / R, rB = ptid - jB * R, n = zfull * 32 + jB * 4;
+            if (active && role == 0) {
+                const float* zsrc = rz + zoff;
+#pragma unroll
+                for (int ch = 0; ch < z_chunks; ++ch) {
+                    const int n = ch * 32 + j * 4;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (rB < nrows) {
-                        const float* zs = rz + rB * N + n;
-                        v = *reinterpret_cast<const float4*>(zs);
-                        if (fused_dz) {
-                            const float4 z = *reinterpret_cast<const float4*>(zs + rawz1 / 4);
-                            const size_t co = (g.gr_cur < g.rows ? (size_t)((row0 + rB) / g.gr_cur) * N : 0) + n;
+                    if (row_ok && n < N) {
+                        if (vec_z) v = *reinterpret_cast<const float4*>(zsrc + ch * 32);
+                        else { const float* p = zsrc + ch * 32; v.x = p[0]; if (n + 1 < N) v.y = p[1]; if (n + 2 < N) v.z = p[2]; if (n + 3 < N) v.w = p[3]; }
+                        if (fused_dz) {                            // host guarantees N % 4 == 0 here
+                            const float4 z = *reinterpret_cast<const float4*>(zsrc + rawz1 / 4 + ch * 32);
+                            const size_t co = (g.gr_cur < g.rows ? (size_t)((row0 + r) / g.gr_cur) * N : 0) + n;
                             const float4 a1 = __ldg(reinterpret_cast<const float4*>(g.kc1 + co));
                             const float4 a3 = __ldg(reinterpret_cast<const float4*>(g.kc3 + co));
                             const float4 a0 = __ldg(reinterpret_cast<const float4*>(g.kc0 + co));
@@ -967,34 +1042,19 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
                             v.z = fmaf(a1.z, v.z, fmaf(a3.z, z.z, a0.z)); v.w = fmaf(a1.w, v.w, fmaf(a3.w, z.w, a0.w));
                         }
                     }
-                    const int o = (int)tc::swz32_offset(rB, jB) - (int)sw + zfull * chunk_bytes;  // z_hi already carries this thread's regular slot `sw`
-                    store_split(z_hi + o, z_lo + o, 0, v, PASSES == 3, PASSES == 1 && g.round_bf16 != 0);
+                    store_split(z_hi + ch * chunk_bytes, z_lo + ch * chunk_bytes, 0, v, PASSES == 3, PASSES == 1 && g.round_bf16 != 0);
                 }
             }
-            if (role == 1) {
-                const int pfull = remap_p ? (K >> 5) : p_chunks;
-                if (active) {
-                    const float* psrc = rp + poff;
-                    for (int ch = 0; ch < pfull; ++ch) {
-                        const int k = ch * 32 + j * 4;
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (row_ok && k < K) {
-                            v = *reinterpret_cast<const float4*>(psrc + ch * 32);
-                            if (!plain_p) v = prologue4(pg, v, row0 + r, kk0 + k, true, (g.scale && g.gr_prev < g.rows) ? (size_t)((row0 + r) / g.gr_prev) * g.K_full : 0);
-                        }
-                        store_split(p_hi + ch * chunk_bytes, p_lo + ch * chunk_bytes, 0, v, PASSES == 3, PASSES == 1 && g.round_bf16 != 0);
-                    }
-                }
-                const int vp = remap_p ? ((K & 31) >> 2) : 0;
-                if (ptid < R * vp) {
-                    const int jB = ptid / R, rB = ptid - jB * R, k = pfull * 32 + jB * 4;
+            if (active && role == 1) {
+                const float* psrc = rp + poff;
+                for (int ch = 0; ch < p_chunks; ++ch) {
+                    const int k = ch * 32 + j * 4;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (rB < nrows) {
-                        v = *reinterpret_cast<const float4*>(rp + rB * K + k);
-                        if (!plain_p) v = prologue4(pg, v, row0 + rB, kk0 + k, true, (g.scale && g.gr_prev < g.rows) ? (size_t)((row0 + rB) / g.gr_prev) * g.K_full : 0);
+                    if (row_ok && k < K) {
+                        v = *reinterpret_cast<const float4*>(psrc + ch * 32);
+                        if (!plain_p) v = prologue4(pg, v, row0 + r, kk0 + k, true, (g.scale && g.gr_prev < g.rows) ? (size_t)((row0 + r) / g.gr_prev) * g.K_full : 0);
                     }
-                    const int o = (int)tc::swz32_offset(rB, jB) - (int)sw + pfull * chunk_bytes;
-                    store_split(p_hi + o, p_lo + o, 0, v, PASSES == 3, PASSES == 1 && g.round_bf16 != 0);
+                    store_split(p_hi + ch * chunk_bytes, p_lo + ch * chunk_bytes, 0, v, PASSES == 3, PASSES == 1 && g.round_bf16 != 0);
                 }
             }
             tc::fence_proxy_async();                       // this thread's operand stores -> visible to the MMA (async proxy)

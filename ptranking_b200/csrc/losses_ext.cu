@@ -157,7 +157,7 @@ __global__ void softrank_kernel(const float* __restrict__ scores, const float* _
 // Sinkhorn half-step:  log_v[b][j] = log_nu[b][j] - logsumexp_i( -dist[i][j] / lambda + log_u[b][i] ).
 // One CTA per (tile of 32 columns j, b): lane = column (coalesced reads of dist rows), the 8 warps split the reduction
 // rows i, each lane keeps an online (max, sum-exp) pair, the eight partials of a column are merged through shared
-// memory.  -inf entries follow the reference kernel: log_nu == -inf or an all -inf column give -inf.
+// memory.  Infinite entries follow the reference's CPU form (the one that runs): plain IEEE arithmetic.
 // ---------------------------------------------------------------------------
 constexpr int SINK_WARPS = 8;
 __global__ void sinkstep_kernel(const float* __restrict__ dist, const float* __restrict__ log_nu, const float* __restrict__ log_u,
@@ -182,8 +182,10 @@ __global__ void sinkstep_kernel(const float* __restrict__ dist, const float* __r
         float S = 0.0f;
 #pragma unroll
         for (int w = 0; w < SINK_WARPS; ++w) S += smax[w][lane] > -INFINITY ? ssum[w][lane] * expf(smax[w][lane] - M) : 0.0f;
-        const float lnu = log_nu[(size_t)b * d2 + j];
-        log_v[(size_t)b * d2 + j] = (lnu > -INFINITY && M > -INFINITY) ? lnu - logf(S) - M : -INFINITY;
+        // pytorch_wasserstein.py:289 (the path that runs): log_nu - logsumexp(...), IEEE arithmetic on the infinities --
+        // an all -inf column gives +inf (NaN when log_nu is -inf too); the never-compiled CUDA string would give -inf
+        const float lse = M > -INFINITY ? logf(S) + M : -INFINITY;
+        log_v[(size_t)b * d2 + j] = log_nu[(size_t)b * d2 + j] - lse;
     }
 }
 

@@ -67,8 +67,10 @@ def test_kernel_matches_oracle_fresh_inputs(name, params, shape):
     tol_l = max(TOL, 2.0 * abs(o_loss - fl) / max(abs(fl), 1.0))
     tol_g = max(TOL, 2.0 * rel_err(o_grad, fg))
     assert abs(loss - o_loss) <= tol_l * max(abs(o_loss), 1.0), (loss, o_loss, fl)
-    assert rel_err(grad, o_grad) <= tol_g, (rel_err(grad, o_grad), rel_err(grad, fg), rel_err(o_grad, fg))
-    assert rel_err(grad, fg) <= 5 * TOL and abs(loss - fl) <= 5 * TOL * max(abs(fl), 1.0)
+    # (a gradient that is identically zero in exact arithmetic -- RankCosine on one-document lists -- is compared absolutely)
+    floor = 1e-6 if np.abs(o_grad).max() < 1e-6 else 0.0
+    assert rel_err(grad, o_grad) <= tol_g or np.abs(grad - o_grad).max() <= floor, (rel_err(grad, o_grad), rel_err(grad, fg), rel_err(o_grad, fg))
+    assert (rel_err(grad, fg) <= 5 * TOL or np.abs(grad - fg).max() <= floor) and abs(loss - fl) <= 5 * TOL * max(abs(fl), 1.0)
 
 
 def test_stlistnet_device_noise_is_keyed_and_gumbel():

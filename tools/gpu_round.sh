@@ -15,9 +15,25 @@ for s in $stages; do
     smoke)    timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 ;;
     bench)    timeout 200 python bench.py 2>gpurun_out/bench_n1.err | tail -1 > gpurun_out/bench_n1.json
               python -c "import json; d=json.loads(open('gpurun_out/bench_n1.json').read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches']); print(d['roofline']['kernels_ms_per_step'])" ;;
-    ops)      timeout 300 python tools/op_bench.py > gpurun_out/op_bench.log 2>&1; cp profiles/r0*_op_table.md gpurun_out/; tail -42 gpurun_out/r0*_op_table.md ;;
+    ops)      timeout 300 python tools/op_bench.py > gpurun_out/op_bench.log 2>&1; cp profiles/r02_op_table.md gpurun_out/; tail -60 gpurun_out/r02_op_table.md ;;
     launches) timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python tools/profile_step.py 3 > gpurun_out/ncu_launch.log 2>&1; tail -1 gpurun_out/ncu_launch.log ;;
     full)     timeout 800 bash tools/profile_all.sh 2>&1 | tail -3 ;;
+    ab)       # A/B of the short-last-chunk staging in the forward layer kernel
+              for v in 0 1; do
+                if [ $v = 1 ]; then export PTRB200_NO_PARTIAL=1; else unset PTRB200_NO_PARTIAL; fi
+                timeout 200 python bench.py --steps 50 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/bench_ab_$v.json
+                python -c "import json; d=json.loads(open('gpurun_out/bench_ab_$v.json').read()); print('NO_PARTIAL=$v', round(d['ms_per_step'],4), {k:v for k,v in list(d['roofline']['kernels_ms_per_step'].items())[:6]})"
+              done; unset PTRB200_NO_PARTIAL ;;
+    configs)  for c in a c d e; do
+                timeout 400 python bench.py --config $c 2>gpurun_out/bench_$c.err | tail -1 > gpurun_out/bench_$c.json
+                python -c "import json; d=json.loads(open('gpurun_out/bench_$c.json').read()); print('$c', round(d['value'],1), 'q/s', round(d['ms_per_step'],4), 'ms; e2e', round(d['e2e']['value'],1), '; ref_cuda', d.get('reference_cuda'), '; cpu', d.get('cpu_baseline',{}).get('value'), d['roofline'].get('frac'), d['roofline'].get('step_frac'))" || tail -3 gpurun_out/bench_$c.err
+              done
+              timeout 400 python bench.py --config c --enc-layers 3 2>/dev/null | tail -1 > gpurun_out/bench_c_L3.json
+              for n in 32 1024; do timeout 300 python bench.py --config e --docs $n --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/bench_e_n$n.json; done
+              python -c "import json; [print(f, round(json.loads(open('gpurun_out/'+f).read())['value'],1)) for f in ('bench_c_L3.json','bench_e_n32.json','bench_e_n1024.json')]" ;;
+    parity)   timeout 400 python tools/parity_table.py r02 > gpurun_out/parity_table.log 2>&1; tail -5 gpurun_out/parity_table.log; cp profiles/r02_parity_table.md gpurun_out/ 2>/dev/null ;;
+    dropin)   timeout 600 python tools/dropin_run.py --impl b200 --model LambdaRank > gpurun_out/dropin_run.log 2>&1; grep -v Warning gpurun_out/dropin_run.log | tail -14
+              timeout 600 python tools/dropin_run.py --impl b200 --model ApproxNDCG --sf listsf --queries 120 > gpurun_out/dropin_run_listsf.log 2>&1; grep -v Warning gpurun_out/dropin_run_listsf.log | tail -8 ;;
     *)        echo "unknown stage $s" ;;
   esac
 done
