@@ -849,7 +849,10 @@ static int launch_rows_gemm(int mode, int passes, RowsGemmArgs& g, int ntiles, c
     }
     if (S_out) *S_out = S_default;
     // one-tile-per-CTA kernel; output columns are tiled (144 per CTA) when the layer is wider than one MMA tile likes
-    g.n_tile = g.N <= 144 ? g.N : 144;
+    // (long contractions carry a second TMEM accumulator: 128-column tiles keep the pair inside 256 TMEM columns, so two CTAs
+    //  still share an SM; a layer of up to 144 outputs stays one tile -- it then takes all 512 columns)
+    const bool long_k = passes == 3 && nchunks > 5;
+    g.n_tile = g.N <= 144 ? g.N : (long_k ? 128 : 144);
     const int n_tiles = (g.N + g.n_tile - 1) / g.n_tile;
     const int NPt = ((g.n_tile + 15) / 16) * 16;
     const size_t operands = 32768 + (size_t)NPt * 256, otile = (size_t)128 * g.n_tile * 4;

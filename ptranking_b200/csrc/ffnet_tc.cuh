@@ -80,12 +80,19 @@ static __device__ __forceinline__ float bf16_rn(float x) {
     const uint32_t u = __float_as_uint(x);
     return __uint_as_float((u + 0x7fffu + ((u >> 16) & 1u)) & 0xffff0000u);
 }
-static __device__ __forceinline__ void store_split(unsigned char* hi, unsigned char* lo, uint32_t off, float4 v, bool split, bool to_bf16 = false) {
+// rn: round-to-nearest hi/lo split (unbiased, per-product error 2^-22) instead of the truncating one (2^-20, biased towards
+// zero, 3 instructions per element cheaper) -- used where the contraction is long enough for the bias to show (K > 160)
+static __device__ __forceinline__ void store_split(unsigned char* hi, unsigned char* lo, uint32_t off, float4 v, bool split, bool to_bf16 = false, bool rn = false) {
     if (to_bf16) v = make_float4(bf16_rn(v.x), bf16_rn(v.y), bf16_rn(v.z), bf16_rn(v.w));
     if (split) {
         float4 h, l;
-        tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y);
-        tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
+        if (rn) {
+            tc::split_tf32_rn(v.x, h.x, l.x); tc::split_tf32_rn(v.y, h.y, l.y);
+            tc::split_tf32_rn(v.z, h.z, l.z); tc::split_tf32_rn(v.w, h.w, l.w);
+        } else {
+            tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y);
+            tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
+        }
         *reinterpret_cast<float4*>(hi + off) = h;
         *reinterpret_cast<float4*>(lo + off) = l;
     } else {
@@ -131,8 +138,8 @@ __global__ void pack_b_images_kernel(const __grid_constant__ PackJobs jobs) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[e] = bf16_rn(v[e]);
         }
-        float4 h, l;
-        tc::split_tf32(v[0], h.x, l.x); tc::split_tf32(v[1], h.y, l.y); tc::split_tf32(v[2], h.z, l.z); tc::split_tf32(v[3], h.w, l.w);
+        float4 h, l;          // round-to-nearest split: the images are built once per step, the unbiased split is free here
+        tc::split_tf32_rn(v[0], h.x, l.x); tc::split_tf32_rn(v[1], h.y, l.y); tc::split_tf32_rn(v[2], h.z, l.z); tc::split_tf32_rn(v[3], h.w, l.w);
         if (img_lo) {
             *reinterpret_cast<float4*>(img_hi + off) = h;
             *reinterpret_cast<float4*>(img_lo + off) = l;
@@ -160,8 +167,8 @@ __global__ void pack_b_image_kernel(const float* __restrict__ src, int src_rows,
             for (int e = 0; e < 4; ++e) v[e] = bf16_rn(v[e]);
         }
         const size_t off = (size_t)c * NP * 128 + tc::swz_offset(r, j);
-        float4 h, l;
-        tc::split_tf32(v[0], h.x, l.x); tc::split_tf32(v[1], h.y, l.y); tc::split_tf32(v[2], h.z, l.z); tc::split_tf32(v[3], h.w, l.w);
+        float4 h, l;          // round-to-nearest split: the images are built once per step, the unbiased split is free here
+        tc::split_tf32_rn(v[0], h.x, l.x); tc::split_tf32_rn(v[1], h.y, l.y); tc::split_tf32_rn(v[2], h.z, l.z); tc::split_tf32_rn(v[3], h.w, l.w);
         if (img_lo) {
             *reinterpret_cast<float4*>(img_hi + off) = h;
             *reinterpret_cast<float4*>(img_lo + off) = l;
@@ -208,7 +215,16 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
             slot0 = (row0 / g.seg_len);
         }
     }
-    const uint32_t tmem_cols = NP <= 32 ? 32 : NP <= 64 ? 64 : NP <= 128 ? 128 : 256;
+    // The tensor core accumulates with truncation: the error of a 3xTF32 contraction grows linearly with the number of
+    // accumulate steps.  Contractions longer than 5 chunks (K > 160: the 256- and 512-wide layers of the list
+    // scorer's head / tail nets) therefore keep the small a_lo*b_hi + a_hi*b_lo corrections in an accumulator of their own
+    // -- two thirds of the accumulate steps leave the main chain -- and stage A with the round-to-nearest split; the
+    // epilogue adds the two accumulators in round-to-nearest fp32.
+    const int K = g.K;
+    const int nchunks = (K + 31) / 32;
+    const bool long_k = PASSES == 3 && nchunks > 5;
+    const uint32_t need_cols = (uint32_t)(long_k ? 2 * NP : NP);
+    const uint32_t tmem_cols = need_cols <= 32 ? 32 : need_cols <= 64 ? 64 : need_cols <= 128 ? 128 : need_cols <= 256 ? 256 : 512;
     if (tid == 0) { tc::mbar_init(mbar, 1); tc::mbar_init(bbar, 1); tc::mbar_fence_init(); }
     if (warp == 0) tc::tmem_alloc(slot, tmem_cols);
     tc::fence_before_sync();
@@ -216,8 +232,6 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
     tc::fence_after_sync();
     const uint32_t tmem = *slot;
     const uint32_t idesc = tc::instr_desc(2, 128, NP);
-    const int K = g.K;
-    const int nchunks = (K + 31) / 32;
     constexpr int A_UNITS = 128 * 8 / RG_THREADS;      // 4 units of 16 B per thread per chunk
     size_t coef_off[A_UNITS];                           // (statistics group of the thread's rows) * K
 #pragma unroll
@@ -253,7 +267,7 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
                 v = prologue4(g, v, row0 + r, k, MODE == RG_FWD, coef_off[i]);
                 if (MODE == RG_FWD && g.a_out && blockIdx.y == 0) *reinterpret_cast<float4*>(g.a_out + (size_t)(row0 + r) * K + k) = v;
             } else v = make_float4(0.f, 0.f, 0.f, 0.f);
-            store_split(a_hi, a_lo, tc::swz_offset(r, j), v, PASSES == 3, PASSES == 1 && g.round_bf16 != 0);
+            store_split(a_hi, a_lo, tc::swz_offset(r, j), v, PASSES == 3, PASSES == 1 && g.round_bf16 != 0, long_k);
         }
         tc::fence_proxy_async();
         __syncthreads();
@@ -268,9 +282,15 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
                 if (PASSES == 3) {
                     const uint64_t al = tc::smem_desc_sw128(tc::smem_u32(a_lo) + s * 32, 1024);
                     const uint64_t bl = tc::smem_desc_sw128(tc::smem_u32(b_lo) + s * 32, 1024);
-                    tc::mma_tf32(tmem, al, bh, idesc, acc);
-                    tc::mma_tf32(tmem, ah, bl, idesc, 1u);
-                    tc::mma_tf32(tmem, ah, bh, idesc, 1u);
+                    if (long_k) {
+                        tc::mma_tf32(tmem + (uint32_t)NP, al, bh, idesc, acc);
+                        tc::mma_tf32(tmem + (uint32_t)NP, ah, bl, idesc, 1u);
+                        tc::mma_tf32(tmem, ah, bh, idesc, acc);
+                    } else {
+                        tc::mma_tf32(tmem, al, bh, idesc, acc);
+                        tc::mma_tf32(tmem, ah, bl, idesc, 1u);
+                        tc::mma_tf32(tmem, ah, bh, idesc, 1u);
+                    }
                 } else {
                     tc::mma_tf32(tmem, ah, bh, idesc, acc);
                 }
@@ -290,6 +310,12 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
         for (int c0 = c_begin; c0 < c_end; c0 += 8) {
             float v[8];
             tc::tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (long_k) {
+                float w[8];
+                tc::tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(NP + c0), w);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] += w[e];
+            }
             if (c0 < N) {
                 if (MODE == RG_FWD) {
 #pragma unroll
