@@ -135,7 +135,7 @@ def lambdarank_loss(preds, labels, sigma=1.0):
 
 def _rank_gap_discount(n, disc):
     """delta_ij of lambdaloss.py:36-42: index-wrapped lookup, diagonal zeroed."""
-    ranks = torch.arange(n).float() + 1.0
+    ranks = torch.arange(n, device=disc.device).float() + 1.0
     gap = torch.abs(ranks[:, None] - ranks[None, :]).long()
     d = torch.abs(torch.pow(disc[gap - 1], -1.0) - torch.pow(disc[gap], -1.0))
     d.diagonal().zero_()
@@ -152,7 +152,7 @@ def lambdaloss_loss(preds, labels, k=5, sigma=1.0, loss_type="NDCG_Loss2++", mu=
     desc_preds, order = torch.sort(target, dim=1, descending=True)
     pred_rankings = torch.gather(ideal, 1, order)
     n = target.size(1)
-    disc = 1.0 / torch.log2(torch.arange(n, dtype=torch.float) + 2.0)
+    disc = 1.0 / torch.log2(torch.arange(n, dtype=torch.float, device=preds.device) + 2.0)
     n_gains = gains(pred_rankings) / dcg_at_k(ideal)
     if loss_type == "NDCG_Loss1":                       # :33-34 (valid for B == 1 only)
         w = n_gains / disc
@@ -167,7 +167,7 @@ def lambdaloss_loss(preds, labels, k=5, sigma=1.0, loss_type="NDCG_Loss2++", mu=
     diffs = torch.where(torch.isnan(diffs), torch.zeros_like(diffs), diffs)     # :116
     wp = (torch.sigmoid(sigma * diffs).clamp(min=EPS_LAMBDALOSS) ** w).clamp(min=EPS_LAMBDALOSS)
     log_wp = torch.log2(wp)
-    trunc = torch.zeros((n, n), dtype=torch.bool)
+    trunc = torch.zeros((n, n), dtype=torch.bool, device=preds.device)
     trunc[:k, :k] = True
     if loss_type in ("NDCG_Loss2", "NDCG_Loss2++"):
         pair_mask = (pred_rankings.unsqueeze(2) - pred_rankings.unsqueeze(1)) > 0
@@ -186,7 +186,7 @@ def shuffle_ties_perm(labels: torch.Tensor, generator: Optional[torch.Generator]
     """ltr_adhoc/util/sampling_utils.py:13-28: indices ordering labels descending,
     ties broken by a fresh random permutation per row."""
     B, n = labels.shape
-    perms = torch.stack([torch.randperm(n, generator=generator) for _ in range(B)], dim=0)
+    perms = torch.stack([torch.randperm(n, generator=generator) for _ in range(B)], dim=0).to(labels.device)   # (sampling_utils.py:16-22: B host-side randperms, then moved to the device)
     shuffled = torch.gather(labels, 1, perms)
     desc = torch.argsort(shuffled, descending=True)
     return torch.gather(perms, 1, desc)

@@ -104,15 +104,15 @@ class Evaluator:
         With ``k`` given, lists shorter than k do not count (ranker.py:41-42 skips such batches; in a ragged batch the
         rule applies per query -- the kernel reports 0 for them)."""
         for batch in test_data:
-            if len(batch) == 5:
-                ids, X, y, offsets, max_len = batch
+            if len(batch) >= 5:
+                ids, X, y, offsets, max_len = batch[:5]
                 lens = (offsets[1:] - offsets[:-1]).cpu()
                 counted = int((lens >= k).sum()) if k is not None else len(ids)
                 if counted == 0:
                     continue
                 off_d = offsets.to(self.device, non_blocking=True)
                 preds, labels = self._scores_and_labels(X, y, off_d, max_len)
-                yield counted, preds, labels, dict(offsets=off_d, max_len=max_len)
+                yield counted, preds, labels, dict(offsets=off_d, max_len=max_len, buckets=batch[5] if len(batch) > 5 else None)
             else:
                 ids, X, y = batch
                 if k is not None and y.size(1) < k:
@@ -300,7 +300,8 @@ class NeuralRanker(Evaluator):
             ids, X, y = batch[0], batch[1], batch[2]
             with torch.cuda.stream(copier):
                 Xd, yd = X.to(self.device, non_blocking=True), y.to(self.device, non_blocking=True)
-                ragged = dict(offsets=batch[3].to(self.device, non_blocking=True), max_len=int(batch[4])) if len(batch) == 5 else {}
+                ragged = dict(offsets=batch[3].to(self.device, non_blocking=True), max_len=int(batch[4]),
+                              buckets=batch[5] if len(batch) > 5 else None) if len(batch) >= 5 else {}
                 ready = torch.cuda.Event()
                 ready.record(copier)
             return ids, Xd, yd, ready, ragged
@@ -373,4 +374,4 @@ class NeuralRanker(Evaluator):
         """The ragged-batch description a loss kernel needs, out of custom_loss_function's kwargs."""
         if kwargs.get('offsets') is None:
             return {}
-        return dict(offsets=kwargs['offsets'], max_len=kwargs['max_len'])
+        return dict(offsets=kwargs['offsets'], max_len=kwargs['max_len'], buckets=kwargs.get('buckets'))

@@ -114,9 +114,31 @@ class LengthBucketedBatches:
         return out
 
 
+def length_buckets(lens_desc: Sequence[int], edges: Sequence[int] = (32, 64, 128, 256, 512, 1024)) -> List[Tuple[int, int, int]]:
+    """[(q_begin, q_end, max_len)] over queries sorted by length DESCENDING: one bucket per length class
+    (.., 32], (32, 64], ... (1024, inf), classes holding fewer than 8 queries merged into their longer neighbour."""
+    lens = np.asarray(lens_desc)
+    if len(lens) == 0:
+        return []
+    cls = np.searchsorted(np.asarray(edges), lens, side="left")          # class index grows with length
+    out: List[Tuple[int, int, int]] = []
+    start = 0
+    for i in range(1, len(lens) + 1):
+        if i == len(lens) or cls[i] != cls[start]:
+            if out and (out[-1][1] - out[-1][0] < 8):                    # the previous class is too small for a launch of its own
+                b0, _, ml = out.pop()
+                out.append((b0, i, ml))
+            else:
+                out.append((start, i, int(lens[start])))
+            start = i
+    return out
+
+
 class RaggedBatches:
-    """Iterable of ragged batches ``(qids, X[total,F], y[total], offsets[B+1] int32, max_len)`` -- variable-length
-    lists inside ONE launch.
+    """Iterable of ragged batches ``(qids, X[total,F], y[total], offsets[B+1] int32, max_len, buckets)`` -- variable-length
+    lists inside ONE launch.  Inside a batch the queries are ordered by length, longest first, and
+    ``buckets`` = [(q_begin, q_end, max_len), ...] cuts that order at power-of-two lengths, so the per-list kernels can
+    size their CTAs for each length class instead of for the longest list of the batch (one launch per class).
 
     The reference batches only queries of identical length (data_utils.py:683-742); on real collections (MSLR-WEB30K:
     1..1251 documents per query, mean 119.6, testing/data/testing_data_utils.py:318-326) equal-length buckets hold a
@@ -177,7 +199,7 @@ class RaggedBatches:
         plan = self._plan()
         self.epoch += 1
         for members in plan:
-            qs = [self.queries[i] for i in members]
+            qs = sorted((self.queries[i] for i in members), key=lambda q: -q[1].shape[0])
             lens = np.array([q[1].shape[0] for q in qs], dtype=np.int64)
             total = int(lens.sum())
             X = torch.empty((total, self.num_features), dtype=torch.float32, pin_memory=self.pin)
@@ -189,7 +211,7 @@ class RaggedBatches:
                 X[o: o + Xq.shape[0]] = torch.from_numpy(Xq)
                 y[o: o + Xq.shape[0]] = torch.from_numpy(yq)
                 o += Xq.shape[0]
-            yield [q[0] for q in qs], X, y, offsets, int(lens.max())
+            yield [q[0] for q in qs], X, y, offsets, int(lens.max()), length_buckets(lens)
 
     def stats(self) -> dict:
         lens = np.array([q[1].shape[0] for q in self.queries])

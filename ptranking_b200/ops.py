@@ -68,71 +68,92 @@ def _list_layout(s: torch.Tensor, offsets, max_len):
 # --------------------------------------------------------------------------- #
 # ranking losses
 # --------------------------------------------------------------------------- #
+def _launch_ranges(B, n, offsets, buckets, coupled):
+    """(first query, query count, longest list) per launch.  ``buckets`` (ragged batches only): host-side
+    [(q_begin, q_end, max_len), ...] covering the queries in order -- data.RaggedBatches sorts a batch by length and cuts
+    it at power-of-two lengths, so each launch gets CTAs (and the pair schedule) sized for ITS lists instead of for the
+    longest list of the whole batch.  Losses coupled across the batch (ApproxNDCG's [B]/[B,1] broadcast, RankMSE's mean)
+    take one launch."""
+    if offsets is None or not buckets or coupled:
+        return [(0, B, n)]
+    out = [(int(b0), int(b1) - int(b0), max(int(ml), 1)) for b0, b1, ml in buckets if int(b1) > int(b0)]
+    if sum(c for _, c, _ in out) != B or out[0][0] != 0:
+        raise ValueError("buckets must cover the queries of the batch in order")
+    return out
+
+
 @_on_tensor_device
 def _loss_call(name: str, scores: torch.Tensor, labels: torch.Tensor, params: dict):
-    """-> (loss_per_query[B], grad[B,n]) from one fused kernel launch."""
+    """-> (loss_per_query[B], grad[B,n]) from one fused kernel launch (one per length bucket of a ragged batch)."""
     lib = _lib.load()
     s = _dev_f32(scores, "scores")
     B, n, offsets, op = _list_layout(s, params.get("offsets"), params.get("max_len"))
     grad = torch.empty_like(s)
     loss_q = torch.empty(B, dtype=torch.float32, device=s.device)
     st = _stream_ptr()
+    sp, gp, lq = s.data_ptr(), grad.data_ptr(), loss_q.data_ptr()
+    coupled = name == "RankMSE" or (name == "ApproxNDCG" and bool(params.get("batch_coupled", True)))
+    ranges = _launch_ranges(B, n, offsets, params.get("buckets"), coupled)
     if name == "ListMLE":
         perm = params.get("perm")
         if perm is None:
-            perm = shuffle_ties_perm(labels, offsets=offsets, max_len=n if offsets is not None else None)
+            perm = shuffle_ties_perm(labels, offsets=offsets, max_len=n if offsets is not None else None, buckets=params.get("buckets"))
         perm = perm.to(device=s.device, dtype=torch.int32).contiguous()
         if perm.shape != s.shape:
             raise ValueError(f"perm {tuple(perm.shape)} does not match scores {tuple(s.shape)}")
-        rc = lib.ptrb200_listmle_fwd_bwd(s.data_ptr(), perm.data_ptr(), op, grad.data_ptr(), loss_q.data_ptr(), B, n, st)
+        aux = perm
     else:
         y = _dev_f32(labels, "labels")
         if y.shape != s.shape:
             raise ValueError(f"expected scores/labels of identical shape, got {tuple(s.shape)} / {tuple(y.shape)}")
-        if name == "RankNet":
-            rc = lib.ptrb200_ranknet_fwd_bwd(s.data_ptr(), y.data_ptr(), op, grad.data_ptr(), loss_q.data_ptr(), B, n,
-                                             float(params.get("sigma", 1.0)), st)
+        aux = y
+    yp = aux.data_ptr()
+    unif = None
+    if name == "STListNet":
+        unif = params.get("unif")
+        if unif is not None:
+            unif = _dev_f32(unif, "unif")
+            if unif.shape != s.shape:
+                raise ValueError("unif must have the shape of scores")
+        seed, offset = params.get("seed"), params.get("offset")
+        if seed is None:
+            seed = torch.initial_seed()
+        if offset is None:
+            offset = next_noise_offset()
+    scratch = torch.empty(B + 1, dtype=torch.float32, device=s.device) if name == "ApproxNDCG" else None
+    for q0, Bq, nq in ranges:
+        # a bucket is addressed through its slice of the (absolute) prefix offsets and of the per-query loss vector; the flat
+        # score / label / gradient arrays are shared
+        opq = None if op is None else op + 4 * q0
+        lqq = lq + 4 * q0
+        if name == "ListMLE":
+            rc = lib.ptrb200_listmle_fwd_bwd(sp, yp, opq, gp, lqq, Bq, nq, st)
+        elif name == "RankNet":
+            rc = lib.ptrb200_ranknet_fwd_bwd(sp, yp, opq, gp, lqq, Bq, nq, float(params.get("sigma", 1.0)), st)
         elif name == "LambdaRank":
-            rc = lib.ptrb200_lambdarank_fwd_bwd(s.data_ptr(), y.data_ptr(), op, grad.data_ptr(), loss_q.data_ptr(), B, n,
-                                                float(params.get("sigma", 1.0)), st)
+            rc = lib.ptrb200_lambdarank_fwd_bwd(sp, yp, opq, gp, lqq, Bq, nq, float(params.get("sigma", 1.0)), st)
         elif name == "LambdaLoss":
             lt = _lib.LAMBDALOSS_TYPES[params.get("loss_type", "NDCG_Loss2++")]
-            rc = lib.ptrb200_lambdaloss_fwd_bwd(s.data_ptr(), y.data_ptr(), op, grad.data_ptr(), loss_q.data_ptr(), B, n,
-                                                int(params.get("k", 5)), float(params.get("sigma", 1.0)),
+            rc = lib.ptrb200_lambdaloss_fwd_bwd(sp, yp, opq, gp, lqq, Bq, nq, int(params.get("k", 5)), float(params.get("sigma", 1.0)),
                                                 float(params.get("mu", 5.0)), lt, int(bool(params.get("presort", True))), st)
         elif name == "ListNet":
-            rc = lib.ptrb200_listnet_fwd_bwd(s.data_ptr(), y.data_ptr(), op, grad.data_ptr(), loss_q.data_ptr(), B, n, st)
+            rc = lib.ptrb200_listnet_fwd_bwd(sp, yp, opq, gp, lqq, Bq, nq, st)
         elif name == "ApproxNDCG":
-            scratch = torch.empty(B + 1, dtype=torch.float32, device=s.device)
-            rc = lib.ptrb200_approxndcg_fwd_bwd(s.data_ptr(), y.data_ptr(), op, grad.data_ptr(), loss_q.data_ptr(),
-                                                scratch.data_ptr(), B, n, float(params.get("alpha", 10.0)),
-                                                int(bool(params.get("presort", True))),
-                                                int(bool(params.get("batch_coupled", True))), st)
+            rc = lib.ptrb200_approxndcg_fwd_bwd(sp, yp, opq, gp, lqq, scratch.data_ptr() + 4 * q0, Bq, nq, float(params.get("alpha", 10.0)),
+                                                int(bool(params.get("presort", True))), int(bool(params.get("batch_coupled", True))), st)
         elif name == "RankMSE":
-            rc = lib.ptrb200_rankmse_fwd_bwd(s.data_ptr(), y.data_ptr(), op, grad.data_ptr(), loss_q.data_ptr(), B, n, st)
+            rc = lib.ptrb200_rankmse_fwd_bwd(sp, yp, opq, gp, lqq, Bq, nq, st)
         elif name == "RankCosine":
-            rc = lib.ptrb200_rankcosine_fwd_bwd(s.data_ptr(), y.data_ptr(), op, grad.data_ptr(), loss_q.data_ptr(), B, n, st)
+            rc = lib.ptrb200_rankcosine_fwd_bwd(sp, yp, opq, gp, lqq, Bq, nq, st)
         elif name == "STListNet":
-            unif = params.get("unif")
-            if unif is not None:
-                unif = _dev_f32(unif, "unif")
-                if unif.shape != s.shape:
-                    raise ValueError("unif must have the shape of scores")
-            seed, offset = params.get("seed"), params.get("offset")
-            if seed is None:
-                seed = torch.initial_seed()
-            if offset is None:
-                offset = next_noise_offset()
-            rc = lib.ptrb200_stlistnet_fwd_bwd(s.data_ptr(), y.data_ptr(), op, unif.data_ptr() if unif is not None else None,
-                                               grad.data_ptr(), loss_q.data_ptr(), B, n, float(params.get("temperature", 1.0)),
-                                               seed & (2 ** 64 - 1), offset & (2 ** 64 - 1), st)
+            rc = lib.ptrb200_stlistnet_fwd_bwd(sp, yp, opq, unif.data_ptr() if unif is not None else None, gp, lqq, Bq, nq,
+                                               float(params.get("temperature", 1.0)), seed & (2 ** 64 - 1), offset & (2 ** 64 - 1), st)
         elif name == "SoftRank":
             top_k = params.get("top_k")
-            rc = lib.ptrb200_softrank_fwd_bwd(s.data_ptr(), y.data_ptr(), op, grad.data_ptr(), loss_q.data_ptr(), B, n,
-                                              float(params.get("delta", 2.0)), int(top_k) if top_k else 0, st)
+            rc = lib.ptrb200_softrank_fwd_bwd(sp, yp, opq, gp, lqq, Bq, nq, float(params.get("delta", 2.0)), int(top_k) if top_k else 0, st)
         else:
             raise NotImplementedError(name)
-    _lib.check(rc, f"{name} loss kernel")
+        _lib.check(rc, f"{name} loss kernel")
     return loss_q, grad
 
 
@@ -275,7 +296,7 @@ _tie_offset = 0
 
 @_on_tensor_device
 def shuffle_ties_perm(labels: torch.Tensor, seed: Optional[int] = None, offset: Optional[int] = None,
-                      offsets: Optional[torch.Tensor] = None, max_len: Optional[int] = None) -> torch.Tensor:
+                      offsets: Optional[torch.Tensor] = None, max_len: Optional[int] = None, buckets=None) -> torch.Tensor:
     """int32 ordering (positions within each query's list) of each query's labels, descending, ties in random order;
     same layout as ``labels`` ([B,n], or flat with ``offsets``/``max_len`` for a ragged batch)."""
     global _tie_offset
@@ -288,8 +309,9 @@ def shuffle_ties_perm(labels: torch.Tensor, seed: Optional[int] = None, offset: 
     if offset is None:
         _tie_offset += 1
         offset = _tie_offset
-    _lib.check(lib.ptrb200_shuffle_ties_perm(y.data_ptr(), op, perm.data_ptr(), B, n, seed & (2 ** 64 - 1),
-                                             offset & (2 ** 64 - 1), _stream_ptr()), "shuffle_ties_perm")
+    for q0, Bq, nq in _launch_ranges(B, n, offsets, buckets, False):
+        _lib.check(lib.ptrb200_shuffle_ties_perm(y.data_ptr(), None if op is None else op + 4 * q0, perm.data_ptr(), Bq, nq,
+                                                 seed & (2 ** 64 - 1), offset & (2 ** 64 - 1), _stream_ptr()), "shuffle_ties_perm")
     return perm
 
 
@@ -324,7 +346,7 @@ def standard_scale(X: torch.Tensor, offsets: Optional[torch.Tensor] = None, max_
 # --------------------------------------------------------------------------- #
 @_on_tensor_device
 def ndcg_at_ks(scores: torch.Tensor, labels: torch.Tensor, ks: Sequence[int], presort: bool = False,
-               return_order: bool = False, offsets: Optional[torch.Tensor] = None, max_len: Optional[int] = None):
+               return_order: bool = False, offsets: Optional[torch.Tensor] = None, max_len: Optional[int] = None, buckets=None):
     """Per-query nDCG at the cutoffs ``ks`` -> [B, len(ks)] (zero where k > n).  ``offsets``/``max_len``: ragged batch."""
     lib = _lib.load()
     s, y = _dev_f32(scores, "scores"), _dev_f32(labels, "labels")
@@ -337,9 +359,10 @@ def ndcg_at_ks(scores: torch.Tensor, labels: torch.Tensor, ks: Sequence[int], pr
     arr = (C.c_int32 * len(ks))(*ks_sorted)
     out = torch.empty((B, len(ks)), dtype=torch.float32, device=s.device)
     order = torch.empty(s.shape, dtype=torch.int32, device=s.device) if return_order else None
-    _lib.check(lib.ptrb200_ndcg_at_ks(s.data_ptr(), y.data_ptr(), op, arr, len(ks), out.data_ptr(),
-                                      order.data_ptr() if return_order else None, B, n, int(bool(presort)),
-                                      _stream_ptr()), "ndcg_at_ks")
+    for q0, Bq, nq in _launch_ranges(B, n, offsets, buckets, False):
+        _lib.check(lib.ptrb200_ndcg_at_ks(s.data_ptr(), y.data_ptr(), None if op is None else op + 4 * q0, arr, len(ks),
+                                          out.data_ptr() + 4 * q0 * len(ks), order.data_ptr() if return_order else None, Bq, nq,
+                                          int(bool(presort)), _stream_ptr()), "ndcg_at_ks")
     if order_ix != list(range(len(ks))):
         inv = torch.empty(len(ks), dtype=torch.long)
         inv[torch.tensor(order_ix)] = torch.arange(len(ks))
@@ -350,7 +373,7 @@ def ndcg_at_ks(scores: torch.Tensor, labels: torch.Tensor, ks: Sequence[int], pr
 @_on_tensor_device
 def adhoc_metrics_at_ks(scores: torch.Tensor, labels: torch.Tensor, ks: Sequence[int], presort: bool = False,
                         max_label: Optional[float] = None, offsets: Optional[torch.Tensor] = None,
-                        max_len: Optional[int] = None):
+                        max_len: Optional[int] = None, buckets=None):
     """(nDCG, nERR, AP, P) per query at the cutoffs ``ks`` -> four [B, len(ks)] tensors from one kernel."""
     lib = _lib.load()
     s, y = _dev_f32(scores, "scores"), _dev_f32(labels, "labels")
@@ -363,8 +386,10 @@ def adhoc_metrics_at_ks(scores: torch.Tensor, labels: torch.Tensor, ks: Sequence
     if max_label is None:                       # the reference falls back to the maximum over the batch
         max_label = float(y.max())
     out = torch.empty((B, 4, len(ks)), dtype=torch.float32, device=s.device)
-    _lib.check(lib.ptrb200_adhoc_metrics_at_ks(s.data_ptr(), y.data_ptr(), op, arr, len(ks), out.data_ptr(), B, n,
-                                               int(bool(presort)), float(max_label), _stream_ptr()), "adhoc_metrics_at_ks")
+    for q0, Bq, nq in _launch_ranges(B, n, offsets, buckets, False):
+        _lib.check(lib.ptrb200_adhoc_metrics_at_ks(s.data_ptr(), y.data_ptr(), None if op is None else op + 4 * q0, arr, len(ks),
+                                                   out.data_ptr() + 16 * q0 * len(ks), Bq, nq, int(bool(presort)), float(max_label),
+                                                   _stream_ptr()), "adhoc_metrics_at_ks")
     if order_ix != list(range(len(ks))):
         inv = torch.empty(len(ks), dtype=torch.long)
         inv[torch.tensor(order_ix)] = torch.arange(len(ks))

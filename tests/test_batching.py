@@ -73,3 +73,39 @@ def test_bad_input_is_rejected():
                                ("b", np.zeros((3, 5), np.float32), np.zeros(3, np.float32))], pin_memory=False)
     with pytest.raises(ValueError):
         LengthBucketedBatches([], rank=2, world=2)
+
+
+def test_ragged_batches_pack_by_documents_and_bucket_by_length():
+    """RaggedBatches: queries of any length packed up to the document target; inside a batch longest first, with length
+    buckets that cover the batch in order and bound every list they hold."""
+    from ptranking_b200.data import RaggedBatches, length_buckets
+    rng = np.random.default_rng(0)
+    lens = np.clip(rng.lognormal(4.45, 0.85, 600), 1, 1251).astype(int)
+    queries = [(f"q{i}", rng.standard_normal((n, 5)).astype(np.float32), np.sort(rng.integers(0, 5, n))[::-1].astype(np.float32))
+               for i, n in enumerate(lens)]
+    queries.append(("empty", np.zeros((0, 5), dtype=np.float32), np.zeros(0, dtype=np.float32)))     # skipped like the reference does
+    loader = RaggedBatches(queries, docs_per_batch=20000, presort=False, pin_memory=False)
+    seen, docs = [], 0
+    for ids, X, y, offsets, max_len, buckets in loader:
+        B = len(ids)
+        ln = (offsets[1:] - offsets[:-1]).numpy()
+        assert offsets[0] == 0 and offsets[-1] == X.shape[0] == y.shape[0] and X.shape[1] == 5
+        assert (np.diff(ln) <= 0).all() and ln.max() == max_len and ln.min() >= 1
+        assert buckets[0][0] == 0 and buckets[-1][1] == B and all(a[1] == b[0] for a, b in zip(buckets, buckets[1:]))
+        for b0, b1, ml in buckets:
+            assert ln[b0:b1].max() == ml
+        assert X.shape[0] <= 20000 or B == 1
+        for i, q in enumerate(ids):                       # every query's rows are its own
+            src = queries[int(q[1:])]
+            assert np.array_equal(X[offsets[i]: offsets[i + 1]].numpy(), src[1]) and np.array_equal(y[offsets[i]: offsets[i + 1]].numpy(), src[2])
+        seen += ids
+        docs += X.shape[0]
+    assert sorted(seen) == sorted(f"q{i}" for i in range(600)) and docs == int(lens.sum())
+    st = loader.stats()
+    assert st["queries"] == 600 and st["max_len"] == int(lens.max()) and st["batches"] == len(loader)
+    # data-parallel shards: disjoint, equal batch counts
+    a = RaggedBatches(queries, docs_per_batch=20000, presort=False, pin_memory=False, rank=0, world=2)
+    b = RaggedBatches(queries, docs_per_batch=20000, presort=False, pin_memory=False, rank=1, world=2)
+    ia, ib = [q for batch in a for q in batch[0]], [q for batch in b for q in batch[0]]
+    assert len(a) == len(b) and not set(ia) & set(ib)
+    assert length_buckets([]) == [] and length_buckets([7]) == [(0, 1, 7)]

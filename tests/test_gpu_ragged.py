@@ -283,3 +283,38 @@ def test_ragged_bn2_equals_dense_bn2_on_uniform_lengths():
     ops._dropout_offset = o0                   # same dropout stream for the second call
     b = r.forward_ragged(X.reshape(B * n, F), off, n)
     assert rel_err(b.detach().cpu().numpy(), a.detach().cpu().numpy().reshape(-1)) <= 1e-5
+
+
+@pytest.mark.parametrize("name,params", [("LambdaRank", dict(sigma=1.0)), ("RankNet", dict(sigma=1.0)), ("ListNet", {}), ("SoftRank", dict(delta=2.0)),
+                                         ("LambdaLoss", dict(k=5)), ("ApproxNDCG", dict(alpha=10.0, batch_coupled=False)), ("ListMLE", {})])
+def test_length_buckets_change_launch_geometry_not_results(name, params):
+    """RaggedBatches orders a batch by length and cuts it at power-of-two lengths; each bucket is launched with CTAs sized
+    for its own lists.  Same numbers as the single launch sized for the longest list (different kernels may serve the
+    short and the long lists: fp32-rounding agreement, not bit equality), and the metric kernels agree exactly."""
+    from ptranking_b200 import ops
+    from ptranking_b200.data import length_buckets
+    rng = np.random.default_rng(3)
+    lens = np.sort(np.clip(rng.lognormal(4.45, 0.85, 300), 1, 1251).astype(int))[::-1].copy()
+    lens[0] = 1251
+    S, Y, off = _ragged(list(lens), seed=41, sigmoid=True)
+    s = torch.from_numpy(np.concatenate(S)).to(DEV); y = torch.from_numpy(np.concatenate(Y)).to(DEV)
+    offd = torch.from_numpy(off).to(DEV)
+    buckets = length_buckets(lens)
+    assert len(buckets) >= 4
+    kw = dict(params)
+    if name == "ListMLE":
+        kw["perm"] = ops.shuffle_ties_perm(y, seed=3, offset=1, offsets=offd, max_len=int(lens.max()), buckets=buckets)
+        p2 = ops.shuffle_ties_perm(y, seed=3, offset=1, offsets=offd, max_len=int(lens.max()))
+        assert torch.equal(kw["perm"], p2)              # the tie shuffle is keyed by flat document index: launch geometry is irrelevant
+    l0, q0, g0 = ops.rank_loss_and_grad(name, s, y, offsets=offd, max_len=int(lens.max()), **kw)
+    l1, q1, g1 = ops.rank_loss_and_grad(name, s, y, offsets=offd, max_len=int(lens.max()), buckets=buckets, **kw)
+    assert rel_err(q1.cpu().numpy(), q0.cpu().numpy()) <= 2e-5 and abs(float(l1) - float(l0)) <= 2e-5 * abs(float(l0))
+    g0, g1 = g0.cpu().numpy(), g1.cpu().numpy()
+    for b in range(len(lens)):
+        a, c = g0[off[b]: off[b + 1]], g1[off[b]: off[b + 1]]
+        assert np.abs(a - c).max() <= 2e-5 * max(np.abs(a).max(), 1e-6) + 1e-8, (b, lens[b])
+    nd0 = ops.ndcg_at_ks(s, y, [1, 5, 10], presort=True, offsets=offd, max_len=int(lens.max()))
+    nd1 = ops.ndcg_at_ks(s, y, [1, 5, 10], presort=True, offsets=offd, max_len=int(lens.max()), buckets=buckets)
+    m0 = ops.adhoc_metrics_at_ks(s, y, [1, 5, 10], presort=True, max_label=4.0, offsets=offd, max_len=int(lens.max()))
+    m1 = ops.adhoc_metrics_at_ks(s, y, [1, 5, 10], presort=True, max_label=4.0, offsets=offd, max_len=int(lens.max()), buckets=buckets)
+    assert torch.equal(nd0, nd1) and all(torch.equal(a, c) for a, c in zip(m0, m1))

@@ -72,14 +72,19 @@ for (B, n) in [(1024, 256), (256, 1024)]:
 # the same number of documents, loss kernel alone and the whole training step
 lens = np.clip(rng.lognormal(mean=4.45, sigma=0.85, size=4096), 1, 1251).astype(np.int64)
 take = int(np.searchsorted(np.cumsum(lens), 1 << 18))
-lens = lens[:take]
+lens = np.sort(lens[:take])[::-1].copy()          # data.RaggedBatches orders a batch by length, longest first
+from ptranking_b200.data import length_buckets
+buckets = length_buckets(lens)
 off = np.zeros(len(lens) + 1, dtype=np.int32); off[1:] = np.cumsum(lens)
 total = int(off[-1])
 yr = np.concatenate([-np.sort(-np.maximum(rng.choice(5, size=n_, p=bench.MSLR_P), (np.arange(n_) == 0).astype(np.int64)).astype(np.float32)) for n_ in lens])
 s_r = torch.sigmoid(torch.randn(total, device=dev)); y_r = torch.from_numpy(yr).to(dev); off_d = torch.from_numpy(off).to(dev)
 for name, params in [("LambdaRank", dict(sigma=1.0)), ("ListNet", {}), ("ApproxNDCG", dict(alpha=10.0))]:
     ms = timeit(lambda: ops.rank_loss_and_grad(name, s_r, y_r, offsets=off_d, max_len=int(lens.max()), **params))
-    rows.append((f"{name} RAGGED (lens 1..{int(lens.max())}, mean {lens.mean():.0f})", f"B={len(lens)} docs={total}", ms, len(lens) / ms * 1e3,
+    rows.append((f"{name} RAGGED one launch (lens 1..{int(lens.max())}, mean {lens.mean():.0f})", f"B={len(lens)} docs={total}", ms, len(lens) / ms * 1e3,
+                 12 * total / ms / 1e6, 12 * total / ms / 1e6 / HBM))
+    ms = timeit(lambda: ops.rank_loss_and_grad(name, s_r, y_r, offsets=off_d, max_len=int(lens.max()), buckets=buckets, **params))
+    rows.append((f"{name} RAGGED {len(buckets)} length buckets", f"B={len(lens)} docs={total}", ms, len(lens) / ms * 1e3,
                  12 * total / ms / 1e6, 12 * total / ms / 1e6 / HBM))
 Xs = torch.randn(total, 136, device=dev)
 ms = timeit(lambda: ops.standard_scale(Xs, offsets=off_d, max_len=int(lens.max())))
@@ -100,7 +105,7 @@ for (B, n) in [(1024, 256), (256, 1024), (4096, 32)]:
     rows.append(("LambdaRank train step (fwd+loss+bwd+Adam)", f"B={B} n={n}", ms_s, B / ms_s * 1e3, algo / ms_s / 1e6, algo / ms_s / 1e6 / HBM))
 # the same step on the ragged batch (batch-level BN: one long list to the scorer, per-query offsets to the loss)
 Xr = torch.randn(total, 136, device=dev)
-ms_s = timeit(lambda: r.train_op(Xr, y_r, presort=True, label_type=LABEL_TYPE.MultiLabel, epoch_k=1, offsets=off_d, max_len=int(lens.max())))
+ms_s = timeit(lambda: r.train_op(Xr, y_r, presort=True, label_type=LABEL_TYPE.MultiLabel, epoch_k=1, offsets=off_d, max_len=int(lens.max()), buckets=buckets))
 algo = total * (136 * 4 + 8)
 rows.append((f"LambdaRank train step RAGGED (lens 1..{int(lens.max())})", f"B={len(lens)} docs={total}", ms_s, len(lens) / ms_s * 1e3, algo / ms_s / 1e6, algo / ms_s / 1e6 / HBM))
 rows.append(("   -> documents/s ragged vs uniform 1024x256", "", float('nan'), total / ms_s * 1e3, float('nan'), float('nan')))
