@@ -610,6 +610,8 @@ struct Plan {
     size_t partials_off, s1_off, s2_off, t1_off, t2_off, dbuf0_off, dbuf1_off, wpart_off, k1_off, k3_off, k0_off, sync_off, total;
     bool sync_bn;                                // batch-level BN statistics all-reduced across data-parallel ranks
     bool ragged;                                 // per-query BN2 over a ragged batch (query boundaries from prefix offsets)
+    int pad_k;                                   // > 0: input width zero-padded to this multiple of 4 for the tensor-core path
+    size_t xpad_off, w0pad_off, dw0pad_off, dxpad_off;
 };
 
 // column blocking of the weight gradient: dZ columns in blocks of 128 (MMA M), input columns in blocks of <= 256 (MMA N)
@@ -642,11 +644,16 @@ static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p, int total_
     p.sync_bn = net->sync_bn != 0 && net->norm == PTRB200_NORM_BN;
     p.passes = net->math_mode == PTRB200_MATH_3XTF32 ? 3 : 1;
     p.bf16 = net->math_mode == PTRB200_MATH_BF16;
+    // A feature width that is not a multiple of 4 (MQ2007/2008: 46 features) would push the whole net onto the fp32 SIMT
+    // kernels.  Instead the input and the first weight matrix are zero-padded to the next multiple of 4 (two small copy
+    // kernels per call) and every layer runs on the tensor cores; the padded columns contribute exact zeros.
+    p.pad_k = (p.use_tc && net->dims[0] % 4 != 0) ? ((net->dims[0] + 3) / 4) * 4 : 0;
     for (int l = 0; l < net->num_linear && p.use_tc; ++l) {
-        const int di = net->dims[l], dn = net->dims[l + 1];
+        const int di = (l == 0 && p.pad_k) ? p.pad_k : net->dims[l], dn = net->dims[l + 1];
         // float4 row access needs widths % 4; wider layers are tiled over output columns / weight-gradient blocks
         if (di % 4 != 0 || di > 1024 || dn > 1024 || (dn % 4 != 0 && dn > 4)) p.use_tc = false;
     }
+    if (!p.use_tc) p.pad_k = 0;
     for (int l = 0; l < net->num_linear && p.bf16; ++l)
         if (net->dims[l + 1] != 1 && net->dims[l + 1] % 4 != 0) p.use_tc = false;       // such a layer's data gradient would run unrounded on SIMT
     if (p.bf16 && !p.use_tc) { set_error("ffnet: math_mode bf16 needs layer widths the tensor-core kernels take (multiples of 4, <= 1024)"); return PTRB200_ERR_UNSUPPORTED; }
@@ -673,7 +680,7 @@ static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p, int total_
     int maxd = 0; size_t maxw = 0;
     for (int l = 0; l < p.L; ++l) {
         LayerPlan& lp = p.layer[l];
-        lp.d_in = net->dims[l]; lp.d_out = net->dims[l + 1];
+        lp.d_in = (l == 0 && p.pad_k) ? p.pad_k : net->dims[l]; lp.d_out = net->dims[l + 1];
         if (lp.d_in <= 0 || lp.d_out <= 0) { set_error("ffnet: non-positive layer width"); return PTRB200_ERR_INVALID; }
         if (!net->weight[l] || !net->bias[l]) { set_error("ffnet: layer %d weight/bias is NULL", l); return PTRB200_ERR_INVALID; }
         lp.act = l < p.L - 1 ? net->act_hidden : net->act_tail;
@@ -717,6 +724,13 @@ static int make_plan(const ptrb200_ffnet* net, int B, int n, Plan& p, int total_
             wbytes = need > wbytes ? need : wbytes;
         }
         p.wpart_off = off; off = align_up(off + wbytes, 256);
+    }
+    p.xpad_off = p.w0pad_off = p.dw0pad_off = p.dxpad_off = off;
+    if (p.pad_k) {
+        p.xpad_off = off; off = align_up(off + p.rows * p.pad_k * 4, 256);
+        p.w0pad_off = off; off = align_up(off + (size_t)net->dims[1] * p.pad_k * 4, 256);
+        p.dw0pad_off = off; off = align_up(off + (size_t)net->dims[1] * p.pad_k * 4, 256);
+        p.dxpad_off = off; off = align_up(off + p.rows * p.pad_k * 4, 256);
     }
     p.total = off;
     return PTRB200_OK;
@@ -777,6 +791,17 @@ __global__ void dgrad_rank1_kernel(const float* __restrict__ dz, const float* __
             v.w = ((uint32_t)(dd >> 48)) >= drop.thr ? v.w * drop.scale : 0.0f;
         }
         reinterpret_cast<float4*>(dIn)[u] = v;
+    }
+}
+
+// dst[r, 0..kd) = src[r, 0..ks) (zero beyond ks when widening; truncated when narrowing): the zero-padding of the feature
+// matrix / first weight matrix to a multiple of 4 columns, and the way back for their gradients
+__global__ void copy_cols_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t rows, int ks, int kd) {
+    const size_t total = rows * (size_t)kd;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / kd;
+        const int k = (int)(i - r * kd);
+        dst[i] = k < ks ? src[r * ks + k] : 0.0f;
     }
 }
 
@@ -1395,6 +1420,15 @@ int ptrb200_ffnet_forward(const ptrb200_ffnet* net, const float* X, float* out, 
     char* ws = static_cast<char*>(workspace);
     cudaStream_t st = (cudaStream_t)stream;
     const float drop = (training & 1) ? net->dropout_p : 0.0f;
+    ptrb200_ffnet padded;
+    if (p.pad_k) {          // zero-pad the features and the first weight matrix to a multiple of 4 columns (make_plan)
+        float* Xp = reinterpret_cast<float*>(ws + p.xpad_off);
+        float* Wp = reinterpret_cast<float*>(ws + p.w0pad_off);
+        PTRB200_LAUNCH(copy_cols_kernel, elementwise_blocks(p.rows * p.pad_k), 256, 0, st, X, Xp, p.rows, net->dims[0], p.pad_k);
+        PTRB200_LAUNCH(copy_cols_kernel, elementwise_blocks((size_t)net->dims[1] * p.pad_k), 256, 0, st, net->weight[0], Wp, (size_t)net->dims[1], net->dims[0], p.pad_k);
+        padded = *net; padded.dims[0] = p.pad_k; padded.weight[0] = Wp;
+        net = &padded; X = Xp;
+    }
     if (p.ragged) return forward_ragged(net, p, X, offsets, out, ws, drop, seed, offset, st, (training & PTRB200_FFNET_FORWARD_ONLY) != 0);
     if (p.use_tc) return forward_tc(net, p, X, out, ws, drop, seed, offset, st, (training & PTRB200_FFNET_FORWARD_ONLY) != 0);
     const float* in = X;
@@ -1443,6 +1477,22 @@ int ptrb200_ffnet_backward(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* 
     char* ws = static_cast<char*>(workspace);
     cudaStream_t st = (cudaStream_t)stream;
     const float drop = (training & 1) ? net->dropout_p : 0.0f;
+    if (p.pad_k) {          // the forward call left the padded features and first weight matrix in the workspace
+        ptrb200_ffnet padded = *net;
+        ptrb200_ffnet_grads pg = *grads;
+        padded.dims[0] = p.pad_k; padded.weight[0] = reinterpret_cast<const float*>(ws + p.w0pad_off);
+        pg.weight[0] = reinterpret_cast<float*>(ws + p.dw0pad_off);
+        float* dXp = dX ? reinterpret_cast<float*>(ws + p.dxpad_off) : nullptr;
+        const float* Xp = reinterpret_cast<const float*>(ws + p.xpad_off);
+        rc = p.ragged ? backward_ragged(&padded, &pg, p, Xp, offsets, dOut, dXp, ws, drop, seed, offset, st)
+                      : backward_tc(&padded, &pg, p, Xp, dOut, dXp, ws, drop, seed, offset, st);
+        if (rc) return rc;
+        if (!grads->weight[0]) { set_error("ffnet_backward: layer 0 grad buffer NULL"); return PTRB200_ERR_INVALID; }
+        PTRB200_LAUNCH(copy_cols_kernel, elementwise_blocks((size_t)net->dims[1] * net->dims[0]), 256, 0, st, (const float*)pg.weight[0], grads->weight[0],
+                       (size_t)net->dims[1], p.pad_k, net->dims[0]);
+        if (dX) PTRB200_LAUNCH(copy_cols_kernel, elementwise_blocks(p.rows * net->dims[0]), 256, 0, st, (const float*)dXp, dX, p.rows, p.pad_k, net->dims[0]);
+        return check_launch("ffnet_backward(padded)");
+    }
     if (p.ragged) return backward_ragged(net, grads, p, X, offsets, dOut, dX, ws, drop, seed, offset, st);
     if (p.use_tc) return backward_tc(net, grads, p, X, dOut, dX, ws, drop, seed, offset, st);
     double* part = reinterpret_cast<double*>(ws + p.partials_off);
