@@ -34,6 +34,10 @@ for s in $stages; do
     parity)   timeout 400 python tools/parity_table.py r02 > gpurun_out/parity_table.log 2>&1; tail -5 gpurun_out/parity_table.log; cp profiles/r02_parity_table.md gpurun_out/ 2>/dev/null ;;
     dropin)   timeout 600 python tools/dropin_run.py --impl b200 --model LambdaRank > gpurun_out/dropin_run.log 2>&1; grep -v Warning gpurun_out/dropin_run.log | tail -14
               timeout 600 python tools/dropin_run.py --impl b200 --model ApproxNDCG --sf listsf --queries 120 > gpurun_out/dropin_run_listsf.log 2>&1; grep -v Warning gpurun_out/dropin_run_listsf.log | tail -8 ;;
+    benchA)   timeout 400 python bench.py --config a 2>gpurun_out/bench_a.err | tail -1 > gpurun_out/bench_a.json
+              python -c "import json; d=json.loads(open('gpurun_out/bench_a.json').read()); print('a', round(d['value'],1), round(d['ms_per_step'],4), d.get('reference_cuda'), list(d['roofline']['kernels_ms_per_step'].items())[:6])" ;;
+    benchDE)  for c in d e; do timeout 400 python bench.py --config $c --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/bench_${c}_nocpu.json; done ;;
+    profile)  timeout 1500 bash tools/profile_r02.sh launches b c d e 2>&1 | tail -20 ;;
     *)        echo "unknown stage $s" ;;
   esac
 done
