@@ -853,6 +853,12 @@ static int launch_rows_gemm(int mode, int passes, RowsGemmArgs& g, int ntiles, c
         x.stats_mode = (!g.partials || stats_kind == 0) ? 0 : (stats_kind == 1 ? 1 : 2);
         const int grid = ntiles < 148 ? ntiles : 148;
         if (S_out) *S_out = x.stats_mode == 1 ? grid : S_default;
+#define RW_CASE_K(M, P, A, KT, TAG)                                                                 \
+        if (mode == M && passes == P && act_t == A && g.K == KT) {                                  \
+            if ((rc = opt_in_smem(rows_gemm_ws_kernel<M, P, A, KT>, ws_smem))) return rc;           \
+            PTRB200_LAUNCH_TAG(TAG, (rows_gemm_ws_kernel<M, P, A, KT>), grid, RW_THREADS, ws_smem, st, g, x); \
+            return PTRB200_OK;                                                                      \
+        }
 #define RW_CASE(M, P, A, TAG)                                                                       \
         if (mode == M && passes == P && act_t == A) {                                               \
             if ((rc = opt_in_smem(rows_gemm_ws_kernel<M, P, A>, ws_smem))) return rc;               \
@@ -861,6 +867,14 @@ static int launch_rows_gemm(int mode, int passes, RowsGemmArgs& g, int ntiles, c
         }
         // the prologue activation is a template parameter for the common codes, -1 = generic run-time switch
         const int act_t = (g.act == PTRB200_AF_NONE || g.act == PTRB200_AF_RELU || g.act == PTRB200_AF_GELU || g.act == PTRB200_AF_SIGM) ? g.act : -1;
+        // width-specialised instantiations for the default scorer (136 features, 100-wide hidden layers); PTRB200_NO_KT=1 skips them
+        static const bool no_kt = getenv("PTRB200_NO_KT") != nullptr;
+        if (!no_kt) {
+            RW_CASE_K(RG_FWD, 3, PTRB200_AF_NONE, 136, "rows_gemm_ws_fwd") RW_CASE_K(RG_FWD, 3, PTRB200_AF_GELU, 100, "rows_gemm_ws_fwd")
+            RW_CASE_K(RG_DGRAD, 3, PTRB200_AF_NONE, 100, "rows_gemm_ws_dgrad")
+            RW_CASE_K(RG_FWD, 1, PTRB200_AF_NONE, 136, "rows_gemm_ws_fwd") RW_CASE_K(RG_FWD, 1, PTRB200_AF_GELU, 100, "rows_gemm_ws_fwd")
+            RW_CASE_K(RG_DGRAD, 1, PTRB200_AF_NONE, 100, "rows_gemm_ws_dgrad")
+        }
         RW_CASE(RG_FWD, 3, PTRB200_AF_NONE, "rows_gemm_ws_fwd") RW_CASE(RG_FWD, 3, PTRB200_AF_RELU, "rows_gemm_ws_fwd")
         RW_CASE(RG_FWD, 3, PTRB200_AF_GELU, "rows_gemm_ws_fwd") RW_CASE(RG_FWD, 3, PTRB200_AF_SIGM, "rows_gemm_ws_fwd")
         RW_CASE(RG_FWD, 3, -1, "rows_gemm_ws_fwd")
@@ -870,6 +884,7 @@ static int launch_rows_gemm(int mode, int passes, RowsGemmArgs& g, int ntiles, c
         RW_CASE(RG_DGRAD, 3, PTRB200_AF_NONE, "rows_gemm_ws_dgrad")
         RW_CASE(RG_DGRAD, 1, PTRB200_AF_NONE, "rows_gemm_ws_dgrad")
 #undef RW_CASE
+#undef RW_CASE_K
         return PTRB200_ERR_INVALID;
     }
     if (S_out) *S_out = S_default;

@@ -441,11 +441,15 @@ static __device__ __forceinline__ float warp_colsum8(const float (&v)[8], int la
 }
 
 // ACT: the prologue activation as a compile-time constant (PTRB200_AF_*), or -1 to read g.act at run time
-template <int MODE, int PASSES, int ACT>
+// KT:  the contraction width as a compile-time constant (0 = read g.K at run time).  The producers spend more instructions
+//      on row / chunk address arithmetic, bounds predicates and the prefetch bookkeeping than on the prologue itself; with
+//      K known the chunk loops unroll completely and that arithmetic folds into immediates (instantiated for the widths
+//      of the default scorer, 136 and 100).
+template <int MODE, int PASSES, int ACT, int KT = 0>
 __global__ void __launch_bounds__(RW_THREADS, 1) rows_gemm_ws_kernel(RowsGemmArgs g, RowsWsExtra x) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int NP = g.NP, K = g.K, N = g.N, nchunks = x.nchunks;
+    const int NP = g.NP, K = KT ? KT : g.K, N = g.N, nchunks = KT ? (KT + 31) / 32 : x.nchunks;
     const int wchunk = NP * 128;
     unsigned char* w_hi = base;                                   // [nchunks][NP][128 B]
     unsigned char* w_lo = w_hi + (size_t)nchunks * wchunk;
@@ -495,7 +499,8 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rows_gemm_ws_kernel(RowsGemmArg
                 if (it >= 2) tc::mbar_wait(accfree + b, ((it - 2) >> 1) & 1);
                 tc::fence_after_sync();
                 const uint32_t dacc = tmem + (uint32_t)b * acc_cols;
-                for (int c = 0; c < nchunks; ++c, ++q) {
+    #pragma unroll (KT ? 8 : 1)
+            for (int c = 0; c < nchunks; ++c, ++q) {
                     const int s = q & 1;
                     tc::mbar_wait(aready + s, (q >> 1) & 1);
                     tc::fence_after_sync();
@@ -575,7 +580,8 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rows_gemm_ws_kernel(RowsGemmArg
                     kco[i] = (fused_dz && g.gr_cur < g.rows) ? (size_t)((row0 + min(r_[i], nrows - 1)) / g.gr_cur) * K + j4 : (size_t)j4;
                     dq[i] = (uint64_t)e0 >> 2;
                 }
-                for (int c = 0; c < nchunks; ++c, ++q) {
+    #pragma unroll 1
+            for (int c = 0; c < nchunks; ++c, ++q) {
                     const int s = q & 1;
                     const float4 cur[2] = {pre[0], pre[1]};
                     const float4 cur2[2] = {pre2[0], pre2[1]};
@@ -724,7 +730,8 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rows_gemm_ws_kernel(RowsGemmArg
                     kco[i] = (fused_dz && g.gr_cur < g.rows) ? (size_t)((row0 + min(r_[i], nrows - 1)) / g.gr_cur) * K + j4 : (size_t)j4;
                     dq[i] = (uint64_t)e0 >> 2;
                 }
-                for (int c = 0; c < nchunks; ++c, ++q) {
+    #pragma unroll (KT ? 8 : 1)
+            for (int c = 0; c < nchunks; ++c, ++q) {
                     const int s = q & 1;
                     const float4 cur[2] = {pre[0], pre[1]};
                     const float4 cur2[2] = {pre2[0], pre2[1]};
