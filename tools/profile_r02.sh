@@ -21,7 +21,7 @@ for stage in "${@:-launches b c d e}"; do
       cap b rows_gemm_ws_kernel 17 rows_gemm_dgrad
       cap b wgrad_tc 7 wgrad
       cap b colstat4 6 colstat
-      cap b pairwise_bce 1 loss ;;
+      cap b "lambdarank_runs|pairwise_bce" 1 loss ;;
     c)  # list scorer (L=3): attention GEMMs (QK^T and PV), row softmax, the wide-layer kernels, ApproxNDCG
       export ENC_LAYERS=3
       cap c bgemm_nt_tc_kernel 18 attn_qk
