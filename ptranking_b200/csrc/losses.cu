@@ -227,9 +227,10 @@ __global__ void lambdarank_runs_kernel(const float* __restrict__ scores, const f
     float* ng = ys + nmax;
     float* dinv = ng + nmax;
     int* rk = reinterpret_cast<int*>(dinv + nmax);              // predicted rank of document i
-    float* red = reinterpret_cast<float*>(rk + nmax);
+    float* gown = reinterpret_cast<float*>(rk + nmax);          // each document's own share of its gradient
+    float* red = gown + nmax;
     float* part = red + 33;                                     // [warps][nmax] partner contributions
-    const int b = blockIdx.x, i = threadIdx.x, lane = i & 31, warp = i >> 5, nwarps = blockDim.x >> 5;
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const ListSpan sp = list_span(offsets, b, nmax);
     const int n = sp.n, npow2 = offsets ? next_pow2(n) : npow2max;
     if (n == 0) { if (threadIdx.x == 0) loss_q[b] = 0.0f; return; }
@@ -244,36 +245,42 @@ __global__ void lambdarank_runs_kernel(const float* __restrict__ scores, const f
     __syncthreads();
     for (int t = threadIdx.x; t < n; t += blockDim.x) dinv[t] = 1.0f / log2_rank(rk[t]);
     __syncthreads();
-    const bool mine = i < n;
-    const float si = mine ? ss[i] : 0.0f, yi = mine ? ys[i] : 0.0f, gi = mine ? ng[i] : 0.0f, di = mine ? dinv[i] : 0.0f;
-    const int ri = mine ? rk[i] : 0;
-    int start = 0;                                              // first index carrying label yi (labels sorted descending)
-    if (mine) {
-        int lo = 0, hi = i;                                     // ys[lo..hi] is non-increasing and ys[i] == yi
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (ys[mid] > yi) lo = mid + 1; else hi = mid; }
-        start = lo;
-    }
-    int trips = start;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, o));
-    float own = 0.0f, loss = 0.0f;
+    float loss = 0.0f;
     float* prow = part + (size_t)warp * nmax;
-    for (int p = 0; p < trips; ++p) {
-        float gp = 0.0f;                                        // this lane's contribution to document p's gradient
-        if (p < start) {
-            const float sj = ss[p], yj = ys[p], gj = ng[p], dj = dinv[p];
-            const bool first = ri < rk[p];                      // the better-ranked document is the pair's first element
-            const float g = pair_term<true>(first ? si : sj, first ? sj : si, first ? yi : yj, first ? yj : yi,
-                                            first ? gi : gj, first ? gj : gi, first ? di : dj, first ? dj : di, sigma, loss);
-            own += first ? g : -g;
-            gp = first ? -g : g;
+    // lists longer than the CTA are walked in passes of blockDim documents (warps stay aligned with label runs)
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const bool mine = i < n;
+        const float si = mine ? ss[i] : 0.0f, yi = mine ? ys[i] : 0.0f, gi = mine ? ng[i] : 0.0f, di = mine ? dinv[i] : 0.0f;
+        const int ri = mine ? rk[i] : 0;
+        int start = 0;                                          // first index carrying label yi (labels sorted descending)
+        if (mine) {
+            int lo = 0, hi = i;                                 // ys[lo..hi] is non-increasing and ys[i] == yi
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (ys[mid] > yi) lo = mid + 1; else hi = mid; }
+            start = lo;
         }
-        gp = warp_sum(gp);
-        if (lane == 0) prow[p] += gp;
+        int trips = start;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, o));
+        float own = 0.0f;
+        for (int p = 0; p < trips; ++p) {
+            float gp = 0.0f;                                    // this lane's contribution to document p's gradient
+            if (p < start) {
+                const float sj = ss[p], yj = ys[p], gj = ng[p], dj = dinv[p];
+                const bool first = ri < rk[p];                  // the better-ranked document is the pair's first element
+                const float g = pair_term<true>(first ? si : sj, first ? sj : si, first ? yi : yj, first ? yj : yi,
+                                                first ? gi : gj, first ? gj : gi, first ? di : dj, first ? dj : di, sigma, loss);
+                own += first ? g : -g;
+                gp = first ? -g : g;
+            }
+            gp = warp_sum(gp);
+            if (lane == 0) prow[p] += gp;
+        }
+        if (mine) gown[i] = own;
     }
     __syncthreads();
-    if (mine) {
-        float tot = own;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float tot = gown[i];
         for (int w = 0; w < nwarps; ++w) tot += part[(size_t)w * nmax + i];
         grad[sp.base + i] = tot;
     }
@@ -688,9 +695,12 @@ static int launch_pairwise(const float* scores, const float* labels, const int32
     const int npow2 = next_pow2(n);
     const size_t smem = (LAMBDA ? (size_t)npow2 * 8 : 0) + (size_t)n * 4 * 6 + 33 * 4;
     static const bool no_runs = getenv("PTRB200_NO_RUNS") != nullptr;      // debugging switch: keep the circulant schedule
-    if (LAMBDA && n <= 512 && !no_runs) {       // tie pairs skipped: one thread per document, partners = the better-labelled prefix
-        const int threads = block_threads(n);
-        const size_t smem_r = (size_t)npow2 * 8 + (size_t)n * 4 * 5 + 33 * 4 + (size_t)(threads / 32) * n * 4;
+    // tie pairs skipped: partners = the better-labelled prefix.  One thread per document up to 512; longer lists (up to 2048)
+    // are walked in passes by 1024 threads (512 when the per-warp partner rows would not fit in shared memory otherwise)
+    int threads = n <= 512 ? block_threads(n) : 1024;
+    size_t smem_r = (size_t)npow2 * 8 + (size_t)n * 4 * 6 + 33 * 4 + (size_t)(threads / 32) * n * 4;
+    if (smem_r > 227 * 1024 && n > 512) { threads = 512; smem_r = (size_t)npow2 * 8 + (size_t)n * 4 * 6 + 33 * 4 + (size_t)(threads / 32) * n * 4; }
+    if (LAMBDA && n <= 2048 && smem_r <= 227 * 1024 && !no_runs) {
         if ((rc = allow_smem(lambdarank_runs_kernel, smem_r))) return rc;
         PTRB200_LAUNCH_TAG("pairwise_bce_kernel<LAMBDA>", lambdarank_runs_kernel, B, threads, smem_r, stream,
                            scores, labels, grad, loss_q, offsets, n, npow2, sigma);

@@ -114,9 +114,10 @@ class LengthBucketedBatches:
         return out
 
 
-def length_buckets(lens_desc: Sequence[int], edges: Sequence[int] = (32, 64, 128, 256, 512, 1024)) -> List[Tuple[int, int, int]]:
+def length_buckets(lens_desc: Sequence[int], edges: Sequence[int] = (128, 512)) -> List[Tuple[int, int, int]]:
     """[(q_begin, q_end, max_len)] over queries sorted by length DESCENDING: one bucket per length class
-    (.., 32], (32, 64], ... (1024, inf), classes holding fewer than 8 queries merged into their longer neighbour."""
+    (.., 128], (128, 512], (512, inf) -- the classes at which the pairwise-loss kernels change CTA size and schedule --
+    classes holding fewer than 8 queries merged into their longer neighbour."""
     lens = np.asarray(lens_desc)
     if len(lens) == 0:
         return []
@@ -137,8 +138,9 @@ def length_buckets(lens_desc: Sequence[int], edges: Sequence[int] = (32, 64, 128
 class RaggedBatches:
     """Iterable of ragged batches ``(qids, X[total,F], y[total], offsets[B+1] int32, max_len, buckets)`` -- variable-length
     lists inside ONE launch.  Inside a batch the queries are ordered by length, longest first, and
-    ``buckets`` = [(q_begin, q_end, max_len), ...] cuts that order at power-of-two lengths, so the per-list kernels can
-    size their CTAs for each length class instead of for the longest list of the batch (one launch per class).
+    ``buckets`` = [(q_begin, q_end, max_len), ...] cuts that order into length classes, so the O(n^2) loss kernels can
+    size their CTAs and pair schedule for each class instead of for the longest list of the batch (one launch per class,
+    the long-list class on a side stream).
 
     The reference batches only queries of identical length (data_utils.py:683-742); on real collections (MSLR-WEB30K:
     1..1251 documents per query, mean 119.6, testing/data/testing_data_utils.py:318-326) equal-length buckets hold a

@@ -92,8 +92,11 @@ def _loss_call(name: str, scores: torch.Tensor, labels: torch.Tensor, params: di
     loss_q = torch.empty(B, dtype=torch.float32, device=s.device)
     st = _stream_ptr()
     sp, gp, lq = s.data_ptr(), grad.data_ptr(), loss_q.data_ptr()
+    # Length buckets pay for the O(n^2) losses only (the O(n) ones are launch-bound: one launch is best), and not for losses
+    # coupled across the batch (ApproxNDCG's [B]/[B,1] broadcast, RankMSE's mean over queries)
+    quadratic = name in ("RankNet", "LambdaRank", "LambdaLoss", "SoftRank", "ApproxNDCG")
     coupled = name == "RankMSE" or (name == "ApproxNDCG" and bool(params.get("batch_coupled", True)))
-    ranges = _launch_ranges(B, n, offsets, params.get("buckets"), coupled)
+    ranges = _launch_ranges(B, n, offsets, params.get("buckets"), coupled or not quadratic)
     if name == "ListMLE":
         perm = params.get("perm")
         if perm is None:
@@ -121,11 +124,19 @@ def _loss_call(name: str, scores: torch.Tensor, labels: torch.Tensor, params: di
         if offset is None:
             offset = next_noise_offset()
     scratch = torch.empty(B + 1, dtype=torch.float32, device=s.device) if name == "ApproxNDCG" else None
-    for q0, Bq, nq in ranges:
+    # The first bucket holds the longest lists: few CTAs that run long.  It goes onto a side stream so that the short-list
+    # buckets (many CTAs, done quickly) fill the rest of the GPU meanwhile; the buckets write disjoint slices.
+    side = None
+    if len(ranges) > 1:
+        cur = torch.cuda.current_stream(s.device)
+        side = _side_stream(s.device)
+        side.wait_stream(cur)
+    for bi, (q0, Bq, nq) in enumerate(ranges):
         # a bucket is addressed through its slice of the (absolute) prefix offsets and of the per-query loss vector; the flat
         # score / label / gradient arrays are shared
         opq = None if op is None else op + 4 * q0
         lqq = lq + 4 * q0
+        st = side.cuda_stream if (side is not None and bi == 0) else _stream_ptr()
         if name == "ListMLE":
             rc = lib.ptrb200_listmle_fwd_bwd(sp, yp, opq, gp, lqq, Bq, nq, st)
         elif name == "RankNet":
@@ -154,7 +165,19 @@ def _loss_call(name: str, scores: torch.Tensor, labels: torch.Tensor, params: di
         else:
             raise NotImplementedError(name)
         _lib.check(rc, f"{name} loss kernel")
+    if side is not None:
+        torch.cuda.current_stream(s.device).wait_stream(side)
     return loss_q, grad
+
+
+_side_streams = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = torch.device(device).index
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
 
 
 _noise_offset = 0

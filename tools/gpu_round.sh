@@ -38,6 +38,19 @@ for s in $stages; do
               python -c "import json; d=json.loads(open('gpurun_out/bench_a.json').read()); print('a', round(d['value'],1), round(d['ms_per_step'],4), d.get('reference_cuda'), list(d['roofline']['kernels_ms_per_step'].items())[:6])" ;;
     benchDE)  for c in d e; do timeout 400 python bench.py --config $c --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/bench_${c}_nocpu.json; done ;;
     profile)  timeout 1500 bash tools/profile_r02.sh launches b c d e 2>&1 | tail -20 ;;
+    abkt)     # A/B of the width-specialised layer kernels
+              for v in 0 1; do
+                if [ $v = 1 ]; then export PTRB200_NO_KT=1; else unset PTRB200_NO_KT; fi
+                timeout 200 python bench.py --steps 50 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/bench_abkt_$v.json
+                python -c "import json; d=json.loads(open('gpurun_out/bench_abkt_$v.json').read()); print('NO_KT=$v', round(d['ms_per_step'],4), {k:v for k,v in list(d['roofline']['kernels_ms_per_step'].items())[:6]})"
+              done; unset PTRB200_NO_KT ;;
+    multi)    # two ranks: device-side data-parallel test + the N=2 bench line (weak + strong scaling)
+              timeout 900 python -m pytest tests/test_gpu_multirank.py -m gpu -q -x --timeout 400 --tb=short > gpurun_out/multirank_test.log 2>&1; grep -v Warning gpurun_out/multirank_test.log | tail -25
+              timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 100 --warmup 3 2>gpurun_out/bench_n2.err | tail -1 > gpurun_out/bench_n2.json
+              python -c "import json; d=json.loads(open('gpurun_out/bench_n2.json').read()); print('N=2', round(d['value'],1), round(d['ms_per_step'],4), 'strong', d.get('strong_scaling'))" || tail -5 gpurun_out/bench_n2.err
+              PTRANKING_B200_OVERLAP=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 2 --steps 100 --warmup 3 2>/dev/null | tail -1 > gpurun_out/bench_n2_nooverlap.json
+              python -c "import json; d=json.loads(open('gpurun_out/bench_n2_nooverlap.json').read()); print('N=2 no overlap', round(d['value'],1), round(d['ms_per_step'],4))"
+              timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 bench.py --impl reference --gpus 2 --steps 5 --warmup 3 2>/dev/null | tail -1 | cut -c1-300 ;;
     *)        echo "unknown stage $s" ;;
   esac
 done
