@@ -288,7 +288,7 @@ def test_ragged_bn2_equals_dense_bn2_on_uniform_lengths():
 @pytest.mark.parametrize("name,params", [("LambdaRank", dict(sigma=1.0)), ("RankNet", dict(sigma=1.0)), ("ListNet", {}), ("SoftRank", dict(delta=2.0)),
                                          ("LambdaLoss", dict(k=5)), ("ApproxNDCG", dict(alpha=10.0, batch_coupled=False)), ("ListMLE", {})])
 def test_length_buckets_change_launch_geometry_not_results(name, params):
-    """RaggedBatches orders a batch by length and cuts it at power-of-two lengths; each bucket is launched with CTAs sized
+    """RaggedBatches orders a batch by length and cuts it into at most three length classes; each class is launched with CTAs sized
     for its own lists.  Same numbers as the single launch sized for the longest list (different kernels may serve the
     short and the long lists: fp32-rounding agreement, not bit equality), and the metric kernels agree exactly."""
     from ptranking_b200 import ops
@@ -300,7 +300,7 @@ def test_length_buckets_change_launch_geometry_not_results(name, params):
     s = torch.from_numpy(np.concatenate(S)).to(DEV); y = torch.from_numpy(np.concatenate(Y)).to(DEV)
     offd = torch.from_numpy(off).to(DEV)
     buckets = length_buckets(lens)
-    assert len(buckets) == 3
+    assert 2 <= len(buckets) <= 3
     kw = dict(params)
     if name == "ListMLE":
         kw["perm"] = ops.shuffle_ties_perm(y, seed=3, offset=1, offsets=offd, max_len=int(lens.max()), buckets=buckets)
