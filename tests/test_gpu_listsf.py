@@ -50,6 +50,26 @@ def test_attention_tc_and_simt_share_the_dropout_stream():
         assert rel_err(b, a) <= 1e-5
 
 
+@pytest.mark.parametrize("shape", [(2, 150, 2, 68), (1, 512, 2, 68), (3, 24, 2, 12), (2, 260, 1, 136)])
+@pytest.mark.parametrize("p", [0.0, 0.25])
+def test_attention_tc_aligned_kernel_equals_general_kernel(shape, p, monkeypatch):
+    """The alignment-specialised batched-GEMM kernel stages the same operand images and issues the same MMAs as the
+    general one (which remains the path of shapes that are not multiples of four): identical bits, dropout included."""
+    from ptranking_b200 import ops
+    B, n, H, D = shape
+    torch.manual_seed(n)
+    Q0, K0, V0, G = (torch.randn(B, n, H * D, device=DEV) for _ in range(4))
+    outs = []
+    for general in ("0", "1"):
+        monkeypatch.setenv("PTRB200_BGEMM_GENERAL", general)
+        Q, K, V = (t.clone().requires_grad_(True) for t in (Q0, K0, V0))
+        o = ops.attention(Q, K, V, H, p, seed=21, offset=2, impl="tc")
+        (o * G).sum().backward()
+        outs.append([t.detach().clone() for t in (o, Q.grad, K.grad, V.grad)])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("impl", ["simt", "tc"])
 def test_attention_dropout_consistent_between_forward_and_backward(impl, monkeypatch):
     from ptranking_b200 import ops
