@@ -298,6 +298,17 @@ int ptrb200_attention_tc_bwd(const float* Q, const float* K, const float* V, con
                              float* dQ, float* dK, float* dV, float* scratch,
                              int B, int n, int H, int D, float dropout_p, uint64_t seed, uint64_t offset, int passes,
                              ptrb200_stream_t stream);
+/* The same two calls over row-pitched operands: ld_qkv = floats between consecutive documents of Q, K and V (and of dQ,
+ * dK, dV), ld_o = the same for O and dO; 0 = packed (H*D).  With Q|K|V side by side in one [B,n,3*H*D] tensor -- the
+ * output of ONE 136->408 projection instead of the reference's three (list_ranker.py:233-235) -- the call takes
+ * Q = qkv, K = qkv + H*D, V = qkv + 2*H*D, ld_qkv = 3*H*D, and the backward call fills the matching gradient tensor. */
+int ptrb200_attention_tc_fwd_ld(const float* Q, const float* K, const float* V, float* O, float* P_out, float* scratch,
+                                int B, int n, int H, int D, int ld_qkv, int ld_o, float dropout_p, uint64_t seed,
+                                uint64_t offset, int passes, ptrb200_stream_t stream);
+int ptrb200_attention_tc_bwd_ld(const float* Q, const float* K, const float* V, const float* P, const float* dO,
+                                float* dQ, float* dK, float* dV, float* scratch,
+                                int B, int n, int H, int D, int ld_qkv, int ld_o, float dropout_p, uint64_t seed,
+                                uint64_t offset, int passes, ptrb200_stream_t stream);
 /* LayerNorm.forward, ptranking/base/list_ranker.py:165-174: y = a_2 (x - mean) / (std_unbiased + eps) + b_2 per row;
  * mean/std[rows] are kept for backward. */
 int ptrb200_layernorm_fwd(const float* x, const float* a2, const float* b2, float* y, float* mean, float* stdv,

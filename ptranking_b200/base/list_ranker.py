@@ -41,11 +41,26 @@ class MultiheadAttention(nn.Module):
         self.w_q, self.w_k, self.w_v = nn.Linear(hid_dim, hid_dim), nn.Linear(hid_dim, hid_dim), nn.Linear(hid_dim, hid_dim)
         self.fc = nn.Linear(hid_dim, hid_dim, bias=True)
 
+    def projection_parameters(self):
+        """Order in which the ranker lays this block out in its flat parameter buffer: the three projection weights
+        side by side (then their biases), so that forward() can treat them as ONE [3*hid, hid] matrix in place."""
+        return [self.w_q.weight, self.w_k.weight, self.w_v.weight, self.w_q.bias, self.w_k.bias, self.w_v.bias,
+                self.fc.weight, self.fc.bias]
+
     def forward(self, x):
-        Q = ops.linear(x, self.w_q.weight, self.w_q.bias)
-        K = ops.linear(x, self.w_k.weight, self.w_k.bias)
-        V = ops.linear(x, self.w_v.weight, self.w_v.bias)
-        ctx = ops.attention(Q, K, V, self.n_heads, self.p if self.training else 0.0)
+        p = self.p if self.training else 0.0
+        if ops.attention_impl() in ("tc", "tc_tf32") and os.environ.get("PTRANKING_B200_FUSED_QKV", "1") == "1":
+            # Q|K|V = x [Wq;Wk;Wv]^T + [bq;bk;bv]: one hid -> 3*hid contraction (column for column the reference's three,
+            # list_ranker.py:233-235), read in place by the attention kernels; its backward is one data-gradient and
+            # one weight-gradient contraction instead of three each plus two tensor additions
+            W = ops.adjacent_rows(self.w_q.weight, self.w_k.weight, self.w_v.weight)
+            b = ops.adjacent_rows(self.w_q.bias, self.w_k.bias, self.w_v.bias)
+            ctx = ops.attention_packed(ops.linear(x, W, b), self.n_heads, p)
+        else:
+            Q = ops.linear(x, self.w_q.weight, self.w_q.bias)
+            K = ops.linear(x, self.w_k.weight, self.w_k.bias)
+            V = ops.linear(x, self.w_v.weight, self.w_v.bias)
+            ctx = ops.attention(Q, K, V, self.n_heads, p)
         return ops.linear(ctx, self.fc.weight, self.fc.bias)
 
 
@@ -133,8 +148,17 @@ class ListNeuralRanker(NeuralRanker):
         return self.ini_listsf(**self.sf_para_dict[self.sf_para_dict['sf_id']])
 
     def get_parameters(self):
-        return list(self.list_sf['head_ffnns'].parameters()) + list(self.list_sf['encoder'].parameters()) + \
-               list(self.list_sf['tail_ffnns'].parameters())
+        """Same set as the reference (list_ranker.py:297-301); inside the encoder each attention block's projection
+        weights are listed side by side (MultiheadAttention.projection_parameters) -- the order only decides the layout
+        of the flat parameter / gradient buffers, checkpoints are per-module state_dicts."""
+        enc, seen = [], set()
+        for m in self.list_sf['encoder'].modules():
+            if isinstance(m, MultiheadAttention):
+                for p in m.projection_parameters():
+                    if id(p) not in seen:
+                        seen.add(id(p)); enc.append(p)
+        enc += [p for p in self.list_sf['encoder'].parameters() if id(p) not in seen]
+        return list(self.list_sf['head_ffnns'].parameters()) + enc + list(self.list_sf['tail_ffnns'].parameters())
 
     def ini_listsf(self, num_features=None, ff_dims=[128, 256, 512], out_dim=1, AF='R', TL_AF='GE', apply_tl_af=False,
                    BN=True, bn_type=None, bn_affine=False, n_heads=2, encoder_layers=3, dropout=0.1, encoder_type=None):

@@ -454,17 +454,19 @@ int64_t ptrb200_attention_tc_workspace_floats(int B, int n, int H, int D, int ba
 }
 
 // P_out[B*H, n, n] receives the (un-dropped) attention probabilities and must be kept for the backward pass.
-int ptrb200_attention_tc_fwd(const float* Q, const float* K, const float* V, float* O, float* P_out, float* scratch,
-                             int B, int n, int H, int D, float dropout_p, uint64_t seed, uint64_t offset, int passes,
-                             ptrb200_stream_t stream) {
+int ptrb200_attention_tc_fwd_ld(const float* Q, const float* K, const float* V, float* O, float* P_out, float* scratch,
+                                int B, int n, int H, int D, int ld_qkv, int ld_o, float dropout_p, uint64_t seed,
+                                uint64_t offset, int passes, ptrb200_stream_t stream) {
     if (!Q || !K || !V || !O || !P_out || !scratch || B <= 0 || n <= 0 || H <= 0 || D <= 0) { set_error("attention_tc_fwd: bad arguments"); return PTRB200_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
     const int Z = B * H, HD = H * D;
-    const long long sb = (long long)n * HD, sh = D, nn = (long long)n * n;
+    const int lq = ld_qkv > 0 ? ld_qkv : HD, lo = ld_o > 0 ? ld_o : HD;
+    if (lq < HD || lo < HD) { set_error("attention_tc_fwd: row pitch below H*D"); return PTRB200_ERR_INVALID; }
+    const long long sb = (long long)n * lq, sbo = (long long)n * lo, sh = D, nn = (long long)n * n;
     int rc;
     BGemmArgs g{};
     // S = Q K^T / sqrt(D)
-    g.A = Q; g.B = K; g.C = P_out; g.M = n; g.N = n; g.K = D; g.lda = HD; g.ldb = HD; g.ldc = n;
+    g.A = Q; g.B = K; g.C = P_out; g.M = n; g.N = n; g.K = D; g.lda = lq; g.ldb = lq; g.ldc = n;
     g.sAb = sb; g.sAh = sh; g.sBb = sb; g.sBh = sh; g.sCb = nn * H; g.sCh = nn; g.H = H; g.alpha = 1.0f / sqrtf((float)D);
     if ((rc = launch_bgemm(g, Z, passes, st, "attn_tc_qk"))) return rc;
     const size_t rows = (size_t)Z * n;
@@ -472,49 +474,64 @@ int ptrb200_attention_tc_fwd(const float* Q, const float* K, const float* V, flo
     // O = dropout(P) V : V is the [K = key, N = d] row-major factor, consumed MN-major
     (void)scratch;
     BGemmArgs o{};
-    o.A = P_out; o.B = V; o.C = O; o.M = n; o.N = D; o.K = n; o.lda = n; o.ldb = HD; o.ldc = HD; o.b_mn = 1;
-    o.sAb = nn * H; o.sAh = nn; o.sBb = sb; o.sBh = sh; o.sCb = sb; o.sCh = sh; o.H = H; o.alpha = 1.0f;
+    o.A = P_out; o.B = V; o.C = O; o.M = n; o.N = D; o.K = n; o.lda = n; o.ldb = lq; o.ldc = lo; o.b_mn = 1;
+    o.sAb = nn * H; o.sAh = nn; o.sBb = sb; o.sBh = sh; o.sCb = sbo; o.sCh = sh; o.H = H; o.alpha = 1.0f;
     o.drop_mode = 1; o.drop = make_drop(dropout_p, seed, offset);
     if ((rc = launch_bgemm(o, Z, passes, st, "attn_tc_pv"))) return rc;
     return check_launch("attention_tc_fwd");
 }
 
-int ptrb200_attention_tc_bwd(const float* Q, const float* K, const float* V, const float* P, const float* dO,
-                             float* dQ, float* dK, float* dV, float* scratch,
+int ptrb200_attention_tc_fwd(const float* Q, const float* K, const float* V, float* O, float* P_out, float* scratch,
                              int B, int n, int H, int D, float dropout_p, uint64_t seed, uint64_t offset, int passes,
                              ptrb200_stream_t stream) {
+    return ptrb200_attention_tc_fwd_ld(Q, K, V, O, P_out, scratch, B, n, H, D, 0, 0, dropout_p, seed, offset, passes, stream);
+}
+
+int ptrb200_attention_tc_bwd_ld(const float* Q, const float* K, const float* V, const float* P, const float* dO,
+                                float* dQ, float* dK, float* dV, float* scratch,
+                                int B, int n, int H, int D, int ld_qkv, int ld_o, float dropout_p, uint64_t seed,
+                                uint64_t offset, int passes, ptrb200_stream_t stream) {
     if (!Q || !K || !V || !P || !dO || !dQ || !dK || !dV || !scratch || B <= 0 || n <= 0 || H <= 0 || D <= 0) { set_error("attention_tc_bwd: bad arguments"); return PTRB200_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
     const int Z = B * H, HD = H * D;
-    const long long sb = (long long)n * HD, sh = D, nn = (long long)n * n;
+    const int lq = ld_qkv > 0 ? ld_qkv : HD, lo = ld_o > 0 ? ld_o : HD;
+    if (lq < HD || lo < HD) { set_error("attention_tc_bwd: row pitch below H*D"); return PTRB200_ERR_INVALID; }
+    const long long sb = (long long)n * lq, sbo = (long long)n * lo, sh = D, nn = (long long)n * n;
     float* dS = scratch;                    // [Z,n,n]
     const DropCfg drop = make_drop(dropout_p, seed, offset);
     const float inv_scale = 1.0f / sqrtf((float)D);
     int rc;
     // dA_d = dO V^T
     BGemmArgs a{};
-    a.A = dO; a.B = V; a.C = dS; a.M = n; a.N = n; a.K = D; a.lda = HD; a.ldb = HD; a.ldc = n;
-    a.sAb = sb; a.sAh = sh; a.sBb = sb; a.sBh = sh; a.sCb = nn * H; a.sCh = nn; a.H = H; a.alpha = 1.0f;
+    a.A = dO; a.B = V; a.C = dS; a.M = n; a.N = n; a.K = D; a.lda = lo; a.ldb = lq; a.ldc = n;
+    a.sAb = sbo; a.sAh = sh; a.sBb = sb; a.sBh = sh; a.sCb = nn * H; a.sCh = nn; a.H = H; a.alpha = 1.0f;
     if ((rc = launch_bgemm(a, Z, passes, st, "attn_tc_dp"))) return rc;
     const size_t rows = (size_t)Z * n;
     PTRB200_LAUNCH(softmax_bwd_rows_kernel, (unsigned)((rows + 7) / 8), 256, 0, st, P, dS, rows, n, inv_scale, drop);
     // dQ = dS K : K is the [K = key, N = d] factor (MN-major B)
     BGemmArgs q{};
-    q.A = dS; q.B = K; q.C = dQ; q.M = n; q.N = D; q.K = n; q.lda = n; q.ldb = HD; q.ldc = HD; q.b_mn = 1;
+    q.A = dS; q.B = K; q.C = dQ; q.M = n; q.N = D; q.K = n; q.lda = n; q.ldb = lq; q.ldc = lq; q.b_mn = 1;
     q.sAb = nn * H; q.sAh = nn; q.sBb = sb; q.sBh = sh; q.sCb = sb; q.sCh = sh; q.H = H; q.alpha = 1.0f;
     if ((rc = launch_bgemm(q, Z, passes, st, "attn_tc_dq"))) return rc;
     // dK = dS^T Q : dS itself is the [K = query, M = key] factor (MN-major A), Q the [K = query, N = d] factor (MN-major B)
     BGemmArgs k{};
-    k.A = dS; k.B = Q; k.C = dK; k.M = n; k.N = D; k.K = n; k.lda = n; k.ldb = HD; k.ldc = HD; k.a_mn = 1; k.b_mn = 1;
+    k.A = dS; k.B = Q; k.C = dK; k.M = n; k.N = D; k.K = n; k.lda = n; k.ldb = lq; k.ldc = lq; k.a_mn = 1; k.b_mn = 1;
     k.sAb = nn * H; k.sAh = nn; k.sBb = sb; k.sBh = sh; k.sCb = sb; k.sCh = sh; k.H = H; k.alpha = 1.0f;
     if ((rc = launch_bgemm(k, Z, passes, st, "attn_tc_dk"))) return rc;
     // dV = dropout(P)^T dO : same shapes, the dropout mask regenerated through the transposed view
     BGemmArgs v{};
-    v.A = P; v.B = dO; v.C = dV; v.M = n; v.N = D; v.K = n; v.lda = n; v.ldb = HD; v.ldc = HD; v.a_mn = 1; v.b_mn = 1;
-    v.sAb = nn * H; v.sAh = nn; v.sBb = sb; v.sBh = sh; v.sCb = sb; v.sCh = sh; v.H = H; v.alpha = 1.0f;
+    v.A = P; v.B = dO; v.C = dV; v.M = n; v.N = D; v.K = n; v.lda = n; v.ldb = lo; v.ldc = lq; v.a_mn = 1; v.b_mn = 1;
+    v.sAb = nn * H; v.sAh = nn; v.sBb = sbo; v.sBh = sh; v.sCb = sb; v.sCh = sh; v.H = H; v.alpha = 1.0f;
     v.drop_mode = 2; v.drop = drop;
     if ((rc = launch_bgemm(v, Z, passes, st, "attn_tc_dv"))) return rc;
     return check_launch("attention_tc_bwd");
+}
+
+int ptrb200_attention_tc_bwd(const float* Q, const float* K, const float* V, const float* P, const float* dO,
+                             float* dQ, float* dK, float* dV, float* scratch,
+                             int B, int n, int H, int D, float dropout_p, uint64_t seed, uint64_t offset, int passes,
+                             ptrb200_stream_t stream) {
+    return ptrb200_attention_tc_bwd_ld(Q, K, V, P, dO, dQ, dK, dV, scratch, B, n, H, D, 0, 0, dropout_p, seed, offset, passes, stream);
 }
 
 }  // extern "C"

@@ -686,6 +686,94 @@ def attention(Q, K, V, n_heads: int, dropout_p: float = 0.0, seed: Optional[int]
     return _AttentionTC.apply(Q, K, V, int(n_heads), float(dropout_p), int(seed), int(offset), 3 if impl == "tc" else 1)
 
 
+class _AdjacentRows(torch.autograd.Function):
+    """Stack parameter tensors along dim 0.  When they already sit side by side in one storage (the ranker's flat
+    parameter buffer orders an attention block's three projection weights that way) the stack is a strided view of that
+    storage -- no copy, no kernel; otherwise a plain copy.  Backward hands every tensor its rows of the gradient."""
+
+    @staticmethod
+    def forward(ctx, *ts):
+        ctx.sizes = [t.shape[0] for t in ts]
+        first = ts[0]
+        off, adjacent = first.storage_offset(), True
+        for t in ts:
+            adjacent = adjacent and t.is_contiguous() and t.shape[1:] == first.shape[1:] and t.dtype == first.dtype \
+                and t.untyped_storage().data_ptr() == first.untyped_storage().data_ptr() and t.storage_offset() == off
+            off += t.numel()
+        if adjacent:
+            return torch.as_strided(first.detach(), (sum(ctx.sizes), *first.shape[1:]), first.stride(), first.storage_offset())
+        return torch.cat([t.detach() for t in ts], 0)
+
+    @staticmethod
+    def backward(ctx, g):
+        return tuple(torch.split(g, ctx.sizes, 0))
+
+
+def adjacent_rows(*ts: torch.Tensor) -> torch.Tensor:
+    return _AdjacentRows.apply(*ts)
+
+
+class _AttentionTCPacked(torch.autograd.Function):
+    """_AttentionTC over Q|K|V side by side in one [B,n,3*F] tensor (the output of one F -> 3F projection): the kernels
+    read the three column blocks in place through their row pitch and the backward pass fills one [B,n,3*F] gradient."""
+
+    @staticmethod
+    @_on_tensor_device
+    def forward(ctx, qkv, n_heads, dropout_p, seed, offset, passes):
+        lib = _lib.load()
+        qkv = _dev_f32(qkv, "qkv")
+        B, n, F3 = qkv.shape
+        F = F3 // 3
+        D = F // n_heads
+        O = torch.empty((B, n, F), dtype=torch.float32, device=qkv.device)
+        P = torch.empty((B * n_heads, n, n), dtype=torch.float32, device=qkv.device)
+        scratch = torch.empty(lib.ptrb200_attention_tc_workspace_floats(B, n, n_heads, D, 0), dtype=torch.float32, device=qkv.device)
+        q = qkv.data_ptr()
+        _lib.check(lib.ptrb200_attention_tc_fwd_ld(q, q + 4 * F, q + 8 * F, O.data_ptr(), P.data_ptr(), scratch.data_ptr(),
+                                                   B, n, n_heads, D, F3, 0, float(dropout_p), seed, offset, passes,
+                                                   _stream_ptr()), "attention_tc_fwd")
+        ctx.save_for_backward(qkv, P)
+        ctx.cfg = (n_heads, float(dropout_p), seed, offset, passes)
+        return O
+
+    @staticmethod
+    @_on_tensor_device
+    def backward(ctx, dO):
+        lib = _lib.load()
+        qkv, P = ctx.saved_tensors
+        H, p, seed, offset, passes = ctx.cfg
+        B, n, F3 = qkv.shape
+        F = F3 // 3
+        dO = _dev_f32(dO, "dO")
+        dqkv = torch.empty_like(qkv)
+        scratch = torch.empty(lib.ptrb200_attention_tc_workspace_floats(B, n, H, F // H, 1), dtype=torch.float32, device=qkv.device)
+        q, g = qkv.data_ptr(), dqkv.data_ptr()
+        _lib.check(lib.ptrb200_attention_tc_bwd_ld(q, q + 4 * F, q + 8 * F, P.data_ptr(), dO.data_ptr(),
+                                                   g, g + 4 * F, g + 8 * F, scratch.data_ptr(),
+                                                   B, n, H, F // H, F3, 0, p, seed, offset, passes, _stream_ptr()), "attention_tc_bwd")
+        return dqkv, None, None, None, None, None
+
+
+def attention_impl() -> str:
+    return os.environ.get("PTRANKING_B200_ATTN", "tc")
+
+
+def attention_packed(qkv, n_heads: int, dropout_p: float = 0.0, seed: Optional[int] = None, offset: Optional[int] = None,
+                     impl: Optional[str] = None):
+    """:func:`attention` for Q|K|V stored side by side in the last dimension of one tensor (tensor-core paths only)."""
+    if seed is None:
+        seed = torch.initial_seed() & (2 ** 64 - 1)
+    if offset is None:
+        offset = next_dropout_offset()
+    if impl is None:
+        impl = attention_impl()
+    if impl not in ("tc", "tc_tf32"):
+        raise ValueError(f"attention_packed needs a tensor-core impl, got {impl!r}")
+    if qkv.shape[-1] % (3 * n_heads) != 0:
+        raise ValueError("last dimension must be 3 * n_heads * head_dim")
+    return _AttentionTCPacked.apply(qkv, int(n_heads), float(dropout_p), int(seed), int(offset), 3 if impl == "tc" else 1)
+
+
 class _LayerNormRef(torch.autograd.Function):
     @staticmethod
     @_on_tensor_device

@@ -17,6 +17,17 @@ for s in $stages; do
               python -c "import json; d=json.loads(open('gpurun_out/bench_n1.json').read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches']); print(d['roofline']['kernels_ms_per_step'])" ;;
     ops)      timeout 300 python tools/op_bench.py > gpurun_out/op_bench.log 2>&1; cp profiles/r02_op_table.md gpurun_out/; tail -60 gpurun_out/r02_op_table.md ;;
     launches) timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python tools/profile_step.py 3 > gpurun_out/ncu_launch.log 2>&1; tail -1 gpurun_out/ncu_launch.log ;;
+    abc)      # config c (list scorer, L=6): aligned bgemm kernel and fused Q|K|V projection, each switched off in turn
+              for v in base general_bgemm separate_qkv; do
+                unset PTRB200_BGEMM_GENERAL PTRANKING_B200_FUSED_QKV
+                [ $v = general_bgemm ] && export PTRB200_BGEMM_GENERAL=1
+                [ $v = separate_qkv ] && export PTRANKING_B200_FUSED_QKV=0
+                timeout 300 python bench.py --config c --no-cpu-baseline 2>gpurun_out/bench_c_$v.err | tail -1 > gpurun_out/bench_c_$v.json
+                python -c "import json; d=json.loads(open('gpurun_out/bench_c_$v.json').read()); print('$v', round(d['value'],1), 'q/s', round(d['ms_per_step'],4), 'ms', {k:v for k,v in list(d['roofline']['kernels_ms_per_step'].items())[:12]})" || tail -3 gpurun_out/bench_c_$v.err
+              done; unset PTRB200_BGEMM_GENERAL PTRANKING_B200_FUSED_QKV ;;
+    launchesc) # per-launch list of one list-scorer step (config c, L=3)
+              ENC_LAYERS=3 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_c.csv python tools/profile_step.py 2 0 c > gpurun_out/ncu_launch_c.log 2>&1; tail -1 gpurun_out/ncu_launch_c.log
+              python tools/launch_table.py gpurun_out/launches_c.csv > gpurun_out/launch_table_c.txt; head -1 gpurun_out/launch_table_c.txt ;;
     full)     timeout 800 bash tools/profile_all.sh 2>&1 | tail -3 ;;
     ab)       # A/B of the short-last-chunk staging in the forward layer kernel
               for v in 0 1; do
