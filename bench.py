@@ -401,6 +401,9 @@ def run_b200(args, cfg):
             "config": {"workload": cfg["workload"], "config_key": cfg["key"],
                        "queries_per_gpu_per_step": B, "n_docs": n, "n_features": F,
                        "parallelism": f"dp{world}",
+                       "gradient_exchange": ("none (one GPU)" if world == 1 else
+                                             "summed inside the optimizer kernel over NVLink peer memory (CUDA IPC), one launch" if getattr(ranker.grad_bucket, "peer", None) is not None
+                                             else "ncclAllReduce(SUM) of the flat gradient buffer, then the optimizer kernel"),
                        "l2": f"inputs (2 x {h2d / 1e6:.0f} MB rotating batches) " + ("larger than" if 2 * h2d > 126e6 else "NOT larger than") + " the 126 MB L2",
                        "normalisation": "BN (reference default, batch statistics" + (", synchronised over ranks)" if b200dist.sync_bn_active() else " per rank)") if cfg["sf"]["sf_id"] == "pointsf" else "none (listsf default)",
                        "math": ("GEMM operands rounded to bf16, fp32 accumulate" if cfg["math"] == "bf16" else

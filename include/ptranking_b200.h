@@ -274,6 +274,38 @@ int ptrb200_rmsprop_step(float* param, const float* grad, float* square_avg, int
                          double lr, double alpha, double eps, double weight_decay,
                          ptrb200_stream_t stream);
 
+/* ---- data-parallel gradient exchange over NVLink peer memory ------------------------------ */
+/* The reference has no distributed code.  One process per GPU (torchrun); the sum of the ranks' flat gradient buffers
+ * that precedes optimizer.step() in a data-parallel run is folded INTO the step kernel: every rank maps the other ranks'
+ * buffers (CUDA IPC), the kernel synchronises through system-scope flags and reads the W buffers directly over NVLink
+ * (see csrc/optim.cu).  The library exports / maps the memory; exchanging the 64-byte handles between the processes is
+ * the caller's business (ptranking_b200.dist does it through torch.distributed).
+ * ptrb200_peer_alloc is the ONE place where the library allocates device memory (CUDA IPC needs a cudaMalloc base). */
+#define PTRB200_MAX_PEERS 16
+typedef struct ptrb200_peer_group {
+    int world, rank;
+    const float* grads[PTRB200_MAX_PEERS];   /* rank r's gradient buffer of this step, as mapped into THIS process (own included) */
+    uint32_t* flags[PTRB200_MAX_PEERS];      /* rank r's flag pad: `world` uint32, zero at allocation, never reset */
+    uint32_t epoch;                          /* 1, 2, 3, ... : one value per exchange, the same on every rank */
+    int* error;                              /* optional device int (own memory): 1 + r if rank r never arrived within 4 s */
+} ptrb200_peer_group;
+int ptrb200_peer_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle64);   /* cudaMalloc + zero + export */
+int ptrb200_peer_open(const unsigned char* handle64, void** dev_ptr);             /* map another process's export */
+int ptrb200_peer_close(void* dev_ptr);
+int ptrb200_peer_free(void* dev_ptr);
+/* out[count] = sum over ranks of grads[r][0..count) -- the bare exchange (rank order 0..W-1 on every rank) */
+int ptrb200_peer_allreduce_sum(const ptrb200_peer_group* grp, float* out, int64_t count, ptrb200_stream_t stream);
+/* ptrb200_adam_step / adagrad_step / rmsprop_step with grad = that sum, in one launch */
+int ptrb200_adam_step_peer(const ptrb200_peer_group* grp, float* param, float* exp_avg, float* exp_avg_sq, int64_t count,
+                           double lr, double beta1, double beta2, double eps, double weight_decay, int step,
+                           ptrb200_stream_t stream);
+int ptrb200_adagrad_step_peer(const ptrb200_peer_group* grp, float* param, float* state_sum, int64_t count,
+                              double lr, double lr_decay, double eps, double weight_decay, int step,
+                              ptrb200_stream_t stream);
+int ptrb200_rmsprop_step_peer(const ptrb200_peer_group* grp, float* param, float* square_avg, int64_t count,
+                              double lr, double alpha, double eps, double weight_decay,
+                              ptrb200_stream_t stream);
+
 /* ---- multi-head self-attention list scorer ------------------------------------------------ */
 /* MultiheadAttention.forward, ptranking/base/list_ranker.py:226-248: for every (query b, head h)
  * O = dropout(softmax(Q K^T / sqrt(D))) V, flash-style (no [n,n] tensor in HBM).  Q,K,V,O: [B,n,H*D] with head h

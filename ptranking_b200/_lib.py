@@ -95,6 +95,42 @@ SIGNATURES = {
                                     _I, _I, _fp, _I, _I, _U64, _U64, _fp]),
 }
 
+MAX_PEERS = 16
+
+
+class PeerGroup(C.Structure):
+    """struct ptrb200_peer_group"""
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("grads", _fp * MAX_PEERS), ("flags", _fp * MAX_PEERS),
+                ("epoch", C.c_uint32), ("error", _fp)]
+
+
+_D = C.c_double
+_PG = C.POINTER(PeerGroup)
+SIGNATURES.update({
+    "ptrb200_peer_alloc": (_I, [_I64, C.POINTER(C.c_void_p), C.c_char_p]),
+    "ptrb200_peer_open": (_I, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "ptrb200_peer_close": (_I, [_fp]),
+    "ptrb200_peer_free": (_I, [_fp]),
+    "ptrb200_peer_allreduce_sum": (_I, [_PG, _fp, _I64, _fp]),
+    "ptrb200_adam_step_peer": (_I, [_PG, _fp, _fp, _fp, _I64, _D, _D, _D, _D, _D, _I, _fp]),
+    "ptrb200_adagrad_step_peer": (_I, [_PG, _fp, _fp, _I64, _D, _D, _D, _D, _I, _fp]),
+    "ptrb200_rmsprop_step_peer": (_I, [_PG, _fp, _fp, _I64, _D, _D, _D, _D, _fp]),
+})
+
+
+def peer_alloc(nbytes: int):
+    """-> (device pointer, 64-byte CUDA IPC handle) of a zeroed allocation on the current device."""
+    ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+    check(load().ptrb200_peer_alloc(int(nbytes), C.byref(ptr), handle), "peer_alloc")
+    return int(ptr.value), handle.raw
+
+
+def peer_open(handle: bytes) -> int:
+    ptr = C.c_void_p()
+    check(load().ptrb200_peer_open(C.create_string_buffer(bytes(handle), 64), C.byref(ptr)), "peer_open")
+    return int(ptr.value)
+
+
 HOOK_ALLREDUCE_F64, HOOK_LAYER_GRADS_READY = 1, 2
 # int hook(int what, int layer, void* ptr, int64_t count, void* stream, void* user)
 HOOK_T = C.CFUNCTYPE(C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)

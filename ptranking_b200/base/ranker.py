@@ -35,7 +35,8 @@ class FlatAdam(optim.Optimizer):
         g = self.param_groups[0]
         self.num_steps += 1
         ops.adam_step(self.bucket.flat_param, self.bucket.flat, self.exp_avg, self.exp_avg_sq, self.num_steps,
-                      lr=g['lr'], betas=g['betas'], eps=g['eps'], weight_decay=g['weight_decay'])
+                      lr=g['lr'], betas=g['betas'], eps=g['eps'], weight_decay=g['weight_decay'], peer=self.bucket.peer_group())
+        self.bucket.advance()
 
 
 class FlatAdagrad(optim.Optimizer):
@@ -54,7 +55,8 @@ class FlatAdagrad(optim.Optimizer):
         g = self.param_groups[0]
         self.num_steps += 1
         ops.adagrad_step(self.bucket.flat_param, self.bucket.flat, self.state_sum, self.num_steps, lr=g['lr'],
-                         lr_decay=g['lr_decay'], eps=g['eps'], weight_decay=g['weight_decay'])
+                         lr_decay=g['lr_decay'], eps=g['eps'], weight_decay=g['weight_decay'], peer=self.bucket.peer_group())
+        self.bucket.advance()
 
 
 class FlatRMSprop(optim.Optimizer):
@@ -71,7 +73,8 @@ class FlatRMSprop(optim.Optimizer):
             raise RuntimeError("FlatRMSprop: a parameter was re-allocated outside the flat buffer (use copy_ / load_state_dict)")
         g = self.param_groups[0]
         ops.rmsprop_step(self.bucket.flat_param, self.bucket.flat, self.square_avg, lr=g['lr'], alpha=g['alpha'],
-                         eps=g['eps'], weight_decay=g['weight_decay'])
+                         eps=g['eps'], weight_decay=g['weight_decay'], peer=self.bucket.peer_group())
+        self.bucket.advance()
 
 
 @unique
@@ -241,6 +244,8 @@ class NeuralRanker(Evaluator):
         # data parallel: every replica must start from rank 0's weights (xavier_normal_ draws from the per-process
         # torch seed); the all-reduced gradient is only meaningful when applied to identical replicas
         b200dist.broadcast_parameters(self.grad_bucket, src=0)
+        # ... and, on one node, the gradient sum moves into the optimizer kernel (NVLink peer memory; NCCL otherwise)
+        self.grad_bucket.enable_peer()
 
     def backward_and_step(self, batch_loss):
         """The tail every reference loss class ends with (e.g. lambdarank.py:58-60), plus the

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 
 #include "../../include/ptranking_b200.h"
 

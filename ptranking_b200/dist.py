@@ -112,6 +112,60 @@ def shard_queries(num_queries: int, rank: int, world: int) -> range:
     return range(start, start + base + (1 if rank < rem else 0))
 
 
+class _DeviceMemory:
+    """A raw device allocation presented through __cuda_array_interface__ so that torch can view it without a copy."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class PeerExchange:
+    """Every rank's gradient buffers mapped into every process of the node (CUDA IPC over NVLink / NVSwitch peer
+    memory): the data-parallel gradient SUM is then read by the optimizer kernel itself (csrc/optim.cu), one launch
+    instead of ncclAllReduce + the step.  Layout of a rank's allocation: a 256-byte pad (``world`` arrival flags, an error
+    word) and two gradient buffers used in alternation -- a rank that is already writing step e+1 gradients can never
+    touch what a slower rank still reads for step e, with a single flag exchange per step.  Handles travel through the
+    process group (``all_gather_object``); the library only exports / maps memory (ptrb200_peer_alloc / _open)."""
+
+    PAD, ERR_OFF = 256, 128
+
+    def __init__(self, count: int, device):
+        from . import _lib
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        if self.world > _lib.MAX_PEERS:
+            raise RuntimeError(f"peer exchange supports up to {_lib.MAX_PEERS} ranks")
+        self.count, self.device = int(count), torch.device(device)
+        self.stride = -(-self.count * 4 // 256) * 256
+        with torch.cuda.device(self.device):
+            self.own, handle = _lib.peer_alloc(self.PAD + 2 * self.stride)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle)
+            self.ptrs = [self.own if r == self.rank else _lib.peer_open(handles[r]) for r in range(self.world)]
+            self.bufs = [torch.as_tensor(_DeviceMemory(self.own + self.PAD + k * self.stride, self.count), device=self.device)
+                         for k in (0, 1)]
+        self.epoch = 0
+        dist.barrier()                      # nobody signals into a pad that is not mapped yet
+
+    def group(self, k: int):
+        """The descriptor of the NEXT exchange over buffer ``k`` (advances the step counter)."""
+        from . import _lib
+        self.epoch += 1
+        g = _lib.PeerGroup()
+        g.world, g.rank, g.epoch = self.world, self.rank, self.epoch & 0xffffffff
+        for r, p in enumerate(self.ptrs):
+            g.grads[r] = p + self.PAD + k * self.stride
+            g.flags[r] = p
+        g.error = self.own + self.ERR_OFF
+        return g
+
+    def error(self) -> int:
+        """0, or 1 + the rank that never arrived at some exchange (synchronises the device)."""
+        with torch.cuda.device(self.device):
+            word = torch.as_tensor(_DeviceMemory(self.own + self.ERR_OFF, 1), device=self.device)
+            return int(word.view(torch.int32).item())
+
+
 class GradBucket:
     """Flat fp32 gradient buffer: every parameter's ``.grad`` is a view into it, so a step needs
     one ``all_reduce(SUM)`` (220.8 KB for the default pointwise scorer) instead of one per tensor."""
@@ -132,6 +186,47 @@ class GradBucket:
         self._reduced_from = None          # overlapped all-reduce: flat[_reduced_from:] is already on the side stream
         self._side = None
         self.overlap_from_layer = 1        # start reducing when this layer's gradients are complete (layers above it too)
+        self.peer: Optional[PeerExchange] = None   # gradient sum over NVLink peer memory inside the optimizer kernel
+        self._peer_k = 0
+        for p, v in zip(self.params, self._views()):
+            p.grad = v
+
+    def enable_peer(self) -> bool:
+        """Data parallel on one node: move the gradient buffer into peer-mapped memory so that the optimizer kernel sums
+        the ranks' gradients itself (:class:`PeerExchange`).  All ranks agree on the outcome; on any failure (no peer
+        access, IPC unavailable) every rank keeps the NCCL all-reduce.  PTRANKING_B200_PEER=0 switches it off."""
+        if self.peer is not None:
+            return True
+        if not (is_distributed() and self.distributed and self.flat.is_cuda and dist.get_backend() == "nccl"
+                and os.environ.get("PTRANKING_B200_PEER", "1") == "1"):
+            return False
+        ex, ok = None, 1
+        try:
+            ex = PeerExchange(self.flat.numel(), self.flat.device)
+        except Exception as e:
+            print(f"ptranking_b200.dist: peer exchange unavailable on rank {dist.get_rank()} ({e!r}); using NCCL", flush=True)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.flat.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            return False
+        self.peer = ex
+        self._peer_k = 0
+        self.flat = ex.bufs[0]
+        for p, v in zip(self.params, self._views()):
+            p.grad = v
+        return True
+
+    def peer_group(self):
+        """Descriptor for this step's fused exchange + optimizer launch (None: gradients are reduced by all_reduce())."""
+        return self.peer.group(self._peer_k) if (self.peer is not None and self.distributed) else None
+
+    def advance(self) -> None:
+        """After the step of a peer-exchange bucket: the next step's gradients go to the other buffer."""
+        if self.peer is None:
+            return
+        self._peer_k ^= 1
+        self.flat = self.peer.bufs[self._peer_k]
         for p, v in zip(self.params, self._views()):
             p.grad = v
 
@@ -168,7 +263,7 @@ class GradBucket:
         reduced now; then the compute stream waits for the side stream."""
         global _active_bucket
         _active_bucket = None
-        if not (is_distributed() and self.distributed):
+        if not (is_distributed() and self.distributed) or self.peer is not None:     # peer: the optimizer kernel sums
             return
         upto = self._reduced_from if self._reduced_from is not None else self.flat.numel()
         if upto > 0:
@@ -183,6 +278,8 @@ class GradBucket:
         stream while the layers below are still computing."""
         global _active_bucket
         self._reduced_from = None
+        if self.peer is not None:
+            return
         if is_distributed() and self.distributed and self.flat.is_cuda and os.environ.get("PTRANKING_B200_OVERLAP", "1") == "1":
             _install_hook()
             _active_bucket = self

@@ -123,7 +123,8 @@ def _loss_call(name: str, scores: torch.Tensor, labels: torch.Tensor, params: di
             seed = torch.initial_seed()
         if offset is None:
             offset = next_noise_offset()
-    scratch = torch.empty(B + 1, dtype=torch.float32, device=s.device) if name == "ApproxNDCG" else None
+    # ApproxNDCG scratch: Bq + 1 floats per launch; concurrent buckets get disjoint pieces
+    scratch = torch.empty(B + len(ranges), dtype=torch.float32, device=s.device) if name == "ApproxNDCG" else None
     # The first bucket holds the longest lists: few CTAs that run long.  It goes onto a side stream so that the short-list
     # buckets (many CTAs, done quickly) fill the rest of the GPU meanwhile; the buckets write disjoint slices.
     side = None
@@ -150,7 +151,7 @@ def _loss_call(name: str, scores: torch.Tensor, labels: torch.Tensor, params: di
         elif name == "ListNet":
             rc = lib.ptrb200_listnet_fwd_bwd(sp, yp, opq, gp, lqq, Bq, nq, st)
         elif name == "ApproxNDCG":
-            rc = lib.ptrb200_approxndcg_fwd_bwd(sp, yp, opq, gp, lqq, scratch.data_ptr() + 4 * q0, Bq, nq, float(params.get("alpha", 10.0)),
+            rc = lib.ptrb200_approxndcg_fwd_bwd(sp, yp, opq, gp, lqq, scratch.data_ptr() + 4 * (q0 + bi), Bq, nq, float(params.get("alpha", 10.0)),
                                                 int(bool(params.get("presort", True))), int(bool(params.get("batch_coupled", True))), st)
         elif name == "RankMSE":
             rc = lib.ptrb200_rankmse_fwd_bwd(sp, yp, opq, gp, lqq, Bq, nq, st)
@@ -243,15 +244,31 @@ def sum_f32(x: torch.Tensor) -> torch.Tensor:
 
 @_on_tensor_device
 def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
-              lr: float, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0) -> None:
-    """In-place torch.optim.Adam update of flat fp32 device buffers with identical layouts (one kernel)."""
+              lr: float, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, peer=None) -> None:
+    """In-place torch.optim.Adam update of flat fp32 device buffers with identical layouts (one kernel).
+    ``peer`` (a :class:`_lib.PeerGroup` from ``dist.PeerExchange.group()``): the gradient is the SUM of every rank's
+    buffer, read over NVLink peer memory inside the same kernel -- ``grad`` is then only this rank's share."""
     lib = _lib.load()
     for name, t in (("param", param), ("grad", grad), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == param.numel()):
             raise ValueError(f"adam_step: {name} must be a contiguous fp32 CUDA tensor of {param.numel()} elements")
+    if peer is not None:
+        _lib.check(lib.ptrb200_adam_step_peer(C.byref(peer), param.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
+                                              float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
+                                              _stream_ptr()), "adam_step_peer")
+        return
     _lib.check(lib.ptrb200_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
                                      float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
                                      _stream_ptr()), "adam_step")
+
+
+@_on_tensor_device
+def peer_allreduce_sum(out: torch.Tensor, peer) -> torch.Tensor:
+    """out[i] = sum over ranks of their exchange buffers (rank order, identical on every rank) -- the bare exchange."""
+    if not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous()):
+        raise ValueError("peer_allreduce_sum: out must be a contiguous fp32 CUDA tensor")
+    _lib.check(_lib.load().ptrb200_peer_allreduce_sum(C.byref(peer), out.data_ptr(), out.numel(), _stream_ptr()), "peer_allreduce_sum")
+    return out
 
 
 def _check_flat(who, param, *others):
@@ -262,9 +279,14 @@ def _check_flat(who, param, *others):
 
 @_on_tensor_device
 def adagrad_step(param: torch.Tensor, grad: torch.Tensor, state_sum: torch.Tensor, step: int, lr: float,
-                 lr_decay: float = 0.0, eps: float = 1e-10, weight_decay: float = 0.0) -> None:
-    """In-place torch.optim.Adagrad update of flat fp32 device buffers (one kernel)."""
+                 lr_decay: float = 0.0, eps: float = 1e-10, weight_decay: float = 0.0, peer=None) -> None:
+    """In-place torch.optim.Adagrad update of flat fp32 device buffers (one kernel; ``peer`` as in :func:`adam_step`)."""
     _check_flat("adagrad_step", param, grad, state_sum)
+    if peer is not None:
+        _lib.check(_lib.load().ptrb200_adagrad_step_peer(C.byref(peer), param.data_ptr(), state_sum.data_ptr(), param.numel(),
+                                                         float(lr), float(lr_decay), float(eps), float(weight_decay), int(step),
+                                                         _stream_ptr()), "adagrad_step_peer")
+        return
     _lib.check(_lib.load().ptrb200_adagrad_step(param.data_ptr(), grad.data_ptr(), state_sum.data_ptr(), param.numel(),
                                                 float(lr), float(lr_decay), float(eps), float(weight_decay), int(step),
                                                 _stream_ptr()), "adagrad_step")
@@ -272,9 +294,15 @@ def adagrad_step(param: torch.Tensor, grad: torch.Tensor, state_sum: torch.Tenso
 
 @_on_tensor_device
 def rmsprop_step(param: torch.Tensor, grad: torch.Tensor, square_avg: torch.Tensor, lr: float, alpha: float = 0.99,
-                 eps: float = 1e-8, weight_decay: float = 0.0) -> None:
-    """In-place torch.optim.RMSprop (momentum=0, centered=False) update of flat fp32 device buffers (one kernel)."""
+                 eps: float = 1e-8, weight_decay: float = 0.0, peer=None) -> None:
+    """In-place torch.optim.RMSprop (momentum=0, centered=False) update of flat fp32 device buffers (one kernel;
+    ``peer`` as in :func:`adam_step`)."""
     _check_flat("rmsprop_step", param, grad, square_avg)
+    if peer is not None:
+        _lib.check(_lib.load().ptrb200_rmsprop_step_peer(C.byref(peer), param.data_ptr(), square_avg.data_ptr(), param.numel(),
+                                                         float(lr), float(alpha), float(eps), float(weight_decay),
+                                                         _stream_ptr()), "rmsprop_step_peer")
+        return
     _lib.check(_lib.load().ptrb200_rmsprop_step(param.data_ptr(), grad.data_ptr(), square_avg.data_ptr(), param.numel(),
                                                 float(lr), float(alpha), float(eps), float(weight_decay),
                                                 _stream_ptr()), "rmsprop_step")

@@ -43,6 +43,7 @@ def _rel(a, b):
 
 def _worker(rank, world, port, mode):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    os.environ["PTRANKING_B200_PEER"] = "0"       # this worker checks the NCCL path: the reduced gradient stays inspectable
     from ptranking_b200 import dist as b200dist, LABEL_TYPE
     b200dist.init_from_env("nccl")
     dev = f"cuda:{rank}"
@@ -99,6 +100,65 @@ def _worker(rank, world, port, mode):
     assert torch.equal(a.grad_bucket.flat, b.grad_bucket.flat)
     torch.cuda.synchronize()
     dist.destroy_process_group()
+
+
+def _peer_worker(rank, world, port, opt):
+    """The gradient sum inside the optimizer kernel (NVLink peer memory, csrc/optim.cu) against the NCCL all-reduce +
+    step it replaces: same weights after every step (two ranks: a + b is order-free, so bit for bit), replicas identical,
+    the bare exchange equals dist.all_reduce, and no rank ever timed out."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import ptranking_b200
+    from ptranking_b200 import dist as b200dist, ops, LABEL_TYPE
+    b200dist.init_from_env("nccl")
+    dev = f"cuda:{rank}"
+    kw = dict(presort=True, label_type=LABEL_TYPE.MultiLabel)
+    B, n, F = 16, 96, 136
+    X, y = _batch(B, n, F, seed=9)
+    shard = list(b200dist.shard_queries(B, rank, world))
+    Xs, ys = X[shard].to(dev), y[shard].to(dev)
+
+    def make(peer):
+        os.environ["PTRANKING_B200_PEER"] = "1" if peer else "0"
+        sf = dict(sf_id="pointsf", opt=opt, lr=1e-3,
+                  pointsf=dict(num_features=136, num_layers=3, AF="GE", TL_AF="S", apply_tl_af=True, BN=True, bn_type="BN2",
+                               bn_affine=True, dropout=0.0))
+        torch.manual_seed(3)
+        r = ptranking_b200.LambdaRank(sf_para_dict=sf, model_para_dict=dict(model_id="LambdaRank", sigma=1.0), gpu=True, device=dev)
+        r.init(); r.eval_mode()
+        return r
+
+    a, b = make(True), make(False)
+    assert a.grad_bucket.peer is not None, "the peer exchange did not engage"
+    assert b.grad_bucket.peer is None
+    gathered = [torch.empty_like(a.grad_bucket.flat_param) for _ in range(world)]
+    for step in range(4):
+        la, _ = a.train_op(Xs, ys, **kw)
+        lb, _ = b.train_op(Xs, ys, **kw)
+        assert torch.equal(la, lb), (opt, step)
+        assert torch.equal(a.grad_bucket.flat_param, b.grad_bucket.flat_param), (opt, step)
+        dist.all_gather(gathered, a.grad_bucket.flat_param)
+        assert all(torch.equal(g, gathered[0]) for g in gathered), (opt, step)
+    # the bare exchange on the same mapped buffers
+    ex = a.grad_bucket.peer
+    k = a.grad_bucket._peer_k
+    torch.manual_seed(50 + rank)
+    ex.bufs[k].copy_(torch.randn(ex.count, device=dev))
+    ref = ex.bufs[k].clone()
+    dist.all_reduce(ref)
+    torch.cuda.synchronize(); dist.barrier()
+    out = ops.peer_allreduce_sum(torch.empty_like(ref), ex.group(k))
+    assert torch.equal(out, ref)
+    assert ex.error() == 0
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("opt", ["Adam", "Adagrad", "RMS"])
+def test_two_rank_peer_memory_step_equals_nccl_step(opt):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    mp.spawn(_peer_worker, args=(2, _free_port(), opt), nprocs=2, join=True)
 
 
 @pytest.mark.parametrize("mode", ["bn2", "syncbn", "bn_local"])

@@ -58,9 +58,11 @@ for s in $stages; do
     multi)    # two ranks: device-side data-parallel test + the N=2 bench line (weak + strong scaling)
               timeout 900 python -m pytest tests/test_gpu_multirank.py -m gpu -q -x --timeout 400 --tb=short > gpurun_out/multirank_test.log 2>&1; grep -v Warning gpurun_out/multirank_test.log | tail -25
               timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 100 --warmup 3 2>gpurun_out/bench_n2.err | tail -1 > gpurun_out/bench_n2.json
-              python -c "import json; d=json.loads(open('gpurun_out/bench_n2.json').read()); print('N=2', round(d['value'],1), round(d['ms_per_step'],4), 'strong', d.get('strong_scaling'))" || tail -5 gpurun_out/bench_n2.err
-              PTRANKING_B200_OVERLAP=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 2 --steps 100 --warmup 3 2>/dev/null | tail -1 > gpurun_out/bench_n2_nooverlap.json
-              python -c "import json; d=json.loads(open('gpurun_out/bench_n2_nooverlap.json').read()); print('N=2 no overlap', round(d['value'],1), round(d['ms_per_step'],4))"
+              python -c "import json; d=json.loads(open('gpurun_out/bench_n2.json').read()); print('N=2', d['config'].get('gradient_exchange'), round(d['value'],1), round(d['ms_per_step'],4), 'strong', round(d['strong_scaling']['ms_per_step'],4))" || tail -5 gpurun_out/bench_n2.err
+              PTRANKING_B200_PEER=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29520 bench.py --gpus 2 --steps 100 --warmup 3 2>/dev/null | tail -1 > gpurun_out/bench_n2_nccl.json
+              python -c "import json; d=json.loads(open('gpurun_out/bench_n2_nccl.json').read()); print('N=2 NCCL overlapped', round(d['value'],1), round(d['ms_per_step'],4), 'strong', round(d['strong_scaling']['ms_per_step'],4))"
+              PTRANKING_B200_PEER=0 PTRANKING_B200_OVERLAP=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 2 --steps 100 --warmup 3 2>/dev/null | tail -1 > gpurun_out/bench_n2_nooverlap.json
+              python -c "import json; d=json.loads(open('gpurun_out/bench_n2_nooverlap.json').read()); print('N=2 NCCL no overlap', round(d['value'],1), round(d['ms_per_step'],4), 'strong', round(d['strong_scaling']['ms_per_step'],4))"
               timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 bench.py --impl reference --gpus 2 --steps 5 --warmup 3 2>/dev/null | tail -1 | cut -c1-300 ;;
     *)        echo "unknown stage $s" ;;
   esac
