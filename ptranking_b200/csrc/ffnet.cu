@@ -822,7 +822,7 @@ static size_t wgrad_smem(int N, int K, int KP, int& R, int passes, int& stages, 
     for (R = 32; R >= min_R; R >>= 1) {
         const size_t op = (size_t)(4 + p_chunks) * R * 128 * (passes == 3 ? 2 : 1);
         const size_t rawz = (((size_t)R * N * 4 + 127) / 128 * 128) * (fused_dz ? 2 : 1), rawp = ((size_t)R * K * 4 + 127) / 128 * 128;
-        const size_t fixed = 1024 + 2 * op + 128;
+        const size_t fixed = 1024 + 2 * op + 128 + 3 * 128 * 4;      // + barriers + the coefficient rows of the folded normalisation backward
         for (stages = WG_MAX_STAGES; stages >= 2; --stages)
             if (fixed + stages * (rawz + rawp) <= limit) return fixed + stages * (rawz + rawp);
     }

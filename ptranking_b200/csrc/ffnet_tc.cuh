@@ -1027,25 +1027,52 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
         }
     } else {
         // ======================= producer warps =======================
+        // 16 warps turn a raw tile into the two MN-major operands.  Everything here is issue-bound (profiles/): shared memory
+        // is addressed through 32-bit shared-space addresses (ld.shared / st.shared, no generic 64-bit pointer math), the
+        // units that are pure padding (columns beyond N resp. K) are zeroed once and never touched again, the two roles
+        // split both operands so that neither idles, and with a single statistics group (batch-level BN) the three
+        // coefficient rows of the folded normalisation backward sit in shared memory instead of being re-read per unit.
         RowsGemmArgs pg{};
         pg.scale = g.scale; pg.shift = g.shift; pg.act = g.act; pg.gr_prev = g.gr_prev; pg.K = g.K_full; pg.drop = g.drop;
         const bool plain_p = !g.scale && g.act == PTRB200_AF_NONE && !g.drop.thr;   // layer input already materialised
-        const int ptid = tid & 255, role = tid >> 8;      // role 0 stages the dZ operand, role 1 the layer-input operand
+        const int ptid = tid & 255, role = tid >> 8;      // role 0: dZ chunks {0,3} + input chunks {0,2,..}; role 1: dZ {1,2} + input {1,3,..}
         const int r = ptid >> 3, j = ptid & 7;            // one 16-byte unit per thread per 32-column chunk (R*8 <= 256)
         const bool vec_z = (N & 3) == 0;
         const bool active = ptid < R * 8;
         const uint32_t sw = tc::swz32_offset(r, j);       // this thread's slot inside every operand chunk
-        const int zoff = r * N + j * 4, poff = r * K + j * 4;
+        const uint32_t op_s = tc::smem_u32(opbuf), raw_s = tc::smem_u32(rawbuf), coef_s = tc::smem_u32(tail) + 128u;
+        const uint32_t stage_bytes = (uint32_t)(rawz_bytes + rawp_bytes);
+        const uint32_t zsrc_off = (uint32_t)(r * N + j * 4) * 4u, psrc_off = (uint32_t)rawz_bytes + (uint32_t)(r * K + j * 4) * 4u;
+        const uint32_t z_lo_off = (uint32_t)(z_chunks * chunk_bytes);
+        const uint32_t p_hi_off = (uint32_t)((PASSES == 3 ? 2 : 1) * z_chunks * chunk_bytes), p_lo_off = p_hi_off + (uint32_t)(p_chunks * chunk_bytes);
+        const bool single_group = fused_dz && g.gr_cur >= g.rows;
+        {   // padding units are zero for the whole kernel; the coefficient rows of the one statistics group are staged once
+            for (int e = tid; e < 2 * op_bytes / 16; e += WG_PRODUCERS) tc::sts128(op_s + (uint32_t)e * 16u, make_float4(0.f, 0.f, 0.f, 0.f));
+            if (single_group)
+                for (int e = tid; e < 3 * 128; e += WG_PRODUCERS) {
+                    const int which = e >> 7, n = e & 127;
+                    const float* src = which == 0 ? g.kc1 : which == 1 ? g.kc3 : g.kc0;
+                    reinterpret_cast<float*>(tail + 128)[e] = n < N ? __ldg(src + m0 + n) : 0.0f;
+                }
+            asm volatile("bar.sync 1, %0;" ::"n"(WG_PRODUCERS) : "memory");
+        }
+        auto put = [&](uint32_t hi_addr, uint32_t lo_addr, float4 v) {
+            if (PASSES == 3) {
+                float4 h, l;
+                tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y); tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
+                tc::sts128(hi_addr, h); tc::sts128(lo_addr, l);
+            } else {
+                if (g.round_bf16) v = make_float4(bf16_rn(v.x), bf16_rn(v.y), bf16_rn(v.z), bf16_rn(v.w));
+                tc::sts128(hi_addr, v);
+            }
+        };
         int s = 0;
         for (int it = 0; it < my_tiles; ++it) {
             const int t = blockIdx.x + it * gridDim.x, o = it & 1;
             const int row0 = t * R, nrows = min(R, g.rows - row0);
-            unsigned char* z_hi = opbuf + o * op_bytes + sw;
-            unsigned char* z_lo = z_hi + z_chunks * chunk_bytes;
-            unsigned char* p_hi = z_hi + (PASSES == 3 ? 2 : 1) * z_chunks * chunk_bytes;
-            unsigned char* p_lo = p_hi + p_chunks * chunk_bytes;
+            const uint32_t zb = op_s + (uint32_t)(o * op_bytes) + sw;       // this thread's slot in chunk 0 of the dZ (hi) operand
+            const uint32_t rbase = raw_s + (uint32_t)s * stage_bytes;
             float* rz = reinterpret_cast<float*>(rawbuf + s * (rawz_bytes + rawp_bytes));
-            const float* rp = reinterpret_cast<const float*>(rawbuf + s * (rawz_bytes + rawp_bytes) + rawz_bytes);
             uint64_t* fbar = full + s;
             const int fpar = (it / stages) & 1;
             s = s + 1 == stages ? 0 : s + 1;
@@ -1056,38 +1083,47 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
             }
             tc::mbar_wait(fbar, fpar);
             const bool row_ok = r < nrows;
-            if (active && role == 0) {
-                const float* zsrc = rz + zoff;
+            if (active) {
+                // ---- dZ operand: two of the four 32-column chunks ----
+                const size_t grp_off = (fused_dz && !single_group) ? (size_t)((row0 + r) / g.gr_cur) * g.N_full + m0 : 0;   // one division per tile
 #pragma unroll
-                for (int ch = 0; ch < z_chunks; ++ch) {
+                for (int h = 0; h < 2; ++h) {
+                    const int ch = role == 0 ? (h == 0 ? 0 : 3) : (h == 0 ? 1 : 2);
                     const int n = ch * 32 + j * 4;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (row_ok && n < N) {
-                        if (vec_z) v = *reinterpret_cast<const float4*>(zsrc + ch * 32);
-                        else { const float* p = zsrc + ch * 32; v.x = p[0]; if (n + 1 < N) v.y = p[1]; if (n + 2 < N) v.z = p[2]; if (n + 3 < N) v.w = p[3]; }
-                        if (fused_dz) {                            // host guarantees N % 4 == 0 here
-                            const float4 z = *reinterpret_cast<const float4*>(zsrc + rawz1 / 4 + ch * 32);
-                            const size_t co = (g.gr_cur < g.rows ? (size_t)((row0 + r) / g.gr_cur) * N : 0) + n;
-                            const float4 a1 = __ldg(reinterpret_cast<const float4*>(g.kc1 + co));
-                            const float4 a3 = __ldg(reinterpret_cast<const float4*>(g.kc3 + co));
-                            const float4 a0 = __ldg(reinterpret_cast<const float4*>(g.kc0 + co));
-                            v.x = fmaf(a1.x, v.x, fmaf(a3.x, z.x, a0.x)); v.y = fmaf(a1.y, v.y, fmaf(a3.y, z.y, a0.y));
-                            v.z = fmaf(a1.z, v.z, fmaf(a3.z, z.z, a0.z)); v.w = fmaf(a1.w, v.w, fmaf(a3.w, z.w, a0.w));
+                    if (n < N) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row_ok) {
+                            const uint32_t src = rbase + zsrc_off + (uint32_t)ch * 128u;
+                            if (vec_z) v = tc::lds128(src);
+                            else { v.x = tc::lds32(src); if (n + 1 < N) v.y = tc::lds32(src + 4); if (n + 2 < N) v.z = tc::lds32(src + 8); if (n + 3 < N) v.w = tc::lds32(src + 12); }
+                            if (fused_dz) {                            // host guarantees N % 4 == 0 here
+                                const float4 z = tc::lds128(src + (uint32_t)rawz1);
+                                float4 a1, a3, a0;
+                                if (single_group) {
+                                    a1 = tc::lds128(coef_s + (uint32_t)n * 4u); a3 = tc::lds128(coef_s + 512u + (uint32_t)n * 4u); a0 = tc::lds128(coef_s + 1024u + (uint32_t)n * 4u);
+                                } else {
+                                    a1 = __ldg(reinterpret_cast<const float4*>(g.kc1 + grp_off + n));
+                                    a3 = __ldg(reinterpret_cast<const float4*>(g.kc3 + grp_off + n));
+                                    a0 = __ldg(reinterpret_cast<const float4*>(g.kc0 + grp_off + n));
+                                }
+                                v.x = fmaf(a1.x, v.x, fmaf(a3.x, z.x, a0.x)); v.y = fmaf(a1.y, v.y, fmaf(a3.y, z.y, a0.y));
+                                v.z = fmaf(a1.z, v.z, fmaf(a3.z, z.z, a0.z)); v.w = fmaf(a1.w, v.w, fmaf(a3.w, z.w, a0.w));
+                            }
                         }
+                        put(zb + (uint32_t)(ch * chunk_bytes), zb + z_lo_off + (uint32_t)(ch * chunk_bytes), v);
                     }
-                    store_split(z_hi + ch * chunk_bytes, z_lo + ch * chunk_bytes, 0, v, PASSES == 3, PASSES == 1 && g.round_bf16 != 0);
                 }
-            }
-            if (active && role == 1) {
-                const float* psrc = rp + poff;
-                for (int ch = 0; ch < p_chunks; ++ch) {
+                // ---- layer-input operand: every other chunk ----
+                for (int ch = role; ch < p_chunks; ch += 2) {
                     const int k = ch * 32 + j * 4;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (row_ok && k < K) {
-                        v = *reinterpret_cast<const float4*>(psrc + ch * 32);
-                        if (!plain_p) v = prologue4(pg, v, row0 + r, kk0 + k, true, (g.scale && g.gr_prev < g.rows) ? (size_t)((row0 + r) / g.gr_prev) * g.K_full : 0);
+                    if (k < K) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row_ok) {
+                            v = tc::lds128(rbase + psrc_off + (uint32_t)ch * 128u);
+                            if (!plain_p) v = prologue4(pg, v, row0 + r, kk0 + k, true, (g.scale && g.gr_prev < g.rows) ? (size_t)((row0 + r) / g.gr_prev) * g.K_full : 0);
+                        }
+                        put(zb + p_hi_off + (uint32_t)(ch * chunk_bytes), zb + p_lo_off + (uint32_t)(ch * chunk_bytes), v);
                     }
-                    store_split(p_hi + ch * chunk_bytes, p_lo + ch * chunk_bytes, 0, v, PASSES == 3, PASSES == 1 && g.round_bf16 != 0);
                 }
             }
             tc::fence_proxy_async();                       // this thread's operand stores -> visible to the MMA (async proxy)

@@ -17,6 +17,11 @@ for s in $stages; do
               python -c "import json; d=json.loads(open('gpurun_out/bench_n1.json').read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches']); print(d['roofline']['kernels_ms_per_step'])" ;;
     ops)      timeout 300 python tools/op_bench.py > gpurun_out/op_bench.log 2>&1; cp profiles/r02_op_table.md gpurun_out/; tail -60 gpurun_out/r02_op_table.md ;;
     launches) timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python tools/profile_step.py 3 > gpurun_out/ncu_launch.log 2>&1; tail -1 gpurun_out/ncu_launch.log ;;
+    quick)    # headline + list-scorer step, kernel shares only
+              for c in b c; do
+                timeout 300 python bench.py --config $c --steps 50 --no-cpu-baseline 2>gpurun_out/bench_q_$c.err | tail -1 > gpurun_out/bench_q_$c.json
+                python -c "import json; d=json.loads(open('gpurun_out/bench_q_$c.json').read()); print('$c', round(d['value'],1), 'q/s', round(d['ms_per_step'],4), 'ms', {k:v for k,v in list(d['roofline']['kernels_ms_per_step'].items())[:8]})" || tail -3 gpurun_out/bench_q_$c.err
+              done ;;
     abc)      # config c (list scorer, L=6): aligned bgemm kernel and fused Q|K|V projection, each switched off in turn
               for v in base general_bgemm separate_qkv; do
                 unset PTRB200_BGEMM_GENERAL PTRANKING_B200_FUSED_QKV
