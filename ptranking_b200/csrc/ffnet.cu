@@ -817,15 +817,29 @@ static int opt_in_smem(K kernel, size_t bytes) {
 
 // picks the row-tile height R (32/16/8) and ring depth so the kernel's buffers fit the 227 KB of one SM
 static size_t wgrad_smem(int N, int K, int KP, int& R, int passes, int& stages, bool fused_dz = false, int min_R = 8) {
+    // The kernel is fed by TMA bulk copies of whole row tiles; one SM's share of HBM bandwidth (~45 GB/s) makes a
+    // 30-40 KB tile take most of a microsecond to land, so the raw ring must run at least two tiles ahead of the
+    // producers (measured: 2 stages -> the producers wait for data half of the time).  Prefer the largest tile height
+    // that leaves room for >= 3 stages; fall back to the largest tile that fits at all.
     const int p_chunks = (KP + 31) / 32;
     const size_t limit = 227 * 1024;
-    for (R = 32; R >= min_R; R >>= 1) {
-        const size_t op = (size_t)(4 + p_chunks) * R * 128 * (passes == 3 ? 2 : 1);
-        const size_t rawz = (((size_t)R * N * 4 + 127) / 128 * 128) * (fused_dz ? 2 : 1), rawp = ((size_t)R * K * 4 + 127) / 128 * 128;
+    static const int heights[] = {32, 24, 16, 8};
+    auto fit = [&](int rows, int& st) -> size_t {
+        const size_t op = (size_t)(4 + p_chunks) * rows * 128 * (passes == 3 ? 2 : 1);
+        const size_t rawz = (((size_t)rows * N * 4 + 127) / 128 * 128) * (fused_dz ? 2 : 1), rawp = ((size_t)rows * K * 4 + 127) / 128 * 128;
         const size_t fixed = 1024 + 2 * op + 128 + 3 * 128 * 4;      // + barriers + the coefficient rows of the folded normalisation backward
-        for (stages = WG_MAX_STAGES; stages >= 2; --stages)
-            if (fixed + stages * (rawz + rawp) <= limit) return fixed + stages * (rawz + rawp);
-    }
+        for (st = WG_MAX_STAGES; st >= 2; --st)
+            if (fixed + st * (rawz + rawp) <= limit) return fixed + st * (rawz + rawp);
+        return 0;
+    };
+    static const bool deep = !(getenv("PTRB200_WG_SHALLOW") && getenv("PTRB200_WG_SHALLOW")[0] == '1');   // A/B switch
+    for (int pass = deep ? 0 : 1; pass < 2; ++pass)
+        for (int h : heights) {
+            if (h < min_R) continue;
+            int st = 0;
+            const size_t bytes = fit(h, st);
+            if (bytes && (pass == 1 || st >= 3)) { R = h; stages = st; return bytes; }
+        }
     R = 8; stages = 2;
     return limit + 1;        // does not fit
 }
@@ -1279,7 +1293,7 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
                 int Rf = 32, stf = 0;
                 const int KPl = ((lp.d_in + 15) / 16) * 16;
                 fuse_dz = lp.d_out % 4 == 0 && lp.d_out <= 128 && lp.d_in <= 256 && (l == 0 || rows_ws_fits(lp.d_out, lp.d_in, p.passes)) &&
-                          wgrad_smem(lp.d_out, lp.d_in, KPl, Rf, p.passes, stf, true, 32) <= (size_t)227 * 1024;
+                          wgrad_smem(lp.d_out, lp.d_in, KPl, Rf, p.passes, stf, true, 24) <= (size_t)227 * 1024;
                 if (fuse_dz) { tail.k1 = reinterpret_cast<float*>(ws + p.k1_off); tail.k3 = reinterpret_cast<float*>(ws + p.k3_off); tail.k0 = reinterpret_cast<float*>(ws + p.k0_off); }
             }
             const double* fin_part = part;
@@ -1328,7 +1342,7 @@ static int backward_tc(const ptrb200_ffnet* net, const ptrb200_ffnet_grads* grad
                 w.Z2 = Z; w.gr_cur = p.gr;
                 w.kc1 = reinterpret_cast<const float*>(ws + p.k1_off); w.kc3 = reinterpret_cast<const float*>(ws + p.k3_off); w.kc0 = reinterpret_cast<const float*>(ws + p.k0_off);
             }
-            const size_t smem = wgrad_smem(w.N, w.K, w.KP, w.tile_rows, p.passes, w.stages, fuse_dz, fuse_dz ? 32 : 8);
+            const size_t smem = wgrad_smem(w.N, w.K, w.KP, w.tile_rows, p.passes, w.stages, fuse_dz, fuse_dz ? 24 : 8);
             const dim3 grid(wb.gx, wb.mblocks, wb.kblocks);   // persistent CTAs per (dZ block, input block), fed by the TMA ring
             if (p.passes == 3) { if ((rc = opt_in_smem(wgrad_tc_kernel<3>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<3>, grid, WG_THREADS, smem, st, w); }
             else { if ((rc = opt_in_smem(wgrad_tc_kernel<1>, smem))) return rc; PTRB200_LAUNCH_TAG("wgrad_tc", wgrad_tc_kernel<1>, grid, WG_THREADS, smem, st, w); }

@@ -280,7 +280,7 @@ class GradBucket:
         self._reduced_from = None
         if self.peer is not None:
             return
-        if is_distributed() and self.distributed and self.flat.is_cuda and os.environ.get("PTRANKING_B200_OVERLAP", "1") == "1":
+        if is_distributed() and self.distributed and self.flat.is_cuda and os.environ.get("PTRANKING_B200_OVERLAP", "0") == "1":
             _install_hook()
             _active_bucket = self
 

@@ -22,6 +22,14 @@ for s in $stages; do
                 timeout 300 python bench.py --config $c --steps 50 --no-cpu-baseline 2>gpurun_out/bench_q_$c.err | tail -1 > gpurun_out/bench_q_$c.json
                 python -c "import json; d=json.loads(open('gpurun_out/bench_q_$c.json').read()); print('$c', round(d['value'],1), 'q/s', round(d['ms_per_step'],4), 'ms', {k:v for k,v in list(d['roofline']['kernels_ms_per_step'].items())[:8]})" || tail -3 gpurun_out/bench_q_$c.err
               done ;;
+    abwg)     # A/B of the deeper TMA ring (shorter row tiles) in the weight-gradient kernel
+              for v in 0 1; do
+                if [ $v = 1 ]; then export PTRB200_WG_SHALLOW=1; else unset PTRB200_WG_SHALLOW; fi
+                for c in b c; do
+                  timeout 300 python bench.py --config $c --steps 50 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/bench_abwg_${c}_$v.json
+                  python -c "import json; d=json.loads(open('gpurun_out/bench_abwg_${c}_$v.json').read()); print('SHALLOW=$v', '$c', round(d['ms_per_step'],4), 'wgrad', d['roofline']['kernels_ms_per_step'].get('wgrad_tc'))"
+                done
+              done; unset PTRB200_WG_SHALLOW ;;
     abc)      # config c (list scorer, L=6): aligned bgemm kernel and fused Q|K|V projection, each switched off in turn
               for v in base general_bgemm separate_qkv; do
                 unset PTRB200_BGEMM_GENERAL PTRANKING_B200_FUSED_QKV

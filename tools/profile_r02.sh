@@ -24,8 +24,8 @@ for stage in "${@:-launches b c d e}"; do
       cap b "lambdarank_runs|pairwise_bce" 1 loss ;;
     c)  # list scorer (L=3): attention GEMMs (QK^T and PV), row softmax, the wide-layer kernels, ApproxNDCG
       export ENC_LAYERS=3
-      cap c bgemm_nt_tc_kernel 18 attn_qk
-      cap c bgemm_nt_tc_kernel 19 attn_pv
+      cap c "bgemm_(fast|nt_tc)_kernel" 18 attn_qk
+      cap c "bgemm_(fast|nt_tc)_kernel" 19 attn_pv
       cap c softmax_rows_kernel 3 softmax
       cap c softmax_bwd_rows_kernel 3 softmax_bwd
       cap c rows_gemm_tc_kernel 34 rows_gemm_tc
