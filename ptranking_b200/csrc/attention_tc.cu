@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(BG_THREADS) bgemm_nt_tc_kernel(BGemmArgs g) {
 // cannot assume quad alignment); B units beyond the padded tile width are never touched.  The attention core's six
 // contractions all qualify; odd shapes keep the general kernel.
 template <int PASSES, int A_MN, int B_MN, int DROP>
-__global__ void __launch_bounds__(BG_THREADS, 3) bgemm_fast_kernel(BGemmArgs g) {
+__global__ void __launch_bounds__(BG_THREADS, 2) bgemm_fast_kernel(BGemmArgs g) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* a_hi = base;
@@ -272,17 +272,27 @@ __global__ void __launch_bounds__(BG_THREADS, 3) bgemm_fast_kernel(BGemmArgs g) 
     const bool drop_on = DROP != 0 && g.drop.thr != 0;
     const uint32_t thr = g.drop.thr; const float dscale = g.drop.scale;
 
-    for (int c = 0; c < nchunks; ++c) {
+    // global -> registers one chunk AHEAD: the loads of chunk c+1 are in flight while chunk c is split, stored, synchronised
+    // and multiplied (a CTA has no other way to hide HBM latency: its chunks are strictly sequential)
+    float4 nav[4], nbv[4];
+    auto load_chunk = [&](int c) {
         const int k0 = c * 32;
-        float4 av[4], bv[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const bool ka = A_MN ? (k0 + km + 8 * i < K) : (k0 + jk * 4 < K);
             const bool kb = B_MN ? (k0 + km + 8 * i < K) : (k0 + jk * 4 < K);
-            av[i] = (ka && ((am >> i) & 1u)) ? __ldg(reinterpret_cast<const float4*>(pa + i * sa)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            bv[i] = (kb && ((bm >> i) & 1u)) ? __ldg(reinterpret_cast<const float4*>(pb + i * sb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            nav[i] = (ka && ((am >> i) & 1u)) ? __ldg(reinterpret_cast<const float4*>(pa + i * sa)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            nbv[i] = (kb && ((bm >> i) & 1u)) ? __ldg(reinterpret_cast<const float4*>(pb + i * sb)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         pa += A_MN ? (size_t)32 * g.lda : 32; pb += B_MN ? (size_t)32 * g.ldb : 32;
+    };
+    load_chunk(0);
+    for (int c = 0; c < nchunks; ++c) {
+        const int k0 = c * 32;
+        float4 av[4], bv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { av[i] = nav[i]; bv[i] = nbv[i]; }
+        if (c + 1 < nchunks) load_chunk(c + 1);
         if (c > 0) tc::mbar_wait(mbar, (c - 1) & 1);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {

@@ -817,10 +817,7 @@ static int opt_in_smem(K kernel, size_t bytes) {
 
 // picks the row-tile height R (32/16/8) and ring depth so the kernel's buffers fit the 227 KB of one SM
 static size_t wgrad_smem(int N, int K, int KP, int& R, int passes, int& stages, bool fused_dz = false, int min_R = 8) {
-    // The kernel is fed by TMA bulk copies of whole row tiles; one SM's share of HBM bandwidth (~45 GB/s) makes a
-    // 30-40 KB tile take most of a microsecond to land, so the raw ring must run at least two tiles ahead of the
-    // producers (measured: 2 stages -> the producers wait for data half of the time).  Prefer the largest tile height
-    // that leaves room for >= 3 stages; fall back to the largest tile that fits at all.
+    // Largest tile height whose operand buffers and a >= 2-deep raw ring fit; as many ring stages as then fit.
     const int p_chunks = (KP + 31) / 32;
     const size_t limit = 227 * 1024;
     static const int heights[] = {32, 24, 16, 8};
@@ -832,7 +829,9 @@ static size_t wgrad_smem(int N, int K, int KP, int& R, int passes, int& stages, 
             if (fixed + st * (rawz + rawp) <= limit) return fixed + st * (rawz + rawp);
         return 0;
     };
-    static const bool deep = !(getenv("PTRB200_WG_SHALLOW") && getenv("PTRB200_WG_SHALLOW")[0] == '1');   // A/B switch
+    // (measured on the box, PTRB200_WG_DEEP=1: 24-row tiles with a 4-deep ring are 2.5 % SLOWER on the headline step than
+    //  32-row tiles with 2 stages -- a quarter of the producer threads idle on a 24-row tile -- so depth is opt-in)
+    static const bool deep = getenv("PTRB200_WG_DEEP") && getenv("PTRB200_WG_DEEP")[0] == '1';
     for (int pass = deep ? 0 : 1; pass < 2; ++pass)
         for (int h : heights) {
             if (h < min_R) continue;
@@ -909,7 +908,7 @@ static int launch_rows_gemm(int mode, int passes, RowsGemmArgs& g, int ntiles, c
     g.n_tile = g.N <= 144 ? g.N : (long_k ? 128 : 144);
     const int n_tiles = (g.N + g.n_tile - 1) / g.n_tile;
     const int NPt = ((g.n_tile + 15) / 16) * 16;
-    const size_t operands = 32768 + (size_t)NPt * 256, otile = (size_t)128 * g.n_tile * 4;
+    const size_t operands = 32768 + (size_t)2 * NPt * 256, otile = (size_t)128 * g.n_tile * 4;      // A hi|lo + two weight-chunk stages
     g.tail_off = (int)(((operands > otile ? operands : otile) + 15) / 16 * 16);
     const size_t smem = 1024 + (size_t)g.tail_off + 64;
     const dim3 rg_grid(ntiles, n_tiles);

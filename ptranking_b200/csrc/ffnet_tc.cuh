@@ -191,12 +191,14 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
     const int NP = ((N + 15) / 16) * 16;
     unsigned char* a_hi = base;                       // 128 rows x 128 B
     unsigned char* a_lo = a_hi + 16384;
-    unsigned char* b_hi = a_lo + 16384;               // NP rows x 128 B
-    unsigned char* b_lo = b_hi + NP * 128;
+    // weight chunk, double buffered: [2][hi | lo], NP rows x 128 B each (the copy of chunk c+1 is issued as soon as the MMAs
+    // of chunk c-1 have released its buffer, a whole chunk ahead of its use)
+    unsigned char* b_buf = a_lo + 16384;
+    const uint32_t b_stage = (uint32_t)NP * 128u * (PASSES == 3 ? 2u : 1u);
     unsigned char* tail = base + g.tail_off;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(tail);
-    uint64_t* bbar = mbar + 1;
-    uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 2);
+    uint64_t* bbar = mbar + 1;                        // [2]
+    uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 3);
     float* otile = reinterpret_cast<float*>(base);    // epilogue staging [128][N], aliases the operand buffers
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
     const bool long_k = PASSES == 3 && nchunks > 5;
     const uint32_t need_cols = (uint32_t)(long_k ? 2 * NP : NP);
     const uint32_t tmem_cols = need_cols <= 32 ? 32 : need_cols <= 64 ? 64 : need_cols <= 128 ? 128 : need_cols <= 256 ? 256 : 512;
-    if (tid == 0) { tc::mbar_init(mbar, 1); tc::mbar_init(bbar, 1); tc::mbar_fence_init(); }
+    if (tid == 0) { tc::mbar_init(mbar, 1); tc::mbar_init(bbar, 1); tc::mbar_init(bbar + 1, 1); tc::mbar_fence_init(); }
     if (warp == 0) tc::tmem_alloc(slot, tmem_cols);
     tc::fence_before_sync();
     __syncthreads();
@@ -240,23 +242,37 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
         coef_off[i] = (g.scale && g.gr_prev < g.rows) ? (size_t)((row0 + min(r, nrows - 1)) / g.gr_prev) * K : 0;
     }
 
-    for (int c = 0; c < nchunks; ++c) {
-        const int k0 = c * 32;
-        // ---- global -> registers (issued before waiting on the previous chunk's MMAs) ----
-        float4 av[A_UNITS];
+    // ---- global -> registers one chunk AHEAD: the loads of chunk c+1 fly while chunk c is staged, synchronised and
+    // multiplied (a tile's chunks are strictly sequential and few CTAs share an SM at list-scorer row counts, so nothing
+    // else hides the HBM latency: measured 4 us per chunk without the prefetch) ----
+    float4 nav[A_UNITS];
+    auto load_chunk = [&](int c) {
 #pragma unroll
         for (int i = 0; i < A_UNITS; ++i) {
-            const int u = tid + i * RG_THREADS, r = u >> 3, j = u & 7, k = k0 + j * 4;
-            av[i] = (r < nrows) ? ldg4_guard(g.P + (size_t)(row0 + r) * K + k, k, K) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int u = tid + i * RG_THREADS, r = u >> 3, j = u & 7, k = c * 32 + j * 4;
+            nav[i] = (r < nrows) ? ldg4_guard(g.P + (size_t)(row0 + r) * K + k, k, K) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+    };
+    load_chunk(0);
+    for (int c = 0; c < nchunks; ++c) {
+        const int k0 = c * 32;
+        float4 av[A_UNITS];
+#pragma unroll
+        for (int i = 0; i < A_UNITS; ++i) av[i] = nav[i];
+        if (c + 1 < nchunks) load_chunk(c + 1);
         if (c > 0) tc::mbar_wait(mbar, (c - 1) & 1);
-        // ---- B: one TMA bulk copy per operand image chunk (no SM instructions beyond the issue) ----
+        // ---- B: one TMA bulk copy per operand image chunk (no SM instructions beyond the issue), one chunk ahead ----
         if (tid == 0) {
-            const uint32_t bytes = (uint32_t)NP * 128u;
-            const size_t src = ((size_t)c * NP_full + n0) * 128u;       // rows [n0, n0+NP) of chunk c
-            tc::mbar_expect_tx(bbar, PASSES == 3 ? 2 * bytes : bytes);
-            tc::bulk_g2s(b_hi, g.b_img_hi + src, bytes, bbar);
-            if (PASSES == 3) tc::bulk_g2s(b_lo, g.b_img_lo + src, bytes, bbar);
+            auto fetch_b = [&](int cc) {
+                const uint32_t bytes = (uint32_t)NP * 128u;
+                const size_t src = ((size_t)cc * NP_full + n0) * 128u;       // rows [n0, n0+NP) of chunk cc
+                unsigned char* dst = b_buf + (size_t)(cc & 1) * b_stage;
+                tc::mbar_expect_tx(bbar + (cc & 1), PASSES == 3 ? 2 * bytes : bytes);
+                tc::bulk_g2s(dst, g.b_img_hi + src, bytes, bbar + (cc & 1));
+                if (PASSES == 3) tc::bulk_g2s(dst + bytes, g.b_img_lo + src, bytes, bbar + (cc & 1));
+            };
+            if (c == 0) fetch_b(0);
+            if (c + 1 < nchunks) fetch_b(c + 1);      // its buffer was last read by chunk c-1, whose MMAs have completed
         }
         // ---- A: prologue + split + swizzled store ----
 #pragma unroll
@@ -272,16 +288,17 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
         tc::fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
-            tc::mbar_wait(bbar, c & 1);                       // weights chunk has landed
+            tc::mbar_wait(bbar + (c & 1), (c >> 1) & 1);      // weights chunk has landed
             tc::fence_after_sync();
             const int ksteps = min(4, (K - k0 + 7) / 8);
+            const uint32_t b_hi_s = tc::smem_u32(b_buf) + (uint32_t)(c & 1) * b_stage, b_lo_s = b_hi_s + (uint32_t)NP * 128u;
             for (int s = 0; s < ksteps; ++s) {
                 const uint64_t ah = tc::smem_desc_sw128(tc::smem_u32(a_hi) + s * 32, 1024);
-                const uint64_t bh = tc::smem_desc_sw128(tc::smem_u32(b_hi) + s * 32, 1024);
+                const uint64_t bh = tc::smem_desc_sw128(b_hi_s + s * 32, 1024);
                 const uint32_t acc = (c == 0 && s == 0) ? 0u : 1u;
                 if (PASSES == 3) {
                     const uint64_t al = tc::smem_desc_sw128(tc::smem_u32(a_lo) + s * 32, 1024);
-                    const uint64_t bl = tc::smem_desc_sw128(tc::smem_u32(b_lo) + s * 32, 1024);
+                    const uint64_t bl = tc::smem_desc_sw128(b_lo_s + s * 32, 1024);
                     if (long_k) {
                         tc::mma_tf32(tmem + (uint32_t)NP, al, bh, idesc, acc);
                         tc::mma_tf32(tmem + (uint32_t)NP, ah, bl, idesc, 1u);

@@ -24,12 +24,22 @@ for s in $stages; do
               done ;;
     abwg)     # A/B of the deeper TMA ring (shorter row tiles) in the weight-gradient kernel
               for v in 0 1; do
-                if [ $v = 1 ]; then export PTRB200_WG_SHALLOW=1; else unset PTRB200_WG_SHALLOW; fi
+                if [ $v = 1 ]; then export PTRB200_WG_DEEP=1; else unset PTRB200_WG_DEEP; fi
                 for c in b c; do
                   timeout 300 python bench.py --config $c --steps 50 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/bench_abwg_${c}_$v.json
-                  python -c "import json; d=json.loads(open('gpurun_out/bench_abwg_${c}_$v.json').read()); print('SHALLOW=$v', '$c', round(d['ms_per_step'],4), 'wgrad', d['roofline']['kernels_ms_per_step'].get('wgrad_tc'))"
+                  python -c "import json; d=json.loads(open('gpurun_out/bench_abwg_${c}_$v.json').read()); print('DEEP=$v', '$c', round(d['ms_per_step'],4), 'wgrad', d['roofline']['kernels_ms_per_step'].get('wgrad_tc'))"
                 done
-              done; unset PTRB200_WG_SHALLOW ;;
+              done; unset PTRB200_WG_DEEP ;;
+    multi8)   # 8 ranks: headline bench with the peer-memory exchange and with NCCL, config d (LambdaLoss n=1024), the reference arm
+              for v in peer nccl; do
+                if [ $v = nccl ]; then export PTRANKING_B200_PEER=0; else unset PTRANKING_B200_PEER; fi
+                timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --steps 100 --warmup 3 2>gpurun_out/bench_n8_$v.err | tail -1 > gpurun_out/bench_n8_$v.json
+                python -c "import json; d=json.loads(open('gpurun_out/bench_n8_$v.json').read()); print('N=8 $v', d['config'].get('gradient_exchange')[:40], round(d['value'],1), round(d['ms_per_step'],4), 'strong', round(d['strong_scaling']['ms_per_step'],4), 'e2e', round(d['e2e']['value'],1))" || tail -5 gpurun_out/bench_n8_$v.err
+              done; unset PTRANKING_B200_PEER
+              timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29532 bench.py --config d --gpus 8 --steps 50 --warmup 3 2>gpurun_out/bench_d_n8.err | tail -1 > gpurun_out/bench_d_n8.json
+              python -c "import json; d=json.loads(open('gpurun_out/bench_d_n8.json').read()); print('N=8 config d', round(d['value'],1), round(d['ms_per_step'],4))" || tail -5 gpurun_out/bench_d_n8.err
+              timeout 300 python bench.py --steps 100 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/bench_n1_same_box.json
+              python -c "import json; d=json.loads(open('gpurun_out/bench_n1_same_box.json').read()); print('N=1 same box', round(d['value'],1), round(d['ms_per_step'],4))" ;;
     abc)      # config c (list scorer, L=6): aligned bgemm kernel and fused Q|K|V projection, each switched off in turn
               for v in base general_bgemm separate_qkv; do
                 unset PTRB200_BGEMM_GENERAL PTRANKING_B200_FUSED_QKV
