@@ -1167,8 +1167,14 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgradArgs g) {
                 for (int e = 0; e < 8; ++e) v[e] = 0.0f;
             }
             if (n < N) {
+                float* drow = dst + (size_t)n * g.K_full + c0;
+                if (c0 + 8 <= K && ((g.K_full | kk0) & 3) == 0 && (reinterpret_cast<uintptr_t>(g.partials) & 15) == 0) {
+                    *reinterpret_cast<float4*>(drow) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(drow + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                } else {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) if (c0 + e < K) dst[(size_t)n * g.K_full + c0 + e] = v[e];
+                    for (int e = 0; e < 8; ++e) if (c0 + e < K) drow[e] = v[e];
+                }
             }
         }
     }
