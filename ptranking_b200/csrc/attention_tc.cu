@@ -371,207 +371,6 @@ __global__ void __launch_bounds__(BG_THREADS, 2) bgemm_fast_kernel(BGemmArgs g) 
     if (warp == 0) tc::tmem_dealloc(tmem, tmem_cols);
 }
 
-// ---- whole-row attention kernels: the [128 x n] score tile never leaves the SM ---------------------------------------
-// For lists of up to 512 documents a CTA owns 128 query rows of one (query, head) and ALL n key columns: the n <= 512 fp32
-// scores are exactly the 512 TMEM columns.  The contraction (K = head width <= 128, K-major operands) runs tile by tile over
-// the keys with the query operand staged once; the epilogue then works on complete rows in TMEM:
-//   MODE 0 (forward):   S = alpha * Q K^T  ->  P = softmax(S)            written once           (replaces bgemm + softmax_rows)
-//   MODE 1 (backward):  dP = dO V^T        ->  dS = P o (dropmask(dP) - rowsum(P o dropmask(dP))) * inv_scale
-//                                                                                              (replaces bgemm + softmax_bwd_rows)
-// i.e. per layer one write of S, one read-modify-write of S, one write of dP and its read-modify-write (4 x 134 MB at
-// B=64, n=512) and two launches disappear.  Same arithmetic as the separate kernels: expf on the scaled, max-shifted score,
-// one reciprocal per row, dropout ids = flat index into the [Z,n,n] tensor.  The three MMAs of the 3xTF32 split accumulate
-// into ONE accumulator (K <= 128: the short-contraction rule of rows_gemm_tc).
-struct AttnRowsExtra {
-    const float* P;        // MODE 1: probabilities [Z,n,n] (ldc pitch)
-    float inv_scale;       // MODE 1
-    DropCfg drop;          // MODE 1: dropout that was applied to P in the forward pass
-};
-
-template <int PASSES, int MODE>
-__global__ void __launch_bounds__(BG_THREADS, 1) attn_rows_kernel(BGemmArgs g, AttnRowsExtra x) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* a_buf = base;                      // [4 chunks][hi 16 KB | lo 16 KB]
-    unsigned char* b_buf = base + 4 * 32768;          // [2 stages][hi 16 KB | lo 16 KB]
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(b_buf + 2 * 32768);   // [2]: MMAs reading stage s have completed
-    uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 2);
-    float* red = reinterpret_cast<float*>(mbar + 4);  // [2 halves][128 rows]
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int z = blockIdx.y, zb = z / g.H, zh = z % g.H;
-    const float* A = g.A + zb * g.sAb + zh * g.sAh;
-    const float* B = g.B + zb * g.sBb + zh * g.sBh;
-    float* C = g.C + zb * g.sCb + zh * g.sCh;
-    const int m0 = blockIdx.x * 128;
-    const int K = g.K, N = g.N, M = g.M;
-    const int nchunks = (K + 31) / 32, ntile = (N + 127) / 128, iters = ntile * nchunks;
-    if (tid == 0) { tc::mbar_init(mbar, 1); tc::mbar_init(mbar + 1, 1); tc::mbar_fence_init(); }
-    if (warp == 0) tc::tmem_alloc(slot, 512);
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
-    const uint32_t tmem = *slot;
-
-    // ---- staging geometry (K-major, as in bgemm_fast_kernel) ----
-    const int jk = tid & 7, rk = tid >> 3;
-    const float* pa = A + (size_t)(m0 + rk) * g.lda + jk * 4;
-    const float* pb = B + (size_t)rk * g.ldb + jk * 4;
-    const size_t sa = (size_t)32 * g.lda, sb = (size_t)32 * g.ldb;
-    const uint32_t off = tc::swz_offset(rk, jk);
-    uint32_t am = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) am |= (m0 + rk + 32 * i < M) ? (1u << i) : 0u;
-    float4 nav[4], nbv[4];
-    auto load_iter = [&](int it) {
-        const int t = it / nchunks, c = it - t * nchunks, k0 = c * 32, n0 = t * 128;
-        const bool kin = k0 + jk * 4 < K;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            nbv[i] = (kin && n0 + rk + 32 * i < N) ? __ldg(reinterpret_cast<const float4*>(pb + (size_t)n0 * g.ldb + i * sb + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (t == 0) nav[i] = (kin && ((am >> i) & 1u)) ? __ldg(reinterpret_cast<const float4*>(pa + i * sa + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    };
-    auto put = [&](unsigned char* hi, float4 v) {
-        if (PASSES == 3) {
-            float4 h, l;
-            tc::split_tf32_rn(v.x, h.x, l.x); tc::split_tf32_rn(v.y, h.y, l.y); tc::split_tf32_rn(v.z, h.z, l.z); tc::split_tf32_rn(v.w, h.w, l.w);
-            *reinterpret_cast<float4*>(hi) = h; *reinterpret_cast<float4*>(hi + 16384) = l;
-        } else *reinterpret_cast<float4*>(hi) = v;
-    };
-    load_iter(0);
-    for (int it = 0; it < iters; ++it) {
-        const int t = it / nchunks, c = it - t * nchunks, k0 = c * 32, st = it & 1;
-        float4 av[4], bv[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { av[i] = nav[i]; bv[i] = nbv[i]; }
-        if (it + 1 < iters) load_iter(it + 1);
-        if (it >= 2) tc::mbar_wait(mbar + st, ((it >> 1) - 1) & 1);      // the MMAs of iteration it-2 are done with stage st
-        unsigned char* bs = b_buf + st * 32768;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            put(bs + off + i * 4096, bv[i]);
-            if (t == 0) put(a_buf + c * 32768 + off + i * 4096, av[i]);
-        }
-        tc::fence_proxy_async();
-        __syncthreads();
-        if (warp == 0) {
-            tc::fence_after_sync();
-            const int NPt = ((min(128, N - t * 128) + 15) / 16) * 16;
-            const uint32_t idesc = tc::instr_desc(2, 128, NPt);
-            const int ksteps = min(4, (K - k0 + 7) / 8);
-            uint64_t ah = tc::smem_desc_sw128(tc::smem_u32(a_buf + c * 32768), 1024), al = tc::smem_desc_sw128(tc::smem_u32(a_buf + c * 32768 + 16384), 1024);
-            uint64_t bh = tc::smem_desc_sw128(tc::smem_u32(bs), 1024), bl = tc::smem_desc_sw128(tc::smem_u32(bs + 16384), 1024);
-            if (tc::elect_one()) {
-                const uint32_t acc = tmem + (uint32_t)(t * 128);
-                for (int s = 0; s < ksteps; ++s) {
-                    const uint32_t first = (c == 0 && s == 0) ? 0u : 1u;
-                    if (PASSES == 3) {
-                        tc::mma_tf32(acc, al, bh, idesc, first);
-                        tc::mma_tf32(acc, ah, bl, idesc, 1u);
-                        tc::mma_tf32(acc, ah, bh, idesc, 1u);
-                    } else tc::mma_tf32(acc, ah, bh, idesc, first);
-                    ah += 2; al += 2; bh += 2; bl += 2;
-                }
-                tc::mma_commit(mbar + st);
-            }
-            __syncwarp();
-        }
-    }
-    tc::mbar_wait(mbar + ((iters - 1) & 1), ((iters - 1) >> 1) & 1);     // commits complete in order: the last one covers all
-    tc::fence_after_sync();
-
-    // ---- row epilogue: TMEM lane = query row; the two warps of a lane quarter split the key columns at 256 ----
-    const int q = warp & 3, half = warp >> 2;
-    const int rloc = q * 32 + lane, row = m0 + rloc;
-    const int cbeg = half * 256, cend = min(N, cbeg + 256);
-    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-    float* crow = C + (size_t)min(row, M - 1) * g.ldc;
-    if (MODE == 0) {
-        const float alpha = g.alpha;
-        float m = -INFINITY;
-        for (int c0 = cbeg; c0 < cend; c0 += 16) {
-            float v[16];
-            tc::tmem_ld16(trow + (uint32_t)c0, v);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) if (c0 + e < cend) m = fmaxf(m, __fmul_rn(v[e], alpha));
-        }
-        red[half * 128 + rloc] = m;
-        __syncthreads();
-        m = fmaxf(red[rloc], red[128 + rloc]);
-        __syncthreads();
-        float l = 0.0f;
-        for (int c0 = cbeg; c0 < cend; c0 += 16) {
-            float v[16];
-            tc::tmem_ld16(trow + (uint32_t)c0, v);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) if (c0 + e < cend) l += expf(__fmul_rn(v[e], alpha) - m);
-        }
-        red[half * 128 + rloc] = l;
-        __syncthreads();
-        const float inv = 1.0f / (red[rloc] + red[128 + rloc]);
-        for (int c0 = cbeg; c0 < cend; c0 += 16) {
-            float v[16];
-            tc::tmem_ld16(trow + (uint32_t)c0, v);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = expf(__fmul_rn(v[e], alpha) - m) * inv;
-            if (row < M) {
-#pragma unroll
-                for (int e = 0; e < 16; e += 4)
-                    if (c0 + e < cend) *reinterpret_cast<float4*>(crow + c0 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-            }
-        }
-    } else {
-        const float* prow = x.P + zb * g.sCb + zh * g.sCh + (size_t)min(row, M - 1) * g.ldc;
-        const uint64_t id0 = ((uint64_t)z * M + (uint64_t)min(row, M - 1)) * (uint64_t)N;     // flat index of this row in [Z,n,n]
-        const uint32_t thr = x.drop.thr; const float dscale = x.drop.scale;
-        auto masked = [&](float (&v)[16], int c0) {      // dA = dropmask(dA_d): one 64-bit draw per four elements
-            if (!thr) return;
-#pragma unroll
-            for (int e = 0; e < 16; e += 4) {
-                const uint64_t d = dropout_draw4(x.drop.key, (id0 + (uint64_t)(c0 + e)) >> 2);
-                v[e] = ((uint32_t)d & 0xffffu) >= thr ? v[e] * dscale : 0.0f;
-                v[e + 1] = ((uint32_t)(d >> 16) & 0xffffu) >= thr ? v[e + 1] * dscale : 0.0f;
-                v[e + 2] = ((uint32_t)(d >> 32) & 0xffffu) >= thr ? v[e + 2] * dscale : 0.0f;
-                v[e + 3] = (uint32_t)(d >> 48) >= thr ? v[e + 3] * dscale : 0.0f;
-            }
-        };
-        float acc = 0.0f;
-        for (int c0 = cbeg; c0 < cend; c0 += 16) {
-            float v[16];
-            tc::tmem_ld16(trow + (uint32_t)c0, v);
-            masked(v, c0);
-#pragma unroll
-            for (int e = 0; e < 16; e += 4)
-                if (c0 + e < cend) {
-                    const float4 p = __ldg(reinterpret_cast<const float4*>(prow + c0 + e));
-                    acc = fmaf(p.x, v[e], acc); acc = fmaf(p.y, v[e + 1], acc); acc = fmaf(p.z, v[e + 2], acc); acc = fmaf(p.w, v[e + 3], acc);
-                }
-        }
-        red[half * 128 + rloc] = acc;
-        __syncthreads();
-        acc = red[rloc] + red[128 + rloc];
-        const float isc = x.inv_scale;
-        for (int c0 = cbeg; c0 < cend; c0 += 16) {
-            float v[16];
-            tc::tmem_ld16(trow + (uint32_t)c0, v);
-            masked(v, c0);
-            if (row < M) {
-#pragma unroll
-                for (int e = 0; e < 16; e += 4)
-                    if (c0 + e < cend) {
-                        const float4 p = __ldg(reinterpret_cast<const float4*>(prow + c0 + e));
-                        *reinterpret_cast<float4*>(crow + c0 + e) = make_float4(p.x * (v[e] - acc) * isc, p.y * (v[e + 1] - acc) * isc,
-                                                                                 p.z * (v[e + 2] - acc) * isc, p.w * (v[e + 3] - acc) * isc);
-                    }
-            }
-        }
-    }
-    tc::fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 512);
-}
-
 // in-place row softmax over S[z][i][:] (one warp per row); also emits the per-row log-sum-exp
 __global__ void softmax_rows_kernel(float* __restrict__ S, float* __restrict__ lse, size_t rows, int n) {
     const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -619,32 +418,6 @@ static int launch_bgemm_fast(const BGemmArgs& g, dim3 grid, size_t smem, cudaStr
 static bool bgemm_general_forced() {
     const char* e = getenv("PTRB200_BGEMM_GENERAL");      // read per launch: the parity test flips it inside one process
     return e && e[0] == '1';
-}
-
-// whole-row kernels: K-major operands of width <= 128, lists of <= 512 documents, everything a multiple of four floats
-static bool attn_rows_ok(const BGemmArgs& g, const float* P) {
-    const char* e = getenv("PTRB200_ATTN_UNFUSED");
-    if ((e && e[0] == '1') || bgemm_general_forced()) return false;
-    const auto q4 = [](long long v) { return (v & 3) == 0; };
-    const auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-    return g.N <= 512 && g.K <= 128 && !g.a_mn && !g.b_mn && q4(g.lda) && q4(g.ldb) && q4(g.ldc) && q4(g.N) && q4(g.K) &&
-           q4(g.sAb) && q4(g.sAh) && q4(g.sBb) && q4(g.sBh) && q4(g.sCb) && q4(g.sCh) && a16(g.A) && a16(g.B) && a16(g.C) && (!P || a16(P));
-}
-template <int MODE>
-static int launch_attn_rows(const BGemmArgs& g, const AttnRowsExtra& x, int Z, int passes, cudaStream_t st, const char* tag) {
-    const size_t smem = 1024 + 6 * 32768 + 32 + 2 * 128 * 4 + 64;
-    const dim3 grid((g.M + 127) / 128, Z);
-    cudaError_t e;
-    if (passes == 3) {
-        e = cudaFuncSetAttribute(attn_rows_kernel<3, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("attn_rows smem attr: %s", cudaGetErrorString(e)); return PTRB200_ERR_CUDA; }
-        PTRB200_LAUNCH_TAG(tag, (attn_rows_kernel<3, MODE>), grid, BG_THREADS, smem, st, g, x);
-    } else {
-        e = cudaFuncSetAttribute(attn_rows_kernel<1, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("attn_rows smem attr: %s", cudaGetErrorString(e)); return PTRB200_ERR_CUDA; }
-        PTRB200_LAUNCH_TAG(tag, (attn_rows_kernel<1, MODE>), grid, BG_THREADS, smem, st, g, x);
-    }
-    return PTRB200_OK;
 }
 
 static int launch_bgemm(BGemmArgs& g, int Z, int passes, cudaStream_t st, const char* tag) {
@@ -705,13 +478,9 @@ int ptrb200_attention_tc_fwd_ld(const float* Q, const float* K, const float* V, 
     // S = Q K^T / sqrt(D)
     g.A = Q; g.B = K; g.C = P_out; g.M = n; g.N = n; g.K = D; g.lda = lq; g.ldb = lq; g.ldc = n;
     g.sAb = sb; g.sAh = sh; g.sBb = sb; g.sBh = sh; g.sCb = nn * H; g.sCh = nn; g.H = H; g.alpha = 1.0f / sqrtf((float)D);
-    if (attn_rows_ok(g, nullptr)) {        // scores and softmax in one kernel, the score tile stays in TMEM
-        if ((rc = launch_attn_rows<0>(g, AttnRowsExtra{}, Z, passes, st, "attn_rows_qk_softmax"))) return rc;
-    } else {
-        if ((rc = launch_bgemm(g, Z, passes, st, "attn_tc_qk"))) return rc;
-        const size_t rows = (size_t)Z * n;
-        PTRB200_LAUNCH(softmax_rows_kernel, (unsigned)((rows + 7) / 8), 256, 0, st, P_out, (float*)nullptr, rows, n);
-    }
+    if ((rc = launch_bgemm(g, Z, passes, st, "attn_tc_qk"))) return rc;
+    const size_t rows = (size_t)Z * n;
+    PTRB200_LAUNCH(softmax_rows_kernel, (unsigned)((rows + 7) / 8), 256, 0, st, P_out, (float*)nullptr, rows, n);
     // O = dropout(P) V : V is the [K = key, N = d] row-major factor, consumed MN-major
     (void)scratch;
     BGemmArgs o{};
@@ -746,14 +515,9 @@ int ptrb200_attention_tc_bwd_ld(const float* Q, const float* K, const float* V, 
     BGemmArgs a{};
     a.A = dO; a.B = V; a.C = dS; a.M = n; a.N = n; a.K = D; a.lda = lo; a.ldb = lq; a.ldc = n;
     a.sAb = sbo; a.sAh = sh; a.sBb = sb; a.sBh = sh; a.sCb = nn * H; a.sCh = nn; a.H = H; a.alpha = 1.0f;
-    if (attn_rows_ok(a, P)) {              // dP and the softmax backward in one kernel
-        AttnRowsExtra x{}; x.P = P; x.inv_scale = inv_scale; x.drop = drop;
-        if ((rc = launch_attn_rows<1>(a, x, Z, passes, st, "attn_rows_dp_softmax_bwd"))) return rc;
-    } else {
-        if ((rc = launch_bgemm(a, Z, passes, st, "attn_tc_dp"))) return rc;
-        const size_t rows = (size_t)Z * n;
-        PTRB200_LAUNCH(softmax_bwd_rows_kernel, (unsigned)((rows + 7) / 8), 256, 0, st, P, dS, rows, n, inv_scale, drop);
-    }
+    if ((rc = launch_bgemm(a, Z, passes, st, "attn_tc_dp"))) return rc;
+    const size_t rows = (size_t)Z * n;
+    PTRB200_LAUNCH(softmax_bwd_rows_kernel, (unsigned)((rows + 7) / 8), 256, 0, st, P, dS, rows, n, inv_scale, drop);
     // dQ = dS K : K is the [K = key, N = d] factor (MN-major B)
     BGemmArgs q{};
     q.A = dS; q.B = K; q.C = dQ; q.M = n; q.N = D; q.K = n; q.lda = n; q.ldb = lq; q.ldc = lq; q.b_mn = 1;
