@@ -223,7 +223,9 @@ struct Rank1Src { const float* w; DropCfg drop; int round_bf16; };     // w == N
 
 // (4 resident CTAs per SM = 64 registers: measured best for this latency-bound sweep -- 0.51 ms per step against 0.58 at
 // 3 CTAs/72 registers and 0.62 at 5-6 CTAs with their spills)
-template <int WHAT>
+// ACT >= 0 fixes the activation at compile time (the default scorer's GELU and ReLU): no per-element switch, and only the
+// derivative is evaluated.  ACT = -1 reads it from the NormRef.
+template <int WHAT, int ACT = -1>
 __global__ void __launch_bounds__(256, 4) colstat4_kernel(const float* __restrict__ Z, const float* __restrict__ dA, float* __restrict__ dY_out,
                                 NormRef nr, double* __restrict__ partials, int gr, int C, int S, int slice_rows, Rank1Src rk) {
     extern __shared__ double sh4[];
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(256, 4) colstat4_kernel(const float* __restric
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float xh = nr.mean ? (z[e] - mu[e]) * rs[e] : z[e];
-                const float dy = d[e] * activate(nr.act, a[e] * xh + cc[e]).dy;
+                const float dy = d[e] * activate(ACT >= 0 ? ACT : nr.act, a[e] * xh + cc[e]).dy;
                 o[e] = dy;
                 f1[e] += dy; f2[e] = fmaf(dy, xh, f2[e]);
             }
@@ -358,7 +360,13 @@ static void launch_colstat(cudaStream_t st, const char* tag, const float* Z, con
     } else if (colstat_vectorised(C)) {
         const int Q = C / 4;
         int RY = 256 / Q; if (RY < 1) RY = 1; if (RY > 16) RY = 16;
-        PTRB200_LAUNCH_TAG(tag, colstat4_kernel<WHAT>, grid, dim3(Q, RY), (size_t)RY * Q * 8 * sizeof(double), st, Z, dA, dY, nr, part, gr, C, S, slice_rows, r1);
+        const size_t sm = (size_t)RY * Q * 8 * sizeof(double);
+        if (WHAT == STAT_DY && nr.act == PTRB200_AF_GELU)
+            PTRB200_LAUNCH_TAG(tag, (colstat4_kernel<WHAT, PTRB200_AF_GELU>), grid, dim3(Q, RY), sm, st, Z, dA, dY, nr, part, gr, C, S, slice_rows, r1);
+        else if (WHAT == STAT_DY && nr.act == PTRB200_AF_RELU)
+            PTRB200_LAUNCH_TAG(tag, (colstat4_kernel<WHAT, PTRB200_AF_RELU>), grid, dim3(Q, RY), sm, st, Z, dA, dY, nr, part, gr, C, S, slice_rows, r1);
+        else
+            PTRB200_LAUNCH_TAG(tag, (colstat4_kernel<WHAT, -1>), grid, dim3(Q, RY), sm, st, Z, dA, dY, nr, part, gr, C, S, slice_rows, r1);
     } else {
         PTRB200_LAUNCH_TAG(tag, colstat_kernel<WHAT>, grid, dim3(32, 8), 0, st, Z, dA, dY, nr, part, gr, C, S, slice_rows);
     }
