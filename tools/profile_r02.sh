@@ -28,8 +28,9 @@ for stage in "${@:-launches b c d e}"; do
       cap c "bgemm_(fast|nt_tc)_kernel" 19 attn_pv
       cap c softmax_rows_kernel 3 softmax
       cap c softmax_bwd_rows_kernel 3 softmax_bwd
-      cap c rows_gemm_tc_kernel 34 rows_gemm_tc
-      cap c wgrad_tc 22 wgrad
+      cap c rows_gemm_tc_kernel 24 rows_gemm_tc          # 136 -> 136 output projection of the first encoder layer
+      cap c rows_gemm_tc_kernel 31 rows_gemm_tc_wide     # 256 -> 512 layer of the head net
+      cap c wgrad_tc 15 wgrad                            # its weight gradient (column-blocked)
       cap c approxndcg_kernel 1 loss
       unset ENC_LAYERS ;;
     d)  cap d lambdaloss_kernel 1 loss ;;
