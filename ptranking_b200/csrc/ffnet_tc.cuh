@@ -54,6 +54,8 @@ struct RowsGemmArgs {
 enum { RG_FWD = 0, RG_DGRAD = 1 };
 
 // prologue transform of 4 consecutive elements (row r, columns k..k+3) of P
+// ACT >= 0: the activation is a compile-time constant (no per-element switch); ACT = -1 reads g.act
+template <int ACT = -1>
 static __device__ __forceinline__ float4 prologue4(const RowsGemmArgs& g, float4 v, int row, int k, bool with_dropout, size_t coef_row_off) {
     if (g.scale) {
         const size_t o = coef_row_off + k;
@@ -61,8 +63,9 @@ static __device__ __forceinline__ float4 prologue4(const RowsGemmArgs& g, float4
         const float4 sh = *reinterpret_cast<const float4*>(g.shift + o);
         v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
     }
-    if (g.act != PTRB200_AF_NONE) {
-        v.x = activate(g.act, v.x).y; v.y = activate(g.act, v.y).y; v.z = activate(g.act, v.z).y; v.w = activate(g.act, v.w).y;
+    const int af = ACT >= 0 ? ACT : g.act;
+    if (af != PTRB200_AF_NONE) {
+        v.x = activate(af, v.x).y; v.y = activate(af, v.y).y; v.z = activate(af, v.z).y; v.w = activate(af, v.w).y;
     }
     if (with_dropout && g.drop.thr) {
         const uint64_t e = (uint64_t)row * g.K + k;          // K % 4 == 0: the 4 elements share one draw
@@ -180,7 +183,7 @@ __global__ void pack_b_image_kernel(const float* __restrict__ src, int src_rows,
 
 constexpr int RG_THREADS = 256;
 
-template <int MODE, int PASSES>
+template <int MODE, int PASSES, int ACT = -1>
 __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(RG_THREADS) rows_gemm_tc_kernel(RowsGemmArgs g
             const int u = tid + i * RG_THREADS, r = u >> 3, j = u & 7, k = k0 + j * 4;
             float4 v = av[i];
             if (r < nrows && k < K) {
-                v = prologue4(g, v, row0 + r, k, MODE == RG_FWD, coef_off[i]);
+                v = prologue4<ACT>(g, v, row0 + r, k, MODE == RG_FWD, coef_off[i]);
                 if (MODE == RG_FWD && g.a_out && blockIdx.y == 0) *reinterpret_cast<float4*>(g.a_out + (size_t)(row0 + r) * K + k) = v;
             } else v = make_float4(0.f, 0.f, 0.f, 0.f);
             store_split(a_hi, a_lo, tc::swz_offset(r, j), v, PASSES == 3, PASSES == 1 && g.round_bf16 != 0, long_k);

@@ -8,6 +8,12 @@ cap() {   # cap <cfg> <kernel-regex> <skip> <name>: one launch of the kernel fro
   local cfg=$1 k=$2 s=$3 o=full_$1_$4
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:"$k" -s "$s" -c 1 -o gpurun_out/"$o" -f python tools/profile_step.py 2 0 "$cfg" > gpurun_out/"$o".log 2>&1
   ncu -i gpurun_out/"$o".ncu-rep --page raw --csv > gpurun_out/"$o"_raw.csv 2>/dev/null
+  ncu -i gpurun_out/"$o".ncu-rep --page source --csv 2>/dev/null | python -c "
+import csv, sys
+rows = list(csv.reader(sys.stdin))
+w = csv.writer(sys.stdout)
+for r in rows: w.writerow(r[:6])" > gpurun_out/"$o"_source.csv
+  rm -f gpurun_out/"$o".ncu-rep          # the reports (with imported sources) exceed what a gpurun call brings back; the two CSV pages are what gets read
   tail -1 gpurun_out/"$o".log
 }
 for stage in "${@:-launches b c d e}"; do
