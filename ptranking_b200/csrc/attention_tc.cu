@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(BG_THREADS, 2) bgemm_fast_kernel(BGemmArgs g) 
     unsigned char* a_lo = a_hi + 16384;
     unsigned char* b_hi = a_lo + 16384;
     unsigned char* b_lo = b_hi + 16384;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(b_lo + 16384);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(base + 128 * (BG_NT + 4) * 4);     // beyond the epilogue's staging tile, which overlays the operands
+    (void)b_lo;
     uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -344,13 +345,38 @@ __global__ void __launch_bounds__(BG_THREADS, 2) bgemm_fast_kernel(BGemmArgs g) 
     }
     tc::mbar_wait(mbar, (nchunks - 1) & 1);
     tc::fence_after_sync();
-    {   // epilogue: TMEM lane = row; warps (q, half) split the columns; every extent is a multiple of 4
-        const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, half = warp >> 2;
+    const float alpha = g.alpha;
+    if (N == BG_NT) {
+        // full 128-column tile (the [n,n] score / dP tensors: the 134 MB outputs of the attention core).  TMEM lane = row, so a
+        // direct store has every lane of a warp writing into a different row (32-byte pieces of 32 rows per instruction);
+        // instead the tile goes through shared memory (the operand buffers are free: every MMA has completed) and leaves as
+        // whole 512-byte row segments, one row per warp instruction.
+        constexpr int PITCH = BG_NT + 4;                  // floats; 132 = 4 (mod 32): the row-strided float4 writes are conflict-free
+        float* tile = reinterpret_cast<float*>(base);     // [128][PITCH] = 67,584 B (operands 65,536 B + the slack the host adds)
+        __syncthreads();                                  // (all threads are past their last operand stores; belt and braces)
+        for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 8) {
+            float v[8];
+            tc::tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            for (int a = 1; a < nacc; ++a) {
+                float w[8];
+                tc::tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * NP + c0), w);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] += w[e];
+            }
+            float* t = tile + (q * 32 + lane) * PITCH + c0;
+            *reinterpret_cast<float4*>(t) = make_float4(v[0] * alpha, v[1] * alpha, v[2] * alpha, v[3] * alpha);
+            *reinterpret_cast<float4*>(t + 4) = make_float4(v[4] * alpha, v[5] * alpha, v[6] * alpha, v[7] * alpha);
+        }
+        __syncthreads();
+        const int rows_here = min(128, g.M - m0);
+        for (int r = warp; r < rows_here; r += BG_THREADS / 32)
+            *reinterpret_cast<float4*>(C + (size_t)(m0 + r) * g.ldc + n0 + lane * 4) = *reinterpret_cast<const float4*>(tile + r * PITCH + lane * 4);
+    } else {   // narrow tile: TMEM lane = row; warps (q, half) split the columns; every extent is a multiple of 4
         const int row = m0 + q * 32 + lane;
         const int cols_half = ((NP / 8 + 1) / 2) * 8;
         const int c_begin = half == 0 ? 0 : cols_half, c_end = half == 0 ? min(cols_half, NP) : NP;
         float* crow = C + (size_t)min(row, g.M - 1) * g.ldc + n0;
-        const float alpha = g.alpha;
         for (int c0 = c_begin; c0 < c_end; c0 += 8) {
             float v[8];
             tc::tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
@@ -431,6 +457,7 @@ static int launch_bgemm(BGemmArgs& g, int Z, int passes, cudaStream_t st, const 
                       (g.drop_mode == 0 || (g.drop_mode == 1 && !g.a_mn) || (g.drop_mode == 2 && g.a_mn));
     if (fast) {
         const int drop = g.drop.thr ? g.drop_mode : 0;
+        const size_t smem = 1024 + (size_t)128 * (BG_NT + 4) * 4 + 64;      // operands (64 KB) overlaid by the [128][132] output staging tile
 #define PTRB200_BG_CASE(P, AM, BM, D) if ((passes == 3) == (P == 3) && g.a_mn == AM && g.b_mn == BM && drop == D) return launch_bgemm_fast<P, AM, BM, D>(g, grid, smem, st, tag);
         // the attention core's shapes (list_ranker.py:226-248 forward + autograd), 3xTF32 and single-pass
         PTRB200_BG_CASE(3, 0, 0, 0) PTRB200_BG_CASE(3, 0, 1, 0) PTRB200_BG_CASE(3, 0, 1, 1) PTRB200_BG_CASE(3, 1, 1, 0) PTRB200_BG_CASE(3, 1, 1, 2)
