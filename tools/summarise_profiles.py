@@ -43,7 +43,7 @@ WANT = [("gpu__time_duration.sum", "duration us"), ("dram__bytes_read.sum", "dra
         ("launch__shared_mem_per_block_dynamic", "dyn smem KB")]
 traffic = {}
 NAME_MAP = {"rows_gemm_ws_kernel<0,": "rows_gemm_ws_fwd", "rows_gemm_ws_kernel<1,": "rows_gemm_ws_dgrad", "wgrad_tc_kernel": "wgrad_tc",
-            "colstat4_kernel<1>": "colstat_dy", "norm_bwd_apply4_kernel": "norm_bwd_apply4_kernel", "pairwise_bce_": "pairwise_bce_kernel<LAMBDA>",
+            "colstat4_kernel<1": "colstat_dy", "norm_bwd_apply4_kernel": "norm_bwd_apply4_kernel", "pairwise_bce_": "pairwise_bce_kernel<LAMBDA>",
             "approxndcg_kernel": "approxndcg_kernel", "lambdaloss_kernel": "lambdaloss_kernel", "listmle_kernel": "listmle_kernel"}
 # file-name tag -> key of traffic.json for kernels that share one C++ name (the batched attention GEMM)
 FILE_MAP = {"full_c_attn_qk": "attn_tc_qk", "full_c_attn_pv": "attn_tc_pv", "full_c_softmax": "softmax_rows_kernel",
@@ -67,6 +67,10 @@ with open(os.path.join(P, f"{tag}_kernels_full.md"), "w") as f:
             for m, label in WANT:
                 if m in h:
                     f.write(f"| {label} | {r[h.index(m)]} |\n")
+            stalls = sorted(((float(r[i].replace(",", "")), c) for i, c in enumerate(h) if "issue_stalled" in c and c.endswith("per_issue_active.ratio") and r[i]), reverse=True)[:5]
+            if stalls:
+                f.write("| top warp-stall reasons (warps stalled per issue-active cycle) | " +
+                        ", ".join(f"{c.split('issue_stalled_')[1].split('_per_')[0]} {v:.2f}" for v, c in stalls) + " |\n")
             f.write("\n")
             if "dram__bytes_read.sum" in h:
                 def mb(x):
