@@ -225,8 +225,11 @@ struct Rank1Src { const float* w; DropCfg drop; int round_bf16; };     // w == N
 // 3 CTAs/72 registers and 0.62 at 5-6 CTAs with their spills)
 // ACT >= 0 fixes the activation at compile time (the default scorer's GELU and ReLU): no per-element switch, and only the
 // derivative is evaluated.  ACT = -1 reads it from the NormRef.
-template <int WHAT, int ACT = -1>
-__global__ void __launch_bounds__(256, 4) colstat4_kernel(const float* __restrict__ Z, const float* __restrict__ dA, float* __restrict__ dY_out,
+// PF: the loads of the NEXT row are issued before the current row is processed (the ncu capture of the dY sweep has 53 % of
+// its stall samples on the first use of the freshly loaded Z: with one row in flight per thread the sweep is latency-bound
+// at 37 % of HBM bandwidth); the extra live registers cost the fourth resident CTA.
+template <int WHAT, int ACT = -1, bool PF = false>
+__global__ void __launch_bounds__(256, PF ? 3 : 4) colstat4_kernel(const float* __restrict__ Z, const float* __restrict__ dA, float* __restrict__ dY_out,
                                 NormRef nr, double* __restrict__ partials, int gr, int C, int S, int slice_rows, Rank1Src rk) {
     extern __shared__ double sh4[];
     const int Q = blockDim.x, RY = blockDim.y, q = threadIdx.x, ry = threadIdx.y, c = q * 4;
@@ -245,9 +248,24 @@ __global__ void __launch_bounds__(256, 4) colstat4_kernel(const float* __restric
     double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
     float f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4] = {0.f, 0.f, 0.f, 0.f};
     int since_flush = 0;
+    const bool dense_da = WHAT == STAT_DY && !rk.w;
+    float4 zn = make_float4(0.f, 0.f, 0.f, 0.f), dn = zn;
+    if (PF && r0 + ry < r1) {
+        const size_t o0 = ((size_t)g * gr + r0 + ry) * C + c;
+        zn = __ldg(reinterpret_cast<const float4*>(Z + o0));
+        if (dense_da) dn = __ldg(reinterpret_cast<const float4*>(dA + o0));
+    }
     for (int r = r0 + ry; r < r1; r += RY) {
         const size_t off = ((size_t)g * gr + r) * C + c;
-        const float4 z4 = __ldg(reinterpret_cast<const float4*>(Z + off));
+        float4 z4, dpre = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (PF) {
+            z4 = zn; dpre = dn;
+            if (r + RY < r1) {
+                const size_t o1 = off + (size_t)RY * C;
+                zn = __ldg(reinterpret_cast<const float4*>(Z + o1));
+                if (dense_da) dn = __ldg(reinterpret_cast<const float4*>(dA + o1));
+            }
+        } else z4 = __ldg(reinterpret_cast<const float4*>(Z + off));
         const float z[4] = {z4.x, z4.y, z4.z, z4.w};
         if (WHAT == STAT_MOMENTS) {
 #pragma unroll
@@ -269,7 +287,7 @@ __global__ void __launch_bounds__(256, 4) colstat4_kernel(const float* __restric
                     d4.z = ((uint32_t)(dd >> 32) & 0xffffu) >= rk.drop.thr ? d4.z * rk.drop.scale : 0.0f;
                     d4.w = ((uint32_t)(dd >> 48)) >= rk.drop.thr ? d4.w * rk.drop.scale : 0.0f;
                 }
-            } else d4 = __ldg(reinterpret_cast<const float4*>(dA + off));
+            } else d4 = PF ? dpre : __ldg(reinterpret_cast<const float4*>(dA + off));
             const float d[4] = {d4.x, d4.y, d4.z, d4.w};
             float o[4];
 #pragma unroll
@@ -361,7 +379,12 @@ static void launch_colstat(cudaStream_t st, const char* tag, const float* Z, con
         const int Q = C / 4;
         int RY = 256 / Q; if (RY < 1) RY = 1; if (RY > 16) RY = 16;
         const size_t sm = (size_t)RY * Q * 8 * sizeof(double);
-        if (WHAT == STAT_DY && nr.act == PTRB200_AF_GELU)
+        static const bool no_pf = getenv("PTRB200_NO_CS_PREFETCH") && getenv("PTRB200_NO_CS_PREFETCH")[0] == '1';   // A/B switch
+        if (WHAT == STAT_DY && nr.act == PTRB200_AF_GELU && !no_pf)
+            PTRB200_LAUNCH_TAG(tag, (colstat4_kernel<WHAT, PTRB200_AF_GELU, true>), grid, dim3(Q, RY), sm, st, Z, dA, dY, nr, part, gr, C, S, slice_rows, r1);
+        else if (WHAT == STAT_DY && nr.act == PTRB200_AF_RELU && !no_pf)
+            PTRB200_LAUNCH_TAG(tag, (colstat4_kernel<WHAT, PTRB200_AF_RELU, true>), grid, dim3(Q, RY), sm, st, Z, dA, dY, nr, part, gr, C, S, slice_rows, r1);
+        else if (WHAT == STAT_DY && nr.act == PTRB200_AF_GELU)
             PTRB200_LAUNCH_TAG(tag, (colstat4_kernel<WHAT, PTRB200_AF_GELU>), grid, dim3(Q, RY), sm, st, Z, dA, dY, nr, part, gr, C, S, slice_rows, r1);
         else if (WHAT == STAT_DY && nr.act == PTRB200_AF_RELU)
             PTRB200_LAUNCH_TAG(tag, (colstat4_kernel<WHAT, PTRB200_AF_RELU>), grid, dim3(Q, RY), sm, st, Z, dA, dY, nr, part, gr, C, S, slice_rows, r1);

@@ -40,6 +40,12 @@ for s in $stages; do
               python -c "import json; d=json.loads(open('gpurun_out/bench_d_n8.json').read()); print('N=8 config d', round(d['value'],1), round(d['ms_per_step'],4))" || tail -5 gpurun_out/bench_d_n8.err
               timeout 300 python bench.py --steps 100 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/bench_n1_same_box.json
               python -c "import json; d=json.loads(open('gpurun_out/bench_n1_same_box.json').read()); print('N=1 same box', round(d['value'],1), round(d['ms_per_step'],4))" ;;
+    abcs)     # A/B of the next-row prefetch in the dY / statistics sweep
+              for v in 0 1; do
+                if [ $v = 1 ]; then export PTRB200_NO_CS_PREFETCH=1; else unset PTRB200_NO_CS_PREFETCH; fi
+                timeout 300 python bench.py --steps 50 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/bench_abcs_$v.json
+                python -c "import json; d=json.loads(open('gpurun_out/bench_abcs_$v.json').read()); print('NO_CS_PREFETCH=$v', round(d['ms_per_step'],4), 'colstat_dy', d['roofline']['kernels_ms_per_step'].get('colstat_dy'))"
+              done; unset PTRB200_NO_CS_PREFETCH ;;
     abc)      # config c (list scorer, L=6): aligned bgemm kernel and fused Q|K|V projection, each switched off in turn
               for v in base general_bgemm separate_qkv; do
                 unset PTRB200_BGEMM_GENERAL PTRANKING_B200_FUSED_QKV
