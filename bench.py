@@ -375,23 +375,24 @@ def run_b200(args, cfg):
     # ---- baselines (rank 0, N=1 only) -----------------------------------------
     cpu = ref_b1 = ref_cuda = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        torch.set_num_threads(host_threads())
-        r = reference_run(cfg, steps=40, warmup=2, B=cfg["cpu_B"], budget_s=15.0)
-        cpu = {"value": r["qps"], "unit": "queries/s", "cores": r["cores"], "kind": "port",
-               "sample": f"{r['steps']} steps x {r['B']} queries x {n} docs (oracle/ref_port.py train_op, fp32 CPU PyTorch ops)"}
-        # the reference's own batching: B = max(1, 100 // n) queries per step (data_utils.py:683-718)
-        B1 = max(1, 100 // n)
-        r1 = reference_run(cfg, steps=200, warmup=3, B=B1, budget_s=5.0)
+        # GPU-side comparators first: both are (partly) launch-bound, and the worker threads of the CPU runs below keep
+        # spinning for a while after a parallel region -- measured 0.62 ms vs 2.0 ms per B = 1 step depending on the order
+        B1 = max(1, 100 // n)       # the reference's own batching: B = max(1, 100 // n) queries per step (data_utils.py:683-718)
         one = [(X[:B1].contiguous(), y[:B1].contiguous()) for X, y in devb]
         ms1, _ = timed(one, 50, 5)
-        ref_b1 = {"queries_per_step": B1, "cpu_port_qps": r1["qps"], "b200_qps": B1 * 50 / (ms1 / 1e3),
-                  "b200_ms_per_step": ms1 / 50, "note": "launch-latency bound on the GPU: ~50 kernel launches per step"}
         try:
             rc = reference_run(cfg, steps=10, warmup=3, B=B, budget_s=60.0, device=dev)
             ref_cuda = {"value": rc["qps"], "unit": "queries/s", "ms_per_step": rc["ms_per_step"], "queries_per_step": B,
                         "kind": "port", "what": "oracle/ref_port.py train_op as PyTorch eager on cuda:0 (the reference's `-cuda 0` path)"}
         except Exception as e:      # e.g. the [B,n,n] temporaries do not fit
             ref_cuda = {"unavailable": repr(e)[:200]}
+        torch.set_num_threads(host_threads())
+        r = reference_run(cfg, steps=40, warmup=2, B=cfg["cpu_B"], budget_s=15.0)
+        cpu = {"value": r["qps"], "unit": "queries/s", "cores": r["cores"], "kind": "port",
+               "sample": f"{r['steps']} steps x {r['B']} queries x {n} docs (oracle/ref_port.py train_op, fp32 CPU PyTorch ops)"}
+        r1 = reference_run(cfg, steps=200, warmup=3, B=B1, budget_s=5.0)
+        ref_b1 = {"queries_per_step": B1, "cpu_port_qps": r1["qps"], "b200_qps": B1 * 50 / (ms1 / 1e3),
+                  "b200_ms_per_step": ms1 / 50, "note": "launch-latency bound on the GPU: ~50 kernel launches per step"}
 
     if rank == 0:
         line = {
