@@ -12,7 +12,9 @@
  *     [B,n,F] features), int32 for index data.
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
  *   - no allocation inside the library: the caller passes every output and
- *     workspace buffer; ptrb200_*_workspace_bytes() says how much.
+ *     workspace buffer; ptrb200_*_workspace_bytes() says how much.  (The one
+ *     exception is ptrb200_peer_alloc: memory exported to the other processes
+ *     of a node through CUDA IPC has to be a cudaMalloc base.)
  *   - return 0 on success or a negative PTRB200_ERR_* code; nothing throws
  *     across the boundary.  ptrb200_last_error() returns a host string
  *     describing the last failure on the calling thread.
