@@ -137,15 +137,32 @@ class PeerExchange:
             raise RuntimeError(f"peer exchange supports up to {_lib.MAX_PEERS} ranks")
         self.count, self.device = int(count), torch.device(device)
         self.stride = -(-self.count * 4 // 256) * 256
+        # every rank takes part in every collective below whatever happens locally, and all ranks leave through the same
+        # exit (all succeed or all raise) -- a rank that bailed out alone would leave the others inside a collective
+        self.own, handle, problem = None, None, None
         with torch.cuda.device(self.device):
-            self.own, handle = _lib.peer_alloc(self.PAD + 2 * self.stride)
+            try:
+                self.own, handle = _lib.peer_alloc(self.PAD + 2 * self.stride)
+            except Exception as e:
+                problem = e
             handles = [None] * self.world
             dist.all_gather_object(handles, handle)
-            self.ptrs = [self.own if r == self.rank else _lib.peer_open(handles[r]) for r in range(self.world)]
-            self.bufs = [torch.as_tensor(_DeviceMemory(self.own + self.PAD + k * self.stride, self.count), device=self.device)
-                         for k in (0, 1)]
+            self.ptrs = []
+            if all(h is not None for h in handles):
+                try:
+                    self.ptrs = [self.own if r == self.rank else _lib.peer_open(handles[r]) for r in range(self.world)]
+                    self.bufs = [torch.as_tensor(_DeviceMemory(self.own + self.PAD + k * self.stride, self.count), device=self.device)
+                                 for k in (0, 1)]
+                except Exception as e:
+                    problem = e
+            elif problem is None:
+                problem = RuntimeError("another rank could not export its gradient buffer")
+            agreed = torch.tensor([0 if problem is not None else 1], dtype=torch.int32, device=self.device)
+            dist.all_reduce(agreed, op=dist.ReduceOp.MIN)      # also orders "every pad is mapped" before the first signal
+        if int(agreed.item()) == 0:
+            raise RuntimeError(f"peer exchange unavailable: {problem!r}" if problem is not None else
+                               "peer exchange unavailable on another rank")
         self.epoch = 0
-        dist.barrier()                      # nobody signals into a pad that is not mapped yet
 
     def group(self, k: int):
         """The descriptor of the NEXT exchange over buffer ``k`` (advances the step counter)."""
@@ -200,15 +217,10 @@ class GradBucket:
         if not (is_distributed() and self.distributed and self.flat.is_cuda and dist.get_backend() == "nccl"
                 and os.environ.get("PTRANKING_B200_PEER", "1") == "1"):
             return False
-        ex, ok = None, 1
         try:
-            ex = PeerExchange(self.flat.numel(), self.flat.device)
+            ex = PeerExchange(self.flat.numel(), self.flat.device)      # all ranks succeed or all raise (see its __init__)
         except Exception as e:
-            print(f"ptranking_b200.dist: peer exchange unavailable on rank {dist.get_rank()} ({e!r}); using NCCL", flush=True)
-            ok = 0
-        flag = torch.tensor([ok], dtype=torch.int32, device=self.flat.device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
+            print(f"ptranking_b200.dist: rank {dist.get_rank()}: {e}; gradients go through the NCCL all-reduce", flush=True)
             return False
         self.peer = ex
         self._peer_k = 0
