@@ -276,6 +276,14 @@ int ptrb200_rmsprop_step(float* param, const float* grad, float* square_avg, int
                          double lr, double alpha, double eps, double weight_decay,
                          ptrb200_stream_t stream);
 
+/* Ragged <-> padded layout change for the list scorer (no counterpart: the reference batches equal-length lists only,
+ * data_utils.py:683-742): padded[b, r, :] = flat[offsets[b] + r, :] for r < len_b, else 0; unpad is the inverse gather.
+ * offsets: int32[B+1] prefix offsets, n_max: padded list length, F: row width (1 for score vectors). */
+int ptrb200_pad_lists(const float* flat, const int32_t* offsets, float* padded, int B, int n_max, int F,
+                      ptrb200_stream_t stream);
+int ptrb200_unpad_lists(const float* padded, const int32_t* offsets, float* flat, int B, int n_max, int F,
+                        ptrb200_stream_t stream);
+
 /* ---- data-parallel gradient exchange over NVLink peer memory ------------------------------ */
 /* The reference has no distributed code.  One process per GPU (torchrun); the sum of the ranks' flat gradient buffers
  * that precedes optimizer.step() in a data-parallel run is folded INTO the step kernel: every rank maps the other ranks'
@@ -335,10 +343,12 @@ int ptrb200_attention_tc_bwd(const float* Q, const float* K, const float* V, con
 /* The same two calls over row-pitched operands: ld_qkv = floats between consecutive documents of Q, K and V (and of dQ,
  * dK, dV), ld_o = the same for O and dO; 0 = packed (H*D).  With Q|K|V side by side in one [B,n,3*H*D] tensor -- the
  * output of ONE 136->408 projection instead of the reference's three (list_ranker.py:233-235) -- the call takes
- * Q = qkv, K = qkv + H*D, V = qkv + 2*H*D, ld_qkv = 3*H*D, and the backward call fills the matching gradient tensor. */
+ * Q = qkv, K = qkv + H*D, V = qkv + 2*H*D, ld_qkv = 3*H*D, and the backward call fills the matching gradient tensor.
+ * key_lens (forward; NULL = every list has n documents): int32[B], query b attends to its first key_lens[b] documents only
+ * -- a ragged batch padded to n (ptrb200_pad_lists); masked probabilities are exactly 0, so the backward call needs nothing. */
 int ptrb200_attention_tc_fwd_ld(const float* Q, const float* K, const float* V, float* O, float* P_out, float* scratch,
-                                int B, int n, int H, int D, int ld_qkv, int ld_o, float dropout_p, uint64_t seed,
-                                uint64_t offset, int passes, ptrb200_stream_t stream);
+                                int B, int n, int H, int D, int ld_qkv, int ld_o, const int32_t* key_lens, float dropout_p,
+                                uint64_t seed, uint64_t offset, int passes, ptrb200_stream_t stream);
 int ptrb200_attention_tc_bwd_ld(const float* Q, const float* K, const float* V, const float* P, const float* dO,
                                 float* dQ, float* dK, float* dV, float* scratch,
                                 int B, int n, int H, int D, int ld_qkv, int ld_o, float dropout_p, uint64_t seed,

@@ -81,7 +81,9 @@ SIGNATURES = {
     "ptrb200_attention_tc_workspace_floats": (_I64, [_I, _I, _I, _I, _I]),
     "ptrb200_attention_tc_fwd": (_I, [_fp] * 6 + [_I, _I, _I, _I, _F, _U64, _U64, _I, _fp]),
     "ptrb200_attention_tc_bwd": (_I, [_fp] * 9 + [_I, _I, _I, _I, _F, _U64, _U64, _I, _fp]),
-    "ptrb200_attention_tc_fwd_ld": (_I, [_fp] * 6 + [_I, _I, _I, _I, _I, _I, _F, _U64, _U64, _I, _fp]),
+    "ptrb200_attention_tc_fwd_ld": (_I, [_fp] * 6 + [_I, _I, _I, _I, _I, _I, _fp, _F, _U64, _U64, _I, _fp]),
+    "ptrb200_pad_lists": (_I, [_fp, _fp, _fp, _I, _I, _I, _fp]),
+    "ptrb200_unpad_lists": (_I, [_fp, _fp, _fp, _I, _I, _I, _fp]),
     "ptrb200_attention_tc_bwd_ld": (_I, [_fp] * 9 + [_I, _I, _I, _I, _I, _I, _F, _U64, _U64, _I, _fp]),
     "ptrb200_attention_bwd": (_I, [_fp] * 10 + [_I, _I, _I, _I, _F, _U64, _U64, _fp]),
     "ptrb200_layernorm_fwd": (_I, [_fp, _fp, _fp, _fp, _fp, _fp, _I, _I, _F, _fp]),

@@ -195,6 +195,23 @@ class ListNeuralRanker(NeuralRanker):
             raise NotImplementedError
         return torch.squeeze(tail(z), dim=2)
 
+    def forward_ragged(self, flat_q_doc_vectors, offsets, max_len):
+        """[total_docs, F] + int32 offsets[B+1] -> flat scores [total_docs] for lists of different lengths (the reference can
+        only batch equal-length lists, data_utils.py:683-742).  The batch is padded to ``max_len`` on the device, the
+        attention masks every query's padded keys (probability exactly 0), all other layers are row-wise, and the scores of
+        the real documents are gathered back -- so each query sees exactly what it would see alone.  Batch- or
+        list-level normalisation in the head / tail nets would mix padding into its statistics and is refused."""
+        cfg = self.sf_para_dict[self.sf_para_dict['sf_id']]
+        if cfg.get('BN', True):
+            raise NotImplementedError("ragged batches through the list scorer need BN=False (the listsf default of the drop-in run)")
+        X = flat_q_doc_vectors
+        total = X.shape[0]
+        offs = offsets.to(device=X.device, dtype=torch.int32).contiguous()
+        lens = (offs[1:] - offs[:-1]).contiguous()
+        with ops.key_lens_context(lens):
+            scores = self.forward(ops.pad_lists(X, offs, int(max_len)))        # [B, max_len]
+        return ops.unpad_lists(scores.contiguous(), offs, total)
+
     def eval_mode(self):
         for part in self.list_sf.values():
             part.eval()

@@ -397,20 +397,25 @@ __global__ void __launch_bounds__(BG_THREADS, 2) bgemm_fast_kernel(BGemmArgs g) 
     if (warp == 0) tc::tmem_dealloc(tmem, tmem_cols);
 }
 
-// in-place row softmax over S[z][i][:] (one warp per row); also emits the per-row log-sum-exp
-__global__ void softmax_rows_kernel(float* __restrict__ S, float* __restrict__ lse, size_t rows, int n) {
+// in-place row softmax over S[z][i][:] (one warp per row); also emits the per-row log-sum-exp.
+// key_lens (optional, [B]): only the first key_lens[b] keys of query b exist (a ragged batch padded to n); the others get
+// probability exactly 0, so padded documents influence nothing (their own rows are never read back).
+__global__ void softmax_rows_kernel(float* __restrict__ S, float* __restrict__ lse, size_t rows, int n,
+                                    const int32_t* __restrict__ key_lens, int rows_per_query) {
     const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
     float* s = S + row * n;
+    const int nk = key_lens ? max(1, min(n, key_lens[row / (size_t)rows_per_query])) : n;
     float m = -INFINITY;
-    for (int j = lane; j < n; j += 32) m = fmaxf(m, s[j]);
+    for (int j = lane; j < nk; j += 32) m = fmaxf(m, s[j]);
     m = warp_max(m);
     float l = 0.0f;
-    for (int j = lane; j < n; j += 32) { const float e = expf(s[j] - m); s[j] = e; l += e; }
+    for (int j = lane; j < nk; j += 32) { const float e = expf(s[j] - m); s[j] = e; l += e; }
     l = warp_sum(l);
     const float inv = 1.0f / l;
-    for (int j = lane; j < n; j += 32) s[j] *= inv;
+    for (int j = lane; j < nk; j += 32) s[j] *= inv;
+    for (int j = nk + lane; j < n; j += 32) s[j] = 0.0f;
     if (lane == 0 && lse) lse[row] = m + logf(l);
 }
 
@@ -492,8 +497,8 @@ int64_t ptrb200_attention_tc_workspace_floats(int B, int n, int H, int D, int ba
 
 // P_out[B*H, n, n] receives the (un-dropped) attention probabilities and must be kept for the backward pass.
 int ptrb200_attention_tc_fwd_ld(const float* Q, const float* K, const float* V, float* O, float* P_out, float* scratch,
-                                int B, int n, int H, int D, int ld_qkv, int ld_o, float dropout_p, uint64_t seed,
-                                uint64_t offset, int passes, ptrb200_stream_t stream) {
+                                int B, int n, int H, int D, int ld_qkv, int ld_o, const int32_t* key_lens, float dropout_p,
+                                uint64_t seed, uint64_t offset, int passes, ptrb200_stream_t stream) {
     if (!Q || !K || !V || !O || !P_out || !scratch || B <= 0 || n <= 0 || H <= 0 || D <= 0) { set_error("attention_tc_fwd: bad arguments"); return PTRB200_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
     const int Z = B * H, HD = H * D;
@@ -507,7 +512,7 @@ int ptrb200_attention_tc_fwd_ld(const float* Q, const float* K, const float* V, 
     g.sAb = sb; g.sAh = sh; g.sBb = sb; g.sBh = sh; g.sCb = nn * H; g.sCh = nn; g.H = H; g.alpha = 1.0f / sqrtf((float)D);
     if ((rc = launch_bgemm(g, Z, passes, st, "attn_tc_qk"))) return rc;
     const size_t rows = (size_t)Z * n;
-    PTRB200_LAUNCH(softmax_rows_kernel, (unsigned)((rows + 7) / 8), 256, 0, st, P_out, (float*)nullptr, rows, n);
+    PTRB200_LAUNCH(softmax_rows_kernel, (unsigned)((rows + 7) / 8), 256, 0, st, P_out, (float*)nullptr, rows, n, key_lens, H * n);
     // O = dropout(P) V : V is the [K = key, N = d] row-major factor, consumed MN-major
     (void)scratch;
     BGemmArgs o{};
@@ -521,7 +526,7 @@ int ptrb200_attention_tc_fwd_ld(const float* Q, const float* K, const float* V, 
 int ptrb200_attention_tc_fwd(const float* Q, const float* K, const float* V, float* O, float* P_out, float* scratch,
                              int B, int n, int H, int D, float dropout_p, uint64_t seed, uint64_t offset, int passes,
                              ptrb200_stream_t stream) {
-    return ptrb200_attention_tc_fwd_ld(Q, K, V, O, P_out, scratch, B, n, H, D, 0, 0, dropout_p, seed, offset, passes, stream);
+    return ptrb200_attention_tc_fwd_ld(Q, K, V, O, P_out, scratch, B, n, H, D, 0, 0, nullptr, dropout_p, seed, offset, passes, stream);
 }
 
 int ptrb200_attention_tc_bwd_ld(const float* Q, const float* K, const float* V, const float* P, const float* dO,

@@ -6,6 +6,7 @@ arithmetic of the hot path happens in Python/ATen here.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import functools
 import os
@@ -627,6 +628,93 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, math_mode:
     return ffnet_apply(x, _linear_specs[key], [weight, bias], training=False, seed=0, offset=0)
 
 
+# ---- ragged batches through the list scorer: pad in, mask the padded keys, gather out ----------------------------------
+_key_lens: Optional[torch.Tensor] = None      # int32[B] on the device while a padded ragged batch is inside the list scorer
+
+
+@contextlib.contextmanager
+def key_lens_context(lens: Optional[torch.Tensor]):
+    """Inside the context every tensor-core attention call masks, for query b, the keys at positions >= lens[b]."""
+    global _key_lens
+    prev, _key_lens = _key_lens, lens
+    try:
+        yield
+    finally:
+        _key_lens = prev
+
+
+class _PadLists(torch.autograd.Function):
+    """flat [total, F] + offsets[B+1] -> padded [B, n_max, F] (zeros behind each list); backward gathers the rows back."""
+
+    @staticmethod
+    @_on_tensor_device
+    def forward(ctx, flat, offsets, n_max):
+        lib = _lib.load()
+        flat = _dev_f32(flat, "flat")
+        F = flat.shape[1] if flat.dim() == 2 else 1
+        B = offsets.numel() - 1
+        out = torch.empty((B, n_max, F) if flat.dim() == 2 else (B, n_max), dtype=torch.float32, device=flat.device)
+        _lib.check(lib.ptrb200_pad_lists(flat.data_ptr(), offsets.data_ptr(), out.data_ptr(), B, n_max, F, _stream_ptr()), "pad_lists")
+        ctx.save_for_backward(offsets)
+        ctx.shape = tuple(flat.shape)
+        return out
+
+    @staticmethod
+    @_on_tensor_device
+    def backward(ctx, g):
+        (offsets,) = ctx.saved_tensors
+        lib = _lib.load()
+        g = _dev_f32(g, "g")
+        F = ctx.shape[1] if len(ctx.shape) == 2 else 1
+        out = torch.empty(ctx.shape, dtype=torch.float32, device=g.device)
+        _lib.check(lib.ptrb200_unpad_lists(g.data_ptr(), offsets.data_ptr(), out.data_ptr(), offsets.numel() - 1, g.shape[1], F,
+                                           _stream_ptr()), "unpad_lists")
+        return out, None, None
+
+
+class _UnpadLists(torch.autograd.Function):
+    """padded [B, n_max(, F)] -> flat [total(, F)]; backward pads the gradient (zeros at the padding)."""
+
+    @staticmethod
+    @_on_tensor_device
+    def forward(ctx, padded, offsets, total):
+        lib = _lib.load()
+        padded = _dev_f32(padded, "padded")
+        F = padded.shape[2] if padded.dim() == 3 else 1
+        B, n_max = padded.shape[0], padded.shape[1]
+        out = torch.empty((total, F) if padded.dim() == 3 else (total,), dtype=torch.float32, device=padded.device)
+        _lib.check(lib.ptrb200_unpad_lists(padded.data_ptr(), offsets.data_ptr(), out.data_ptr(), B, n_max, F, _stream_ptr()), "unpad_lists")
+        ctx.save_for_backward(offsets)
+        ctx.shape = tuple(padded.shape)
+        return out
+
+    @staticmethod
+    @_on_tensor_device
+    def backward(ctx, g):
+        (offsets,) = ctx.saved_tensors
+        lib = _lib.load()
+        g = _dev_f32(g, "g")
+        F = ctx.shape[2] if len(ctx.shape) == 3 else 1
+        out = torch.empty(ctx.shape, dtype=torch.float32, device=g.device)
+        _lib.check(lib.ptrb200_pad_lists(g.data_ptr(), offsets.data_ptr(), out.data_ptr(), ctx.shape[0], ctx.shape[1], F,
+                                         _stream_ptr()), "pad_lists")
+        return out, None, None
+
+
+def _offsets_i32(offsets: torch.Tensor, device) -> torch.Tensor:
+    return offsets.to(device=device, dtype=torch.int32).contiguous()
+
+
+def pad_lists(flat: torch.Tensor, offsets: torch.Tensor, n_max: int) -> torch.Tensor:
+    """Ragged rows [total, F] (or [total]) -> dense [B, n_max, F] ([B, n_max]), zero behind each list (differentiable)."""
+    return _PadLists.apply(flat, _offsets_i32(offsets, flat.device), int(n_max))
+
+
+def unpad_lists(padded: torch.Tensor, offsets: torch.Tensor, total: int) -> torch.Tensor:
+    """Inverse of :func:`pad_lists`: the first len_b rows of every list, concatenated (differentiable)."""
+    return _UnpadLists.apply(padded, _offsets_i32(offsets, padded.device), int(total))
+
+
 class _Attention(torch.autograd.Function):
     @staticmethod
     @_on_tensor_device
@@ -659,6 +747,15 @@ class _Attention(torch.autograd.Function):
         return dQ, dK, dV, None, None, None, None
 
 
+def _key_lens_ptr(B: int, device):
+    """Device pointer of the active key-length vector (None outside :func:`key_lens_context`)."""
+    if _key_lens is None:
+        return None
+    if _key_lens.numel() != B or _key_lens.device != device or _key_lens.dtype != torch.int32:
+        raise ValueError("key_lens_context: expected an int32 vector with one entry per query on the tensors' device")
+    return _key_lens.data_ptr()
+
+
 class _AttentionTC(torch.autograd.Function):
     """Tensor-core attention: batched tcgen05 GEMMs around a materialised [B*H,n,n] probability tensor."""
 
@@ -672,9 +769,9 @@ class _AttentionTC(torch.autograd.Function):
         O = torch.empty_like(Q)
         P = torch.empty((B * n_heads, n, n), dtype=torch.float32, device=Q.device)
         scratch = torch.empty(lib.ptrb200_attention_tc_workspace_floats(B, n, n_heads, D, 0), dtype=torch.float32, device=Q.device)
-        _lib.check(lib.ptrb200_attention_tc_fwd(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), P.data_ptr(),
-                                                scratch.data_ptr(), B, n, n_heads, D, float(dropout_p), seed, offset, passes,
-                                                _stream_ptr()), "attention_tc_fwd")
+        _lib.check(lib.ptrb200_attention_tc_fwd_ld(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), P.data_ptr(),
+                                                   scratch.data_ptr(), B, n, n_heads, D, 0, 0, _key_lens_ptr(B, Q.device),
+                                                   float(dropout_p), seed, offset, passes, _stream_ptr()), "attention_tc_fwd")
         ctx.save_for_backward(Q, K, V, P)
         ctx.cfg = (n_heads, float(dropout_p), seed, offset, passes)
         return O
@@ -708,6 +805,8 @@ def attention(Q, K, V, n_heads: int, dropout_p: float = 0.0, seed: Optional[int]
     if impl is None:
         impl = os.environ.get("PTRANKING_B200_ATTN", "tc")
     if impl == "simt":
+        if _key_lens is not None:
+            raise NotImplementedError("padded ragged batches need a tensor-core attention impl (PTRANKING_B200_ATTN=tc)")
         return _Attention.apply(Q, K, V, int(n_heads), float(dropout_p), int(seed), int(offset))
     if impl not in ("tc", "tc_tf32"):
         raise ValueError(f"unknown attention impl {impl!r}")
@@ -758,8 +857,8 @@ class _AttentionTCPacked(torch.autograd.Function):
         scratch = torch.empty(lib.ptrb200_attention_tc_workspace_floats(B, n, n_heads, D, 0), dtype=torch.float32, device=qkv.device)
         q = qkv.data_ptr()
         _lib.check(lib.ptrb200_attention_tc_fwd_ld(q, q + 4 * F, q + 8 * F, O.data_ptr(), P.data_ptr(), scratch.data_ptr(),
-                                                   B, n, n_heads, D, F3, 0, float(dropout_p), seed, offset, passes,
-                                                   _stream_ptr()), "attention_tc_fwd")
+                                                   B, n, n_heads, D, F3, 0, _key_lens_ptr(B, qkv.device), float(dropout_p), seed, offset,
+                                                   passes, _stream_ptr()), "attention_tc_fwd")
         ctx.save_for_backward(qkv, P)
         ctx.cfg = (n_heads, float(dropout_p), seed, offset, passes)
         return O

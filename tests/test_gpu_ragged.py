@@ -318,3 +318,55 @@ def test_length_buckets_change_launch_geometry_not_results(name, params):
     m0 = ops.adhoc_metrics_at_ks(s, y, [1, 5, 10], presort=True, max_label=4.0, offsets=offd, max_len=int(lens.max()))
     m1 = ops.adhoc_metrics_at_ks(s, y, [1, 5, 10], presort=True, max_label=4.0, offsets=offd, max_len=int(lens.max()), buckets=buckets)
     assert torch.equal(nd0, nd1) and all(torch.equal(a, c) for a, c in zip(m0, m1))
+
+
+@pytest.mark.parametrize("enc", ["DASALC", "AllRank", "AttnDIN"])
+def test_list_scorer_ragged_batch_equals_query_by_query(enc):
+    """Lists of different lengths through the attention scorer in ONE padded batch (pad -> masked softmax -> gather) give
+    every query the scores, and every parameter the gradient, that processing the queries one by one gives (the dense path is
+    pinned to the reference by the fixtures of tests/test_gpu_listsf.py; F = 24 is a multiple of four, so the aligned
+    batched-GEMM kernel and the fused Q|K|V projection are on the path)."""
+    import ptranking_b200
+    from ptranking_b200 import ops
+    F = 24
+    sf = dict(sf_id="listsf", opt="Adagrad", lr=1e-3,
+              listsf=dict(num_features=F, ff_dims=[16, 32, 24], AF="R", TL_AF="GE", apply_tl_af=False, BN=False, bn_type="BN2",
+                          bn_affine=False, n_heads=2, encoder_layers=2, encoder_type=enc, dropout=0.0))
+    torch.manual_seed(11)
+    r = ptranking_b200.ListNet(sf_para_dict=sf, gpu=True, device=DEV)
+    r.init()
+    r.train_mode()                                    # dropout is 0: training mode exercises the backward by-products
+    lens = [40, 17, 33, 5, 64, 1, 28]
+    rng = np.random.default_rng(5)
+    X = torch.from_numpy(rng.standard_normal((sum(lens), F)).astype(np.float32)).to(DEV)
+    y = torch.from_numpy(rng.integers(0, 5, sum(lens)).astype(np.float32)).to(DEV)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    offd = torch.from_numpy(off).to(DEV)
+    params = r.get_parameters()
+
+    def grads_of(loss):
+        for p in params:
+            p.grad = None
+        loss.backward()
+        return [p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p) for p in params]
+
+    s_rag = r.forward_ragged(X, offd, max(lens))
+    assert s_rag.shape == (sum(lens),)
+    g_rag = grads_of((s_rag * torch.cos(torch.arange(sum(lens), device=DEV, dtype=torch.float32))).sum())
+    s_one, total = [], None
+    for b, n in enumerate(lens):
+        sq = r.forward(X[off[b]: off[b + 1]].unsqueeze(0))[0]
+        s_one.append(sq)
+    s_cat = torch.cat(s_one)
+    g_one = grads_of((s_cat * torch.cos(torch.arange(sum(lens), device=DEV, dtype=torch.float32))).sum())
+    assert rel_err(s_rag.detach().cpu().numpy(), s_cat.detach().cpu().numpy()) <= 1e-5
+    scale = max(float(g.abs().max()) for g in g_one)
+    for p, a, c in zip(params, g_rag, g_one):
+        assert float((a - c).abs().max()) <= 2e-5 * scale, tuple(p.shape)
+    # and one optimizer step on the ragged batch through the public training entry point
+    loss, stop = r.train_op(X, y, offsets=offd, max_len=max(lens), presort=False, label_type=ptranking_b200.LABEL_TYPE.MultiLabel)
+    assert torch.isfinite(loss) and not stop
+    # pad / unpad are inverse gathers
+    P = ops.pad_lists(X, offd, max(lens))
+    assert P.shape == (len(lens), max(lens), F) and torch.equal(ops.unpad_lists(P, offd, sum(lens)), X)
+    assert float(P[1, lens[1]:].abs().max()) == 0.0
