@@ -335,7 +335,8 @@ def test_list_scorer_ragged_batch_equals_query_by_query(enc):
     torch.manual_seed(11)
     r = ptranking_b200.ListNet(sf_para_dict=sf, gpu=True, device=DEV)
     r.init()
-    r.train_mode()                                    # dropout is 0: training mode exercises the backward by-products
+    r.eval_mode()           # the tail net keeps the factory's dropout 0.1 whatever is configured (list_ranker.py:340-341): masks are
+                            # keyed by position in the batch, so the comparison runs without dropout; autograd is still on
     lens = [40, 17, 33, 5, 64, 1, 28]
     rng = np.random.default_rng(5)
     X = torch.from_numpy(rng.standard_normal((sum(lens), F)).astype(np.float32)).to(DEV)
