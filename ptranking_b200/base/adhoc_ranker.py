@@ -32,8 +32,8 @@ class AdhocNeuralRanker(PointNeuralRanker, ListNeuralRanker):
     def forward(self, batch_q_doc_vectors):
         return self._base().forward(self, batch_q_doc_vectors)
 
-    def forward_ragged(self, flat_q_doc_vectors, offsets, max_len):
-        return self._base().forward_ragged(self, flat_q_doc_vectors, offsets, max_len)
+    def forward_ragged(self, flat_q_doc_vectors, offsets, max_len, buckets=None):
+        return self._base().forward_ragged(self, flat_q_doc_vectors, offsets, max_len, buckets=buckets)
 
     def eval_mode(self):
         self._base().eval_mode(self)

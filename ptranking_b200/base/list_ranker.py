@@ -195,22 +195,32 @@ class ListNeuralRanker(NeuralRanker):
             raise NotImplementedError
         return torch.squeeze(tail(z), dim=2)
 
-    def forward_ragged(self, flat_q_doc_vectors, offsets, max_len):
+    def forward_ragged(self, flat_q_doc_vectors, offsets, max_len, buckets=None):
         """[total_docs, F] + int32 offsets[B+1] -> flat scores [total_docs] for lists of different lengths (the reference can
-        only batch equal-length lists, data_utils.py:683-742).  The batch is padded to ``max_len`` on the device, the
-        attention masks every query's padded keys (probability exactly 0), all other layers are row-wise, and the scores of
-        the real documents are gathered back -- so each query sees exactly what it would see alone.  Batch- or
-        list-level normalisation in the head / tail nets would mix padding into its statistics and is refused."""
+        only batch equal-length lists, data_utils.py:683-742).  The batch is padded on the device, the attention masks
+        every query's padded keys (probability exactly 0), all other layers are row-wise, and the scores of the real
+        documents are gathered back -- so each query sees exactly what it would see alone.  With ``buckets``
+        (data.RaggedBatches: the batch sorted by length and cut into length classes) every class is padded to ITS longest
+        list only.  Batch- or list-level normalisation in the head / tail nets would mix padding into its statistics and
+        is refused."""
         cfg = self.sf_para_dict[self.sf_para_dict['sf_id']]
         if cfg.get('BN', True):
             raise NotImplementedError("ragged batches through the list scorer need BN=False (the listsf default of the drop-in run)")
         X = flat_q_doc_vectors
         total = X.shape[0]
         offs = offsets.to(device=X.device, dtype=torch.int32).contiguous()
-        lens = (offs[1:] - offs[:-1]).contiguous()
-        with ops.key_lens_context(lens):
-            scores = self.forward(ops.pad_lists(X, offs, int(max_len)))        # [B, max_len]
-        return ops.unpad_lists(scores.contiguous(), offs, total)
+        B = offs.numel() - 1
+        classes = [(int(q0), int(q1), max(int(ml), 1)) for q0, q1, ml in buckets if int(q1) > int(q0)] if buckets else []
+        if not classes:
+            classes = [(0, B, max(int(max_len), 1))]
+        if classes[0][0] != 0 or classes[-1][1] != B or any(a[1] != b[0] for a, b in zip(classes, classes[1:])):
+            raise ValueError("buckets must cover the queries of the batch in order")
+        padded = []
+        for q0, q1, nmax in classes:
+            sub = offs[q0: q1 + 1]                      # absolute prefix offsets: the kernels index the whole flat batch
+            with ops.key_lens_context((sub[1:] - sub[:-1]).contiguous()):
+                padded.append(self.forward(ops.pad_lists(X, sub, nmax)).contiguous())     # [q1 - q0, nmax]
+        return ops.unpad_buckets(padded, offs, total, [c[0] for c in classes])
 
     def eval_mode(self):
         for part in self.list_sf.values():

@@ -42,9 +42,9 @@ class PointNeuralRanker(NeuralRanker):
         num_docs = batch_q_doc_vectors.size(1)
         return self.point_sf(batch_q_doc_vectors).view(-1, num_docs)
 
-    def forward_ragged(self, flat_q_doc_vectors, offsets, max_len):
+    def forward_ragged(self, flat_q_doc_vectors, offsets, max_len, buckets=None):
         """[total_docs, F] -> [total_docs]: the pointwise scorer acts per document, so a ragged batch is one long list
-        to it; only per-query normalisation (BN2) needs the offsets."""
+        to it; only per-query normalisation (BN2) needs the offsets (length classes are of no use here)."""
         return self.point_sf(flat_q_doc_vectors, offsets=offsets, max_len=max_len).view(-1)
 
     def eval_mode(self):

@@ -352,7 +352,7 @@ class NeuralRanker(Evaluator):
         """ranker.py:589-603."""
         stop_training = False
         if kwargs.get('offsets') is not None:     # ragged batch: flat [total_docs, F] features, per-query offsets
-            batch_preds = self.forward_ragged(batch_q_doc_vectors, kwargs['offsets'], kwargs['max_len'])
+            batch_preds = self.forward_ragged(batch_q_doc_vectors, kwargs['offsets'], kwargs['max_len'], buckets=kwargs.get('buckets'))
         else:
             batch_preds = self.forward(batch_q_doc_vectors)
         if 'epoch_k' in kwargs and kwargs['epoch_k'] is not None and kwargs['epoch_k'] % self.stop_check_freq == 0:
@@ -365,9 +365,9 @@ class NeuralRanker(Evaluator):
     def forward(self, batch_q_doc_vectors):
         pass
 
-    def forward_ragged(self, flat_q_doc_vectors, offsets, max_len):
+    def forward_ragged(self, flat_q_doc_vectors, offsets, max_len, buckets=None):
         """[total_docs, F] + int32 offsets[B+1] -> flat scores [total_docs] (no counterpart in the reference, whose
-        batches are dense)."""
+        batches are dense).  ``buckets``: data.RaggedBatches' length classes [(q_begin, q_end, max_len)]."""
         raise NotImplementedError("this scorer has no ragged-batch path")
 
     def predict(self, batch_q_doc_vectors):

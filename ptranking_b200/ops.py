@@ -666,7 +666,7 @@ class _PadLists(torch.autograd.Function):
         lib = _lib.load()
         g = _dev_f32(g, "g")
         F = ctx.shape[1] if len(ctx.shape) == 2 else 1
-        out = torch.empty(ctx.shape, dtype=torch.float32, device=g.device)
+        out = torch.zeros(ctx.shape, dtype=torch.float32, device=g.device)     # offsets may address a sub-range of the rows
         _lib.check(lib.ptrb200_unpad_lists(g.data_ptr(), offsets.data_ptr(), out.data_ptr(), offsets.numel() - 1, g.shape[1], F,
                                            _stream_ptr()), "unpad_lists")
         return out, None, None
@@ -699,6 +699,44 @@ class _UnpadLists(torch.autograd.Function):
         _lib.check(lib.ptrb200_pad_lists(g.data_ptr(), offsets.data_ptr(), out.data_ptr(), ctx.shape[0], ctx.shape[1], F,
                                          _stream_ptr()), "pad_lists")
         return out, None, None
+
+
+class _UnpadBuckets(torch.autograd.Function):
+    """Padded score blocks of consecutive query ranges -> one flat [total] vector (every block gathers into ITS rows through
+    the absolute prefix offsets); backward pads the gradient block by block."""
+
+    @staticmethod
+    @_on_tensor_device
+    def forward(ctx, offsets, total, q0s, *blocks):
+        lib = _lib.load()
+        blocks = [_dev_f32(b, "block") for b in blocks]
+        out = torch.empty((total,), dtype=torch.float32, device=blocks[0].device)
+        for q0, b in zip(q0s, blocks):
+            _lib.check(lib.ptrb200_unpad_lists(b.data_ptr(), offsets.data_ptr() + 4 * q0, out.data_ptr(), b.shape[0], b.shape[1], 1,
+                                               _stream_ptr()), "unpad_lists")
+        ctx.save_for_backward(offsets)
+        ctx.q0s, ctx.shapes = list(q0s), [tuple(b.shape) for b in blocks]
+        return out
+
+    @staticmethod
+    @_on_tensor_device
+    def backward(ctx, g):
+        (offsets,) = ctx.saved_tensors
+        lib = _lib.load()
+        g = _dev_f32(g, "g")
+        outs = []
+        for q0, shp in zip(ctx.q0s, ctx.shapes):
+            o = torch.empty(shp, dtype=torch.float32, device=g.device)
+            _lib.check(lib.ptrb200_pad_lists(g.data_ptr(), offsets.data_ptr() + 4 * q0, o.data_ptr(), shp[0], shp[1], 1, _stream_ptr()), "pad_lists")
+            outs.append(o)
+        return (None, None, None, *outs)
+
+
+def unpad_buckets(blocks: Sequence[torch.Tensor], offsets: torch.Tensor, total: int, q0s: Sequence[int]) -> torch.Tensor:
+    """Flat [total] scores from padded blocks [B_k, n_k] of consecutive query ranges starting at queries ``q0s``."""
+    if sum(b.shape[0] for b in blocks) != offsets.numel() - 1:
+        raise ValueError("the blocks must cover every query once")
+    return _UnpadBuckets.apply(_offsets_i32(offsets, blocks[0].device), int(total), [int(q) for q in q0s], *blocks)
 
 
 def _offsets_i32(offsets: torch.Tensor, device) -> torch.Tensor:

@@ -364,8 +364,15 @@ def test_list_scorer_ragged_batch_equals_query_by_query(enc):
     scale = max(float(g.abs().max()) for g in g_one)
     for p, a, c in zip(params, g_rag, g_one):
         assert float((a - c).abs().max()) <= 2e-5 * scale, tuple(p.shape)
+    # the same batch cut into two query ranges, each padded to its own longest list
+    s_cls = r.forward_ragged(X, offd, max(lens), buckets=[(0, 3, 40), (3, 7, 64)])
+    g_cls = grads_of((s_cls * torch.cos(torch.arange(sum(lens), device=DEV, dtype=torch.float32))).sum())
+    assert rel_err(s_cls.detach().cpu().numpy(), s_cat.detach().cpu().numpy()) <= 1e-5
+    for p, a, c in zip(params, g_cls, g_one):
+        assert float((a - c).abs().max()) <= 2e-5 * scale, tuple(p.shape)
     # and one optimizer step on the ragged batch through the public training entry point
-    loss, stop = r.train_op(X, y, offsets=offd, max_len=max(lens), presort=False, label_type=ptranking_b200.LABEL_TYPE.MultiLabel)
+    loss, stop = r.train_op(X, y, offsets=offd, max_len=max(lens), buckets=[(0, 3, 40), (3, 7, 64)], presort=False,
+                            label_type=ptranking_b200.LABEL_TYPE.MultiLabel)
     assert torch.isfinite(loss) and not stop
     # pad / unpad are inverse gathers
     P = ops.pad_lists(X, offd, max(lens))

@@ -131,6 +131,21 @@ for L in (3, 6):
         torch.cuda.synchronize()
         listsf_kernels = {k: (v[0] / 2, v[1] / 2) for k, v in _lib.kernel_timings().items()}
         _lib.kernel_timings(enable=False)
+        # the same number of documents as lists of different lengths (MSLR-shaped, capped at 512): one padded batch, and
+        # the batch cut into RaggedBatches' length classes, each padded to its own longest list
+        ll = np.clip(rng.lognormal(mean=4.45, sigma=0.85, size=2048), 1, 512).astype(np.int64)
+        ll = np.sort(ll[: int(np.searchsorted(np.cumsum(ll), B * n))])[::-1].copy()
+        lo = np.zeros(len(ll) + 1, dtype=np.int32); lo[1:] = np.cumsum(ll)
+        tot_l = int(lo[-1])
+        Xl = torch.randn(tot_l, 136, device=dev)
+        yl = torch.from_numpy(np.concatenate([-np.sort(-rng.choice(5, size=int(n_), p=bench.MSLR_P).astype(np.float32)) for n_ in ll])).to(dev)
+        lo_d = torch.from_numpy(lo).to(dev)
+        for label, bk in (("one padded batch", None), (f"{len(length_buckets(ll, edges=(64, 192)))} length classes", length_buckets(ll, edges=(64, 192)))):
+            ms_r = timeit(lambda: rl.train_op(Xl, yl, presort=True, label_type=LABEL_TYPE.MultiLabel, epoch_k=1, offsets=lo_d,
+                                              max_len=int(ll.max()), buckets=bk), iters=5, warm=2)
+            rows.append((f"ApproxNDCG + listsf DASALC L={L} train step RAGGED, {label} (lens 1..{int(ll.max())}, mean {ll.mean():.0f})",
+                         f"B={len(ll)} docs={tot_l}", ms_r, len(ll) / ms_r * 1e3, float('nan'), float('nan')))
+        rows.append((f"   -> documents/s ragged (length classes); uniform 64x512: {B * n / ms_s * 1e3:,.0f}", "", float('nan'), tot_l / ms_r * 1e3, float('nan'), float('nan')))
 
 os.makedirs("profiles", exist_ok=True)
 with open(f"profiles/{tag}_op_table.md", "w") as f:
