@@ -2,13 +2,19 @@
 //
 // MultiheadAttention.forward, ptranking/base/list_ranker.py:226-248:
 //     S = Q K^T / sqrt(d)   ->   A = softmax(S)   ->   A_d = dropout(A)   ->   O = A_d V
-// and its autograd.  Round-1 design ("materialised S"): the five contractions of forward + backward
+// and its autograd.  "Materialised S" design: the six contractions of forward + backward
 //     S = Q K^T,   O = A_d V,   dA_d = dO V^T,   dQ = dS K,   dK = dS^T Q,   dV = A_d^T dO
-// all run through ONE batched, strided  C[z] = alpha * op(A[z]) * B[z]^T  kernel (kind::tf32, 3xTF32 split, fp32
+// all run through a batched, strided  C[z] = alpha * op(A[z]) * B[z]^T  kernel (kind::tf32, 3xTF32 split, fp32
 // accumulation in TMEM); row softmax / softmax-backward are streaming SIMT kernels over the [n,n] score tensor.  A factor that
 // enters a contraction transposed (V, K, Q, dO as [key|query, d]; dS and A_d as [query, key] for dK / dV) is consumed in place
 // as an MN-major tcgen05 operand, never transposed in memory.  The [n,n] tensors live in HBM (n <= 1024 per
-// list: 134 MB per layer at B=64, n=512, 2 heads) -- the fully fused flash variant is the follow-up.
+// list: 134 MB per layer at B=64, n=512, 2 heads).
+// Two kernels implement the batched GEMM: bgemm_nt_tc_kernel takes any shape; bgemm_fast_kernel (every extent, pitch and
+// base address a multiple of four floats -- the attention core's own shapes) has the operand layouts and the dropout view
+// as template parameters, loads one K-chunk ahead and writes full-width tiles through shared memory; both produce the
+// same bits.  The row-pitched entry points (_ld) read Q|K|V side by side from one projection output and take per-query key
+// counts for padded ragged batches.  A version that kept the score tile in TMEM across QK^T and the softmax was built,
+// measured slower (one CTA per SM, strictly serial phases) and removed: DESIGN.md 4.
 #include "common.cuh"
 #include "tc.cuh"
 
