@@ -151,9 +151,15 @@ class RaggedBatches:
 
     def __init__(self, queries: Iterable[Query], docs_per_batch: int = 1 << 18, max_queries: Optional[int] = None,
                  presort: bool = True, shuffle_seed: Optional[int] = None, rank: int = 0, world: int = 1,
-                 pin_memory: Optional[bool] = None, max_list_len: int = 4096):
+                 pin_memory: Optional[bool] = None, max_list_len: int = 4096, bucket_edges: Sequence[int] = (128, 512)):
+        """``bucket_edges``: upper ends of the length classes a batch is cut into (:func:`length_buckets`).  The default
+        suits the pairwise-loss kernels; the list scorer pads every class to its longest list and attention work grows
+        with the square of that length, so it is better served by finer classes, e.g. (32, 64, 128, 256)."""
         if docs_per_batch < 1 or world < 1 or not (0 <= rank < world):
             raise ValueError("docs_per_batch >= 1 and 0 <= rank < world are required")
+        if list(bucket_edges) != sorted(set(int(e) for e in bucket_edges)) or any(int(e) < 1 for e in bucket_edges):
+            raise ValueError("bucket_edges must be increasing positive lengths")
+        self.bucket_edges = tuple(int(e) for e in bucket_edges)
         self.docs_per_batch, self.max_queries = int(docs_per_batch), max_queries
         self.shuffle_seed, self.rank, self.world = shuffle_seed, rank, world
         self.pin = torch.cuda.is_available() if pin_memory is None else bool(pin_memory)
@@ -213,7 +219,7 @@ class RaggedBatches:
                 X[o: o + Xq.shape[0]] = torch.from_numpy(Xq)
                 y[o: o + Xq.shape[0]] = torch.from_numpy(yq)
                 o += Xq.shape[0]
-            yield [q[0] for q in qs], X, y, offsets, int(lens.max()), length_buckets(lens)
+            yield [q[0] for q in qs], X, y, offsets, int(lens.max()), length_buckets(lens, edges=self.bucket_edges)
 
     def stats(self) -> dict:
         lens = np.array([q[1].shape[0] for q in self.queries])

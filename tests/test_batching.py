@@ -109,3 +109,22 @@ def test_ragged_batches_pack_by_documents_and_bucket_by_length():
     ia, ib = [q for batch in a for q in batch[0]], [q for batch in b for q in batch[0]]
     assert len(a) == len(b) and not set(ia) & set(ib)
     assert length_buckets([]) == [] and length_buckets([7]) == [(0, 1, 7)]
+
+
+def test_ragged_batches_take_custom_length_classes():
+    """Finer classes for the list scorer (attention pads every class to its longest list): the classes still cover the batch
+    in order, each holds lists no longer than its first one, and bad edges are rejected."""
+    from ptranking_b200.data import RaggedBatches
+    rng = np.random.default_rng(0)
+    lens = np.clip(rng.lognormal(4.0, 0.8, 300), 1, 400).astype(int)
+    queries = [(f"q{i}", rng.standard_normal((n, 5)).astype(np.float32), rng.integers(0, 3, n).astype(np.float32)) for i, n in enumerate(lens)]
+    rb = RaggedBatches(queries, docs_per_batch=1 << 20, pin_memory=False, bucket_edges=(16, 32, 64, 128, 256))
+    (ids, X, y, offsets, max_len, buckets), = list(rb)
+    assert len(buckets) >= 4 and buckets[0][0] == 0 and buckets[-1][1] == len(ids)
+    blens = (offsets[1:] - offsets[:-1]).numpy()
+    for (a0, a1, ml), nxt in zip(buckets, buckets[1:] + [None]):
+        assert ml == blens[a0] == blens[a0:a1].max()
+        if nxt is not None:
+            assert nxt[0] == a1
+    with pytest.raises(ValueError):
+        RaggedBatches(queries, bucket_edges=(64, 32))
