@@ -128,3 +128,28 @@ def test_ragged_batches_take_custom_length_classes():
             assert nxt[0] == a1
     with pytest.raises(ValueError):
         RaggedBatches(queries, bucket_edges=(64, 32))
+
+
+def test_length_buckets_invariants_property():
+    """For any descending length vector and any increasing edges: the classes tile [0, N) in order and every class records
+    the length of its first (= longest) list -- what the kernels size their CTAs / padding by."""
+    from hypothesis import given, settings, strategies as st
+    from ptranking_b200.data import length_buckets
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.integers(1, 2000), min_size=0, max_size=300),
+           st.lists(st.integers(1, 1500), min_size=1, max_size=5, unique=True))
+    def check(lens, edges):
+        lens = sorted(lens, reverse=True)
+        edges = sorted(edges)
+        out = length_buckets(lens, edges=edges)
+        if not lens:
+            assert out == []
+            return
+        assert out[0][0] == 0 and out[-1][1] == len(lens)
+        for (a0, a1, ml), nxt in zip(out, out[1:] + [None]):
+            assert a0 < a1 and ml == lens[a0] == max(lens[a0:a1])
+            if nxt is not None:
+                assert nxt[0] == a1
+
+    check()
